@@ -1,0 +1,830 @@
+// =============================================================================
+// bp_kernels.cuh — hand-written fp64 kernels of libbpcuda for sm_100a.
+//
+// This header is compiled ONCE PER MODEL: codegen.cpp emits a prelude with the model's
+// compile-time shape (BP_N types, BP_E events, BP_P parameters, ...), the user's rate
+// expressions as device functions (bp_rates / bp_rates_vjp), the generator assembly as
+// straight-line code (bp_assemble / bp_assemble_vjp), the prior table, and then includes this
+// file; NVRTC compiles the translation unit for sm_100a.  The same header is compiled by nvcc
+// into libbpcuda.so with a default prelude (the build()/ptxas -v/SASS check) and by g++ with
+// BP_HOSTSIM for the per-thread core (tests only).
+//
+// What it computes (reference: jproney/bpinference, paths under /root/reference):
+//   transform + Jacobian      declarations emitted by parse_prior, R/stan_utils.R:397-410;
+//                             sigma_obs: stanfiles/multitype_noise_template.stan:103
+//   generator A, C            stanfiles/multitype_template.stan:23-43
+//   moments                   the ODE of multitype_template.stan:50-58 solved in closed form
+//                             (see "moment system" below)
+//   mu, Sigma per observation multitype_template.stan:137-149
+//   multi_normal score        multitype_template.stan:152 ; noise variant multitype_noise_template.stan:153
+//   one-type closed form      stanfiles/one_type_template.stan:37-46
+//   priors                    `ThetaK ~ name(params)` emitted at R/stan_utils.R:395
+//   log_lik                   stanfiles/multitype_loo_block.stan:31, simple_birth_death_loo_block.stan:11
+// and the reverse-mode gradient of all of it w.r.t. the unconstrained parameters.
+//
+// Moment system.  The template integrates single-ancestor moments M (n x n) and D (n x n^2) and then
+// contracts them with init_pop[k].  Because that contraction is linear, the state of ONE observation
+//     y = (mu, Sigma),  mu = M^T z0,  Sigma = sum_l z0_l (D_l - m_l m_l^T)
+// obeys its own closed linear ODE of dimension n + n(n+1)/2:
+//     mu'    = A^T mu
+//     Sigma' = A^T Sigma + Sigma A + sum_l mu_l H_l ,   H_l = C_l + diag(a_l) - a_l e_l^T - e_l a_l^T
+// (a_l = row l of A), with y(0) = (z0, 0).  y(t) = exp(t L) y(0) is evaluated as the action of the
+// matrix exponential on one vector: a Taylor series whose degree is chosen from ||tL|| for a 2^-55
+// truncation bound, in sub-steps when ||tL|| exceeds what BP_MCAP stored terms can cover.  The reverse
+// sweep is the exact adjoint of that series (Horner form), which needs the series terms in reverse
+// order: they are kept in shared memory, one column per thread.
+// =============================================================================
+#ifndef BP_KERNELS_CUH
+#define BP_KERNELS_CUH
+
+#ifndef BP_HD   // normally supplied by the generated prelude
+#ifdef BP_HOSTSIM
+#define BP_HD inline
+#define BP_GLOBAL_CONST static const
+#else
+#define BP_HD __device__ __forceinline__
+#define BP_GLOBAL_CONST __constant__ const
+typedef double real;
+#endif
+#endif
+
+#define BP_S (BP_N * (BP_N + 1) / 2)
+#define BP_D (BP_N + BP_S)
+// partial sums one CTA hands to the epilogue: lp, d/dTheta[BP_P], d/dsigma_obs, Taylor applications
+#define BP_NPART (BP_P + 3)
+
+// status bits — same values as include/bpcuda.h
+#define BP_ST_NOT_PD 1
+#define BP_ST_RATE_NONFINITE 2
+#define BP_ST_ONETYPE_SINGULAR 4
+#define BP_ST_PRIOR_SUPPORT 8
+
+#define BP_SMAX 4096   // more sub-steps than this: the rates are treated as non-finite (chain rejected)
+
+// index of (i,j) in the packed upper triangle of a symmetric n x n matrix
+BP_HD constexpr int bp_sidx(int i, int j) {
+  return i <= j ? i * BP_N - i * (i - 1) / 2 + (j - i) : j * BP_N - j * (j - 1) / 2 + (i - j);
+}
+
+BP_HD bool bp_finite(real v) {
+#ifdef BP_HOSTSIM
+  return std::isfinite(bp_val(v));
+#else
+  return isfinite(v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// L(w) = (A^T mu, A^T S + S A + sum_l mu_l H_l)        (forward moment operator)
+BP_HD void bp_L_apply(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], const real (&wmu)[BP_N],
+                      const real (&wS)[BP_S], real (&omu)[BP_N], real (&oS)[BP_S]) {
+#pragma unroll
+  for (int j = 0; j < BP_N; ++j) {
+    real s = A[0 * BP_N + j] * wmu[0];
+#pragma unroll
+    for (int i = 1; i < BP_N; ++i) s += A[i * BP_N + j] * wmu[i];
+    omu[j] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+#pragma unroll
+    for (int j = i; j < BP_N; ++j) {
+      real s = wmu[0] * H[0 * BP_S + bp_sidx(i, j)];
+#pragma unroll
+      for (int l = 1; l < BP_N; ++l) s += wmu[l] * H[l * BP_S + bp_sidx(i, j)];
+      if (i == j) {
+        real d = A[0 * BP_N + i] * wS[bp_sidx(0, i)];
+#pragma unroll
+        for (int k = 1; k < BP_N; ++k) d += A[k * BP_N + i] * wS[bp_sidx(k, i)];
+        s += d + d;
+      } else {
+#pragma unroll
+        for (int k = 0; k < BP_N; ++k) s += A[k * BP_N + i] * wS[bp_sidx(k, j)] + A[k * BP_N + j] * wS[bp_sidx(k, i)];
+      }
+      oS[bp_sidx(i, j)] = s;
+    }
+  }
+}
+
+// L^T(wb) = (A a + [<Sb, H_i>]_i , A Sb + Sb A^T)       (adjoint operator; Sb is a full symmetric
+// cotangent stored packed, inner products count off-diagonals twice)
+BP_HD void bp_LT_apply(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], const real (&bmu)[BP_N],
+                       const real (&bS)[BP_S], real (&omu)[BP_N], real (&oS)[BP_S]) {
+  real b2[BP_S];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+    for (int j = i; j < BP_N; ++j) b2[bp_sidx(i, j)] = (i == j) ? bS[bp_sidx(i, j)] : bS[bp_sidx(i, j)] + bS[bp_sidx(i, j)];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+    real s = A[i * BP_N + 0] * bmu[0];
+#pragma unroll
+    for (int j = 1; j < BP_N; ++j) s += A[i * BP_N + j] * bmu[j];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) s += H[i * BP_S + q] * b2[q];
+    omu[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+#pragma unroll
+    for (int j = i; j < BP_N; ++j) {
+      real s;
+      if (i == j) {
+        real d = A[i * BP_N + 0] * bS[bp_sidx(0, i)];
+#pragma unroll
+        for (int k = 1; k < BP_N; ++k) d += A[i * BP_N + k] * bS[bp_sidx(k, i)];
+        s = d + d;
+      } else {
+        s = A[i * BP_N + 0] * bS[bp_sidx(0, j)] + A[j * BP_N + 0] * bS[bp_sidx(0, i)];
+#pragma unroll
+        for (int k = 1; k < BP_N; ++k) s += A[i * BP_N + k] * bS[bp_sidx(k, j)] + A[j * BP_N + k] * bS[bp_sidx(k, i)];
+      }
+      oS[bp_sidx(i, j)] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one sub-step  y <- sum_{k=0}^{m} (hL)^k/k! y   (m applications of L).  Term k (k >= 1) is written
+// to store[(k-1)*BP_D + comp][.] when do_store; term 0 is the step's input, kept by the caller.
+BP_HD void bp_step_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real h, int m, real (&ymu)[BP_N],
+                       real (&yS)[BP_S], bool do_store, real* store, int stride) {
+  real wmu[BP_N], wS[BP_S];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) wmu[i] = ymu[i];
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) wS[q] = yS[q];
+  for (int k = 0; k < m; ++k) {
+    real lmu[BP_N], lS[BP_S];
+    bp_L_apply(A, H, wmu, wS, lmu, lS);
+    const real al = h * bp_rk[k];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) { wmu[i] = al * lmu[i]; ymu[i] += wmu[i]; }
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) { wS[q] = al * lS[q]; yS[q] += wS[q]; }
+    if (do_store && k + 1 < m) {
+      real* p = store + (size_t)k * BP_D * stride;
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) p[i * stride] = wmu[i];
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) p[(BP_N + q) * stride] = wS[q];
+    }
+  }
+}
+
+// exact adjoint of bp_step_fwd.  (bmu,bS): in = cotangent of the step's output, out = cotangent of its
+// input.  (y0mu,y0S) = the step's input (term 0).  Accumulates gA += dlp/dA, gH += dlp/dH.
+BP_HD void bp_step_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real h, int m, const real (&y0mu)[BP_N],
+                       const real (&y0S)[BP_S], const real* store, int stride, real (&bmu)[BP_N], real (&bS)[BP_S],
+                       real (&gA)[BP_N * BP_N], real (&gH)[BP_N * BP_S]) {
+  real vmu[BP_N], vS[BP_S];   // Horner accumulator wb_k
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) vmu[i] = bmu[i];
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) vS[q] = bS[q];
+  for (int k = m - 1; k >= 0; --k) {
+    const real al = h * bp_rk[k];
+    real amu[BP_N], aS[BP_S];   // al * w_k.mu,  2 al * w_k.S
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) amu[i] = al * y0mu[i];
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) aS[q] = (al + al) * y0S[q];
+    } else {
+      const real* p = store + (size_t)(k - 1) * BP_D * stride;
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) amu[i] = al * p[i * stride];
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) aS[q] = (al + al) * p[(BP_N + q) * stride];
+    }
+    // gA[i][j] += al ( w.mu_i v.mu_j + 2 sum_k w.S_ik v.S_kj ) ; gH[l] += al w.mu_l v.S
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+      for (int j = 0; j < BP_N; ++j) {
+        real s = amu[i] * vmu[j];
+#pragma unroll
+        for (int q = 0; q < BP_N; ++q) s += aS[bp_sidx(i, q)] * vS[bp_sidx(q, j)];
+        gA[i * BP_N + j] += s;
+      }
+#pragma unroll
+    for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) gH[l * BP_S + q] += amu[l] * vS[q];
+    real tmu[BP_N], tS[BP_S];
+    bp_LT_apply(A, H, vmu, vS, tmu, tS);
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) vmu[i] = bmu[i] + al * tmu[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) vS[q] = bS[q] + al * tS[q];
+  }
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) bmu[i] = vmu[i];
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) bS[q] = vS[q];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pop_vec[k] ~ multi_normal(mu, Sigma): lp = -1/2 log det Sigma - 1/2 r^T Sigma^-1 r  (Stan's `~` drops
+// -(n/2) log 2 pi; add_const restores it for log_lik).  Writes bmu = dlp/dmu, bS = dlp/dSigma (full
+// symmetric, packed).  Returns false when Sigma is not positive definite / not finite.
+BP_HD bool bp_mvn_score(const real (&x)[BP_N], const real (&mu)[BP_N], const real (&S)[BP_S], real& lp, real (&bmu)[BP_N],
+                        real (&bS)[BP_S]) {
+  real Lc[BP_N][BP_N], Li[BP_N][BP_N], idiag[BP_N];
+  real ld = real(0.0);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < BP_N; ++j) {
+    real d = S[bp_sidx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+    if (!(d > real(0.0)) || !bp_finite(d)) ok = false;
+    const real sd = sqrt(d);
+    Lc[j][j] = sd;
+    idiag[j] = real(1.0) / sd;
+    ld += log(d);
+#pragma unroll
+    for (int i = j + 1; i < BP_N; ++i) {
+      real s = S[bp_sidx(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= Lc[i][k] * Lc[j][k];
+      Lc[i][j] = s * idiag[j];
+    }
+  }
+  if (!ok) return false;
+  // inverse of the lower-triangular factor
+#pragma unroll
+  for (int j = 0; j < BP_N; ++j) {
+    Li[j][j] = idiag[j];
+#pragma unroll
+    for (int i = j + 1; i < BP_N; ++i) {
+      real s = real(0.0);
+#pragma unroll
+      for (int k = j; k < i; ++k) s -= Lc[i][k] * Li[k][j];
+      Li[i][j] = s * idiag[i];
+    }
+  }
+  real a[BP_N];
+  real q = real(0.0);
+  bool fin = true;
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+    real s = real(0.0);
+#pragma unroll
+    for (int k = 0; k <= i; ++k) s += Li[i][k] * (x[k] - mu[k]);
+    a[i] = s;
+    q += s * s;
+    if (!bp_finite(s)) fin = false;
+  }
+  if (!fin) return false;
+  lp = real(-0.5) * (ld + q);
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+    real s = real(0.0);
+#pragma unroll
+    for (int k = i; k < BP_N; ++k) s += Li[k][i] * a[k];
+    bmu[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+    for (int j = i; j < BP_N; ++j) {
+      real si = real(0.0);
+#pragma unroll
+      for (int k = j; k < BP_N; ++k) si += Li[k][i] * Li[k][j];
+      bS[bp_sidx(i, j)] = real(0.5) * (bmu[i] * bmu[j] - si);
+    }
+  return true;
+}
+
+// ||A||_1 (max column abs sum); the Lyapunov part of L is bounded by twice that
+BP_HD real bp_norm1(const real (&A)[BP_N * BP_N]) {
+  real a1 = real(0.0);
+#pragma unroll
+  for (int j = 0; j < BP_N; ++j) {
+    real s = real(0.0);
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) s += fabs(A[i * BP_N + j]);
+    a1 = (s > a1) ? s : a1;   // NaN in s never wins; callers test the rates for finiteness separately
+  }
+  return a1;
+}
+
+struct BpPlan { int s; int m; real h; };
+
+// sub-steps and series degree for duration t: scaled norm th = 2 ||A||_1 t / s <= BP_THETA_CAP,
+// applications m = 1 + min{ d : th <= bp_th[d] }  (bp_th[d]^d / d! = 2^-55)
+BP_HD bool bp_make_plan(real a1, real t, BpPlan& p) {
+  const real xx = (a1 + a1) * t;
+  if (!(xx >= real(0.0)) || !bp_finite(xx)) return false;
+  int s = 1;
+  if (xx > real(BP_THETA_CAP)) {
+    const real sr = ceil(xx / real(BP_THETA_CAP));
+    if (sr > real((double)BP_SMAX)) return false;
+#ifdef BP_HOSTSIM
+    s = (int)bp_val(sr);
+#else
+    s = (int)sr;
+#endif
+  }
+  p.s = s;
+  p.h = t / real((double)s);
+  const real th = xx / real((double)s);
+  int d = 1;
+  while (d < BP_MCAP && th > real(bp_th[d])) ++d;
+  p.m = d + 1;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one observation of the multitype templates: forward series, score, reverse series.
+// Accumulates lp, gA, gH, sb (d/dsigma_obs), apps; ORs status.  store/stride: this thread's term column.
+#if BP_KIND != 2
+BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
+                         const real (&xo)[BP_N], real t, real sigma, real* store, int stride, real& lp, real (&gA)[BP_N * BP_N],
+                         real (&gH)[BP_N * BP_S], real& sb, int& status, int& apps) {
+  BpPlan p;
+  if (!bp_make_plan(a1, t, p)) { status |= BP_ST_RATE_NONFINITE; return; }
+  apps += p.s * p.m;   // algorithmic applications of L (and as many of L^T); recomputed sub-steps are not counted
+  real bmu[BP_N], bS[BP_S];
+  bool scored = false;
+  for (int target = p.s - 1; target >= 0; --target) {
+    // forward from the observation's initial state up to and including sub-step `target`; only that
+    // sub-step's terms are stored (earlier sub-steps are recomputed when their turn comes: p.s is 1
+    // unless ||tL|| is large)
+    real ymu[BP_N], yS[BP_S], y0mu[BP_N], y0S[BP_S];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) ymu[i] = z0[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) yS[q] = real(0.0);
+    for (int j = 0; j <= target; ++j) {
+      if (j == target) {
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) y0mu[i] = ymu[i];
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q) y0S[q] = yS[q];
+      }
+      bp_step_fwd(A, H, p.h, p.m, ymu, yS, j == target, store, stride);
+    }
+    if (!scored) {
+      scored = true;
+#if BP_NOISE
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
+#endif
+      real lpk;
+      if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) { status |= BP_ST_NOT_PD; return; }
+      lp += lpk;
+#if BP_NOISE
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += sigma * bS[bp_sidx(i, i)]; }
+#endif
+    }
+    bp_step_bwd(A, H, p.h, p.m, y0mu, y0S, store, stride, bmu, bS, gA, gH);
+  }
+}
+
+// forward only: per-observation log_lik with the normalising constant (LOO block)
+BP_HD real bp_obs_loglik(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
+                         const real (&xo)[BP_N], real t, real sigma) {
+  BpPlan p;
+  const real nan_ = real(0.0) / real(0.0);
+  if (!bp_make_plan(a1, t, p)) return nan_;
+  real ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) ymu[i] = z0[i];
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) yS[q] = real(0.0);
+  for (int j = 0; j < p.s; ++j) bp_step_fwd(A, H, p.h, p.m, ymu, yS, false, (real*)0, 0);
+#if BP_NOISE
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
+#endif
+  real lpk;
+  if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) return nan_;
+  return lpk - real(0.5 * BP_N * 1.8378770664093454835606594728112);   // n/2 log(2 pi)
+}
+#endif  // BP_KIND != 2
+
+// ---------------------------------------------------------------------------------------------
+// one observation of the one-type template (stanfiles/one_type_template.stan:38-45):
+//   g = b - d, e = exp(t g), mu = e z0, var = (e (b (2e - 1) - d)/g - e^2) z0, x ~ normal(mu, sqrt(var))
+// rb[0], rb[1] += dlp/db, dlp/dd.
+BP_HD void bp_onetype_obs(real b, real d, real t, real z0, real x, real& lp, real (&rb)[2], int& status, bool add_const) {
+  const real g = b - d;
+  if (g == real(0.0) || !bp_finite(g)) { status |= BP_ST_ONETYPE_SINGULAR; return; }
+  const real e = exp(t * g);
+  const real mu = e * z0;
+  const real Nn = b * (real(2.0) * e - real(1.0)) - d;
+  const real ig = real(1.0) / g;
+  const real q = e * Nn * ig - e * e;
+  const real var = q * z0;
+  if (!(var > real(0.0)) || !bp_finite(var)) { status |= BP_ST_ONETYPE_SINGULAR; return; }
+  const real iv = real(1.0) / var;
+  const real res = x - mu;
+  lp += real(-0.5) * log(var) - real(0.5) * res * res * iv - (add_const ? real(0.91893853320467274178) : real(0.0));
+  const real dmu = res * iv;
+  const real dvar = real(0.5) * (res * res * iv - real(1.0)) * iv;
+  const real te = t * e;
+  const real common = e * Nn * ig * ig;
+  const real dq_db = (te * Nn + e * (real(2.0) * e - real(1.0) + real(2.0) * b * te)) * ig - common - real(2.0) * te * e;
+  const real dq_dd = (-te * Nn - e * (real(2.0) * b * te + real(1.0))) * ig + common + real(2.0) * te * e;
+  rb[0] += dmu * te * z0 + dvar * z0 * dq_db;
+  rb[1] += -dmu * te * z0 + dvar * z0 * dq_dd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// priors: log-density kernel of Theta_k up to additive constants (Stan `~`), its derivative, support.
+// ids follow ALLOWED_DISTRIBUTIONS (R/sysdata.rda, consumed at R/stan_utils.R:373-390).
+#define BP_PR_NORMAL 0
+#define BP_PR_EXP_MOD_NORMAL 1
+#define BP_PR_SKEW_NORMAL 2
+#define BP_PR_STUDENT_T 3
+#define BP_PR_CAUCHY 4
+#define BP_PR_DOUBLE_EXPONENTIAL 5
+#define BP_PR_LOGISTIC 6
+#define BP_PR_GUMBEL 7
+#define BP_PR_LOGNORMAL 8
+#define BP_PR_CHI_SQUARE 9
+#define BP_PR_INV_CHI_SQUARE 10
+#define BP_PR_SCALED_INV_CHI_SQUARE 11
+#define BP_PR_EXPONENTIAL 12
+#define BP_PR_GAMMA 13
+#define BP_PR_INV_GAMMA 14
+#define BP_PR_WEIBULL 15
+#define BP_PR_FRECHET 16
+#define BP_PR_RAYLEIGH 17
+#define BP_PR_PARETO 18
+#define BP_PR_PARETO_TYPE_2 19
+#define BP_PR_BETA 20
+#define BP_PR_UNIFORM 21
+
+#ifndef BP_HOSTSIM
+// log(erfc(z)) and d/dz, stable for large z through erfcx
+__device__ inline void bp_log_erfc(double z, double& le, double& dle) {
+  const double two_over_sqrtpi = 1.1283791670955125739;
+  if (z > 0.0) {
+    const double ex = erfcx(z);
+    le = log(ex) - z * z;
+    dle = -two_over_sqrtpi / ex;
+  } else {
+    const double ec = erfc(z);
+    le = log(ec);
+    dle = -two_over_sqrtpi * exp(-z * z) / ec;
+  }
+}
+
+__device__ inline bool bp_prior(int id, double p0, double p1, double p2, double y, double& lp, double& g) {
+  const double SQ2 = 1.4142135623730950488;
+  bool ok = true;
+  switch (id) {
+    case BP_PR_NORMAL: { const double z = (y - p0) / p1; lp = -0.5 * z * z; g = -z / p1; break; }
+    case BP_PR_EXP_MOD_NORMAL: {
+      const double z = (p0 + p2 * p1 * p1 - y) / (SQ2 * p1); double le, dle; bp_log_erfc(z, le, dle);
+      lp = -p2 * y + le; g = -p2 - dle / (SQ2 * p1); break; }
+    case BP_PR_SKEW_NORMAL: {
+      const double z = (y - p0) / p1; double le, dle; bp_log_erfc(-p2 * z / SQ2, le, dle);
+      lp = -0.5 * z * z + le; g = -z / p1 - dle * p2 / (SQ2 * p1); break; }
+    case BP_PR_STUDENT_T: { const double z = (y - p1) / p2; lp = -0.5 * (p0 + 1.0) * log1p(z * z / p0); g = -(p0 + 1.0) * z / (p2 * p0 * (1.0 + z * z / p0)); break; }
+    case BP_PR_CAUCHY: { const double z = (y - p0) / p1; lp = -log1p(z * z); g = -2.0 * z / (p1 * (1.0 + z * z)); break; }
+    case BP_PR_DOUBLE_EXPONENTIAL: { const double r = y - p0; lp = -fabs(r) / p1; g = (r > 0.0 ? -1.0 : (r < 0.0 ? 1.0 : 0.0)) / p1; break; }
+    case BP_PR_LOGISTIC: { const double z = (y - p0) / p1; const double em = exp(-z); lp = -z - 2.0 * log1p(em); g = (-1.0 + 2.0 * em / (1.0 + em)) / p1; break; }
+    case BP_PR_GUMBEL: { const double z = (y - p0) / p1; const double em = exp(-z); lp = -z - em; g = (-1.0 + em) / p1; break; }
+    case BP_PR_LOGNORMAL: { ok = y > 0.0; const double ly = log(y); const double z = (ly - p0) / p1; lp = -ly - 0.5 * z * z; g = (-1.0 - z / p1) / y; break; }
+    case BP_PR_CHI_SQUARE: { ok = y >= 0.0; lp = (0.5 * p0 - 1.0) * log(y) - 0.5 * y; g = (0.5 * p0 - 1.0) / y - 0.5; break; }
+    case BP_PR_INV_CHI_SQUARE: { ok = y > 0.0; lp = -(0.5 * p0 + 1.0) * log(y) - 0.5 / y; g = -(0.5 * p0 + 1.0) / y + 0.5 / (y * y); break; }
+    case BP_PR_SCALED_INV_CHI_SQUARE: { ok = y > 0.0; const double c = 0.5 * p0 * p1 * p1; lp = -(0.5 * p0 + 1.0) * log(y) - c / y; g = -(0.5 * p0 + 1.0) / y + c / (y * y); break; }
+    case BP_PR_EXPONENTIAL: { ok = y >= 0.0; lp = -p0 * y; g = -p0; break; }
+    case BP_PR_GAMMA: { ok = y >= 0.0; lp = (p0 - 1.0) * log(y) - p1 * y; g = (p0 - 1.0) / y - p1; break; }
+    case BP_PR_INV_GAMMA: { ok = y > 0.0; lp = -(p0 + 1.0) * log(y) - p1 / y; g = -(p0 + 1.0) / y + p1 / (y * y); break; }
+    case BP_PR_WEIBULL: { ok = y >= 0.0; const double w = pow(y / p1, p0); lp = (p0 - 1.0) * log(y) - w; g = (p0 - 1.0) / y - p0 * w / y; break; }
+    case BP_PR_FRECHET: { ok = y > 0.0; const double w = pow(y / p1, -p0); lp = -(p0 + 1.0) * log(y) - w; g = -(p0 + 1.0) / y + p0 * w / y; break; }
+    case BP_PR_RAYLEIGH: { ok = y >= 0.0; lp = log(y) - y * y / (2.0 * p0 * p0); g = 1.0 / y - y / (p0 * p0); break; }
+    case BP_PR_PARETO: { ok = y >= p0; lp = -(p1 + 1.0) * log(y); g = -(p1 + 1.0) / y; break; }
+    case BP_PR_PARETO_TYPE_2: { ok = y >= p0; lp = -(p2 + 1.0) * log1p((y - p0) / p1); g = -(p2 + 1.0) / (p1 + y - p0); break; }
+    case BP_PR_BETA: { ok = (y >= 0.0) && (y <= 1.0); lp = (p0 - 1.0) * log(y) + (p1 - 1.0) * log1p(-y); g = (p0 - 1.0) / y - (p1 - 1.0) / (1.0 - y); break; }
+    case BP_PR_UNIFORM: { ok = (y >= p0) && (y <= p1); lp = 0.0; g = 0.0; break; }
+    default: ok = false; lp = 0.0; g = 0.0;
+  }
+  return ok && isfinite(lp);
+}
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+
+// ---- prologue: unconstrained -> constrained, one thread per chain -------------------------------
+// theta[c][k] = lo + (hi - lo) inv_logit(u) for bounded parameters, u otherwise; sigma_obs = exp(u).
+extern "C" __global__ void bp_prologue(const double* __restrict__ u, int nchains, double* __restrict__ theta,
+                                       int* __restrict__ status) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchains) return;
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) {
+    const double uk = u[(size_t)c * BP_DIM + k];
+    double th = uk;
+    if (bp_has_bounds[k]) {
+      const double s = (uk >= 0.0) ? 1.0 / (1.0 + exp(-uk)) : exp(uk) / (1.0 + exp(uk));
+      th = bp_lo[k] + (bp_hi[k] - bp_lo[k]) * s;
+    }
+    theta[(size_t)c * BP_DIM + k] = th;
+  }
+#if BP_NOISE
+  theta[(size_t)c * BP_DIM + BP_P] = exp(u[(size_t)c * BP_DIM + BP_P]);
+#endif
+  status[c] = 0;
+}
+
+// ---- block reduction of BP_NPART partial sums, fixed order (deterministic) ----------------------
+__device__ __forceinline__ double bp_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// vals: this thread's BP_NPART sums.  scratch: >= BP_NPART * (BP_THREADS/32) doubles of shared memory.
+__device__ __forceinline__ void bp_block_reduce_store(double (&vals)[BP_NPART], double* scratch, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = BP_THREADS / 32;
+#pragma unroll
+  for (int i = 0; i < BP_NPART; ++i) {
+    const double s = bp_warp_sum(vals[i]);
+    if (lane == 0) scratch[i * NW + warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < BP_NPART) {
+    double s = 0.0;
+    for (int w = 0; w < NW; ++w) s += scratch[threadIdx.x * NW + w];
+    out[threadIdx.x] = s;
+  }
+}
+
+struct BpObsArgs {
+  const double* theta;   // [C][BP_DIM]
+  const double* z0;      // [BP_N][npad]   init_pop, SoA, sorted
+  const double* xo;      // [BP_N][npad]   pop_vec
+  const double* t;       // [npad]         duration of each observation
+  const double* xv;      // [BP_KDEP][npad] dependent variables of each observation (only when BP_XDEP)
+  double* part;          // [C][ntiles][BP_NPART]
+  int* status;           // [C]
+  double* loglik;        // [C][N] (bp_*_loglik only)
+  const int* perm;       // [npad] original index of sorted observation (bp_*_loglik only)
+  int nobs, npad, tile, ntiles, nchains;
+};
+
+#if BP_KIND != 2
+// ---- fused per-(chain, observation) kernel of the multitype templates ---------------------------
+// grid (ntiles, C); CTA = BP_THREADS threads = one tile of one chain; thread i takes observations
+// tile*T + i, + BP_THREADS, ... (coalesced SoA loads).  Dynamic shared memory: the Taylor-term store,
+// BP_MCAP * BP_D doubles per thread, laid out [term][component][thread] (conflict-free).
+extern "C" __global__ void __launch_bounds__(BP_THREADS, 1) bp_fused(BpObsArgs a) {
+  extern __shared__ double bp_smem[];
+  const int c = blockIdx.y;
+  const int tid = threadIdx.x;
+  double* store = bp_smem + tid;
+
+  double th[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+#if BP_NOISE
+  const double sigma = th[BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  double lp = 0.0, sb = 0.0;
+  double cb[BP_P];
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
+  int status = 0, apps = 0;
+
+  double A[BP_N * BP_N], H[BP_N * BP_S], gA[BP_N * BP_N], gH[BP_N * BP_S];
+  double r[BP_E], xk[BP_KDEP];
+  double a1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < BP_N * BP_N; ++i) gA[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
+#if !BP_XDEP
+  {
+#pragma unroll
+    for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+    bp_rates(th, xk, r);
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+    if (!fin) status |= BP_ST_RATE_NONFINITE;
+    bp_assemble(r, A, H);
+    a1 = bp_norm1(A);
+  }
+#endif
+  const int k0 = blockIdx.x * a.tile;
+  const int k1 = min(a.nobs, k0 + a.tile);
+  if (!(status & BP_ST_RATE_NONFINITE)) {
+    for (int k = k0 + tid; k < k1; k += BP_THREADS) {
+      double z0[BP_N], xo[BP_N];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+      const double t = a.t[k];
+#if BP_XDEP
+#pragma unroll
+      for (int q = 0; q < BP_KDEP; ++q) xk[q] = a.xv[(size_t)q * a.npad + k];
+      bp_rates(th, xk, r);
+      bool fin = true;
+#pragma unroll
+      for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+      if (!fin) { status |= BP_ST_RATE_NONFINITE; continue; }
+      bp_assemble(r, A, H);
+      a1 = bp_norm1(A);
+#pragma unroll
+      for (int i = 0; i < BP_N * BP_N; ++i) gA[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
+#endif
+      bp_obs_lpgrad(A, H, a1, z0, xo, t, sigma, store, BP_THREADS, lp, gA, gH, sb, status, apps);
+#if BP_XDEP
+      double rb[BP_E];
+      bp_assemble_vjp(gA, gH, rb);
+      bp_rates_vjp(th, xk, rb, cb);
+#endif
+    }
+  }
+#if !BP_XDEP
+  {
+    double rb[BP_E];
+    bp_assemble_vjp(gA, gH, rb);
+    bp_rates_vjp(th, xk, rb, cb);
+  }
+#endif
+  double vals[BP_NPART];
+  vals[0] = lp;
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) vals[1 + k] = cb[k];
+  vals[BP_P + 1] = sb;
+  vals[BP_P + 2] = (double)apps;
+  __syncthreads();   // the term store is dead: reuse its first words as reduction scratch
+  bp_block_reduce_store(vals, bp_smem, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
+  if (status) atomicOr(a.status + c, status);
+}
+
+// ---- per-observation log_lik (LOO block), forward only -----------------------------------------
+extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_loglik(BpObsArgs a) {
+  const int c = blockIdx.y;
+  const int k = blockIdx.x * BP_THREADS + threadIdx.x;
+  if (k >= a.nobs) return;
+  double th[BP_DIM];
+#pragma unroll
+  for (int q = 0; q < BP_DIM; ++q) th[q] = a.theta[(size_t)c * BP_DIM + q];
+#if BP_NOISE
+  const double sigma = th[BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP], z0[BP_N], xo[BP_N];
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = 0.0;
+#if BP_XDEP
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = a.xv[(size_t)q * a.npad + k];
+#endif
+  bp_rates(th, xk, r);
+  bp_assemble(r, A, H);
+  const double a1 = bp_norm1(A);
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+  a.loglik[(size_t)c * a.nobs + a.perm[k]] = bp_obs_loglik(A, H, a1, z0, xo, a.t[k], sigma);
+}
+#else   // BP_KIND == 2
+// ---- one-type template: thread per (chain, observation) -----------------------------------------
+extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_onetype(BpObsArgs a) {
+  __shared__ double scratch[BP_NPART * (BP_THREADS / 32)];
+  const int c = blockIdx.y;
+  const int tid = threadIdx.x;
+  double th[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+  double lp = 0.0;
+  double cb[BP_P], r[BP_E], rb[2] = {0.0, 0.0}, xk[BP_KDEP];
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+  int status = 0;
+#if !BP_XDEP
+  bp_rates(th, xk, r);
+  if (!isfinite(r[0]) || !isfinite(r[1])) status |= BP_ST_RATE_NONFINITE;
+#endif
+  const int k0 = blockIdx.x * a.tile;
+  const int k1 = min(a.nobs, k0 + a.tile);
+  if (!status) {
+    for (int k = k0 + tid; k < k1; k += BP_THREADS) {
+#if BP_XDEP
+#pragma unroll
+      for (int q = 0; q < BP_KDEP; ++q) xk[q] = a.xv[(size_t)q * a.npad + k];
+      bp_rates(th, xk, r);
+      if (!isfinite(r[0]) || !isfinite(r[1])) { status |= BP_ST_RATE_NONFINITE; continue; }
+      rb[0] = 0.0; rb[1] = 0.0;
+#endif
+      bp_onetype_obs(r[0], r[1], a.t[k], a.z0[k], a.xo[k], lp, rb, status, false);
+#if BP_XDEP
+      bp_rates_vjp(th, xk, rb, cb);
+#endif
+    }
+  }
+#if !BP_XDEP
+  bp_rates_vjp(th, xk, rb, cb);
+#endif
+  double vals[BP_NPART];
+  vals[0] = lp;
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) vals[1 + k] = cb[k];
+  vals[BP_P + 1] = 0.0;
+  vals[BP_P + 2] = 0.0;
+  bp_block_reduce_store(vals, scratch, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
+  if (status) atomicOr(a.status + c, status);
+}
+
+extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_loglik(BpObsArgs a) {
+  const int c = blockIdx.y;
+  const int k = blockIdx.x * BP_THREADS + threadIdx.x;
+  if (k >= a.nobs) return;
+  double th[BP_DIM], r[BP_E], xk[BP_KDEP], rb[2] = {0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < BP_DIM; ++q) th[q] = a.theta[(size_t)c * BP_DIM + q];
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = 0.0;
+#if BP_XDEP
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = a.xv[(size_t)q * a.npad + k];
+#endif
+  bp_rates(th, xk, r);
+  double lp = 0.0;
+  int st = 0;
+  bp_onetype_obs(r[0], r[1], a.t[k], a.z0[k], a.xo[k], lp, rb, st, true);
+  a.loglik[(size_t)c * a.nobs + a.perm[k]] = st ? (0.0 / 0.0) : lp;
+}
+#endif  // BP_KIND
+
+// ---- epilogue: one thread per chain ---------------------------------------------------------------
+// sums the tile partials in tile order, adds priors and the log-Jacobian, applies the chain rule of the
+// bound transform, and rejects the chain (lp = -inf, grad = 0) when any status bit is set.
+extern "C" __global__ void bp_epilogue(const double* __restrict__ u, const double* __restrict__ theta,
+                                       const double* __restrict__ part, int ntiles, int nchains, int jacobian,
+                                       double* __restrict__ lp_out, double* __restrict__ grad_out, int* __restrict__ status,
+                                       double* __restrict__ apps_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchains) return;
+  double acc[BP_NPART];
+#pragma unroll
+  for (int i = 0; i < BP_NPART; ++i) acc[i] = 0.0;
+  for (int tI = 0; tI < ntiles; ++tI) {
+    const double* p = part + ((size_t)c * ntiles + tI) * BP_NPART;
+#pragma unroll
+    for (int i = 0; i < BP_NPART; ++i) acc[i] += p[i];
+  }
+  double lp = acc[0];
+  int st = status[c];
+  double grad[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) {
+    const double th = theta[(size_t)c * BP_DIM + k];
+    const double uk = u[(size_t)c * BP_DIM + k];
+    double pl, pg;
+    if (!bp_prior(bp_prior_id[k], bp_prior_par[k][0], bp_prior_par[k][1], bp_prior_par[k][2], th, pl, pg)) { st |= BP_ST_PRIOR_SUPPORT; pl = 0.0; pg = 0.0; }
+    lp += pl;
+    double gth = acc[1 + k] + pg;
+    if (bp_has_bounds[k]) {
+      const double s = (uk >= 0.0) ? 1.0 / (1.0 + exp(-uk)) : exp(uk) / (1.0 + exp(uk));
+      gth *= (bp_hi[k] - bp_lo[k]) * s * (1.0 - s);
+      if (jacobian) {
+        const double au = fabs(uk);
+        lp += log(bp_hi[k] - bp_lo[k]) - au - 2.0 * log1p(exp(-au));
+        gth += 1.0 - 2.0 * s;
+      }
+    }
+    grad[k] = gth;
+  }
+#if BP_NOISE
+  {
+    // sigma_obs ~ normal(0, .1) on sigma_obs > 0 (multitype_noise_template.stan:131); sigma_obs = exp(u)
+    const double sig = theta[(size_t)c * BP_DIM + BP_P];
+    lp += -0.5 * (sig / 0.1) * (sig / 0.1);
+    double g = (acc[BP_P + 1] - sig / 0.01) * sig;
+    if (jacobian) { lp += u[(size_t)c * BP_DIM + BP_P]; g += 1.0; }
+    grad[BP_P] = g;
+  }
+#endif
+  bool bad = st != 0 || !isfinite(lp);
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) bad = bad || !isfinite(grad[k]);
+  if (bad && st == 0) st = BP_ST_RATE_NONFINITE;
+  status[c] = st;
+  lp_out[c] = bad ? -(1.0 / 0.0) : lp;
+  if (grad_out) {
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) grad_out[(size_t)c * BP_DIM + k] = bad ? 0.0 : grad[k];
+  }
+  if (apps_out) apps_out[c] = acc[BP_P + 2];
+}
+#endif  // !BP_HOSTSIM
+
+#endif  // BP_KERNELS_CUH

@@ -1,0 +1,536 @@
+// bpcuda.cpp — host side of libbpcuda: handles, NVRTC compilation, data repacking, launches.
+// The C ABI is include/bpcuda.h; each entry point there cites the reference interface it replaces.
+// There is NO CPU fallback: every evaluate/sample entry point fails with BPC_E_CUDA without a device.
+#include "bpcuda.h"
+
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "bpcuda_internal.hpp"
+#include "codegen.hpp"
+#include "rexpr.hpp"
+
+extern "C" const char bp_kernels_cuh_text[];   // bp_kernels.cuh embedded at build time (embed_header.py)
+
+namespace bpc {
+
+thread_local std::string g_last_error;
+thread_local long long g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(BPC_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define BPC_CUDA(call)                                      \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+static int compile_model(bpc_model* m) {
+  nvrtcProgram prog;
+  const char* hdr_src[] = {bp_kernels_cuh_text};
+  const char* hdr_name[] = {"bp_kernels.cuh"};
+  if (nvrtcCreateProgram(&prog, m->source.c_str(), "bp_model.cu", 1, hdr_src, hdr_name) != NVRTC_SUCCESS)
+    return fail(BPC_E_COMPILE, "nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+  const nvrtcResult rc = nvrtcCompileProgram(prog, 4, opts);
+  size_t logsz = 0;
+  nvrtcGetProgramLogSize(prog, &logsz);
+  std::string log(logsz, '\0');
+  if (logsz > 1) nvrtcGetProgramLog(prog, &log[0]);
+  if (rc != NVRTC_SUCCESS) {
+    nvrtcDestroyProgram(&prog);
+    return fail(BPC_E_COMPILE, "NVRTC compilation failed:\n" + log);
+  }
+  size_t sz = 0;
+  if (nvrtcGetCUBINSize(prog, &sz) != NVRTC_SUCCESS || sz == 0) {
+    nvrtcDestroyProgram(&prog);
+    return fail(BPC_E_COMPILE, "NVRTC produced no cubin");
+  }
+  m->cubin.resize(sz);
+  nvrtcGetCUBIN(prog, m->cubin.data());
+  nvrtcDestroyProgram(&prog);
+  m->compile_log = log;
+  return BPC_OK;
+}
+
+int model_load(bpc_model* m, int device, Loaded** out) {
+  auto it = m->loaded.find(device);
+  if (it != m->loaded.end()) { *out = &it->second; return BPC_OK; }
+  BPC_CUDA(cudaSetDevice(device));
+  Loaded L;
+  BPC_CUDA(cudaLibraryLoadData(&L.lib, m->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  BPC_CUDA(cudaLibraryGetKernel(&L.prologue, L.lib, "bp_prologue"));
+  BPC_CUDA(cudaLibraryGetKernel(&L.epilogue, L.lib, "bp_epilogue"));
+  BPC_CUDA(cudaLibraryGetKernel(&L.loglik, L.lib, "bp_loglik"));
+  if (m->spec.kind == BPC_SIMPLE_BD) {
+    BPC_CUDA(cudaLibraryGetKernel(&L.obs, L.lib, "bp_onetype"));
+    L.obs_smem = 0;
+  } else {
+    BPC_CUDA(cudaLibraryGetKernel(&L.obs, L.lib, "bp_fused"));
+    const int n = m->spec.ntypes;
+    const int D = n + n * (n + 1) / 2;
+    L.obs_smem = (size_t)m->spec.mcap * D * m->spec.threads * sizeof(double);
+    BPC_CUDA(cudaKernelSetAttributeForDevice(L.obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.obs_smem, device));
+    if (cudaLibraryGetKernel(&L.grouped, L.lib, "bp_grouped") != cudaSuccess) { L.grouped = nullptr; cudaGetLastError(); }
+  }
+  auto ins = m->loaded.emplace(device, L);
+  *out = &ins.first->second;
+  return BPC_OK;
+}
+
+}  // namespace bpc
+
+using namespace bpc;
+
+// =============================================================================================
+extern "C" {
+
+int bpc_abi_version(void) { return BPC_ABI_VERSION; }
+const char* bpc_last_error(void) { return g_last_error.c_str(); }
+
+int bpc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+long long bpc_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// ---- expression front end --------------------------------------------------------------------
+int bpc_check_expr(const char* expr, int max_params, int max_dep) {
+  try {
+    NodePtr n = parse_r(expr ? expr : "");
+    check_valid(*n, max_params, max_dep);
+    return BPC_OK;
+  } catch (const std::exception& e) { return fail(BPC_E_EXPR, e.what()); }
+}
+
+static int copy_out(const std::string& s, char* out, int cap) {
+  if (!out || cap <= (int)s.size()) return fail(BPC_E_INVALID, "output buffer too small");
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return BPC_OK;
+}
+
+int bpc_expr_to_stan(const char* expr, int max_params, int max_dep, char* out, int out_cap) {
+  try {
+    NodePtr n = parse_r(expr ? expr : "");
+    return copy_out(to_stan(*n, max_params, max_dep), out, out_cap);
+  } catch (const std::exception& e) { return fail(BPC_E_EXPR, e.what()); }
+}
+
+int bpc_expr_deparse(const char* expr, char* out, int out_cap) {
+  try {
+    NodePtr n = parse_r(expr ? expr : "");
+    return copy_out(deparse(*n), out, out_cap);
+  } catch (const std::exception& e) { return fail(BPC_E_EXPR, e.what()); }
+}
+
+static PriorSpec to_spec(const bpc_prior& p) {
+  PriorSpec s;
+  s.name = p.name ? p.name : "";
+  s.nparams = p.nparams;
+  for (int i = 0; i < 3; ++i) s.params[i] = (i < p.nparams) ? p.params[i] : 0.0;
+  s.has_bounds = p.has_bounds != 0;
+  s.lower = p.lower;
+  s.upper = p.upper;
+  return s;
+}
+
+int bpc_check_prior(const bpc_prior* prior) {
+  if (!prior) return fail(BPC_E_INVALID, "null prior");
+  if (prior->nparams < 0 || prior->nparams > 3) return fail(BPC_E_PRIOR, prior_id(prior->name ? prior->name : "") < 0 ? "Invalid prior name!" : "Incorrect number of parameters for prior distribution");
+  try {
+    PriorSpec s = to_spec(*prior);
+    validate_prior(s);
+    return BPC_OK;
+  } catch (const std::exception& e) { return fail(BPC_E_PRIOR, e.what()); }
+}
+
+// ---- model -------------------------------------------------------------------------------------
+int bpc_model_create(const bpc_model_desc* d, bpc_model** out) {
+  if (!d || !out) return fail(BPC_E_INVALID, "null argument");
+  *out = nullptr;
+  auto m = std::make_unique<bpc_model>();
+  ModelSpec& s = m->spec;
+  s.ntypes = d->ntypes; s.nevents = d->nevents; s.nparams = d->nparams; s.ndep = d->ndep; s.kind = d->kind;
+  if (d->ntypes < 1 || d->nevents < 1 || !d->e_mat || !d->p_vec || !d->func_deps) return fail(BPC_E_INVALID, "Dimensions of e_mat, p_vec, and func_deps do not agree");
+  if (d->nparams <= 0) return fail(BPC_E_INVALID, "nparams should be an integer number of parameters");
+  if (!d->priors) return fail(BPC_E_INVALID, "incorrect number of priors for model!");
+  s.e_mat.assign(d->e_mat, d->e_mat + (size_t)d->nevents * d->ntypes);
+  s.p_vec.assign(d->p_vec, d->p_vec + d->nevents);
+  for (int e = 0; e < d->nevents; ++e) s.func_deps.emplace_back(d->func_deps[e] ? d->func_deps[e] : "");
+  for (int k = 0; k < d->nparams; ++k) {
+    if (d->priors[k].nparams < 0 || d->priors[k].nparams > 3) return fail(BPC_E_PRIOR, "Incorrect number of parameters for prior distribution");
+    s.priors.push_back(to_spec(d->priors[k]));
+  }
+  try {
+    m->source = generate_cuda(s);
+  } catch (const ExprError& e) {
+    return fail(BPC_E_EXPR, e.what());
+  } catch (const std::exception& e) {
+    const std::string w = e.what();
+    const bool prior = w.find("prior") != std::string::npos || w.find("Positive parameter") != std::string::npos || w.find("bound") != std::string::npos;
+    return fail(prior ? BPC_E_PRIOR : BPC_E_INVALID, w);
+  }
+  for (auto& w : s.warnings) m->warnings += w + "\n";
+  const int rc = compile_model(m.get());
+  if (rc) return rc;
+  *out = m.release();
+  return BPC_OK;
+}
+
+void bpc_model_free(bpc_model* m) {
+  if (!m) return;
+  for (auto& kv : m->loaded) {
+    cudaSetDevice(kv.first);
+    cudaLibraryUnload(kv.second.lib);
+  }
+  delete m;
+}
+
+int bpc_model_dim(const bpc_model* m) { return m ? m->spec.dim : -1; }
+const char* bpc_model_cuda_source(const bpc_model* m) { return m ? m->source.c_str() : ""; }
+const char* bpc_model_warnings(const bpc_model* m) { return m ? m->warnings.c_str() : ""; }
+int bpc_model_cubin(const bpc_model* m, const void** data, unsigned long long* size) {
+  if (!m || !data || !size) return fail(BPC_E_INVALID, "null argument");
+  *data = m->cubin.data();
+  *size = m->cubin.size();
+  return BPC_OK;
+}
+
+// ---- constrain / unconstrain (host arithmetic on a handful of numbers; not the hot path) ---------
+int bpc_constrain(const bpc_model* m, const double* u, int nchains, double* theta) {
+  if (!m || !u || !theta || nchains < 0) return fail(BPC_E_INVALID, "null argument");
+  const ModelSpec& s = m->spec;
+  for (int c = 0; c < nchains; ++c) {
+    for (int k = 0; k < s.nparams; ++k) {
+      const double uk = u[(size_t)c * s.dim + k];
+      const PriorSpec& p = s.priors[k];
+      double th = uk;
+      if (p.has_bounds) {
+        const double sg = uk >= 0 ? 1.0 / (1.0 + std::exp(-uk)) : std::exp(uk) / (1.0 + std::exp(uk));
+        th = p.lower + (p.upper - p.lower) * sg;
+      }
+      theta[(size_t)c * s.dim + k] = th;
+    }
+    if (s.kind == BPC_MULTITYPE_NOISE) theta[(size_t)c * s.dim + s.nparams] = std::exp(u[(size_t)c * s.dim + s.nparams]);
+  }
+  return BPC_OK;
+}
+
+int bpc_unconstrain(const bpc_model* m, const double* theta, int nchains, double* u) {
+  if (!m || !u || !theta || nchains < 0) return fail(BPC_E_INVALID, "null argument");
+  const ModelSpec& s = m->spec;
+  for (int c = 0; c < nchains; ++c) {
+    for (int k = 0; k < s.nparams; ++k) {
+      const double th = theta[(size_t)c * s.dim + k];
+      const PriorSpec& p = s.priors[k];
+      double uk = th;
+      if (p.has_bounds) {
+        const double z = (th - p.lower) / (p.upper - p.lower);
+        uk = std::log(z / (1.0 - z));
+      }
+      u[(size_t)c * s.dim + k] = uk;
+    }
+    if (s.kind == BPC_MULTITYPE_NOISE) u[(size_t)c * s.dim + s.nparams] = std::log(theta[(size_t)c * s.dim + s.nparams]);
+  }
+  return BPC_OK;
+}
+
+// ---- data ----------------------------------------------------------------------------------------
+int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int grouping, bpc_data** out) {
+  if (!m || !d || !out) return fail(BPC_E_INVALID, "null argument");
+  *out = nullptr;
+  const ModelSpec& s = m->spec;
+  const int N = d->ndatapts, n = s.ntypes;
+  const bool simple = s.kind == BPC_SIMPLE_BD;
+  if (N < 0 || !d->var_idx || (N > 0 && (!d->pop_vec || !d->init_pop || !d->times)))
+    return fail(BPC_E_INVALID, "times, initial populations, and final populations must all have same number of rows!");
+  if (d->ndep_levels < 1 || d->ndep < 1 || !d->function_var) return fail(BPC_E_INVALID, "function_var must have at least one level and one column (the dummy matrix(0,1,1) when ndep == 0)");
+  if (s.ndep > 0 && d->ndep < s.ndep) return fail(BPC_E_INVALID, "c_mat does not contain enough dependent variables for the model");
+  if (!simple && (!d->times_idx || d->ntimes_unique < 1)) return fail(BPC_E_INVALID, "times_idx / ntimes_unique missing for a multitype data list");
+  for (int k = 0; k < N; ++k) {
+    if (d->var_idx[k] < 1 || d->var_idx[k] > d->ndep_levels) return fail(BPC_E_INVALID, "var_idx out of range [1, ndep_levels]");
+    if (!simple && (d->times_idx[k] < 1 || d->times_idx[k] > d->ntimes_unique)) return fail(BPC_E_INVALID, "times_idx out of range [1, ntimes_unique]");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(BPC_E_CUDA, "no CUDA device available: libbpcuda has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(BPC_E_INVALID, "device index out of range");
+  BPC_CUDA(cudaSetDevice(device));
+
+  auto dd = std::make_unique<bpc_data>();
+  dd->model = m;
+  dd->device = device;
+  dd->N = N;
+  // per-observation duration and (level, duration) group
+  std::vector<double> t(N);
+  std::vector<long long> gkey(N);
+  for (int k = 0; k < N; ++k) {
+    t[k] = simple ? d->times[k] : d->times[d->times_idx[k] - 1];
+    gkey[k] = simple ? k : (long long)(d->var_idx[k] - 1) * d->ntimes_unique + (d->times_idx[k] - 1);
+  }
+  {
+    std::vector<long long> u(gkey);
+    std::sort(u.begin(), u.end());
+    dd->ngroups = (int)(std::unique(u.begin(), u.end()) - u.begin());
+  }
+  // sort: longest duration first (similar series length within a warp; heavy tiles launch first)
+  std::vector<int> perm(N);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return t[a] > t[b]; });
+  const int npad = ((N + 31) / 32) * 32;
+  dd->npad = npad;
+  const int kd = s.kdep;
+  std::vector<double> hz((size_t)n * npad, 1.0), hx((size_t)n * npad, 1.0), ht(npad, 0.0), hv((size_t)kd * npad, 0.0);
+  std::vector<int> hp(npad, 0);
+  for (int j = 0; j < N; ++j) {
+    const int k = perm[j];
+    for (int i = 0; i < n; ++i) {
+      hz[(size_t)i * npad + j] = d->init_pop[k + (size_t)N * i];
+      hx[(size_t)i * npad + j] = d->pop_vec[k + (size_t)N * i];
+    }
+    ht[j] = t[k];
+    const int v = d->var_idx[k] - 1;
+    for (int q = 0; q < kd; ++q) hv[(size_t)q * npad + j] = (q < d->ndep) ? d->function_var[v + (size_t)d->ndep_levels * q] : 0.0;
+    hp[j] = k;
+  }
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+    int rc = b.alloc(bytes);
+    if (rc) return rc;
+    if (bytes) BPC_CUDA(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return BPC_OK;
+  };
+  int rc;
+  if ((rc = up(dd->z0, hz.data(), hz.size() * 8))) return rc;
+  if ((rc = up(dd->xo, hx.data(), hx.size() * 8))) return rc;
+  if ((rc = up(dd->t, ht.data(), ht.size() * 8))) return rc;
+  if ((rc = up(dd->xv, hv.data(), hv.size() * 8))) return rc;
+  if ((rc = up(dd->perm, hp.data(), hp.size() * 4))) return rc;
+  dd->grouped = false;
+  (void)grouping;
+  BPC_CUDA(cudaStreamCreateWithFlags(&dd->stream, cudaStreamNonBlocking));
+  *out = dd.release();
+  return BPC_OK;
+}
+
+void bpc_data_free(bpc_data* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  for (auto& ev : d->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+int bpc_data_ngroups(const bpc_data* d) { return d ? d->ngroups : -1; }
+int bpc_data_is_grouped(const bpc_data* d) { return d ? (d->grouped ? 1 : 0) : -1; }
+
+}  // extern "C"
+
+// ---- evaluate ------------------------------------------------------------------------------------
+namespace bpc {
+
+// tile (observations per CTA) so that the grid has a few waves of CTAs when the problem allows it
+static void choose_tiling(bpc_data* d, int nchains) {
+  const int T = d->model->spec.threads;
+  const long long total = (long long)d->N * nchains;
+  long long per_thread = total / ((long long)148 * 8 * T);
+  per_thread = std::max(1LL, std::min(8LL, per_thread));
+  d->tile = (int)(T * per_thread);
+  d->ntiles = std::max(1, (d->N + d->tile - 1) / d->tile);
+}
+
+static int ensure_workspace(bpc_data* d, int nchains) {
+  const ModelSpec& s = d->model->spec;
+  if (nchains != d->ws_chains) {
+    choose_tiling(d, nchains);
+    int rc;
+    if ((rc = d->theta.alloc((size_t)nchains * s.dim * 8))) return rc;
+    if ((rc = d->part.alloc((size_t)nchains * d->ntiles * (s.nparams + 3) * 8))) return rc;
+    if ((rc = d->apps.alloc((size_t)nchains * 8))) return rc;
+    d->ws_chains = nchains;
+  }
+  return BPC_OK;
+}
+
+struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
+  const double* theta; const double* z0; const double* xo; const double* t; const double* xv;
+  double* part; int* status; double* loglik; const int* perm;
+  int nobs, npad, tile, ntiles, nchains;
+};
+
+int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
+                 double* grad_dev, int* status_dev, cudaStream_t st) {
+  if (nchains <= 0) return BPC_OK;
+  Loaded* L;
+  int rc = model_load(m, d->device, &L);
+  if (rc) return rc;
+  BPC_CUDA(cudaSetDevice(d->device));
+  if ((rc = ensure_workspace(d, nchains))) return rc;
+  const ModelSpec& s = m->spec;
+  double* theta = (double*)d->theta.p;
+  double* part = (double*)d->part.p;
+  double* apps = (double*)d->apps.p;
+  {
+    void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
+    BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
+  }
+  {
+    ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
+              part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains};
+    void* args[] = {(void*)&a};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (d->timing) {
+      BPC_CUDA(cudaEventCreate(&e0));
+      BPC_CUDA(cudaEventCreate(&e1));
+      BPC_CUDA(cudaEventRecord(e0, st));
+    }
+    BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, nchains), dim3(s.threads), args, L->obs_smem, st));
+    if (d->timing) {
+      BPC_CUDA(cudaEventRecord(e1, st));
+      d->timing_events.emplace_back(e0, e1);
+    }
+  }
+  {
+    int ntiles = d->ntiles;
+    void* args[] = {(void*)&u_dev, (void*)&theta, (void*)&part, (void*)&ntiles, (void*)&nchains, (void*)&jacobian,
+                    (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps};
+    BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
+  }
+  g_launches += 3;
+  return BPC_OK;
+}
+
+}  // namespace bpc
+
+extern "C" {
+
+int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nchains, int jacobian, double* lp_dev,
+                     double* grad_dev, int* status_dev, void* stream) {
+  if (!m || !d || !upars_dev || !lp_dev || !status_dev) return fail(BPC_E_INVALID, "null argument");
+  if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
+  return log_prob_dev(m, d, upars_dev, nchains, jacobian, lp_dev, grad_dev, status_dev, stream ? (cudaStream_t)stream : d->stream);
+}
+
+int bpc_log_prob(bpc_model* m, bpc_data* d, const double* upars, int nchains, int jacobian, double* lp, double* grad,
+                 int* status) {
+  if (!m || !d || !upars || !lp) return fail(BPC_E_INVALID, "null argument");
+  if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
+  if (nchains <= 0) return BPC_OK;
+  BPC_CUDA(cudaSetDevice(d->device));
+  const int dim = m->spec.dim;
+  int rc;
+  if ((rc = d->io_u.alloc((size_t)nchains * dim * 8))) return rc;
+  if ((rc = d->io_lp.alloc((size_t)nchains * 8))) return rc;
+  if ((rc = d->io_grad.alloc((size_t)nchains * dim * 8))) return rc;
+  if ((rc = d->io_status.alloc((size_t)nchains * 4))) return rc;
+  cudaStream_t st = d->stream;
+  BPC_CUDA(cudaMemcpyAsync(d->io_u.p, upars, (size_t)nchains * dim * 8, cudaMemcpyHostToDevice, st));
+  rc = log_prob_dev(m, d, (const double*)d->io_u.p, nchains, jacobian, (double*)d->io_lp.p, grad ? (double*)d->io_grad.p : nullptr,
+                    (int*)d->io_status.p, st);
+  if (rc) return rc;
+  BPC_CUDA(cudaMemcpyAsync(lp, d->io_lp.p, (size_t)nchains * 8, cudaMemcpyDeviceToHost, st));
+  if (grad) BPC_CUDA(cudaMemcpyAsync(grad, d->io_grad.p, (size_t)nchains * dim * 8, cudaMemcpyDeviceToHost, st));
+  if (status) BPC_CUDA(cudaMemcpyAsync(status, d->io_status.p, (size_t)nchains * 4, cudaMemcpyDeviceToHost, st));
+  BPC_CUDA(cudaStreamSynchronize(st));
+  return BPC_OK;
+}
+
+int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* log_lik) {
+  if (!m || !d || !upars || !log_lik) return fail(BPC_E_INVALID, "null argument");
+  if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
+  if (nchains <= 0 || d->N == 0) return BPC_OK;
+  Loaded* L;
+  int rc = model_load(m, d->device, &L);
+  if (rc) return rc;
+  BPC_CUDA(cudaSetDevice(d->device));
+  if ((rc = ensure_workspace(d, nchains))) return rc;
+  const ModelSpec& s = m->spec;
+  const int dim = s.dim;
+  if ((rc = d->io_u.alloc((size_t)nchains * dim * 8))) return rc;
+  if ((rc = d->io_status.alloc((size_t)nchains * 4))) return rc;
+  DevBuf ll;
+  if ((rc = ll.alloc((size_t)nchains * d->N * 8))) return rc;
+  cudaStream_t st = d->stream;
+  BPC_CUDA(cudaMemcpyAsync(d->io_u.p, upars, (size_t)nchains * dim * 8, cudaMemcpyHostToDevice, st));
+  const double* u_dev = (const double*)d->io_u.p;
+  double* theta = (double*)d->theta.p;
+  int* status_dev = (int*)d->io_status.p;
+  {
+    void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
+    BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
+  }
+  {
+    ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
+              nullptr, status_dev, (double*)ll.p, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains};
+    void* args[] = {(void*)&a};
+    BPC_CUDA(cudaLaunchKernel((const void*)L->loglik, dim3((d->N + s.threads - 1) / s.threads, nchains), dim3(s.threads), args, 0, st));
+  }
+  g_launches += 2;
+  BPC_CUDA(cudaMemcpyAsync(log_lik, ll.p, (size_t)nchains * d->N * 8, cudaMemcpyDeviceToHost, st));
+  BPC_CUDA(cudaStreamSynchronize(st));
+  return BPC_OK;
+}
+
+int bpc_kernel_timing(bpc_data* d, int enable) {
+  if (!d) return fail(BPC_E_INVALID, "null argument");
+  d->timing = enable != 0;
+  return BPC_OK;
+}
+
+int bpc_kernel_time_ms(bpc_data* d, int reset, double* total_ms, long long* launches) {
+  if (!d || !total_ms) return fail(BPC_E_INVALID, "null argument");
+  BPC_CUDA(cudaSetDevice(d->device));
+  double tot = 0.0;
+  for (auto& ev : d->timing_events) {
+    BPC_CUDA(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    BPC_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  if (launches) *launches = (long long)d->timing_events.size();
+  if (reset) {
+    for (auto& ev : d->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    d->timing_events.clear();
+  }
+  return BPC_OK;
+}
+
+// Taylor applications of L and L^T that the last bpc_log_prob* call performed, per chain; with the
+// per-application and per-observation constants of DESIGN.md §4 this is the exact algorithmic flop count.
+int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* flops_per_chain) {
+  if (!m || !d || !upars || !flops_per_chain) return fail(BPC_E_INVALID, "null argument");
+  std::vector<double> lp(nchains);
+  int rc = bpc_log_prob(m, d, upars, nchains, 1, lp.data(), nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<double> apps(nchains);
+  BPC_CUDA(cudaMemcpy(apps.data(), d->apps.p, (size_t)nchains * 8, cudaMemcpyDeviceToHost));
+  const ModelSpec& s = m->spec;
+  const FlopModel f = flop_model(s);
+  for (int c = 0; c < nchains; ++c)
+    flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N : apps[c] * (f.per_app_fwd + f.per_app_bwd) + f.per_obs * d->N;
+  return BPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// bpcuda_internal.hpp — handle layouts shared by the translation units of libbpcuda (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "codegen.hpp"
+
+namespace bpc {
+
+extern thread_local std::string g_last_error;
+extern thread_local long long g_launches;
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+// device allocation that only grows
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int alloc(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cap = bytes;
+    return 0;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct Loaded {   // one NVRTC module loaded on one device
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr;
+  size_t obs_smem = 0;
+};
+
+// algorithmic flop constants of the shipped kernels (SURVEY.md §8(d) convention: FMA = 2, div/sqrt/exp/log = 1)
+struct FlopModel { double per_app_fwd, per_app_bwd, per_obs; };
+FlopModel flop_model(const ModelSpec& s);
+
+}  // namespace bpc
+
+struct bpc_model {
+  bpc::ModelSpec spec;
+  std::string source, warnings, compile_log;
+  std::vector<char> cubin;
+  std::map<int, bpc::Loaded> loaded;
+};
+
+struct bpc_data {
+  const bpc_model* model = nullptr;
+  int device = 0;
+  int N = 0, npad = 0, ngroups = 0;
+  bool grouped = false;
+  bpc::DevBuf z0, xo, t, xv, perm;
+  // workspace sized for ws_chains chains
+  int ws_chains = -1, tile = 0, ntiles = 0;
+  bpc::DevBuf theta, part, apps;
+  bpc::DevBuf io_u, io_lp, io_grad, io_status;
+  cudaStream_t stream = nullptr;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+};
+
+namespace bpc {
+int model_load(bpc_model* m, int device, Loaded** out);
+int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
+                 double* grad_dev, int* status_dev, cudaStream_t st);
+}  // namespace bpc

@@ -1,0 +1,215 @@
+/* =============================================================================
+ * bpcuda.h — C ABI of libbpcuda: the B200 (sm_100a) engine behind bpinference's
+ * posterior log-density path.
+ *
+ * The reference (jproney/bpinference, paths below are under /root/reference) has no
+ * FFI of its own: its engine boundary is "R objects handed to rstan".  Every entry
+ * point here replaces one of those hand-offs and cites it.  Nothing in this header
+ * mentions R, Python or torch: plain pointers, sizes and opaque handles.  The R
+ * `.Call` shim (r-package/src/bpcuda_rcall.c) and the Python ctypes mirror
+ * (bpinference_b200/_ffi.py) are thin translations of these signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a BPC_E_* code otherwise; the message of
+ *     the last failure on the calling thread is bpc_last_error().
+ *   - input buffers are borrowed for the duration of the call only; outputs are
+ *     written into caller-allocated arrays; handles are freed with bpc_*_free.
+ *   - matrices handed over in the Stan data list keep R's column-major layout;
+ *     index vectors are 1-based exactly as create_stan_data produces them
+ *     (R/stan_utils.R:57-62).
+ *   - per-chain arrays are chain-major: upars[c*dim + k].
+ *   - pointers named *_dev are device pointers on the handle's device; all others
+ *     are host pointers.
+ * ============================================================================= */
+#ifndef BPCUDA_H
+#define BPCUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPC_ABI_VERSION 1
+
+/* error codes */
+enum {
+  BPC_OK = 0,
+  BPC_E_INVALID = 1,   /* bad argument / failed validation (message mirrors the reference's stop() text) */
+  BPC_E_EXPR = 2,      /* rate expression rejected (R/stan_utils.R:205-364) */
+  BPC_E_PRIOR = 3,     /* prior rejected (R/stan_utils.R:372-459) */
+  BPC_E_COMPILE = 4,   /* NVRTC failed; bpc_last_error() holds the compiler log */
+  BPC_E_CUDA = 5,      /* CUDA runtime error (includes "no device": there is no CPU fallback) */
+  BPC_E_UNSUPPORTED = 6
+};
+
+/* per-chain status bits written by bpc_log_prob / the sampler (a non-zero status means the
+ * chain's lp is -inf and its gradient 0, i.e. what makes Stan reject a proposal) */
+enum {
+  BPC_ST_OK = 0,
+  BPC_ST_NOT_PD = 1,            /* multi_normal: Sigma not positive definite (multitype_template.stan:152) */
+  BPC_ST_RATE_NONFINITE = 2,    /* a generated rate expression produced NaN/Inf */
+  BPC_ST_ONETYPE_SINGULAR = 4,  /* b == d or variance <= 0 in one_type_template.stan:43 */
+  BPC_ST_PRIOR_SUPPORT = 8      /* Theta_k outside the support of its prior (e.g. uniform(0,1) with bounds (0,2)) */
+};
+
+/* which Stan template the model stands for — the `simple_bd` / `noise_model` switches of
+ * generate(), R/stan_utils.R:130,167-187 */
+typedef enum {
+  BPC_MULTITYPE = 0,        /* stanfiles/multitype_template.stan */
+  BPC_MULTITYPE_NOISE = 1,  /* stanfiles/multitype_noise_template.stan */
+  BPC_SIMPLE_BD = 2         /* stanfiles/one_type_template.stan */
+} bpc_template_kind;
+
+/* one prior_dist object: list(name=, params=, bounds=)  (R/stan_utils.R:467-487).
+ * has_bounds == 0 stands for bounds = NA. */
+typedef struct {
+  const char* name;
+  int nparams;
+  double params[3];
+  int has_bounds;
+  double lower, upper;
+} bpc_prior;
+
+/* a bp_model object (R/bp_model.R:12-17) plus the priors list and the template switches that
+ * generate() receives (R/stan_utils.R:130). */
+typedef struct {
+  int ntypes;                     /* ncol(e_mat) */
+  int nevents;                    /* nrow(e_mat) */
+  int nparams;                    /* model$nparams */
+  int ndep;                       /* model$ndep (0 allowed; the data list then carries the dummy ndep = 1) */
+  const double* e_mat;            /* nevents x ntypes, column-major */
+  const int* p_vec;               /* nevents, 1-based parent types */
+  const char* const* func_deps;   /* nevents strings as written by the user / deparse(model$func_deps[[e]]) */
+  const bpc_prior* priors;        /* nparams entries */
+  int kind;                       /* bpc_template_kind */
+} bpc_model_desc;
+
+/* the Stan data list.  Multitype templates: the fields of multitype_template.stan:64-80 as built at
+ * R/stan_utils.R:57-58.  One-type template: one_type_template.stan:2-12 as built at R/stan_utils.R:61-62
+ * (there `times` has one entry per observation and times_idx / ntimes_unique are ignored). */
+typedef struct {
+  int ndatapts;
+  int ntimes_unique;
+  int ndep_levels;
+  int ndep;                    /* columns of function_var (>= 1: dummy column when the model has ndep == 0) */
+  const double* pop_vec;       /* ndatapts x ntypes column-major (vector of length ndatapts for SIMPLE_BD) */
+  const double* init_pop;      /* same shape */
+  const double* times;         /* ntimes_unique durations (ndatapts durations for SIMPLE_BD) */
+  const int* times_idx;        /* ndatapts, 1-based (NULL for SIMPLE_BD) */
+  const double* function_var;  /* ndep_levels x ndep column-major */
+  const int* var_idx;          /* ndatapts, 1-based */
+} bpc_stan_data;
+
+typedef struct bpc_model bpc_model;
+typedef struct bpc_data bpc_data;
+typedef struct bpc_sampler bpc_sampler;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int bpc_abi_version(void);
+const char* bpc_last_error(void);
+/* number of visible CUDA devices (0 without a GPU; never an error) */
+int bpc_device_count(void);
+/* measured FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA); a register-resident DFMA loop
+ * run for `ms` milliseconds.  This is the roofline denominator SURVEY.md §8(d) asks the builder to measure. */
+int bpc_fp64_peak(int device, double ms, double* tflops, double* sm_clock_mhz);
+
+/* ---- expression front end: replaces exp_to_stan / check_valid (R/stan_utils.R:205-364) ------ */
+/* validates one rate expression; on failure returns BPC_E_EXPR and bpc_last_error() is the text of the
+ * reference's stop() (tests/testthat/test_expression_parsing.R:4-47). */
+int bpc_check_expr(const char* expr, int max_params, int max_dep);
+/* writes what exp_to_stan returns (tests/testthat/test_expression_parsing.R:50-54) */
+int bpc_expr_to_stan(const char* expr, int max_params, int max_dep, char* out, int out_cap);
+/* writes R's deparse() of the parsed expression (tests/testthat/test_bpmodel.R:68-69) */
+int bpc_expr_deparse(const char* expr, char* out, int out_cap);
+/* validates a prior_dist (R/stan_utils.R:418-459) */
+int bpc_check_prior(const bpc_prior* prior);
+
+/* ---- model: replaces rstan::stan_model(model_code = generate(model, priors, ...)) ------------ */
+/* (examples/two_type.R:18,25).  Parses func_deps, emits the CUDA translation unit (rate functions, their
+ * reverse-mode derivatives, the generator assembly, and the kernels specialised for this model), compiles
+ * it with NVRTC for sm_100a.  Works without a GPU (compilation only); the module is loaded on first use. */
+int bpc_model_create(const bpc_model_desc* desc, bpc_model** out);
+void bpc_model_free(bpc_model* m);
+/* number of unconstrained dimensions: nparams, +1 (sigma_obs, last) for the noise template
+ * (multitype_noise_template.stan:99-104) */
+int bpc_model_dim(const bpc_model* m);
+/* the generated CUDA source / the compiled cubin (for inspection, caching and cuobjdump) */
+const char* bpc_model_cuda_source(const bpc_model* m);
+int bpc_model_cubin(const bpc_model* m, const void** data, unsigned long long* size);
+/* warnings the front end produced (e.g. Stan integer division of two integer literals) or "" */
+const char* bpc_model_warnings(const bpc_model* m);
+
+/* ---- data: replaces the `data = dat` argument of rstan::sampling (examples/two_type.R:26) ---- */
+/* copies the host arrays, validates index ranges, repacks to the device layout.
+ * grouping: 0 = auto, 1 = force the per-observation fused kernel, 2 = force the grouped two-phase path. */
+int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int grouping, bpc_data** out);
+void bpc_data_free(bpc_data* d);
+int bpc_data_ngroups(const bpc_data* d);    /* distinct (env level, duration) pairs */
+int bpc_data_is_grouped(const bpc_data* d); /* which path log_prob takes */
+
+/* ---- evaluate: replaces rstan::log_prob / rstan::grad_log_prob -------------------------------- */
+/* upars: nchains x dim unconstrained vectors (Theta1..ThetaP, then sigma_obs); jacobian = rstan's
+ * adjust_transform.  lp[nchains]; grad[nchains*dim] or NULL; status[nchains] or NULL.  Host buffers:
+ * the call copies in, launches, copies out and synchronises. */
+int bpc_log_prob(bpc_model* m, bpc_data* d, const double* upars, int nchains, int jacobian,
+                 double* lp, double* grad, int* status);
+/* same with device-resident buffers; asynchronous on `stream` (a cudaStream_t, may be NULL). */
+int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nchains, int jacobian,
+                     double* lp_dev, double* grad_dev, int* status_dev, void* stream);
+/* per-observation log_lik with normalising constants: the generated-quantities LOO blocks
+ * (stanfiles/multitype_loo_block.stan:31, simple_birth_death_loo_block.stan:11).
+ * log_lik: nchains x ndatapts, observation order = the order of the data list. */
+int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* log_lik);
+/* constrained values: Theta [nchains x nparams] (+ sigma_obs) from unconstrained upars, and back */
+int bpc_constrain(const bpc_model* m, const double* upars, int nchains, double* theta);
+int bpc_unconstrain(const bpc_model* m, const double* theta, int nchains, double* upars);
+/* kernel launches issued by this thread's handles since the last reset (bench.py's gpu_launches) */
+long long bpc_launch_count(int reset);
+/* device time in ms of the dominant likelihood kernel accumulated over launches since the last reset,
+ * measured with CUDA events on the launching stream (only when enabled; bench.py's roofline.achieved) */
+int bpc_kernel_timing(bpc_data* d, int enable);
+int bpc_kernel_time_ms(bpc_data* d, int reset, double* total_ms, long long* launches);
+/* exact algorithmic flop count of one evaluation of the likelihood for chain 0 of `upars`, counted by
+ * the shipped kernels themselves in a counting build (SURVEY.md §8(d) convention: FMA = 2) */
+int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* flops_per_chain);
+
+/* ---- sample: replaces rstan::sampling(stan_mod, data, chains, iter, warmup, init, control) ---- */
+typedef struct {
+  int chains;            /* chains on THIS device / rank */
+  int iter;              /* total iterations per chain, warm-up included (rstan's iter) */
+  int warmup;            /* rstan's warmup */
+  double adapt_delta;    /* control$adapt_delta */
+  int max_treedepth;     /* control$max_treedepth: a trajectory has at most 2^max_treedepth leapfrog steps */
+  unsigned long long seed;
+  int chain_id_offset;   /* global id of this rank's first chain (Philox stream = seed, chain id) */
+  const double* inits;   /* chains x nparams CONSTRAINED values (uniform_initialize, R/stan_utils.R:74-87); sigma_obs starts at 0.05;
+                            NULL = uniform(-2,2) on the unconstrained scale as rstan does */
+  int pooled_adaptation; /* 1: mass matrix / step size statistics are pooled across chains (and ranks) */
+} bpc_sample_args;
+
+int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_sampler** out);
+void bpc_sampler_free(bpc_sampler* s);
+/* runs iterations [from, to) (0-based; warm-up first); returns without host synchronisation of draws.
+ * When pooled adaptation is on and `*need_reduce` comes back 1 the caller must sum the buffer returned by
+ * bpc_sampler_stats_dev over all ranks (NCCL all-reduce; identity on one rank) and call
+ * bpc_sampler_apply_stats before continuing: that exchange is the only collective on the path. */
+int bpc_sampler_run(bpc_sampler* s, int from, int to, int* stopped_at, int* need_reduce);
+int bpc_sampler_stats_dev(bpc_sampler* s, double** stats_dev, int* count);
+int bpc_sampler_apply_stats(bpc_sampler* s);
+/* results (host copies).  draws: chains x (iter - warmup) x dim constrained values, then lp__ via lp. */
+int bpc_sampler_draws(bpc_sampler* s, double* draws, double* lp, int* divergent, int* treedepth,
+                      int* n_leapfrog, double* accept_stat, double* stepsize);
+long long bpc_sampler_total_leapfrogs(const bpc_sampler* s);
+/* convenience: whole run on one device, single rank */
+int bpc_sample(bpc_model* m, bpc_data* d, const bpc_sample_args* a, double* draws, double* lp,
+               int* divergent, int* treedepth, int* n_leapfrog, double* accept_stat, double* stepsize);
+
+/* ---- simulate: replaces bp() / bpsims() (R/simulation.R:9-56, 69-131) -------------------------- */
+/* Gillespie simulation of `nrep` replicates on the device (Philox); pops: nrep x ntimes x ntypes. */
+int bpc_simulate(int ntypes, int nevents, const double* e_mat, const int* p_vec, const double* r_vec,
+                 const double* z0, const double* times, int ntimes, int nrep, unsigned long long seed,
+                 int device, double* pops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPCUDA_H */
