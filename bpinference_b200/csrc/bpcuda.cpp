@@ -429,7 +429,7 @@ int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nch
                      double* grad_dev, int* status_dev, void* stream) {
   if (!m || !d || !upars_dev || !lp_dev || !status_dev) return fail(BPC_E_INVALID, "null argument");
   if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
-  return log_prob_dev(m, d, upars_dev, nchains, jacobian, lp_dev, grad_dev, status_dev, stream ? (cudaStream_t)stream : d->stream);
+  return log_prob_dev(m, d, upars_dev, nchains, jacobian, lp_dev, grad_dev, status_dev, (cudaStream_t)stream);
 }
 
 int bpc_log_prob(bpc_model* m, bpc_data* d, const double* upars, int nchains, int jacobian, double* lp, double* grad,

@@ -152,7 +152,7 @@ int bpc_data_is_grouped(const bpc_data* d); /* which path log_prob takes */
  * the call copies in, launches, copies out and synchronises. */
 int bpc_log_prob(bpc_model* m, bpc_data* d, const double* upars, int nchains, int jacobian,
                  double* lp, double* grad, int* status);
-/* same with device-resident buffers; asynchronous on `stream` (a cudaStream_t, may be NULL). */
+/* same with device-resident buffers; asynchronous on `stream` (a cudaStream_t; NULL is CUDA's default stream). */
 int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nchains, int jacobian,
                      double* lp_dev, double* grad_dev, int* status_dev, void* stream);
 /* per-observation log_lik with normalising constants: the generated-quantities LOO blocks
