@@ -44,7 +44,7 @@ class StanData(C.Structure):
 class SampleArgs(C.Structure):
     _fields_ = [("chains", C.c_int), ("iter", C.c_int), ("warmup", C.c_int), ("adapt_delta", C.c_double),
                 ("max_treedepth", C.c_int), ("seed", C.c_ulonglong), ("chain_id_offset", C.c_int),
-                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int)]
+                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double)]
 
 
 # every symbol include/bpcuda.h declares: name -> (restype, argtypes)
@@ -79,9 +79,12 @@ SYMBOLS = {
     "bpc_count_flops": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp]),
     "bpc_sampler_create": (C.c_int, [_vp, _vp, C.POINTER(SampleArgs), C.POINTER(_vp)]),
     "bpc_sampler_free": (None, [_vp]),
-    "bpc_sampler_run": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip]),
-    "bpc_sampler_stats_dev": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
-    "bpc_sampler_apply_stats": (C.c_int, [_vp]),
+    "bpc_sampler_run": (C.c_int, [_vp, C.c_longlong, _ip]),
+    "bpc_sampler_pool_stats": (C.c_int, [_vp, _vp, C.c_int]),
+    "bpc_sampler_pool_apply": (C.c_int, [_vp, _vp]),
+    "bpc_sampler_chain_moments": (C.c_int, [_vp, _vp, C.c_int, _dp]),
+    "bpc_rhat": (C.c_int, [_dp, C.c_int, C.c_int, _dp]),
+    "bpc_sampler_passes": (C.c_longlong, [_vp]),
     "bpc_sampler_draws": (C.c_int, [_vp, _dp, _dp, _ip, _ip, _ip, _dp, _dp]),
     "bpc_sampler_total_leapfrogs": (C.c_longlong, [_vp]),
     "bpc_sample": (C.c_int, [_vp, _vp, C.POINTER(SampleArgs), _dp, _dp, _ip, _ip, _ip, _dp, _dp]),

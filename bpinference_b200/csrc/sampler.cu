@@ -1,15 +1,739 @@
-// sampler.cu — placeholder until the device-resident HMC driver lands (next commit).
+// sampler.cu — device-resident many-chain NUTS driver of libbpcuda (sm_100a).
+//
+// Replaces what `rstan::sampling` does around the log-density path (sampler settings of
+// the reference's examples/*.R): multinomial NUTS with a diagonal metric, dual-averaging step-size
+// adaptation to adapt_delta, Stan's windowed metric adaptation (init buffer / doubling windows / term
+// buffer) and the step-size search that follows every metric update.  The reference runs one chain per R
+// process; here every chain is a small state machine living in HBM, one thread per chain, advanced by ONE
+// leapfrog step per "pass":
+//     pass = bp_prologue + bp_fused/bp_onetype + bp_epilogue   (log density + gradient of all chains, NVRTC module)
+//          + bp_nuts_advance                                   (this file: finish the leapfrog, tree bookkeeping,
+//                                                               U-turn checks, adaptation, start the next leapfrog)
+// Chains do not wait for each other: a chain that ends its trajectory starts the next transition in the same
+// pass.  The tree is built iteratively (leaf by leaf with checkpointed partial momentum sums for the sub-tree
+// U-turn checks), which is the same tree and the same multinomial sampling as the recursive formulation.
+// Random numbers: Philox4x32-10, key = seed, counter = (global chain id, draw index) — reproducible and
+// independent of how chains are sharded over GPUs.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <vector>
+
 #include "bpcuda.h"
 #include "bpcuda_internal.hpp"
+
 using namespace bpc;
-extern "C" {
-int bpc_sampler_create(bpc_model*, bpc_data*, const bpc_sample_args*, bpc_sampler**) { return fail(BPC_E_UNSUPPORTED, "sampler not built yet"); }
-void bpc_sampler_free(bpc_sampler*) {}
-int bpc_sampler_run(bpc_sampler*, int, int, int*, int*) { return fail(BPC_E_UNSUPPORTED, "sampler not built yet"); }
-int bpc_sampler_stats_dev(bpc_sampler*, double**, int*) { return fail(BPC_E_UNSUPPORTED, "sampler not built yet"); }
-int bpc_sampler_apply_stats(bpc_sampler*) { return fail(BPC_E_UNSUPPORTED, "sampler not built yet"); }
-int bpc_sampler_draws(bpc_sampler*, double*, double*, int*, int*, int*, double*, double*) { return fail(BPC_E_UNSUPPORTED, "sampler not built yet"); }
-long long bpc_sampler_total_leapfrogs(const bpc_sampler*) { return 0; }
-int bpc_sample(bpc_model*, bpc_data*, const bpc_sample_args*, double*, double*, int*, int*, int*, double*, double*) { return fail(BPC_E_UNSUPPORTED, "sampler not built yet"); }
-int bpc_simulate(int, int, const double*, const int*, const double*, const double*, const double*, int, int, unsigned long long, int, double*) { return fail(BPC_E_UNSUPPORTED, "simulator not built yet"); }
+
+namespace {
+
+constexpr int MAXD = 12;        // max tree depth supported
+constexpr int MAXDIM = 32;      // max unconstrained dimension
+
+enum Phase { PH_INIT = 0, PH_FIND_EPS_FIRST = 1, PH_FIND_EPS = 2, PH_NUTS = 3, PH_WAIT = 4, PH_DONE = 5, PH_FAILED = 6 };
+
+// scalar double fields
+enum { S_EPS, S_LP_CUR, S_H0, S_LSW, S_SUB_LSW, S_SUM_ACC, S_DA_MU, S_DA_SBAR, S_DA_XBAR, S_DA_CNT, S_LP_PROP, S_LP_SP, S_W_N, S_NLEAP_TOT, NSCAL };
+// vector double fields (dim each)
+enum { V_Q_CUR, V_G_CUR, V_QL, V_PL, V_GL, V_QR, V_PR, V_GR, V_Q_PROP, V_G_PROP, V_Q_SP, V_G_SP, V_RHO, V_RHO_SUB, V_MINV, V_W_MEAN, V_W_M2, NVEC };
+// int fields
+enum { I_PHASE, I_ITER, I_DEPTH, I_NLEAP, I_DIR, I_LEAF, I_DIVERGENT, I_FE_DIR, I_WIN_NEXT, I_WIN_SIZE, I_WIN_COUNTER, I_TRIES, I_RNG, NINT };
+
+struct Params {
+  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits;
+  int init_buffer, term_buffer, base_window;
+  double delta, eps0;
+  unsigned long long seed;
+  double* sd;          // [(NSCAL + NVEC*dim + 2*MAXD*dim)][C]
+  int* si;             // [NINT][C]
+  double* q_eval;      // [C][dim]  position at which the log density is evaluated in the next pass
+  double* lp_eval;     // [C]
+  double* g_eval;      // [C][dim]
+  int* st_eval;        // [C]
+  double* draws;       // [C][nsave][dim]
+  double* d_lp; double* d_acc; double* d_eps; int* d_depth; int* d_nleap; int* d_div;
+  int* counters;       // [0] finished chains, [1] waiting chains, [2] failed chains
+  int has_bounds[MAXDIM];
+  double lo[MAXDIM], hi[MAXDIM];
+};
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
+  const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
 }
+__device__ void philox(unsigned long long seed, unsigned chain, unsigned ctr, unsigned (&out)[4]) {
+  unsigned c0 = ctr, c1 = chain, c2 = 0x2545F491u, c3 = 0u;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Chain {
+  const Params& P;
+  int c;
+  __device__ Chain(const Params& p, int chain) : P(p), c(chain) {}
+  __device__ double& s(int f) const { return P.sd[(size_t)f * P.C + c]; }
+  __device__ double& v(int f, int k) const { return P.sd[(size_t)(NSCAL + f * P.dim + k) * P.C + c]; }
+  __device__ double& rck(int lvl, int k) const { return P.sd[(size_t)(NSCAL + NVEC * P.dim + lvl * P.dim + k) * P.C + c]; }
+  __device__ double& rsck(int lvl, int k) const { return P.sd[(size_t)(NSCAL + NVEC * P.dim + (MAXD + lvl) * P.dim + k) * P.C + c]; }
+  __device__ int& i(int f) const { return P.si[(size_t)f * P.C + c]; }
+  // two uniforms in (0,1) per call
+  __device__ void uniforms(double& u0, double& u1) const {
+    unsigned r[4];
+    philox(P.seed, (unsigned)(P.chain_offset + c), (unsigned)i(I_RNG), r);
+    i(I_RNG) += 1;
+    u0 = (((unsigned long long)r[0] << 21) ^ (r[1] >> 11)) * (1.0 / 9007199254740992.0) + (0.5 / 9007199254740992.0);
+    u1 = (((unsigned long long)r[2] << 21) ^ (r[3] >> 11)) * (1.0 / 9007199254740992.0) + (0.5 / 9007199254740992.0);
+  }
+  __device__ double uniform() const { double a, b; uniforms(a, b); return a; }
+  __device__ void normals(double& z0, double& z1) const {
+    double a, b;
+    uniforms(a, b);
+    const double r = sqrt(-2.0 * log(a));
+    double sn, cs;
+    sincospi(2.0 * b, &sn, &cs);
+    z0 = r * cs; z1 = r * sn;
+  }
+};
+
+__device__ __forceinline__ double logaddexp(double a, double b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  const double m = fmax(a, b);
+  return m + log1p(exp(-fabs(a - b)));
+}
+
+// p ~ N(0, M), M = diag(1/minv); writes into vector field f
+__device__ void sample_momentum(const Chain& ch, int f) {
+  const int dim = ch.P.dim;
+  for (int k = 0; k < dim; k += 2) {
+    double z0, z1;
+    ch.normals(z0, z1);
+    ch.v(f, k) = z0 / sqrt(ch.v(V_MINV, k));
+    if (k + 1 < dim) ch.v(f, k + 1) = z1 / sqrt(ch.v(V_MINV, k + 1));
+  }
+}
+
+__device__ double kinetic(const Chain& ch, int f) {
+  double ke = 0.0;
+  for (int k = 0; k < ch.P.dim; ++k) ke += ch.v(V_MINV, k) * ch.v(f, k) * ch.v(f, k);
+  return 0.5 * ke;
+}
+
+// half kick + drift from the edge (fq, fp, fg) in direction dir; leaves the half-kicked momentum in fp and writes q_eval
+__device__ void start_leapfrog(const Chain& ch, int fq, int fp, int fg, int dir) {
+  const double e = ch.s(S_EPS) * dir;
+  for (int k = 0; k < ch.P.dim; ++k) {
+    const double ph = ch.v(fp, k) + 0.5 * e * ch.v(fg, k);
+    ch.v(fp, k) = ph;
+    ch.P.q_eval[(size_t)ch.c * ch.P.dim + k] = ch.v(fq, k) + e * ch.v(V_MINV, k) * ph;
+  }
+}
+
+// second half kick with the freshly evaluated gradient; the edge becomes the new leaf.  Returns its Hamiltonian.
+__device__ double finish_leapfrog(const Chain& ch, int fq, int fp, int fg, int dir, double& lp_new) {
+  const double e = ch.s(S_EPS) * dir;
+  const int dim = ch.P.dim;
+  lp_new = ch.P.st_eval[ch.c] ? -INFINITY : ch.P.lp_eval[ch.c];
+  for (int k = 0; k < dim; ++k) {
+    const double g = ch.P.g_eval[(size_t)ch.c * dim + k];
+    ch.v(fq, k) = ch.P.q_eval[(size_t)ch.c * dim + k];
+    ch.v(fg, k) = g;
+    ch.v(fp, k) += 0.5 * e * g;
+  }
+  double H = -lp_new + kinetic(ch, fp);
+  if (isnan(H)) H = INFINITY;
+  return H;
+}
+
+__device__ void begin_subtree(const Chain& ch) {
+  ch.i(I_DIR) = ch.uniform() < 0.5 ? -1 : 1;
+  ch.i(I_LEAF) = 0;
+  ch.s(S_SUB_LSW) = -INFINITY;
+  for (int k = 0; k < ch.P.dim; ++k) ch.v(V_RHO_SUB, k) = 0.0;
+  const int dir = ch.i(I_DIR);
+  start_leapfrog(ch, dir > 0 ? V_QR : V_QL, dir > 0 ? V_PR : V_PL, dir > 0 ? V_GR : V_GL, dir);
+}
+
+__device__ void begin_transition(const Chain& ch) {
+  const int dim = ch.P.dim;
+  sample_momentum(ch, V_PL);
+  for (int k = 0; k < dim; ++k) {
+    const double q = ch.v(V_Q_CUR, k), g = ch.v(V_G_CUR, k), p = ch.v(V_PL, k);
+    ch.v(V_QL, k) = q; ch.v(V_QR, k) = q; ch.v(V_GL, k) = g; ch.v(V_GR, k) = g; ch.v(V_PR, k) = p;
+    ch.v(V_Q_PROP, k) = q; ch.v(V_G_PROP, k) = g; ch.v(V_RHO, k) = p;
+  }
+  ch.s(S_LP_PROP) = ch.s(S_LP_CUR);
+  ch.s(S_H0) = -ch.s(S_LP_CUR) + kinetic(ch, V_PL);
+  ch.s(S_LSW) = 0.0;
+  ch.s(S_SUM_ACC) = 0.0;
+  ch.i(I_DEPTH) = 0;
+  ch.i(I_NLEAP) = 0;
+  ch.i(I_DIVERGENT) = 0;
+  ch.i(I_PHASE) = PH_NUTS;
+  begin_subtree(ch);
+}
+
+// Stan's init_stepsize: one trial leapfrog from the current point with a fresh momentum
+__device__ void begin_eps_trial(const Chain& ch, int phase) {
+  const int dim = ch.P.dim;
+  sample_momentum(ch, V_PR);
+  for (int k = 0; k < dim; ++k) { ch.v(V_QR, k) = ch.v(V_Q_CUR, k); ch.v(V_GR, k) = ch.v(V_G_CUR, k); }
+  ch.s(S_H0) = -ch.s(S_LP_CUR) + kinetic(ch, V_PR);
+  ch.i(I_PHASE) = phase;
+  start_leapfrog(ch, V_QR, V_PR, V_GR, 1);
+}
+
+__device__ void restart_dual_averaging(const Chain& ch) {
+  ch.s(S_DA_MU) = log(10.0 * ch.s(S_EPS));
+  ch.s(S_DA_SBAR) = 0.0;
+  ch.s(S_DA_XBAR) = 0.0;
+  ch.s(S_DA_CNT) = 0.0;
+}
+
+__device__ bool uturn_ok(const Chain& ch, int fpa, int fpb, int frho) {   // true = keep going
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < ch.P.dim; ++k) {
+    const double r = ch.v(frho, k), mi = ch.v(V_MINV, k);
+    a += mi * ch.v(fpa, k) * r;
+    b += mi * ch.v(fpb, k) * r;
+  }
+  return a > 0.0 && b > 0.0;
+}
+
+// Stan's windowed_adaptation::compute_next_window
+__device__ void compute_next_window(const Chain& ch) {
+  const int end = ch.P.warmup - ch.P.term_buffer - 1;
+  if (ch.i(I_WIN_NEXT) == end) return;
+  ch.i(I_WIN_SIZE) *= 2;
+  ch.i(I_WIN_NEXT) = ch.i(I_WIN_COUNTER) + ch.i(I_WIN_SIZE);
+  if (ch.i(I_WIN_NEXT) == end) return;
+  const int boundary = ch.i(I_WIN_NEXT) + 2 * ch.i(I_WIN_SIZE);
+  if (boundary >= ch.P.warmup - ch.P.term_buffer) ch.i(I_WIN_NEXT) = end;
+}
+
+__device__ void record_draw(const Chain& ch, int it, double accept) {
+  const Params& P = ch.P;
+  const int sidx = it - P.warmup;
+  if (sidx < 0) return;
+  const int nsave = P.iter - P.warmup;
+  const size_t row = (size_t)ch.c * nsave + sidx;
+  for (int k = 0; k < P.dim; ++k) {
+    const double u = ch.v(V_Q_CUR, k);
+    double th = u;
+    if (k < P.P) {
+      if (P.has_bounds[k]) {
+        const double sg = (u >= 0.0) ? 1.0 / (1.0 + exp(-u)) : exp(u) / (1.0 + exp(u));
+        th = P.lo[k] + (P.hi[k] - P.lo[k]) * sg;
+      }
+    } else {
+      th = exp(u);   // sigma_obs
+    }
+    P.draws[row * P.dim + k] = th;
+  }
+  P.d_lp[row] = ch.s(S_LP_CUR);
+  P.d_acc[row] = accept;
+  P.d_eps[row] = ch.s(S_EPS);
+  P.d_depth[row] = ch.i(I_DEPTH);
+  P.d_nleap[row] = ch.i(I_NLEAP);
+  P.d_div[row] = ch.i(I_DIVERGENT);
+}
+
+// end of a transition: move to the proposal, record, adapt, and start whatever comes next
+__device__ void end_transition(const Chain& ch) {
+  const Params& P = ch.P;
+  const int dim = P.dim;
+  for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = ch.v(V_Q_PROP, k); ch.v(V_G_CUR, k) = ch.v(V_G_PROP, k); }
+  ch.s(S_LP_CUR) = ch.s(S_LP_PROP);
+  const int nl = max(1, ch.i(I_NLEAP));
+  const double accept = ch.s(S_SUM_ACC) / nl;
+  ch.s(S_NLEAP_TOT) += ch.i(I_NLEAP);
+  const int it = ch.i(I_ITER);
+  record_draw(ch, it, accept);
+  ch.i(I_ITER) = it + 1;
+  bool metric_updated = false, wait = false;
+  if (it < P.warmup) {
+    // dual averaging (Stan's stepsize_adaptation::learn_stepsize: gamma 0.05, t0 10, kappa 0.75)
+    const double cnt = ch.s(S_DA_CNT) + 1.0;
+    ch.s(S_DA_CNT) = cnt;
+    const double stat = fmin(1.0, accept);
+    const double eta = 1.0 / (cnt + 10.0);
+    const double sbar = (1.0 - eta) * ch.s(S_DA_SBAR) + eta * (P.delta - stat);
+    ch.s(S_DA_SBAR) = sbar;
+    const double x = ch.s(S_DA_MU) - sbar * sqrt(cnt) / 0.05;
+    const double xeta = pow(cnt, -0.75);
+    ch.s(S_DA_XBAR) = (1.0 - xeta) * ch.s(S_DA_XBAR) + xeta * x;
+    ch.s(S_EPS) = exp(x);
+    // windowed metric adaptation (Stan's var_adaptation::learn_variance)
+    const int wc = ch.i(I_WIN_COUNTER);
+    const bool in_window = wc >= P.init_buffer && wc < P.warmup - P.term_buffer && wc != P.warmup;
+    if (in_window) {
+      const double n = ch.s(S_W_N) + 1.0;
+      ch.s(S_W_N) = n;
+      for (int k = 0; k < dim; ++k) {
+        const double q = ch.v(V_Q_CUR, k);
+        const double d = q - ch.v(V_W_MEAN, k);
+        const double mean = ch.v(V_W_MEAN, k) + d / n;
+        ch.v(V_W_MEAN, k) = mean;
+        ch.v(V_W_M2, k) += d * (q - mean);
+      }
+    }
+    if (wc == ch.i(I_WIN_NEXT) && wc != P.warmup && in_window) {
+      if (P.pooled) {
+        wait = true;   // the pooled metric is set by bp_pool_apply once every chain of every rank is here
+      } else {
+        compute_next_window(ch);
+        const double n = ch.s(S_W_N);
+        for (int k = 0; k < dim; ++k) {
+          const double var = n > 1.0 ? ch.v(V_W_M2, k) / (n - 1.0) : 1.0;
+          ch.v(V_MINV, k) = (n / (n + 5.0)) * var + 1e-3 * (5.0 / (n + 5.0));
+          ch.v(V_W_MEAN, k) = 0.0;
+          ch.v(V_W_M2, k) = 0.0;
+        }
+        ch.s(S_W_N) = 0.0;
+        metric_updated = true;
+      }
+    }
+    ch.i(I_WIN_COUNTER) = wc + 1;
+    if (it + 1 == P.warmup) ch.s(S_EPS) = exp(ch.s(S_DA_XBAR));   // complete_adaptation
+  }
+  if (ch.i(I_ITER) >= P.iter) {
+    ch.i(I_PHASE) = PH_DONE;
+    atomicAdd(P.counters + 0, 1);
+    return;
+  }
+  if (wait) {
+    ch.i(I_PHASE) = PH_WAIT;
+    atomicAdd(P.counters + 1, 1);
+    return;
+  }
+  if (metric_updated) {
+    ch.i(I_FE_DIR) = 0;
+    begin_eps_trial(ch, PH_FIND_EPS_FIRST);
+    return;
+  }
+  begin_transition(ch);
+}
+
+__global__ void bp_nuts_advance(Params P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  Chain ch(P, c);
+  const int phase = ch.i(I_PHASE);
+  const int dim = P.dim;
+  if (phase == PH_DONE || phase == PH_WAIT || phase == PH_FAILED) return;
+
+  if (phase == PH_INIT) {
+    const double lp = P.st_eval[c] ? -INFINITY : P.lp_eval[c];
+    bool ok = isfinite(lp);
+    for (int k = 0; k < dim; ++k) ok = ok && isfinite(P.g_eval[(size_t)c * dim + k]);
+    if (!ok) {
+      // rstan retries random initial values (up to 100 attempts); user-supplied inits that fail are an error there too
+      if (ch.i(I_TRIES) >= 100) { ch.i(I_PHASE) = PH_FAILED; atomicAdd(P.counters + 0, 1); atomicAdd(P.counters + 2, 1); return; }
+      ch.i(I_TRIES) += 1;
+      for (int k = 0; k < dim; ++k) P.q_eval[(size_t)c * dim + k] = 4.0 * ch.uniform() - 2.0;
+      return;
+    }
+    for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = P.q_eval[(size_t)c * dim + k]; ch.v(V_G_CUR, k) = P.g_eval[(size_t)c * dim + k]; }
+    ch.s(S_LP_CUR) = lp;
+    ch.i(I_FE_DIR) = 0;
+    begin_eps_trial(ch, PH_FIND_EPS_FIRST);
+    return;
+  }
+
+  if (phase == PH_FIND_EPS_FIRST || phase == PH_FIND_EPS) {
+    double lp_new;
+    const double H = finish_leapfrog(ch, V_QR, V_PR, V_GR, 1, lp_new);
+    const double dH = ch.s(S_H0) - H;           // -inf when the trial point is rejected
+    const double l08 = -0.22314355131420976;    // log(0.8)
+    if (phase == PH_FIND_EPS_FIRST) {
+      ch.i(I_FE_DIR) = dH > l08 ? 1 : -1;
+      begin_eps_trial(ch, PH_FIND_EPS);
+      return;
+    }
+    const int d = ch.i(I_FE_DIR);
+    const bool stop = (d == 1 && !(dH > l08)) || (d == -1 && !(dH < l08));
+    const double e = ch.s(S_EPS);
+    if (stop || e > 1e7 || e < 1e-300) {
+      restart_dual_averaging(ch);
+      begin_transition(ch);
+      return;
+    }
+    ch.s(S_EPS) = d == 1 ? 2.0 * e : 0.5 * e;
+    begin_eps_trial(ch, PH_FIND_EPS);
+    return;
+  }
+
+  // ---- PH_NUTS: a leapfrog of the sub-tree under construction has just been evaluated ----------
+  const int dir = ch.i(I_DIR);
+  const int fq = dir > 0 ? V_QR : V_QL, fp = dir > 0 ? V_PR : V_PL, fg = dir > 0 ? V_GR : V_GL;
+  double lp_new;
+  const double H = finish_leapfrog(ch, fq, fp, fg, dir, lp_new);
+  ch.i(I_NLEAP) += 1;
+  const double dH = ch.s(S_H0) - H;
+  if (!(H - ch.s(S_H0) <= 1000.0)) {   // divergent (also NaN / rejected points): the sub-tree is discarded
+    ch.i(I_DIVERGENT) = 1;
+    end_transition(ch);
+    return;
+  }
+  // multinomial sampling inside the sub-tree: the new leaf replaces the sub-tree's proposal w.p. w_leaf / w_subtree
+  const double sub_lsw = logaddexp(ch.s(S_SUB_LSW), dH);
+  ch.s(S_SUB_LSW) = sub_lsw;
+  ch.s(S_SUM_ACC) += fmin(1.0, exp(dH));
+  const bool take = ch.uniform() < exp(dH - sub_lsw);
+  for (int k = 0; k < dim; ++k) {
+    ch.v(V_RHO_SUB, k) += ch.v(fp, k);
+    if (take) { ch.v(V_Q_SP, k) = ch.v(fq, k); ch.v(V_G_SP, k) = ch.v(fg, k); }
+  }
+  if (take) ch.s(S_LP_SP) = lp_new;
+  // sub-tree U-turn checks with checkpointed partial sums (leaf index bits select the balanced sub-trees that end here)
+  const int leaf = ch.i(I_LEAF);
+  int idx_max = __popc((unsigned)leaf >> 1);
+  bool turning = false;
+  if ((leaf & 1) == 0) {
+    for (int k = 0; k < dim; ++k) { ch.rck(idx_max, k) = ch.v(fp, k); ch.rsck(idx_max, k) = ch.v(V_RHO_SUB, k); }
+  } else {
+    int ntrail = 0;
+    for (unsigned b = (unsigned)leaf; b & 1u; b >>= 1) ++ntrail;
+    const int idx_min = idx_max - ntrail + 1;
+    for (int lvl = idx_max; lvl >= idx_min && !turning; --lvl) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < dim; ++k) {
+        const double r = ch.v(V_RHO_SUB, k) - ch.rsck(lvl, k) + ch.rck(lvl, k);
+        const double mi = ch.v(V_MINV, k);
+        a += mi * ch.rck(lvl, k) * r;
+        b += mi * ch.v(fp, k) * r;
+      }
+      turning = !(a > 0.0 && b > 0.0);
+    }
+  }
+  ch.i(I_LEAF) = leaf + 1;
+  if (turning) {   // invalid sub-tree: the transition ends with the current tree-level proposal
+    end_transition(ch);
+    return;
+  }
+  const int depth = ch.i(I_DEPTH);
+  if (leaf + 1 < (1 << depth)) {   // keep extending the same sub-tree
+    start_leapfrog(ch, fq, fp, fg, dir);
+    return;
+  }
+  // sub-tree complete: biased progressive sampling at the top level, merge, tree-level U-turn check
+  const double lsw = ch.s(S_LSW);
+  if (sub_lsw > lsw || ch.uniform() < exp(sub_lsw - lsw)) {
+    for (int k = 0; k < dim; ++k) { ch.v(V_Q_PROP, k) = ch.v(V_Q_SP, k); ch.v(V_G_PROP, k) = ch.v(V_G_SP, k); }
+    ch.s(S_LP_PROP) = ch.s(S_LP_SP);
+  }
+  ch.s(S_LSW) = logaddexp(lsw, sub_lsw);
+  for (int k = 0; k < dim; ++k) ch.v(V_RHO, k) += ch.v(V_RHO_SUB, k);
+  ch.i(I_DEPTH) = depth + 1;
+  if (!uturn_ok(ch, V_PL, V_PR, V_RHO) || depth + 1 >= P.max_depth) {
+    end_transition(ch);
+    return;
+  }
+  begin_subtree(ch);
+}
+
+// initial positions and per-chain adaptation state
+__global__ void bp_nuts_init(Params P, const double* __restrict__ inits_u) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  Chain ch(P, c);
+  for (int f = 0; f < NINT; ++f) ch.i(f) = 0;
+  for (int f = 0; f < NSCAL; ++f) ch.s(f) = 0.0;
+  ch.i(I_PHASE) = PH_INIT;
+  ch.s(S_EPS) = P.eps0;
+  ch.i(I_WIN_SIZE) = P.base_window;
+  ch.i(I_WIN_NEXT) = P.init_buffer + P.base_window - 1;
+  for (int k = 0; k < P.dim; ++k) {
+    ch.v(V_MINV, k) = 1.0;
+    ch.v(V_W_MEAN, k) = 0.0;
+    ch.v(V_W_M2, k) = 0.0;
+    P.q_eval[(size_t)c * P.dim + k] = P.have_inits ? inits_u[(size_t)c * P.dim + k] : 4.0 * ch.uniform() - 2.0;
+  }
+  if (P.have_inits) ch.i(I_TRIES) = 100;   // user-supplied initial values are not retried
+}
+
+// pooled adaptation: this rank's (count, sum q, sum q^2) over the window of all its chains, fixed order
+__global__ void bp_pool_stats(Params P, double* __restrict__ out) {
+  const int k = threadIdx.x;   // 0 .. 2*dim
+  if (k > 2 * P.dim) return;
+  double acc = 0.0;
+  for (int c = 0; c < P.C; ++c) {
+    Chain ch(P, c);
+    if (ch.i(I_PHASE) != PH_WAIT) continue;
+    const double n = ch.s(S_W_N);
+    if (k == 0) acc += n;
+    else if (k <= P.dim) acc += n * ch.v(V_W_MEAN, k - 1);
+    else { const double m = ch.v(V_W_MEAN, k - 1 - P.dim); acc += ch.v(V_W_M2, k - 1 - P.dim) + n * m * m; }
+  }
+  out[k] = acc;
+}
+
+__global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  Chain ch(P, c);
+  if (ch.i(I_PHASE) != PH_WAIT) return;
+  const double n = red[0];
+  ch.i(I_WIN_COUNTER) -= 1;          // compute_next_window is defined on the counter of the window's last iteration
+  compute_next_window(ch);
+  ch.i(I_WIN_COUNTER) += 1;
+  for (int k = 0; k < P.dim; ++k) {
+    const double mean = red[1 + k] / n;
+    const double var = n > 1.0 ? (red[1 + P.dim + k] - n * mean * mean) / (n - 1.0) : 1.0;
+    // the regulariser uses the per-chain window length, as if each chain had estimated the variance itself
+    const double nw = ch.s(S_W_N);
+    ch.v(V_MINV, k) = (nw / (nw + 5.0)) * var + 1e-3 * (5.0 / (nw + 5.0));
+    ch.v(V_W_MEAN, k) = 0.0;
+    ch.v(V_W_M2, k) = 0.0;
+  }
+  ch.s(S_W_N) = 0.0;
+  ch.i(I_FE_DIR) = 0;
+  begin_eps_trial(ch, PH_FIND_EPS_FIRST);
+}
+
+// per-dimension sums over this rank's chains of (1, chain mean, chain mean^2, chain variance) of the saved draws
+__global__ void bp_chain_moments(Params P, double* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= P.dim) return;
+  const int ns = P.iter - P.warmup;
+  double cnt = 0.0, sm = 0.0, sm2 = 0.0, sv = 0.0;
+  for (int c = 0; c < P.C; ++c) {
+    if (P.si[(size_t)I_PHASE * P.C + c] == PH_FAILED) continue;
+    double mean = 0.0, m2 = 0.0;
+    for (int i = 0; i < ns; ++i) {
+      const double x = P.draws[((size_t)c * ns + i) * P.dim + k];
+      const double d = x - mean;
+      mean += d / (i + 1);
+      m2 += d * (x - mean);
+    }
+    cnt += 1.0; sm += mean; sm2 += mean * mean; sv += ns > 1 ? m2 / (ns - 1) : 0.0;
+  }
+  out[4 * k + 0] = cnt; out[4 * k + 1] = sm; out[4 * k + 2] = sm2; out[4 * k + 3] = sv;
+}
+
+}  // namespace
+
+struct bpc_sampler {
+  bpc_model* m = nullptr;
+  bpc_data* d = nullptr;
+  Params P{};
+  DevBuf sd, si, q_eval, lp_eval, g_eval, st_eval, draws, d_lp, d_acc, d_eps, d_depth, d_nleap, d_div, counters, pool, moments, inits;
+  long long passes = 0;
+  int* h_counters = nullptr;   // pinned
+  cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_sampler** out) {
+  if (!m || !d || !a || !out) return fail(BPC_E_INVALID, "null argument");
+  *out = nullptr;
+  if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
+  const ModelSpec& sp = m->spec;
+  if (sp.dim > MAXDIM) return fail(BPC_E_UNSUPPORTED, "too many parameters for the sampler");
+  if (a->chains < 1 || a->iter < 1 || a->warmup < 0 || a->warmup >= a->iter) return fail(BPC_E_INVALID, "need chains >= 1 and 0 <= warmup < iter");
+  if (a->max_treedepth < 1 || a->max_treedepth > MAXD) return fail(BPC_E_INVALID, "max_treedepth must be in [1, 12]");
+  if (!(a->adapt_delta > 0.0 && a->adapt_delta < 1.0)) return fail(BPC_E_INVALID, "adapt_delta must be in (0, 1)");
+  cudaError_t e;
+  if ((e = cudaSetDevice(d->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  auto s = std::make_unique<bpc_sampler>();
+  s->m = m; s->d = d;
+  Params& P = s->P;
+  P.C = a->chains; P.dim = sp.dim; P.P = sp.nparams; P.noise = sp.kind == BPC_MULTITYPE_NOISE;
+  P.max_depth = a->max_treedepth; P.iter = a->iter; P.warmup = a->warmup; P.chain_offset = a->chain_id_offset;
+  P.pooled = a->pooled_adaptation ? 1 : 0; P.have_inits = a->inits ? 1 : 0;
+  P.delta = a->adapt_delta; P.eps0 = a->stepsize > 0 ? a->stepsize : 1.0; P.seed = a->seed;
+  // Stan's window schedule (windowed_adaptation): 75 / 25 / 50, rescaled to 15% / 75% / 10% for short warm-ups
+  P.init_buffer = 75; P.term_buffer = 50; P.base_window = 25;
+  if (P.warmup < 20) { P.init_buffer = P.warmup; P.term_buffer = 0; P.base_window = 0; }   // no metric adaptation
+  else if (P.init_buffer + P.base_window + P.term_buffer > P.warmup) {
+    P.init_buffer = (int)(0.15 * P.warmup); P.term_buffer = (int)(0.1 * P.warmup); P.base_window = P.warmup - (P.init_buffer + P.term_buffer);
+  }
+  for (int k = 0; k < MAXDIM; ++k) { P.has_bounds[k] = 0; P.lo[k] = 0; P.hi[k] = 0; }
+  for (int k = 0; k < sp.nparams; ++k) { P.has_bounds[k] = sp.priors[k].has_bounds; P.lo[k] = sp.priors[k].lower; P.hi[k] = sp.priors[k].upper; }
+  const size_t C = P.C, dim = P.dim, ns = P.iter - P.warmup;
+  int rc;
+#define AL(buf, bytes) if ((rc = s->buf.alloc(bytes))) return rc
+  AL(sd, (NSCAL + NVEC * dim + 2 * MAXD * dim) * C * 8);
+  AL(si, (size_t)NINT * C * 4);
+  AL(q_eval, C * dim * 8); AL(lp_eval, C * 8); AL(g_eval, C * dim * 8); AL(st_eval, C * 4);
+  AL(draws, C * ns * dim * 8); AL(d_lp, C * ns * 8); AL(d_acc, C * ns * 8); AL(d_eps, C * ns * 8);
+  AL(d_depth, C * ns * 4); AL(d_nleap, C * ns * 4); AL(d_div, C * ns * 4);
+  AL(counters, 16); AL(pool, (1 + 2 * dim) * 8); AL(moments, 4 * dim * 8);
+#undef AL
+  P.sd = (double*)s->sd.p; P.si = (int*)s->si.p; P.q_eval = (double*)s->q_eval.p; P.lp_eval = (double*)s->lp_eval.p;
+  P.g_eval = (double*)s->g_eval.p; P.st_eval = (int*)s->st_eval.p; P.draws = (double*)s->draws.p; P.d_lp = (double*)s->d_lp.p;
+  P.d_acc = (double*)s->d_acc.p; P.d_eps = (double*)s->d_eps.p; P.d_depth = (int*)s->d_depth.p; P.d_nleap = (int*)s->d_nleap.p;
+  P.d_div = (int*)s->d_div.p; P.counters = (int*)s->counters.p;
+  if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  if ((e = cudaMallocHost(&s->h_counters, 16)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+  cudaMemsetAsync(s->sd.p, 0, s->sd.cap, s->stream);
+  cudaMemsetAsync(s->counters.p, 0, 16, s->stream);
+  cudaMemsetAsync(s->draws.p, 0, C * ns * dim * 8, s->stream);
+  const double* inits_dev = nullptr;
+  if (a->inits) {
+    // constrained initial values -> unconstrained (sigma_obs starts at 0.05)
+    std::vector<double> th(C * dim), u(C * dim);
+    for (size_t c = 0; c < C; ++c) {
+      for (int k = 0; k < sp.nparams; ++k) th[c * dim + k] = a->inits[c * sp.nparams + k];
+      if (P.noise) th[c * dim + sp.nparams] = 0.05;
+    }
+    if ((rc = bpc_unconstrain(m, th.data(), (int)C, u.data()))) return rc;
+    if ((rc = s->inits.alloc(C * dim * 8))) return rc;
+    if ((e = cudaMemcpyAsync(s->inits.p, u.data(), C * dim * 8, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+    cudaStreamSynchronize(s->stream);
+    inits_dev = (const double*)s->inits.p;
+  }
+  bp_nuts_init<<<(P.C + 127) / 128, 128, 0, s->stream>>>(P, inits_dev);
+  g_launches += 1;
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "bp_nuts_init");
+  *out = s.release();
+  return BPC_OK;
+}
+
+void bpc_sampler_free(bpc_sampler* s) {
+  if (!s) return;
+  cudaSetDevice(s->d->device);
+  if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  if (s->h_counters) cudaFreeHost(s->h_counters);
+  delete s;
+}
+
+int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
+  if (!s || !state) return fail(BPC_E_INVALID, "null argument");
+  cudaError_t e;
+  if ((e = cudaSetDevice(s->d->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const Params& P = s->P;
+  *state = 0;
+  long long done_passes = 0;
+  // poll the finished / waiting counters every few passes: cheap for large problems, and for small ones the
+  // polling interval bounds the tail of idle passes
+  const int poll = 16;
+  while (done_passes < max_passes) {
+    const int nb = (int)std::min<long long>(poll, max_passes - done_passes);
+    for (int b = 0; b < nb; ++b) {
+      int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream);
+      if (rc) return rc;
+      bp_nuts_advance<<<(P.C + 127) / 128, 128, 0, s->stream>>>(P);
+      g_launches += 1;
+    }
+    done_passes += nb;
+    s->passes += nb;
+    if ((e = cudaMemcpyAsync(s->h_counters, P.counters, 12, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync");
+    if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(e, "sampler pass");
+    if (s->h_counters[0] >= P.C) { *state = 1; return BPC_OK; }
+    if (P.pooled && s->h_counters[0] + s->h_counters[1] >= P.C && s->h_counters[1] > 0) { *state = 2; return BPC_OK; }
+  }
+  return BPC_OK;
+}
+
+int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count) {
+  if (!s) return fail(BPC_E_INVALID, "null argument");
+  if (stats_dev && count < 1 + 2 * s->P.dim) return fail(BPC_E_INVALID, "stats buffer too small: need 1 + 2*dim doubles");
+  cudaSetDevice(s->d->device);
+  bp_pool_stats<<<1, 2 * MAXDIM + 32, 0, s->stream>>>(s->P, stats_dev ? stats_dev : (double*)s->pool.p);
+  g_launches += 1;
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "bp_pool_stats");
+  return BPC_OK;
+}
+
+int bpc_sampler_pool_apply(bpc_sampler* s, const double* reduced_dev) {
+  if (!s) return fail(BPC_E_INVALID, "null argument");
+  cudaSetDevice(s->d->device);
+  bp_pool_apply<<<(s->P.C + 127) / 128, 128, 0, s->stream>>>(s->P, reduced_dev ? reduced_dev : (const double*)s->pool.p);
+  cudaMemsetAsync(s->P.counters + 1, 0, 4, s->stream);
+  g_launches += 1;
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "bp_pool_apply");
+  return BPC_OK;
+}
+
+int bpc_sampler_draws(bpc_sampler* s, double* draws, double* lp, int* divergent, int* treedepth, int* n_leapfrog,
+                      double* accept_stat, double* stepsize) {
+  if (!s) return fail(BPC_E_INVALID, "null argument");
+  cudaSetDevice(s->d->device);
+  cudaStreamSynchronize(s->stream);
+  const size_t C = s->P.C, ns = s->P.iter - s->P.warmup, dim = s->P.dim;
+  cudaError_t e = cudaSuccess;
+  auto cp = [&](void* dst, const void* src, size_t bytes) { if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+  cp(draws, s->draws.p, C * ns * dim * 8);
+  cp(lp, s->d_lp.p, C * ns * 8);
+  cp(divergent, s->d_div.p, C * ns * 4);
+  cp(treedepth, s->d_depth.p, C * ns * 4);
+  cp(n_leapfrog, s->d_nleap.p, C * ns * 4);
+  cp(accept_stat, s->d_acc.p, C * ns * 8);
+  cp(stepsize, s->d_eps.p, C * ns * 8);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return BPC_OK;
+}
+
+int bpc_sampler_chain_moments(bpc_sampler* s, double* stats_dev, int count, double* stats_host) {
+  if (!s) return fail(BPC_E_INVALID, "null argument");
+  if (stats_dev && count < 4 * s->P.dim) return fail(BPC_E_INVALID, "stats buffer too small: need 4*dim doubles");
+  cudaSetDevice(s->d->device);
+  double* dst = stats_dev ? stats_dev : (double*)s->moments.p;
+  bp_chain_moments<<<1, MAXDIM, 0, s->stream>>>(s->P, dst);
+  g_launches += 1;
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "bp_chain_moments");
+  if (stats_host && (e = cudaMemcpy(stats_host, dst, (size_t)4 * s->P.dim * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return BPC_OK;
+}
+
+int bpc_rhat(const double* red, int dim, int n, double* rhat) {
+  if (!red || !rhat || dim < 1 || n < 2) return fail(BPC_E_INVALID, "bad argument");
+  for (int k = 0; k < dim; ++k) {
+    const double m = red[4 * k], sm = red[4 * k + 1], sm2 = red[4 * k + 2], sv = red[4 * k + 3];
+    if (m < 2) { rhat[k] = std::nan(""); continue; }
+    const double B_over_n = (sm2 - sm * sm / m) / (m - 1.0);   // variance of the chain means
+    const double W = sv / m;
+    const double var_plus = W * (n - 1.0) / n + B_over_n;
+    rhat[k] = std::sqrt(var_plus / W);
+  }
+  return BPC_OK;
+}
+
+long long bpc_sampler_total_leapfrogs(bpc_sampler* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->d->device);
+  cudaStreamSynchronize(s->stream);
+  std::vector<double> v(s->P.C);
+  if (cudaMemcpy(v.data(), s->P.sd + (size_t)S_NLEAP_TOT * s->P.C, (size_t)s->P.C * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  double t = 0;
+  for (double x : v) t += x;
+  return (long long)t;
+}
+
+long long bpc_sampler_passes(const bpc_sampler* s) { return s ? s->passes : 0; }
+
+int bpc_sample(bpc_model* m, bpc_data* d, const bpc_sample_args* a, double* draws, double* lp, int* divergent, int* treedepth,
+               int* n_leapfrog, double* accept_stat, double* stepsize) {
+  bpc_sampler* s = nullptr;
+  int rc = bpc_sampler_create(m, d, a, &s);
+  if (rc) return rc;
+  int state = 0;
+  while (state != 1) {
+    if ((rc = bpc_sampler_run(s, 1 << 20, &state))) break;
+    if (state == 2) {
+      if ((rc = bpc_sampler_pool_stats(s, nullptr, 0))) break;
+      if ((rc = bpc_sampler_pool_apply(s, nullptr))) break;
+    }
+  }
+  if (!rc) rc = bpc_sampler_draws(s, draws, lp, divergent, treedepth, n_leapfrog, accept_stat, stepsize);
+  if (!rc && s->h_counters[2] > 0) { bpc_sampler_free(s); return fail(BPC_E_INVALID, "initialization failed for some chains: log density or gradient not finite at 100 random initial values"); }
+  bpc_sampler_free(s);
+  return rc;
+}
+
+int bpc_simulate(int, int, const double*, const int*, const double*, const double*, const double*, int, int, unsigned long long, int, double*) {
+  return fail(BPC_E_UNSUPPORTED, "device simulator not built yet: use bpinference_b200.bpsims");
+}
+
+}  // extern "C"

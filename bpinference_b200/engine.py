@@ -180,6 +180,13 @@ class BpCudaModel:
         _ffi.check(_ffi.lib().bpc_unconstrain(self.handle, _ffi.dptr(t), t.shape[0], _ffi.dptr(out)))
         return out[0] if np.ndim(theta) == 1 else out
 
+    def sampling(self, dat, chains: int = 4, iter: int = 2000, warmup=None, init="random", control=None, seed: int = 1,
+                 pooled_adaptation: bool = False, device=None):
+        """rstan::sampling — see bpinference_b200.fit.sampling."""
+        from .fit import sampling
+        return sampling(self, dat, chains=chains, iter=iter, warmup=warmup, init=init, control=control, seed=seed,
+                        pooled_adaptation=pooled_adaptation, device=device)
+
     def flops_per_chain(self, dat, upars):
         d = self._data(dat)
         u = np.ascontiguousarray(np.atleast_2d(_f64(upars)))

@@ -173,32 +173,49 @@ int bpc_kernel_time_ms(bpc_data* d, int reset, double* total_ms, long long* laun
 int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* flops_per_chain);
 
 /* ---- sample: replaces rstan::sampling(stan_mod, data, chains, iter, warmup, init, control) ---- */
+/* (examples/two_type.R:26; sampler settings of examples/*.R).  Device-resident NUTS (multinomial, diagonal
+ * metric, Stan's windowed warm-up and dual averaging): every chain is a state machine advanced by one leapfrog
+ * step per pass; one pass = one fused log-density+gradient evaluation of ALL chains + one bookkeeping kernel.
+ * Random numbers are Philox4x32-10 keyed by (seed, global chain id), so a chain's draws do not depend on how
+ * chains are sharded over GPUs. */
 typedef struct {
   int chains;            /* chains on THIS device / rank */
   int iter;              /* total iterations per chain, warm-up included (rstan's iter) */
   int warmup;            /* rstan's warmup */
   double adapt_delta;    /* control$adapt_delta */
-  int max_treedepth;     /* control$max_treedepth: a trajectory has at most 2^max_treedepth leapfrog steps */
+  int max_treedepth;     /* control$max_treedepth (<= 12): a trajectory has at most 2^max_treedepth - 1 leapfrog steps */
   unsigned long long seed;
-  int chain_id_offset;   /* global id of this rank's first chain (Philox stream = seed, chain id) */
-  const double* inits;   /* chains x nparams CONSTRAINED values (uniform_initialize, R/stan_utils.R:74-87); sigma_obs starts at 0.05;
+  int chain_id_offset;   /* global id of this rank's first chain */
+  const double* inits;   /* chains x nparams CONSTRAINED values (uniform_initialize, R/stan_utils.R:74-87; sigma_obs starts at 0.05);
                             NULL = uniform(-2,2) on the unconstrained scale as rstan does */
-  int pooled_adaptation; /* 1: mass matrix / step size statistics are pooled across chains (and ranks) */
+  int pooled_adaptation; /* 0: every chain adapts its own metric (rstan).  1: the metric of each warm-up window is estimated from
+                            the draws of all chains of all ranks — the one collective on the path (see bpc_sampler_pool_*) */
+  double stepsize;       /* initial step size (0 = 1.0 as rstan) */
 } bpc_sample_args;
 
 int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_sampler** out);
 void bpc_sampler_free(bpc_sampler* s);
-/* runs iterations [from, to) (0-based; warm-up first); returns without host synchronisation of draws.
- * When pooled adaptation is on and `*need_reduce` comes back 1 the caller must sum the buffer returned by
- * bpc_sampler_stats_dev over all ranks (NCCL all-reduce; identity on one rank) and call
- * bpc_sampler_apply_stats before continuing: that exchange is the only collective on the path. */
-int bpc_sampler_run(bpc_sampler* s, int from, int to, int* stopped_at, int* need_reduce);
-int bpc_sampler_stats_dev(bpc_sampler* s, double** stats_dev, int* count);
-int bpc_sampler_apply_stats(bpc_sampler* s);
-/* results (host copies).  draws: chains x (iter - warmup) x dim constrained values, then lp__ via lp. */
+/* advances all chains by at most max_passes passes.  *state: 0 = more passes needed, 1 = all chains finished,
+ * 2 = (pooled adaptation) all chains reached the end of a warm-up window and wait for the pooled metric. */
+int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state);
+/* pooled adaptation, state 2: bpc_sampler_pool_stats writes this rank's sums (count, sum q_k, sum q_k^2; 1 + 2*dim doubles)
+ * into the caller's DEVICE buffer stats_dev; the caller adds the buffers of all ranks in place (ncclAllReduce /
+ * torch.distributed.all_reduce) and hands the result to bpc_sampler_pool_apply.  On one rank both pointers may be
+ * NULL: an internal buffer is used. */
+int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count);
+int bpc_sampler_pool_apply(bpc_sampler* s, const double* reduced_dev);
+/* results (host copies).  draws: chains x (iter - warmup) x dim CONSTRAINED values (Theta1..P, sigma_obs);
+ * lp: lp__ ; per-draw sampler parameters as rstan::get_sampler_params reports them.  Any pointer may be NULL. */
 int bpc_sampler_draws(bpc_sampler* s, double* draws, double* lp, int* divergent, int* treedepth,
                       int* n_leapfrog, double* accept_stat, double* stepsize);
-long long bpc_sampler_total_leapfrogs(const bpc_sampler* s);
+/* sums for cross-chain convergence diagnostics: for every dimension (count of chains, sum of chain means, sum of
+ * squared chain means, sum of chain variances) of the saved draws, 4*dim doubles, written to the caller's device
+ * buffer (to be added over ranks) and/or to a host buffer; either may be NULL.  Then bpc_rhat. */
+int bpc_sampler_chain_moments(bpc_sampler* s, double* stats_dev, int count, double* stats_host);
+/* potential scale reduction (the statistic check_rhat reads, R/stan_utils.R:516-533) from the reduced sums */
+int bpc_rhat(const double* reduced_moments, int dim, int draws_per_chain, double* rhat);
+long long bpc_sampler_total_leapfrogs(bpc_sampler* s);
+long long bpc_sampler_passes(const bpc_sampler* s);
 /* convenience: whole run on one device, single rank */
 int bpc_sample(bpc_model* m, bpc_data* d, const bpc_sample_args* a, double* draws, double* lp,
                int* divergent, int* treedepth, int* n_leapfrog, double* accept_stat, double* stepsize);
