@@ -71,6 +71,8 @@ SYMBOLS = {
     "bpc_log_prob": (C.c_int, [_vp, _vp, _dp, C.c_int, C.c_int, _dp, _dp, _ip]),
     "bpc_log_prob_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "bpc_log_lik": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp]),
+    "bpc_moments": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp, _dp]),
+    "bpc_flop_model": (C.c_int, [_vp, _dp, _dp, _dp]),
     "bpc_constrain": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "bpc_unconstrain": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "bpc_launch_count": (C.c_longlong, [C.c_int]),

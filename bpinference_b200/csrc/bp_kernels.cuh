@@ -184,18 +184,19 @@ BP_HD void bp_step_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S
   for (int q = 0; q < BP_S; ++q) vS[q] = bS[q];
   for (int k = m - 1; k >= 0; --k) {
     const real al = h * bp_rk[k];
+    const real al2 = al + al;
     real amu[BP_N], aS[BP_S];   // al * w_k.mu,  2 al * w_k.S
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < BP_N; ++i) amu[i] = al * y0mu[i];
 #pragma unroll
-      for (int q = 0; q < BP_S; ++q) aS[q] = (al + al) * y0S[q];
+      for (int q = 0; q < BP_S; ++q) aS[q] = al2 * y0S[q];
     } else {
       const real* p = store + (size_t)(k - 1) * BP_D * stride;
 #pragma unroll
       for (int i = 0; i < BP_N; ++i) amu[i] = al * p[i * stride];
 #pragma unroll
-      for (int q = 0; q < BP_S; ++q) aS[q] = (al + al) * p[(BP_N + q) * stride];
+      for (int q = 0; q < BP_S; ++q) aS[q] = al2 * p[(BP_N + q) * stride];
     }
     // gA[i][j] += al ( w.mu_i v.mu_j + 2 sum_k w.S_ik v.S_kj ) ; gH[l] += al w.mu_l v.S
 #pragma unroll
@@ -692,6 +693,41 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_loglik(BpObsArgs a) 
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
   a.loglik[(size_t)c * a.nobs + a.perm[k]] = bp_obs_loglik(A, H, a1, z0, xo, a.t[k], sigma);
+}
+
+// ---- mean vector and covariance matrix of every (chain, observation): what calculate_moments returns
+// (R/calculate_moments.R:79-86).  out: [C][N][BP_N + BP_N*BP_N] = mu then Sigma (row-major), original order.
+extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_moments(BpObsArgs a) {
+  const int c = blockIdx.y;
+  const int k = blockIdx.x * BP_THREADS + threadIdx.x;
+  if (k >= a.nobs) return;
+  double th[BP_DIM];
+#pragma unroll
+  for (int q = 0; q < BP_DIM; ++q) th[q] = a.theta[(size_t)c * BP_DIM + q];
+  double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP], ymu[BP_N], yS[BP_S];
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = 0.0;
+#if BP_XDEP
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = a.xv[(size_t)q * a.npad + k];
+#endif
+  bp_rates(th, xk, r);
+  bp_assemble(r, A, H);
+  const double a1 = bp_norm1(A);
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) ymu[i] = a.z0[(size_t)i * a.npad + k];
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) yS[q] = 0.0;
+  BpPlan p;
+  const bool ok = bp_make_plan(a1, a.t[k], p);
+  if (ok) for (int j = 0; j < p.s; ++j) bp_step_fwd(A, H, p.h, p.m, ymu, yS, false, (double*)0, 0);
+  double* o = a.loglik + ((size_t)c * a.nobs + a.perm[k]) * (BP_N + BP_N * BP_N);
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) o[i] = ok ? ymu[i] : (0.0 / 0.0);
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+    for (int j = 0; j < BP_N; ++j) o[BP_N + i * BP_N + j] = ok ? yS[bp_sidx(i, j)] : (0.0 / 0.0);
 }
 #else   // BP_KIND == 2
 // ---- one-type template: thread per (chain, observation) -----------------------------------------

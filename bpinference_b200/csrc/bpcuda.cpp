@@ -89,6 +89,7 @@ int model_load(bpc_model* m, int device, Loaded** out) {
     L.obs_smem = (size_t)m->spec.mcap * D * m->spec.threads * sizeof(double);
     BPC_CUDA(cudaKernelSetAttributeForDevice(L.obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.obs_smem, device));
     if (cudaLibraryGetKernel(&L.grouped, L.lib, "bp_grouped") != cudaSuccess) { L.grouped = nullptr; cudaGetLastError(); }
+    BPC_CUDA(cudaLibraryGetKernel(&L.moments, L.lib, "bp_moments"));
   }
   auto ins = m->loaded.emplace(device, L);
   *out = &ins.first->second;
@@ -489,6 +490,55 @@ int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, dou
   g_launches += 2;
   BPC_CUDA(cudaMemcpyAsync(log_lik, ll.p, (size_t)nchains * d->N * 8, cudaMemcpyDeviceToHost, st));
   BPC_CUDA(cudaStreamSynchronize(st));
+  return BPC_OK;
+}
+
+int bpc_moments(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* mu, double* sigma) {
+  if (!m || !d || !upars || !mu || !sigma) return fail(BPC_E_INVALID, "null argument");
+  if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
+  if (m->spec.kind == BPC_SIMPLE_BD) return fail(BPC_E_UNSUPPORTED, "bpc_moments needs a multitype model (the one-type template has its closed form)");
+  if (nchains <= 0 || d->N == 0) return BPC_OK;
+  Loaded* L;
+  int rc = model_load(m, d->device, &L);
+  if (rc) return rc;
+  BPC_CUDA(cudaSetDevice(d->device));
+  if ((rc = ensure_workspace(d, nchains))) return rc;
+  const ModelSpec& s = m->spec;
+  const int dim = s.dim, n = s.ntypes, W = n + n * n;
+  if ((rc = d->io_u.alloc((size_t)nchains * dim * 8))) return rc;
+  if ((rc = d->io_status.alloc((size_t)nchains * 4))) return rc;
+  DevBuf out;
+  if ((rc = out.alloc((size_t)nchains * d->N * W * 8))) return rc;
+  cudaStream_t st = d->stream;
+  BPC_CUDA(cudaMemcpyAsync(d->io_u.p, upars, (size_t)nchains * dim * 8, cudaMemcpyHostToDevice, st));
+  const double* u_dev = (const double*)d->io_u.p;
+  double* theta = (double*)d->theta.p;
+  int* status_dev = (int*)d->io_status.p;
+  {
+    void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
+    BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
+  }
+  {
+    ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
+              nullptr, status_dev, (double*)out.p, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains};
+    void* args[] = {(void*)&a};
+    BPC_CUDA(cudaLaunchKernel((const void*)L->moments, dim3((d->N + s.threads - 1) / s.threads, nchains), dim3(s.threads), args, 0, st));
+  }
+  g_launches += 2;
+  std::vector<double> h((size_t)nchains * d->N * W);
+  BPC_CUDA(cudaMemcpyAsync(h.data(), out.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  BPC_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < (size_t)nchains * d->N; ++i) {
+    for (int j = 0; j < n; ++j) mu[i * n + j] = h[i * W + j];
+    for (int j = 0; j < n * n; ++j) sigma[i * n * n + j] = h[i * W + n + j];
+  }
+  return BPC_OK;
+}
+
+int bpc_flop_model(const bpc_model* m, double* per_app_fwd, double* per_app_bwd, double* per_obs) {
+  if (!m || !per_app_fwd || !per_app_bwd || !per_obs) return fail(BPC_E_INVALID, "null argument");
+  const FlopModel f = flop_model(m->spec);
+  *per_app_fwd = f.per_app_fwd; *per_app_bwd = f.per_app_bwd; *per_obs = f.per_obs;
   return BPC_OK;
 }
 

@@ -493,7 +493,7 @@ struct Lowerer {
               v.i = a.i / b.i;   // Stan int division truncates; stanc warns
               if (a.i % b.i != 0)
                 warnings.push_back("Stan integer division: " + std::to_string(a.i) + " / " + std::to_string(b.i) + " evaluates to " + std::to_string(v.i) +
-                                   " in rate expression of event " + std::to_string(e + 1) + " (write a decimal point to get real division)");
+                                   " in rate expression of event " + std::to_string(e + 1) + " (R pastes whole numbers without a decimal point, so Stan sees two ints; write the quotient as a decimal literal)");
             }
             return v;
           }

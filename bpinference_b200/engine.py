@@ -168,6 +168,21 @@ class BpCudaModel:
         _ffi.check(_ffi.lib().bpc_log_lik(self.handle, d.handle, _ffi.dptr(u), u.shape[0], _ffi.dptr(out)))
         return out
 
+    def moments(self, dat, upars):
+        """(mu [C, N, n], Sigma [C, N, n, n]) of the final population of every observation (bpc_moments)."""
+        d = self._data(dat)
+        u = np.ascontiguousarray(np.atleast_2d(_f64(upars)))
+        n = self.ntypes
+        mu = np.empty((u.shape[0], d.ndatapts, n))
+        sig = np.empty((u.shape[0], d.ndatapts, n, n))
+        _ffi.check(_ffi.lib().bpc_moments(self.handle, d.handle, _ffi.dptr(u), u.shape[0], _ffi.dptr(mu), _ffi.dptr(sig)))
+        return mu, sig
+
+    def flop_model(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _ffi.check(_ffi.lib().bpc_flop_model(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(per_app_fwd=a.value, per_app_bwd=b.value, per_obs=c.value)
+
     def constrain_pars(self, upars):
         u = np.ascontiguousarray(np.atleast_2d(_f64(upars)))
         out = np.empty_like(u)

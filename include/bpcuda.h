@@ -159,6 +159,10 @@ int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nch
  * (stanfiles/multitype_loo_block.stan:31, simple_birth_death_loo_block.stan:11).
  * log_lik: nchains x ndatapts, observation order = the order of the data list. */
 int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* log_lik);
+/* mean vector and covariance matrix of the final population of every (chain, observation): what
+ * calculate_moments returns (R/calculate_moments.R:11-88: mu_mat, sigma_mat) for the rates the chain's parameters imply.
+ * mu: nchains x ndatapts x ntypes; sigma: nchains x ndatapts x ntypes x ntypes (row-major), data-list order. */
+int bpc_moments(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* mu, double* sigma);
 /* constrained values: Theta [nchains x nparams] (+ sigma_obs) from unconstrained upars, and back */
 int bpc_constrain(const bpc_model* m, const double* upars, int nchains, double* theta);
 int bpc_unconstrain(const bpc_model* m, const double* theta, int nchains, double* upars);
@@ -168,6 +172,9 @@ long long bpc_launch_count(int reset);
  * measured with CUDA events on the launching stream (only when enabled; bench.py's roofline.achieved) */
 int bpc_kernel_timing(bpc_data* d, int enable);
 int bpc_kernel_time_ms(bpc_data* d, int reset, double* total_ms, long long* launches);
+/* algorithmic operation counts of the shipped kernels (FMA = 2): per application of L in the forward series, per
+ * application of L^T in the reverse sweep, and per observation outside the series.  No GPU needed. */
+int bpc_flop_model(const bpc_model* m, double* per_app_fwd, double* per_app_bwd, double* per_obs);
 /* exact algorithmic flop count of one evaluation of the likelihood for chain 0 of `upars`, counted by
  * the shipped kernels themselves in a counting build (SURVEY.md §8(d) convention: FMA = 2) */
 int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* flops_per_chain);

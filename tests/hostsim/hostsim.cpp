@@ -24,6 +24,9 @@ inline real& operator-=(real& a, real b) { a = a - b; return a; }
 inline bool operator>(real a, real b) { return a.v > b.v; }
 inline bool operator<(real a, real b) { return a.v < b.v; }
 inline bool operator==(real a, real b) { return a.v == b.v; }
+inline bool operator>=(real a, real b) { return a.v >= b.v; }
+inline bool operator<=(real a, real b) { return a.v <= b.v; }
+inline bool operator!=(real a, real b) { return a.v != b.v; }
 inline real sqrt(real a) { ++g_ops; return real(std::sqrt(a.v)); }
 inline real exp(real a) { ++g_ops; return real(std::exp(a.v)); }
 inline real log(real a) { ++g_ops; return real(std::log(a.v)); }
@@ -82,7 +85,13 @@ int hs_obs(const double* theta, const double* x, const double* z0, const double*
   bp_assemble_vjp(gA, gH, rb);
 #else
   real rb2[2] = {real(0.0), real(0.0)};
+#ifdef BP_COUNTED
+  const uint64_t before = g_ops;
+#endif
   bp_onetype_obs(r[0], r[1], real(t), real(z0[0]), real(xo[0]), lp, rb2, status, false);
+#ifdef BP_COUNTED
+  if (ops_out) ops_out[1] = g_ops - before;
+#endif
   rb[0] = rb2[0]; rb[1] = rb2[1];
 #endif
   bp_rates_vjp(th, xk, rb, cb);

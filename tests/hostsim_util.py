@@ -17,7 +17,8 @@ _CACHE = {}
 
 def build(engine, counted=False):
     src = engine.cuda_source
-    key = hashlib.sha1((src + str(counted)).encode()).hexdigest()[:16]
+    deps = open(os.path.join(_CSRC, "bp_kernels.cuh")).read() + open(os.path.join(_HERE, "hostsim", "hostsim.cpp")).read()
+    key = hashlib.sha1((src + deps + str(counted)).encode()).hexdigest()[:16]
     if key in _CACHE:
         return _CACHE[key]
     d = os.path.join(tempfile.gettempdir(), "bp_hostsim_" + key)

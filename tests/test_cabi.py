@@ -1,0 +1,70 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/bpcuda.h declares; codegen + NVRTC work
+on the CPU box; evaluation entry points fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bpinference_b200 as bp
+from bpinference_b200 import _ffi, synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "bpcuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bpc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 35
+    L = ctypes.CDLL(_ffi.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(_ffi.SYMBOLS) == names          # the ctypes mirror binds exactly the declared surface
+    assert _ffi.lib().bpc_abi_version() == 1
+
+
+def test_codegen_and_nvrtc_without_gpu():
+    cfg = syn.make_config("cfg3", chains=2)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"], simple_bd=True)
+    src = eng.cuda_source
+    assert "#define BP_KIND 2" in src and "#define BP_XDEP 1" in src and "exp(" in src and "bp_rates_vjp" in src
+    cub = eng.cubin()
+    assert cub[:4] == b"\x7fELF" and len(cub) > 10000          # sm_100a machine code from NVRTC
+    assert eng.dim == 5
+
+
+def test_stan_integer_division_quirk_is_reproduced_and_reported():
+    """`1/2` pasted into Stan is integer division (= 0); the front end follows Stan and warns."""
+    mod = bp.bp_model([[2.0], [0.0]], [1, 1], ["1/2*c[1]", "c[2]*(3/2.)*1.5"], 2, 0)
+    eng = bp.stan_model(mod, [bp.prior_dist("uniform", [0, 1], [0, 2])] * 2)
+    assert "integer division" in eng.warnings
+    assert "0.0 * c[0]" in eng.cuda_source          # 1/2 -> 0
+    assert "c[1] * 1.0" in eng.cuda_source          # R deparses `2.` as 2, so 3/2. is int division too -> 1
+    assert "* 1.5" in eng.cuda_source
+
+
+def test_no_cpu_fallback():
+    if _ffi.lib().bpc_device_count() > 0:
+        pytest.skip("a GPU is present")
+    cfg = syn.make_config("cfg1", chains=2)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"], simple_bd=True)
+    with pytest.raises(_ffi.BpcError) as e:
+        eng.log_prob_grad(cfg["data"], cfg["upars"])
+    assert e.value.code == _ffi.E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_constrain_roundtrip_host():
+    cfg = syn.make_config("cfg4", chains=3)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"], noise_model=True)
+    th = eng.constrain_pars(cfg["upars"])
+    assert th.shape == (3, 4) and (th[:, :3] > 0).all() and (th[:, :3] < 2).all() and (th[:, 3] > 0).all()
+    np.testing.assert_allclose(eng.unconstrain_pars(th), cfg["upars"], rtol=1e-12)
