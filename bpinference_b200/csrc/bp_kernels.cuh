@@ -30,7 +30,7 @@
 //     Sigma' = A^T Sigma + Sigma A + sum_l mu_l H_l ,   H_l = C_l + diag(a_l) - a_l e_l^T - e_l a_l^T
 // (a_l = row l of A), with y(0) = (z0, 0).  y(t) = exp(t L) y(0) is evaluated as the action of the
 // matrix exponential on one vector: a Taylor series whose degree is chosen from ||tL|| for a 2^-55
-// truncation bound, in sub-steps when ||tL|| exceeds what BP_MCAP stored terms can cover.  The reverse
+// truncation bound, in sub-steps when ||tL|| exceeds what a series of BP_MCAP + 1 applications can cover.  The reverse
 // sweep is the exact adjoint of that series (Horner form), which needs the series terms in reverse
 // order: they are kept in shared memory, one column per thread.
 // =============================================================================
@@ -75,38 +75,55 @@ BP_HD bool bp_finite(real v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// structural sparsity of the generator: codegen sets bit (i*n+j) of BP_AMASK when A[i][j] can be non-zero for this
+// model's events, bit (l*s+q) of BP_HMASK for H_l[q].  After unrolling the tests below are compile-time constants, so
+// products with structural zeros (and gradient accumulators nobody reads) are never emitted.
+#define BP_ANZ(i, j) (((BP_AMASK) >> ((i) * BP_N + (j))) & 1ull)
+#define BP_HNZ(l, q) (((BP_HMASK) >> ((l) * BP_S + (q))) & 1ull)
+
+// s (+)= a*b, the first product initialises s (a multiply, not a multiply-add)
+BP_HD void bp_acc(real& s, bool& have, real a, real b) {
+  if (!have) { s = a * b; have = true; } else { s += a * b; }
+}
+
 // L(w) = (A^T mu, A^T S + S A + sum_l mu_l H_l)        (forward moment operator)
 BP_HD void bp_L_apply(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], const real (&wmu)[BP_N],
                       const real (&wS)[BP_S], real (&omu)[BP_N], real (&oS)[BP_S]) {
 #pragma unroll
   for (int j = 0; j < BP_N; ++j) {
-    real s = A[0 * BP_N + j] * wmu[0];
+    real s = real(0.0);
+    bool have = false;
 #pragma unroll
-    for (int i = 1; i < BP_N; ++i) s += A[i * BP_N + j] * wmu[i];
+    for (int i = 0; i < BP_N; ++i) if (BP_ANZ(i, j)) bp_acc(s, have, A[i * BP_N + j], wmu[i]);
     omu[j] = s;
   }
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) {
 #pragma unroll
     for (int j = i; j < BP_N; ++j) {
-      real s = wmu[0] * H[0 * BP_S + bp_sidx(i, j)];
+      real s = real(0.0);
+      bool have = false;
 #pragma unroll
-      for (int l = 1; l < BP_N; ++l) s += wmu[l] * H[l * BP_S + bp_sidx(i, j)];
+      for (int l = 0; l < BP_N; ++l) if (BP_HNZ(l, bp_sidx(i, j))) bp_acc(s, have, wmu[l], H[l * BP_S + bp_sidx(i, j)]);
       if (i == j) {
-        real d = A[0 * BP_N + i] * wS[bp_sidx(0, i)];
+        real d = real(0.0);
+        bool haved = false;
 #pragma unroll
-        for (int k = 1; k < BP_N; ++k) d += A[k * BP_N + i] * wS[bp_sidx(k, i)];
-        s += d + d;
+        for (int k = 0; k < BP_N; ++k) if (BP_ANZ(k, i)) bp_acc(d, haved, A[k * BP_N + i], wS[bp_sidx(k, i)]);
+        if (haved) { if (have) s = s + real(2.0) * d; else s = d + d; }
       } else {
 #pragma unroll
-        for (int k = 0; k < BP_N; ++k) s += A[k * BP_N + i] * wS[bp_sidx(k, j)] + A[k * BP_N + j] * wS[bp_sidx(k, i)];
+        for (int k = 0; k < BP_N; ++k) {
+          if (BP_ANZ(k, i)) bp_acc(s, have, A[k * BP_N + i], wS[bp_sidx(k, j)]);
+          if (BP_ANZ(k, j)) bp_acc(s, have, A[k * BP_N + j], wS[bp_sidx(k, i)]);
+        }
       }
       oS[bp_sidx(i, j)] = s;
     }
   }
 }
 
-// L^T(wb) = (A a + [<Sb, H_i>]_i , A Sb + Sb A^T)       (adjoint operator; Sb is a full symmetric
+// L^T(z) = (A a + [<Sb, H_i>]_i , A Sb + Sb A^T)       (adjoint operator; Sb is a full symmetric
 // cotangent stored packed, inner products count off-diagonals twice)
 BP_HD void bp_LT_apply(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], const real (&bmu)[BP_N],
                        const real (&bS)[BP_S], real (&omu)[BP_N], real (&oS)[BP_S]) {
@@ -114,30 +131,38 @@ BP_HD void bp_LT_apply(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S
 #pragma unroll
   for (int i = 0; i < BP_N; ++i)
 #pragma unroll
-    for (int j = i; j < BP_N; ++j) b2[bp_sidx(i, j)] = (i == j) ? bS[bp_sidx(i, j)] : bS[bp_sidx(i, j)] + bS[bp_sidx(i, j)];
+    for (int j = i; j < BP_N; ++j) {
+      bool used = false;
+#pragma unroll
+      for (int l = 0; l < BP_N; ++l) used = used || BP_HNZ(l, bp_sidx(i, j));
+      b2[bp_sidx(i, j)] = (i == j || !used) ? bS[bp_sidx(i, j)] : bS[bp_sidx(i, j)] + bS[bp_sidx(i, j)];
+    }
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) {
-    real s = A[i * BP_N + 0] * bmu[0];
+    real s = real(0.0);
+    bool have = false;
 #pragma unroll
-    for (int j = 1; j < BP_N; ++j) s += A[i * BP_N + j] * bmu[j];
+    for (int j = 0; j < BP_N; ++j) if (BP_ANZ(i, j)) bp_acc(s, have, A[i * BP_N + j], bmu[j]);
 #pragma unroll
-    for (int q = 0; q < BP_S; ++q) s += H[i * BP_S + q] * b2[q];
+    for (int q = 0; q < BP_S; ++q) if (BP_HNZ(i, q)) bp_acc(s, have, H[i * BP_S + q], b2[q]);
     omu[i] = s;
   }
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) {
 #pragma unroll
     for (int j = i; j < BP_N; ++j) {
-      real s;
+      real s = real(0.0);
+      bool have = false;
       if (i == j) {
-        real d = A[i * BP_N + 0] * bS[bp_sidx(0, i)];
 #pragma unroll
-        for (int k = 1; k < BP_N; ++k) d += A[i * BP_N + k] * bS[bp_sidx(k, i)];
-        s = d + d;
+        for (int k = 0; k < BP_N; ++k) if (BP_ANZ(i, k)) bp_acc(s, have, A[i * BP_N + k], bS[bp_sidx(k, i)]);
+        if (have) s = s + s;
       } else {
-        s = A[i * BP_N + 0] * bS[bp_sidx(0, j)] + A[j * BP_N + 0] * bS[bp_sidx(0, i)];
 #pragma unroll
-        for (int k = 1; k < BP_N; ++k) s += A[i * BP_N + k] * bS[bp_sidx(k, j)] + A[j * BP_N + k] * bS[bp_sidx(k, i)];
+        for (int k = 0; k < BP_N; ++k) {
+          if (BP_ANZ(i, k)) bp_acc(s, have, A[i * BP_N + k], bS[bp_sidx(k, j)]);
+          if (BP_ANZ(j, k)) bp_acc(s, have, A[j * BP_N + k], bS[bp_sidx(k, i)]);
+        }
       }
       oS[bp_sidx(i, j)] = s;
     }
@@ -145,84 +170,109 @@ BP_HD void bp_LT_apply(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S
 }
 
 // ---------------------------------------------------------------------------------------------
-// one sub-step  y <- sum_{k=0}^{m} (hL)^k/k! y   (m applications of L).  Term k (k >= 1) is written
-// to store[(k-1)*BP_D + comp][.] when do_store; term 0 is the step's input, kept by the caller.
-BP_HD void bp_step_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real h, int m, real (&ymu)[BP_N],
-                       real (&yS)[BP_S], bool do_store, real* store, int stride) {
-  real wmu[BP_N], wS[BP_S];
+// The term store: BP_MSLOT slots of BP_D doubles per thread in shared memory, laid out [slot][component][thread]
+// (conflict-free), used as a RING: term j lives in slot j mod BP_MSLOT, so a forward pass over m terms leaves the
+// last BP_MSLOT of them behind without any test in the loop.  Indexed through BP_SMEM so that no generic-to-shared
+// address conversion is needed inside the loops.
+#ifdef BP_HOSTSIM
+#define BP_SMEM(idx) bp_host_store[(idx)]
+#else
+extern __shared__ double bp_smem[];
+#define BP_SMEM(idx) bp_smem[(idx)]
+#endif
+
+BP_HD void bp_store_term(int addr, int stride, const real (&wmu)[BP_N], const real (&wS)[BP_S]) {
 #pragma unroll
-  for (int i = 0; i < BP_N; ++i) wmu[i] = ymu[i];
+  for (int i = 0; i < BP_N; ++i) BP_SMEM(addr + i * stride) = wmu[i];
 #pragma unroll
-  for (int q = 0; q < BP_S; ++q) wS[q] = yS[q];
-  for (int k = 0; k < m; ++k) {
-    real lmu[BP_N], lS[BP_S];
+  for (int q = 0; q < BP_S; ++q) BP_SMEM(addr + (BP_N + q) * stride) = wS[q];
+}
+
+// Taylor series of one sub-step, y <- y + sum_{j>=1} c_j u_j with the UNSCALED Krylov vectors u_0 = (smu,sS),
+// u_{j+1} = L u_j and c_j = h^j / j!  (keeping u unscaled and scaling inside the accumulation makes every scaling part
+// of an FMA).  Runs `napps` applications of L; `acc` = 0 leaves y untouched ((s) may alias (y)).  With STORE, u_k is
+// written to ring slot k mod BP_MSLOT for k = 0 .. napps-1 (and u_napps too when store_tail).  Returns c_napps in c.
+// The loop is unrolled by two so that the two term buffers alternate without register copies.
+template <bool STORE>
+BP_HD void bp_series_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real h, int napps, const real (&smu)[BP_N],
+                         const real (&sS)[BP_S], bool acc, real (&ymu)[BP_N], real (&yS)[BP_S], bool store_tail, int soff, int stride,
+                         real& c) {
+  real wmu[BP_N], wS[BP_S], lmu[BP_N], lS[BP_S];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) { wmu[i] = smu[i]; lmu[i] = smu[i]; }
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) { wS[q] = sS[q]; lS[q] = sS[q]; }
+  c = real(1.0);
+  const real on = acc ? real(1.0) : real(0.0);
+  const int span = BP_MSLOT * BP_D * stride;
+  int addr = soff;
+  for (int k = 0; k < napps; k += 2) {
+    if (STORE) { bp_store_term(addr, stride, wmu, wS); addr += BP_D * stride; if (addr == soff + span) addr = soff; }
     bp_L_apply(A, H, wmu, wS, lmu, lS);
-    const real al = h * bp_rk[k];
+    c = c * (h * bp_rk[k]);
+    {
+      const real ca = on * c;
 #pragma unroll
-    for (int i = 0; i < BP_N; ++i) { wmu[i] = al * lmu[i]; ymu[i] += wmu[i]; }
+      for (int i = 0; i < BP_N; ++i) ymu[i] += ca * lmu[i];
 #pragma unroll
-    for (int q = 0; q < BP_S; ++q) { wS[q] = al * lS[q]; yS[q] += wS[q]; }
-    if (do_store && k + 1 < m) {
-      real* p = store + (size_t)k * BP_D * stride;
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i) p[i * stride] = wmu[i];
-#pragma unroll
-      for (int q = 0; q < BP_S; ++q) p[(BP_N + q) * stride] = wS[q];
+      for (int q = 0; q < BP_S; ++q) yS[q] += ca * lS[q];
     }
+    if (k + 1 < napps) {
+      if (STORE) { bp_store_term(addr, stride, lmu, lS); addr += BP_D * stride; if (addr == soff + span) addr = soff; }
+      bp_L_apply(A, H, lmu, lS, wmu, wS);
+      c = c * (h * bp_rk[k + 1]);
+      const real ca = on * c;
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) ymu[i] += ca * wmu[i];
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) yS[q] += ca * wS[q];
+    }
+  }
+  if (STORE && store_tail) {
+    if (napps & 1) bp_store_term(addr, stride, lmu, lS); else bp_store_term(addr, stride, wmu, wS);
   }
 }
 
-// exact adjoint of bp_step_fwd.  (bmu,bS): in = cotangent of the step's output, out = cotangent of its
-// input.  (y0mu,y0S) = the step's input (term 0).  Accumulates gA += dlp/dA, gH += dlp/dH.
-BP_HD void bp_step_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real h, int m, const real (&y0mu)[BP_N],
-                       const real (&y0S)[BP_S], const real* store, int stride, real (&bmu)[BP_N], real (&bS)[BP_S],
-                       real (&gA)[BP_N * BP_N], real (&gH)[BP_N * BP_S]) {
-  real vmu[BP_N], vS[BP_S];   // Horner accumulator wb_k
+// Horner steps k = k_hi .. k_lo of the exact adjoint of the series, on the SCALED accumulator z_k = c_k v_k:
+//     z_k = c_k b + L^T z_{k+1},     gA += u_k.mu (x) z_{k+1}.mu + 2 u_k.S z_{k+1}.S,     gH_l += u_k.mu_l z_{k+1}.S
+// (b = cotangent of the sub-step's result, constant; z_m = c_m b; z_0 = cotangent of the sub-step's input).  c enters as
+// c_{k_hi+1} and leaves as c_{k_lo}; hinv = 1/h.  u_k is read from ring slot k mod BP_MSLOT.
+BP_HD void bp_series_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real hinv, int k_hi, int k_lo, int soff, int stride,
+                         const real (&bmu)[BP_N], const real (&bS)[BP_S], real (&zmu)[BP_N], real (&zS)[BP_S], real& c,
+                         real (&gA)[BP_N * BP_N], real (&gH)[BP_N * BP_S]) {
+  const int step = BP_D * stride;
+  int addr = soff + (k_hi % BP_MSLOT) * step;
+  for (int k = k_hi; k >= k_lo; --k) {
+    real umu[BP_N], uS[BP_S];
 #pragma unroll
-  for (int i = 0; i < BP_N; ++i) vmu[i] = bmu[i];
+    for (int i = 0; i < BP_N; ++i) umu[i] = BP_SMEM(addr + i * stride);
 #pragma unroll
-  for (int q = 0; q < BP_S; ++q) vS[q] = bS[q];
-  for (int k = m - 1; k >= 0; --k) {
-    const real al = h * bp_rk[k];
-    const real al2 = al + al;
-    real amu[BP_N], aS[BP_S];   // al * w_k.mu,  2 al * w_k.S
-    if (k == 0) {
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i) amu[i] = al * y0mu[i];
-#pragma unroll
-      for (int q = 0; q < BP_S; ++q) aS[q] = al2 * y0S[q];
-    } else {
-      const real* p = store + (size_t)(k - 1) * BP_D * stride;
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i) amu[i] = al * p[i * stride];
-#pragma unroll
-      for (int q = 0; q < BP_S; ++q) aS[q] = al2 * p[(BP_N + q) * stride];
-    }
-    // gA[i][j] += al ( w.mu_i v.mu_j + 2 sum_k w.S_ik v.S_kj ) ; gH[l] += al w.mu_l v.S
+    for (int q = 0; q < BP_S; ++q) uS[q] = BP_SMEM(addr + (BP_N + q) * stride);
+    addr = (addr == soff) ? soff + (BP_MSLOT - 1) * step : addr - step;
 #pragma unroll
     for (int i = 0; i < BP_N; ++i)
 #pragma unroll
-      for (int j = 0; j < BP_N; ++j) {
-        real s = amu[i] * vmu[j];
+      for (int j = 0; j < BP_N; ++j)
+        if (BP_ANZ(i, j)) {
+          real s2 = uS[bp_sidx(i, 0)] * zS[bp_sidx(0, j)];
 #pragma unroll
-        for (int q = 0; q < BP_N; ++q) s += aS[bp_sidx(i, q)] * vS[bp_sidx(q, j)];
-        gA[i * BP_N + j] += s;
-      }
+          for (int q = 1; q < BP_N; ++q) s2 += uS[bp_sidx(i, q)] * zS[bp_sidx(q, j)];
+          gA[i * BP_N + j] += umu[i] * zmu[j];
+          gA[i * BP_N + j] += real(2.0) * s2;
+        }
 #pragma unroll
     for (int l = 0; l < BP_N; ++l)
 #pragma unroll
-      for (int q = 0; q < BP_S; ++q) gH[l * BP_S + q] += amu[l] * vS[q];
+      for (int q = 0; q < BP_S; ++q)
+        if (BP_HNZ(l, q)) gH[l * BP_S + q] += umu[l] * zS[q];
     real tmu[BP_N], tS[BP_S];
-    bp_LT_apply(A, H, vmu, vS, tmu, tS);
+    bp_LT_apply(A, H, zmu, zS, tmu, tS);
+    c = c * (bp_kp1[k] * hinv);
 #pragma unroll
-    for (int i = 0; i < BP_N; ++i) vmu[i] = bmu[i] + al * tmu[i];
+    for (int i = 0; i < BP_N; ++i) zmu[i] = c * bmu[i] + tmu[i];
 #pragma unroll
-    for (int q = 0; q < BP_S; ++q) vS[q] = bS[q] + al * tS[q];
+    for (int q = 0; q < BP_S; ++q) zS[q] = c * bS[q] + tS[q];
   }
-#pragma unroll
-  for (int i = 0; i < BP_N; ++i) bmu[i] = vmu[i];
-#pragma unroll
-  for (int q = 0; q < BP_S; ++q) bS[q] = vS[q];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -342,46 +392,75 @@ BP_HD bool bp_make_plan(real a1, real t, BpPlan& p) {
 // Accumulates lp, gA, gH, sb (d/dsigma_obs), apps; ORs status.  store/stride: this thread's term column.
 #if BP_KIND != 2
 BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
-                         const real (&xo)[BP_N], real t, real sigma, real* store, int stride, real& lp, real (&gA)[BP_N * BP_N],
+                         const real (&xo)[BP_N], real t, real sigma, int soff, int stride, real& lp, real (&gA)[BP_N * BP_N],
                          real (&gH)[BP_N * BP_S], real& sb, int& status, int& apps) {
   BpPlan p;
   if (!bp_make_plan(a1, t, p)) { status |= BP_ST_RATE_NONFINITE; return; }
-  apps += p.s * p.m;   // algorithmic applications of L (and as many of L^T); recomputed sub-steps are not counted
-  real bmu[BP_N], bS[BP_S];
+  apps += p.s * p.m;   // algorithmic applications of L (and as many of L^T); recomputed terms are not counted
+  // The reverse sweep needs the series terms u_0 .. u_{m-1} in reverse order.  The ring keeps the last BP_MSLOT of
+  // them: when m > BP_MSLOT the upper terms kh .. m-1 are reversed first and the lower terms 0 .. kh-1 are then
+  // recomputed into the ring (kh - 1 extra applications of L; halves the shared memory per thread, which doubles the
+  // warps per SM).
+  const int m = p.m;
+  const bool two = m > BP_MSLOT;
+  const int kh = two ? m - BP_MSLOT : 0;
+  real bmu[BP_N], bS[BP_S], zmu[BP_N], zS[BP_S];
+  real cser = real(1.0);
+  const real hinv = real(1.0) / p.h;
   bool scored = false;
   for (int target = p.s - 1; target >= 0; --target) {
-    // forward from the observation's initial state up to and including sub-step `target`; only that
-    // sub-step's terms are stored (earlier sub-steps are recomputed when their turn comes: p.s is 1
-    // unless ||tL|| is large)
+    // items 0..target-1: plain sub-steps up to the one being reversed (recomputed from the observation's initial
+    // state: p.s is 1 unless ||tL|| is large); item target: that sub-step; item target+1 (only when `two`):
+    // recompute of its lower terms.  One forward loop and one reverse loop serve all of them.
     real ymu[BP_N], yS[BP_S], y0mu[BP_N], y0S[BP_S];
 #pragma unroll
-    for (int i = 0; i < BP_N; ++i) ymu[i] = z0[i];
+    for (int i = 0; i < BP_N; ++i) { ymu[i] = z0[i]; y0mu[i] = z0[i]; }
 #pragma unroll
-    for (int q = 0; q < BP_S; ++q) yS[q] = real(0.0);
-    for (int j = 0; j <= target; ++j) {
-      if (j == target) {
+    for (int q = 0; q < BP_S; ++q) { yS[q] = real(0.0); y0S[q] = real(0.0); }
+    const int nitems = target + (two ? 2 : 1);
+    for (int it = 0; it < nitems; ++it) {
+      const bool is_main = it == target, is_rec = it > target;
+      if (is_main) {
 #pragma unroll
         for (int i = 0; i < BP_N; ++i) y0mu[i] = ymu[i];
 #pragma unroll
         for (int q = 0; q < BP_S; ++q) y0S[q] = yS[q];
       }
-      bp_step_fwd(A, H, p.h, p.m, ymu, yS, j == target, store, stride);
-    }
-    if (!scored) {
-      scored = true;
+      real smu[BP_N], sS[BP_S];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) smu[i] = is_rec ? y0mu[i] : ymu[i];
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) sS[q] = is_rec ? y0S[q] : yS[q];
+      real cfw;
+      bp_series_fwd<true>(A, H, p.h, is_rec ? kh - 1 : m, smu, sS, !is_rec, ymu, yS, is_rec, soff, stride, cfw);
+      if (is_main) {
+        if (!scored) {
+          scored = true;
 #if BP_NOISE
 #pragma unroll
-      for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
+          for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
 #endif
-      real lpk;
-      if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) { status |= BP_ST_NOT_PD; return; }
-      lp += lpk;
+          real lpk;
+          if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) { status |= BP_ST_NOT_PD; return; }
+          lp += lpk;
 #if BP_NOISE
 #pragma unroll
-      for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += sigma * bS[bp_sidx(i, i)]; }
+          for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += sigma * bS[bp_sidx(i, i)]; }
 #endif
+        }
+        cser = cfw;   // c_m: the reverse sweep starts from z_m = c_m b
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) zmu[i] = cser * bmu[i];
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q) zS[q] = cser * bS[q];
+      }
+      if (is_main || is_rec) bp_series_bwd(A, H, hinv, is_main ? m - 1 : kh - 1, is_main ? kh : 0, soff, stride, bmu, bS, zmu, zS, cser, gA, gH);
     }
-    bp_step_bwd(A, H, p.h, p.m, y0mu, y0S, store, stride, bmu, bS, gA, gH);
+    // cotangent of this sub-step's input = cotangent of the previous sub-step's result
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) bmu[i] = zmu[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) bS[q] = zS[q];
   }
 }
 
@@ -396,7 +475,8 @@ BP_HD real bp_obs_loglik(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
   for (int i = 0; i < BP_N; ++i) ymu[i] = z0[i];
 #pragma unroll
   for (int q = 0; q < BP_S; ++q) yS[q] = real(0.0);
-  for (int j = 0; j < p.s; ++j) bp_step_fwd(A, H, p.h, p.m, ymu, yS, false, (real*)0, 0);
+  real cfw;
+  for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, 0, 0, cfw);
 #if BP_NOISE
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
@@ -577,12 +657,10 @@ struct BpObsArgs {
 // ---- fused per-(chain, observation) kernel of the multitype templates ---------------------------
 // grid (ntiles, C); CTA = BP_THREADS threads = one tile of one chain; thread i takes observations
 // tile*T + i, + BP_THREADS, ... (coalesced SoA loads).  Dynamic shared memory: the Taylor-term store,
-// BP_MCAP * BP_D doubles per thread, laid out [term][component][thread] (conflict-free).
-extern "C" __global__ void __launch_bounds__(BP_THREADS, 1) bp_fused(BpObsArgs a) {
-  extern __shared__ double bp_smem[];
+// BP_MSLOT * BP_D doubles per thread (a ring of series terms), laid out [slot][component][thread] (conflict-free).
+extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(BpObsArgs a) {
   const int c = blockIdx.y;
   const int tid = threadIdx.x;
-  double* store = bp_smem + tid;
 
   double th[BP_DIM];
 #pragma unroll
@@ -641,7 +719,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, 1) bp_fused(BpObsArgs a
 #pragma unroll
       for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
 #endif
-      bp_obs_lpgrad(A, H, a1, z0, xo, t, sigma, store, BP_THREADS, lp, gA, gH, sb, status, apps);
+      bp_obs_lpgrad(A, H, a1, z0, xo, t, sigma, tid, BP_THREADS, lp, gA, gH, sb, status, apps);
 #if BP_XDEP
       double rb[BP_E];
       bp_assemble_vjp(gA, gH, rb);
@@ -720,7 +798,8 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_moments(BpObsArgs a)
   for (int q = 0; q < BP_S; ++q) yS[q] = 0.0;
   BpPlan p;
   const bool ok = bp_make_plan(a1, a.t[k], p);
-  if (ok) for (int j = 0; j < p.s; ++j) bp_step_fwd(A, H, p.h, p.m, ymu, yS, false, (double*)0, 0);
+  double cfw;
+  if (ok) for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, 0, 0, cfw);
   double* o = a.loglik + ((size_t)c * a.nobs + a.perm[k]) * (BP_N + BP_N * BP_N);
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) o[i] = ok ? ymu[i] : (0.0 / 0.0);

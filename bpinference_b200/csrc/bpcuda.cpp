@@ -86,7 +86,7 @@ int model_load(bpc_model* m, int device, Loaded** out) {
     BPC_CUDA(cudaLibraryGetKernel(&L.obs, L.lib, "bp_fused"));
     const int n = m->spec.ntypes;
     const int D = n + n * (n + 1) / 2;
-    L.obs_smem = (size_t)m->spec.mcap * D * m->spec.threads * sizeof(double);
+    L.obs_smem = (size_t)m->spec.mslot * D * m->spec.threads * sizeof(double);
     BPC_CUDA(cudaKernelSetAttributeForDevice(L.obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.obs_smem, device));
     if (cudaLibraryGetKernel(&L.grouped, L.lib, "bp_grouped") != cudaSuccess) { L.grouped = nullptr; cudaGetLastError(); }
     BPC_CUDA(cudaLibraryGetKernel(&L.moments, L.lib, "bp_moments"));

@@ -1,6 +1,7 @@
 // codegen.cpp — model description -> CUDA translation unit (see codegen.hpp).
 #include "codegen.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <stdexcept>
@@ -91,10 +92,15 @@ std::string generate_cuda(ModelSpec& m) {
 
   m.dim = P + (m.kind == 1 ? 1 : 0);
   m.kdep = m.ndep > 0 ? m.ndep : 1;
-  m.mcap = 24;
+  m.mcap = 23;   // at most mcap + 1 = 2 * mslot applications per sub-step: the ring is refilled once
   static const int threads_by_n[6] = {0, 256, 192, 128, 64, 32};
   m.threads = (m.kind == 2) ? 256 : threads_by_n[n];
   m.theta_cap = taylor_theta(m.mcap);
+  m.mslot = (m.mcap + 1) / 2;   // terms kept per thread in shared memory; longer series are reversed in two segments
+  {
+    const size_t smem = (size_t)m.mslot * (n + n * (n + 1) / 2) * m.threads * 8 + 1024;
+    m.minblocks = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / smem));
+  }
 
   // rates
   std::string rates_body, vjp_body;
@@ -134,13 +140,28 @@ std::string generate_cuda(ModelSpec& m) {
           Hc[l * S + sidx(a, b)][e] += h;
         }
 
+  // structural sparsity masks (bit i*n+j of A, bit l*S+q of H); all-ones for n = 5 where H would need more than 64 bits
+  unsigned long long amask = 0ull, hmask = 0ull;
+  m.a_nz.assign(n * n, true);
+  m.h_nz.assign(n * S, true);
+  if (n <= 4) {
+    for (int i = 0; i < n * n; ++i) { bool nz = false; for (int e = 0; e < E; ++e) nz = nz || Ac[i][e] != 0.0; m.a_nz[i] = nz; if (nz) amask |= 1ull << i; }
+    for (int i = 0; i < n * S; ++i) { bool nz = false; for (int e = 0; e < E; ++e) nz = nz || Hc[i][e] != 0.0; m.h_nz[i] = nz; if (nz) hmask |= 1ull << i; }
+  } else {
+    amask = ~0ull; hmask = ~0ull;
+  }
+
   std::string s;
-  char buf[512];
+  char buf[768];
   s += "// generated by libbpcuda codegen for one bpinference model — do not edit\n";
   std::snprintf(buf, sizeof buf,
                 "#define BP_N %d\n#define BP_E %d\n#define BP_P %d\n#define BP_DIM %d\n#define BP_KDEP %d\n#define BP_XDEP %d\n"
-                "#define BP_NOISE %d\n#define BP_KIND %d\n#define BP_THREADS %d\n#define BP_MCAP %d\n#define BP_THETA_CAP %s\n",
-                n, E, P, m.dim, m.kdep, m.xdep ? 1 : 0, m.kind == 1 ? 1 : 0, m.kind, m.threads, m.mcap, lit(m.theta_cap).c_str());
+                "#define BP_NOISE %d\n#define BP_KIND %d\n#define BP_THREADS %d\n#define BP_MCAP %d\n#define BP_MSLOT %d\n#define BP_MINBLOCKS %d\n"
+                "#define BP_THETA_CAP %s\n",
+                n, E, P, m.dim, m.kdep, m.xdep ? 1 : 0, m.kind == 1 ? 1 : 0, m.kind, m.threads, m.mcap, m.mslot, m.minblocks,
+                lit(m.theta_cap).c_str());
+  s += buf;
+  std::snprintf(buf, sizeof buf, "#define BP_AMASK 0x%llxull\n#define BP_HMASK 0x%llxull\n", amask, hmask);
   s += buf;
   s += "#ifdef BP_HOSTSIM\n#define BP_HD inline\n#define BP_GLOBAL_CONST static const\n#else\n"
        "#define BP_HD __device__ __forceinline__\n#define BP_GLOBAL_CONST __constant__ const\ntypedef double real;\n#endif\n";
@@ -149,6 +170,8 @@ std::string generate_cuda(ModelSpec& m) {
   for (int d = 1; d <= m.mcap; ++d) s += ", " + lit(taylor_theta(d));
   s += "};\nBP_GLOBAL_CONST double bp_rk[BP_MCAP + 1] = {";
   for (int k = 0; k <= m.mcap; ++k) s += (k ? ", " : "") + lit(1.0 / (k + 1));
+  s += "};\nBP_GLOBAL_CONST double bp_kp1[BP_MCAP + 1] = {";
+  for (int k = 0; k <= m.mcap; ++k) s += (k ? ", " : "") + lit((double)(k + 1));
   s += "};\n";
   // prior table
   s += "BP_GLOBAL_CONST int bp_prior_id[BP_P] = {";

@@ -27,8 +27,11 @@ struct ModelSpec {
   int kdep = 1;       // stored columns of dependent variables (>= 1)
   bool xdep = false;  // some rate reads x[k]
   int threads = 128;  // CTA size of the per-observation kernels
-  int mcap = 24;      // Taylor terms kept per thread in shared memory
+  int mcap = 23;      // the series has at most mcap + 1 applications of L per sub-step
+  int mslot = 12;     // Taylor terms kept per thread in shared memory
+  int minblocks = 1;  // CTAs per SM the shared-memory footprint allows
   double theta_cap = 0;
+  std::vector<bool> a_nz, h_nz;   // structural non-zeros of A [n*n] and H [n*s]
   std::vector<std::string> warnings;
 };
 

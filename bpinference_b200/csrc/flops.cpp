@@ -1,12 +1,17 @@
-// flops.cpp — algorithmic operation counts of the shipped kernels (bp_kernels.cuh), by hand count of
-// their loops.  Convention of SURVEY.md §8(d): add/mul = 1, FMA = 2, div/sqrt/exp/log = 1.
-// tests/test_hostsim.py recounts the same device functions with a counting scalar and pins these formulas.
+// flops.cpp — algorithmic operation counts of the shipped kernels (bp_kernels.cuh), by walking the same loops
+// with the same structural-sparsity masks.  Convention of SURVEY.md §8(d): add/mul = 1, FMA = 2,
+// div/sqrt/exp/log = 1.  tests/test_kernel_core_host.py recounts the same device functions with a counting
+// scalar and pins these numbers to 1 %.
 #include "bpcuda_internal.hpp"
 
 namespace bpc {
 
+namespace {
+inline double acc_chain(int terms) { return terms > 0 ? 2.0 * terms - 1.0 : 0.0; }   // first product is a multiply
+}
+
 FlopModel flop_model(const ModelSpec& sp) {
-  const double n = sp.ntypes, S = n * (n + 1) / 2, D = n + S;
+  const int n = sp.ntypes, S = n * (n + 1) / 2, D = n + S;
   FlopModel f;
   if (sp.kind == 2) {
     // bp_onetype_obs: value + gradient w.r.t. (b, d)
@@ -14,23 +19,54 @@ FlopModel flop_model(const ModelSpec& sp) {
     f.per_obs = 70.0;
     return f;
   }
-  // bp_L_apply: mu part n(2n-1); per packed pair the H contraction (2n-1) plus the Lyapunov part
-  // (diagonal 2n+1, off-diagonal 4n); bp_step_fwd adds al (1), w = al*l (D), y += w (D)
-  const double L_apply = n * (2 * n - 1) + n * (2 * n - 1 + 2 * n + 1) + (S - n) * (2 * n - 1 + 4 * n);
-  f.per_app_fwd = L_apply + 2 * D + 1;
-  // bp_step_bwd: al, al+al (2); amu, aS (D); gA n^2 (2n+2); gH 2nS; bp_LT_apply: doubling (S-n),
-  // mu part n(2n-1+2S), diagonal 2n^2, off-diagonal (S-n)(4n-1); Horner update 2D
-  f.per_app_bwd = 2 + D + n * n * (2 * n + 2) + 2 * n * S + (S - n) + n * (2 * n - 1 + 2 * S) + 2 * n * n + (S - n) * (4 * n - 1) + 2 * D;
-  // per observation: plan (4) and lp accumulation (1), Cholesky + inverse factor + solves + cotangents, noise terms
+  auto sidx = [n](int i, int j) { if (i > j) std::swap(i, j); return i * n - i * (i - 1) / 2 + (j - i); };
+  auto anz = [&](int i, int j) { return sp.a_nz.empty() ? true : (bool)sp.a_nz[i * n + j]; };
+  auto hnz = [&](int l, int q) { return sp.h_nz.empty() ? true : (bool)sp.h_nz[l * S + q]; };
+  // ---- bp_L_apply
+  double L = 0;
+  for (int j = 0; j < n; ++j) { int t = 0; for (int i = 0; i < n; ++i) t += anz(i, j); L += acc_chain(t); }
+  for (int i = 0; i < n; ++i)
+    for (int j = i; j < n; ++j) {
+      int t = 0;
+      for (int l = 0; l < n; ++l) t += hnz(l, sidx(i, j));
+      if (i == j) {
+        int td = 0;
+        for (int k = 0; k < n; ++k) td += anz(k, i);
+        L += acc_chain(t) + acc_chain(td) + (td > 0 ? (t > 0 ? 2 : 1) : 0);
+      } else {
+        for (int k = 0; k < n; ++k) t += anz(k, i) + anz(k, j);
+        L += acc_chain(t);
+      }
+    }
+  // bp_series_fwd: c update (2), accumulate switch (1), y += c u (2 per component)
+  f.per_app_fwd = L + 3 + 2 * D;
+  // ---- bp_series_bwd
+  double B = 0;
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) if (anz(i, j)) B += (2 * n - 1) + 4;   // s2, two accumulations
+  for (int l = 0; l < n; ++l) for (int q = 0; q < S; ++q) if (hnz(l, q)) B += 2;
+  // bp_LT_apply
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) { bool used = false; for (int l = 0; l < n; ++l) used = used || hnz(l, sidx(i, j)); if (used) B += 1; }
+  for (int i = 0; i < n; ++i) { int t = 0; for (int j = 0; j < n; ++j) t += anz(i, j); for (int q = 0; q < S; ++q) t += hnz(i, q); B += acc_chain(t); }
+  for (int i = 0; i < n; ++i)
+    for (int j = i; j < n; ++j) {
+      int t = 0;
+      if (i == j) { for (int k = 0; k < n; ++k) t += anz(i, k); B += acc_chain(t) + (t > 0 ? 1 : 0); }
+      else { for (int k = 0; k < n; ++k) t += anz(i, k) + anz(j, k); B += acc_chain(t); }
+    }
+  // c update (2), z = c b + t (2 per component)
+  f.per_app_bwd = B + 2 + 2 * D;
+  // ---- per observation outside the series: plan (4), 1/h (1), lp accumulation (1), z_m = c_m b (D), Cholesky, inverse
+  // factor, solves, cotangents, noise terms
   double chol = 0, linv = 0, quad = 0, bmu = 0, bS = 0;
-  for (int j = 0; j < sp.ntypes; ++j) {
-    chol += 2 * j + 4 + (sp.ntypes - 1 - j) * (2 * j + 1);
-    for (int i = j + 1; i < sp.ntypes; ++i) linv += 2 * (i - j) + 1;
+  for (int j = 0; j < n; ++j) {
+    chol += 2 * j + 4 + (n - 1 - j) * (2 * j + 1);
+    for (int i = j + 1; i < n; ++i) linv += 2 * (i - j) + 1;
     quad += 3 * (j + 1) + 2;
-    bmu += 2 * (sp.ntypes - j);
-    for (int i = 0; i <= j; ++i) bS += 2 * (sp.ntypes - j) + 3;
+    bmu += 2 * (n - j);
+    for (int i = 0; i <= j; ++i) bS += 2 * (n - j) + 3;
   }
-  f.per_obs = 5 + chol + linv + quad + 2 + bmu + bS + (sp.kind == 1 ? 6 * n : 0);
+  f.per_obs = 6 + D + chol + linv + quad + 2 + bmu + bS + (sp.kind == 1 ? 6 * n : 0);
   return f;
 }
 

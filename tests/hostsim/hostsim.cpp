@@ -40,6 +40,8 @@ using std::sqrt; using std::exp; using std::log; using std::pow; using std::fabs
 inline double bp_val(double a) { return a; }
 #endif
 
+static real bp_host_store[4096];   // the term ring of the one simulated thread
+
 #include BP_MODEL_SRC
 
 extern "C" {
@@ -69,7 +71,6 @@ int hs_obs(const double* theta, const double* x, const double* z0, const double*
   for (int i = 0; i < BP_N; ++i) { z[i] = real(z0[i]); xx[i] = real(xo[i]); }
   bp_assemble(r, A, H);
   const real a1 = bp_norm1(A);
-  static real store[(BP_MCAP + 1) * BP_D];
 #if BP_NOISE
   const real sigma = th[BP_P];
 #else
@@ -78,7 +79,7 @@ int hs_obs(const double* theta, const double* x, const double* z0, const double*
 #ifdef BP_COUNTED
   const uint64_t before = g_ops;
 #endif
-  bp_obs_lpgrad(A, H, a1, z, xx, real(t), sigma, store, 1, lp, gA, gH, sb, status, apps);
+  bp_obs_lpgrad(A, H, a1, z, xx, real(t), sigma, 0, 1, lp, gA, gH, sb, status, apps);
 #ifdef BP_COUNTED
   if (ops_out) ops_out[1] = g_ops - before;   // the per-observation core alone
 #endif

