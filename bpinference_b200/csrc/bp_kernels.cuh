@@ -281,68 +281,88 @@ BP_HD void bp_series_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 // symmetric, packed).  Returns false when Sigma is not positive definite / not finite.
 BP_HD bool bp_mvn_score(const real (&x)[BP_N], const real (&mu)[BP_N], const real (&S)[BP_S], real& lp, real (&bmu)[BP_N],
                         real (&bS)[BP_S]) {
-  real Lc[BP_N][BP_N], Li[BP_N][BP_N], idiag[BP_N];
-  real ld = real(0.0);
+  // square-root-free factorisation Sigma = L D L^T (L unit lower triangular): positive definite <=> all d_j > 0.
+  // Costs n reciprocals and one logarithm (of the product of the pivots) instead of n square roots, n reciprocals and
+  // n logarithms; these are long dependent chains in fp64, so they matter more than their flop count suggests.
+  real Lc[BP_N][BP_N], Li[BP_N][BP_N], dj[BP_N], id[BP_N];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < BP_N; ++j) {
+    real v[BP_N];
     real d = S[bp_sidx(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+    for (int k = 0; k < j; ++k) { v[k] = Lc[j][k] * dj[k]; d -= Lc[j][k] * v[k]; }
     if (!(d > real(0.0)) || !bp_finite(d)) ok = false;
-    const real sd = sqrt(d);
-    Lc[j][j] = sd;
-    idiag[j] = real(1.0) / sd;
-    ld += log(d);
+    dj[j] = d;
+    id[j] = real(1.0) / d;
 #pragma unroll
     for (int i = j + 1; i < BP_N; ++i) {
       real s = S[bp_sidx(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= Lc[i][k] * Lc[j][k];
-      Lc[i][j] = s * idiag[j];
+      for (int k = 0; k < j; ++k) s -= Lc[i][k] * v[k];
+      Lc[i][j] = s * id[j];
     }
   }
   if (!ok) return false;
-  // inverse of the lower-triangular factor
+  // log det = log prod d_j when the product cannot over/underflow, the sum of logs otherwise
+  real prod = dj[0];
+  bool safe = dj[0] > real(1e-60) && dj[0] < real(1e60);
+#pragma unroll
+  for (int j = 1; j < BP_N; ++j) { prod = prod * dj[j]; safe = safe && dj[j] > real(1e-60) && dj[j] < real(1e60); }
+  real ld;
+  if (safe) {
+    ld = log(prod);
+  } else {
+    ld = log(dj[0]);
+#pragma unroll
+    for (int j = 1; j < BP_N; ++j) ld += log(dj[j]);
+  }
+  // inverse of the unit lower-triangular factor
 #pragma unroll
   for (int j = 0; j < BP_N; ++j) {
-    Li[j][j] = idiag[j];
 #pragma unroll
     for (int i = j + 1; i < BP_N; ++i) {
-      real s = real(0.0);
+      real s = -Lc[i][j];
 #pragma unroll
-      for (int k = j; k < i; ++k) s -= Lc[i][k] * Li[k][j];
-      Li[i][j] = s * idiag[i];
+      for (int k = j + 1; k < i; ++k) s -= Lc[i][k] * Li[k][j];
+      Li[i][j] = s;
     }
   }
-  real a[BP_N];
+  real z[BP_N], a[BP_N];
   real q = real(0.0);
   bool fin = true;
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) {
-    real s = real(0.0);
+    real s = x[i] - mu[i];
 #pragma unroll
-    for (int k = 0; k <= i; ++k) s += Li[i][k] * (x[k] - mu[k]);
-    a[i] = s;
-    q += s * s;
+    for (int k = 0; k < i; ++k) s += Li[i][k] * (x[k] - mu[k]);
+    z[i] = s;
+    a[i] = s * id[i];
+    q += s * a[i];
     if (!bp_finite(s)) fin = false;
   }
   if (!fin) return false;
   lp = real(-0.5) * (ld + q);
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) {
-    real s = real(0.0);
+    real s = a[i];
 #pragma unroll
-    for (int k = i; k < BP_N; ++k) s += Li[k][i] * a[k];
+    for (int k = i + 1; k < BP_N; ++k) s += Li[k][i] * a[k];
     bmu[i] = s;
   }
+  // Sigma^-1 = Li^T D^-1 Li ; W[k][i] = Li[k][i] / d_k
+  real W[BP_N][BP_N];
+#pragma unroll
+  for (int k = 0; k < BP_N; ++k)
+#pragma unroll
+    for (int i = 0; i < k; ++i) W[k][i] = Li[k][i] * id[k];
 #pragma unroll
   for (int i = 0; i < BP_N; ++i)
 #pragma unroll
     for (int j = i; j < BP_N; ++j) {
-      real si = real(0.0);
+      real si = (i == j) ? id[j] : W[j][i];
 #pragma unroll
-      for (int k = j; k < BP_N; ++k) si += Li[k][i] * Li[k][j];
+      for (int k = j + 1; k < BP_N; ++k) si += W[k][i] * Li[k][j];
       bS[bp_sidx(i, j)] = real(0.5) * (bmu[i] * bmu[j] - si);
     }
   return true;
@@ -364,25 +384,29 @@ BP_HD real bp_norm1(const real (&A)[BP_N * BP_N]) {
 struct BpPlan { int s; int m; real h; };
 
 // sub-steps and series degree for duration t: scaled norm th = 2 ||A||_1 t / s <= BP_THETA_CAP,
-// applications m = 1 + min{ d : th <= bp_th[d] }  (bp_th[d]^d / d! = 2^-55)
-BP_HD bool bp_make_plan(real a1, real t, BpPlan& p) {
+// applications m = 1 + min{ d : th <= bp_th[d] }  (bp_th[d]^d / d! = 2^-55).  `dhint` carries the degree found for
+// the previous observation of this thread: observations are sorted by duration, so the search usually moves by 0 or 1.
+BP_HD bool bp_make_plan(real a1, real t, BpPlan& p, int& dhint) {
   const real xx = (a1 + a1) * t;
   if (!(xx >= real(0.0)) || !bp_finite(xx)) return false;
-  int s = 1;
+  real th = xx;
+  p.s = 1;
+  p.h = t;
   if (xx > real(BP_THETA_CAP)) {
     const real sr = ceil(xx / real(BP_THETA_CAP));
     if (sr > real((double)BP_SMAX)) return false;
 #ifdef BP_HOSTSIM
-    s = (int)bp_val(sr);
+    p.s = (int)bp_val(sr);
 #else
-    s = (int)sr;
+    p.s = (int)sr;
 #endif
+    p.h = t / sr;
+    th = xx / sr;
   }
-  p.s = s;
-  p.h = t / real((double)s);
-  const real th = xx / real((double)s);
-  int d = 1;
+  int d = dhint;
+  while (d > 1 && !(th > real(bp_th[d - 1]))) --d;
   while (d < BP_MCAP && th > real(bp_th[d])) ++d;
+  dhint = d;
   p.m = d + 1;
   return true;
 }
@@ -393,9 +417,9 @@ BP_HD bool bp_make_plan(real a1, real t, BpPlan& p) {
 #if BP_KIND != 2
 BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
                          const real (&xo)[BP_N], real t, real sigma, int soff, int stride, real& lp, real (&gA)[BP_N * BP_N],
-                         real (&gH)[BP_N * BP_S], real& sb, int& status, int& apps) {
+                         real (&gH)[BP_N * BP_S], real& sb, int& status, int& apps, int& dhint) {
   BpPlan p;
-  if (!bp_make_plan(a1, t, p)) { status |= BP_ST_RATE_NONFINITE; return; }
+  if (!bp_make_plan(a1, t, p, dhint)) { status |= BP_ST_RATE_NONFINITE; return; }
   apps += p.s * p.m;   // algorithmic applications of L (and as many of L^T); recomputed terms are not counted
   // The reverse sweep needs the series terms u_0 .. u_{m-1} in reverse order.  The ring keeps the last BP_MSLOT of
   // them: when m > BP_MSLOT the upper terms kh .. m-1 are reversed first and the lower terms 0 .. kh-1 are then
@@ -468,8 +492,9 @@ BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 BP_HD real bp_obs_loglik(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
                          const real (&xo)[BP_N], real t, real sigma) {
   BpPlan p;
+  int dhint = 1;
   const real nan_ = real(0.0) / real(0.0);
-  if (!bp_make_plan(a1, t, p)) return nan_;
+  if (!bp_make_plan(a1, t, p, dhint)) return nan_;
   real ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) ymu[i] = z0[i];
@@ -674,7 +699,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
   double cb[BP_P];
 #pragma unroll
   for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
-  int status = 0, apps = 0;
+  int status = 0, apps = 0, dhint = 1;
 
   double A[BP_N * BP_N], H[BP_N * BP_S], gA[BP_N * BP_N], gH[BP_N * BP_S];
   double r[BP_E], xk[BP_KDEP];
@@ -719,7 +744,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
 #pragma unroll
       for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
 #endif
-      bp_obs_lpgrad(A, H, a1, z0, xo, t, sigma, tid, BP_THREADS, lp, gA, gH, sb, status, apps);
+      bp_obs_lpgrad(A, H, a1, z0, xo, t, sigma, tid, BP_THREADS, lp, gA, gH, sb, status, apps, dhint);
 #if BP_XDEP
       double rb[BP_E];
       bp_assemble_vjp(gA, gH, rb);
@@ -797,7 +822,8 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_moments(BpObsArgs a)
 #pragma unroll
   for (int q = 0; q < BP_S; ++q) yS[q] = 0.0;
   BpPlan p;
-  const bool ok = bp_make_plan(a1, a.t[k], p);
+  int dhint = 1;
+  const bool ok = bp_make_plan(a1, a.t[k], p, dhint);
   double cfw;
   if (ok) for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, 0, 0, cfw);
   double* o = a.loglik + ((size_t)c * a.nobs + a.perm[k]) * (BP_N + BP_N * BP_N);

@@ -56,17 +56,18 @@ FlopModel flop_model(const ModelSpec& sp) {
     }
   // c update (2), z = c b + t (2 per component)
   f.per_app_bwd = B + 2 + 2 * D;
-  // ---- per observation outside the series: plan (4), 1/h (1), lp accumulation (1), z_m = c_m b (D), Cholesky, inverse
-  // factor, solves, cotangents, noise terms
-  double chol = 0, linv = 0, quad = 0, bmu = 0, bS = 0;
+  // ---- per observation outside the series (single sub-step): plan (2), 1/h (1), lp accumulation (1), z_m = c_m b (D),
+  // square-root-free LDL^T factorisation with one logarithm, inverse factor, solves, cotangents, noise terms
+  double fac = 0, linv = 0, quad = 0, bmu = 0, bS = 0;
   for (int j = 0; j < n; ++j) {
-    chol += 2 * j + 4 + (n - 1 - j) * (2 * j + 1);
-    for (int i = j + 1; i < n; ++i) linv += 2 * (i - j) + 1;
-    quad += 3 * (j + 1) + 2;
-    bmu += 2 * (n - j);
-    for (int i = 0; i <= j; ++i) bS += 2 * (n - j) + 3;
+    fac += 3 * j + 1 + (n - 1 - j) * (2 * j + 1);
+    for (int i = j + 1; i < n; ++i) linv += 2 * (i - j - 1);
+    quad += 4 + 3 * j;
+    bmu += 2 * (n - 1 - j);
+    for (int i = 0; i <= j; ++i) bS += 2 * (n - 1 - j) + 3;
   }
-  f.per_obs = 6 + D + chol + linv + quad + 2 + bmu + bS + (sp.kind == 1 ? 6 * n : 0);
+  const double logdet = (n - 1) + 1, W = n * (n - 1) / 2.0;
+  f.per_obs = 4 + D + fac + logdet + linv + quad + 2 + bmu + W + bS + (sp.kind == 1 ? 6 * n : 0);
   return f;
 }
 

@@ -58,7 +58,7 @@ int hs_obs(const double* theta, const double* x, const double* z0, const double*
   for (int k = 0; k < BP_DIM; ++k) th[k] = real(theta[k]);
   for (int k = 0; k < BP_KDEP; ++k) xk[k] = real(x[k]);
   for (int k = 0; k < BP_P; ++k) cb[k] = real(0.0);
-  int status = 0, apps = 0;
+  int status = 0, apps = 0, dhint = 1;
   real lp = real(0.0), sb = real(0.0);
 #ifdef BP_COUNTED
   g_ops = 0;
@@ -79,7 +79,7 @@ int hs_obs(const double* theta, const double* x, const double* z0, const double*
 #ifdef BP_COUNTED
   const uint64_t before = g_ops;
 #endif
-  bp_obs_lpgrad(A, H, a1, z, xx, real(t), sigma, 0, 1, lp, gA, gH, sb, status, apps);
+  bp_obs_lpgrad(A, H, a1, z, xx, real(t), sigma, 0, 1, lp, gA, gH, sb, status, apps, dhint);
 #ifdef BP_COUNTED
   if (ops_out) ops_out[1] = g_ops - before;   // the per-observation core alone
 #endif
