@@ -181,11 +181,17 @@ extern __shared__ double bp_smem[];
 #define BP_SMEM(idx) bp_smem[(idx)]
 #endif
 
-BP_HD void bp_store_term(int addr, int stride, const real (&wmu)[BP_N], const real (&wS)[BP_S]) {
+// where the ring lives: shared memory (bp_fused: one column per thread) or a global scratch buffer (bp_grouped: the
+// few series of a chain, L2-resident)
+struct BpRingShared { BP_HD real& at(int i) const { return BP_SMEM(i); } };
+struct BpRingGlobal { real* base; BP_HD real& at(int i) const { return base[i]; } };
+
+template <class ST>
+BP_HD void bp_store_term(ST st, int addr, int stride, const real (&wmu)[BP_N], const real (&wS)[BP_S]) {
 #pragma unroll
-  for (int i = 0; i < BP_N; ++i) BP_SMEM(addr + i * stride) = wmu[i];
+  for (int i = 0; i < BP_N; ++i) st.at(addr + i * stride) = wmu[i];
 #pragma unroll
-  for (int q = 0; q < BP_S; ++q) BP_SMEM(addr + (BP_N + q) * stride) = wS[q];
+  for (int q = 0; q < BP_S; ++q) st.at(addr + (BP_N + q) * stride) = wS[q];
 }
 
 // Taylor series of one sub-step, y <- y + sum_{j>=1} c_j u_j with the UNSCALED Krylov vectors u_0 = (smu,sS),
@@ -193,9 +199,9 @@ BP_HD void bp_store_term(int addr, int stride, const real (&wmu)[BP_N], const re
 // of an FMA).  Runs `napps` applications of L; `acc` = 0 leaves y untouched ((s) may alias (y)).  With STORE, u_k is
 // written to ring slot k mod BP_MSLOT for k = 0 .. napps-1 (and u_napps too when store_tail).  Returns c_napps in c.
 // The loop is unrolled by two so that the two term buffers alternate without register copies.
-template <bool STORE>
+template <bool STORE, class ST>
 BP_HD void bp_series_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real h, int napps, const real (&smu)[BP_N],
-                         const real (&sS)[BP_S], bool acc, real (&ymu)[BP_N], real (&yS)[BP_S], bool store_tail, int soff, int stride,
+                         const real (&sS)[BP_S], bool acc, real (&ymu)[BP_N], real (&yS)[BP_S], bool store_tail, ST st, int soff, int stride,
                          real& c) {
   real wmu[BP_N], wS[BP_S], lmu[BP_N], lS[BP_S];
 #pragma unroll
@@ -207,7 +213,7 @@ BP_HD void bp_series_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
   const int span = BP_MSLOT * BP_D * stride;
   int addr = soff;
   for (int k = 0; k < napps; k += 2) {
-    if (STORE) { bp_store_term(addr, stride, wmu, wS); addr += BP_D * stride; if (addr == soff + span) addr = soff; }
+    if (STORE) { bp_store_term(st, addr, stride, wmu, wS); addr += BP_D * stride; if (addr == soff + span) addr = soff; }
     bp_L_apply(A, H, wmu, wS, lmu, lS);
     c = c * (h * bp_rk[k]);
     {
@@ -218,7 +224,7 @@ BP_HD void bp_series_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
       for (int q = 0; q < BP_S; ++q) yS[q] += ca * lS[q];
     }
     if (k + 1 < napps) {
-      if (STORE) { bp_store_term(addr, stride, lmu, lS); addr += BP_D * stride; if (addr == soff + span) addr = soff; }
+      if (STORE) { bp_store_term(st, addr, stride, lmu, lS); addr += BP_D * stride; if (addr == soff + span) addr = soff; }
       bp_L_apply(A, H, lmu, lS, wmu, wS);
       c = c * (h * bp_rk[k + 1]);
       const real ca = on * c;
@@ -229,7 +235,7 @@ BP_HD void bp_series_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
     }
   }
   if (STORE && store_tail) {
-    if (napps & 1) bp_store_term(addr, stride, lmu, lS); else bp_store_term(addr, stride, wmu, wS);
+    if (napps & 1) bp_store_term(st, addr, stride, lmu, lS); else bp_store_term(st, addr, stride, wmu, wS);
   }
 }
 
@@ -237,7 +243,8 @@ BP_HD void bp_series_fwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 //     z_k = c_k b + L^T z_{k+1},     gA += u_k.mu (x) z_{k+1}.mu + 2 u_k.S z_{k+1}.S,     gH_l += u_k.mu_l z_{k+1}.S
 // (b = cotangent of the sub-step's result, constant; z_m = c_m b; z_0 = cotangent of the sub-step's input).  c enters as
 // c_{k_hi+1} and leaves as c_{k_lo}; hinv = 1/h.  u_k is read from ring slot k mod BP_MSLOT.
-BP_HD void bp_series_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real hinv, int k_hi, int k_lo, int soff, int stride,
+template <class ST>
+BP_HD void bp_series_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real hinv, int k_hi, int k_lo, ST st, int soff, int stride,
                          const real (&bmu)[BP_N], const real (&bS)[BP_S], real (&zmu)[BP_N], real (&zS)[BP_S], real& c,
                          real (&gA)[BP_N * BP_N], real (&gH)[BP_N * BP_S]) {
   const int step = BP_D * stride;
@@ -245,9 +252,9 @@ BP_HD void bp_series_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
   for (int k = k_hi; k >= k_lo; --k) {
     real umu[BP_N], uS[BP_S];
 #pragma unroll
-    for (int i = 0; i < BP_N; ++i) umu[i] = BP_SMEM(addr + i * stride);
+    for (int i = 0; i < BP_N; ++i) umu[i] = st.at(addr + i * stride);
 #pragma unroll
-    for (int q = 0; q < BP_S; ++q) uS[q] = BP_SMEM(addr + (BP_N + q) * stride);
+    for (int q = 0; q < BP_S; ++q) uS[q] = st.at(addr + (BP_N + q) * stride);
     addr = (addr == soff) ? soff + (BP_MSLOT - 1) * step : addr - step;
 #pragma unroll
     for (int i = 0; i < BP_N; ++i)
@@ -415,16 +422,19 @@ BP_HD bool bp_make_plan(real a1, real t, BpPlan& p, int& dhint) {
 // one observation of the multitype templates: forward series, score, reverse series.
 // Accumulates lp, gA, gH, sb (d/dsigma_obs), apps; ORs status.  store/stride: this thread's term column.
 #if BP_KIND != 2
-BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
-                         const real (&xo)[BP_N], real t, real sigma, int soff, int stride, real& lp, real (&gA)[BP_N * BP_N],
-                         real (&gH)[BP_N * BP_S], real& sb, int& status, int& apps, int& dhint) {
-  BpPlan p;
-  if (!bp_make_plan(a1, t, p, dhint)) { status |= BP_ST_RATE_NONFINITE; return; }
-  apps += p.s * p.m;   // algorithmic applications of L (and as many of L^T); recomputed terms are not counted
-  // The reverse sweep needs the series terms u_0 .. u_{m-1} in reverse order.  The ring keeps the last BP_MSLOT of
-  // them: when m > BP_MSLOT the upper terms kh .. m-1 are reversed first and the lower terms 0 .. kh-1 are then
-  // recomputed into the ring (kh - 1 extra applications of L; halves the shared memory per thread, which doubles the
-  // warps per SM).
+// Forward series from (imu, iS) over p.s sub-steps, `score` turns the final state into its cotangent (b), then the
+// exact reverse sweep accumulates gA, gH.  Shared by bp_fused (state of one observation, score = multi_normal) and
+// bp_grouped (single-ancestor moments, score = the cotangent reduced over the group's observations).
+//
+// The reverse sweep needs the series terms u_0 .. u_{m-1} of a sub-step in reverse order.  The ring keeps the last
+// BP_MSLOT of them: when m > BP_MSLOT the upper terms kh .. m-1 are reversed first and the lower terms 0 .. kh-1 are
+// then recomputed into the ring (kh - 1 extra applications of L; halves the shared memory per thread, which doubles
+// the warps per SM).  With several sub-steps (large ||tL||) only the one being reversed is stored; earlier ones are
+// recomputed from the initial state.  One forward loop and one reverse loop serve all of these cases.
+template <class ST, class SC>
+BP_HD bool bp_series_fwd_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], const BpPlan& p, const real (&imu)[BP_N],
+                             const real (&iS)[BP_S], SC&& score, ST st, int soff, int stride, real (&gA)[BP_N * BP_N],
+                             real (&gH)[BP_N * BP_S]) {
   const int m = p.m;
   const bool two = m > BP_MSLOT;
   const int kh = two ? m - BP_MSLOT : 0;
@@ -433,14 +443,13 @@ BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
   const real hinv = real(1.0) / p.h;
   bool scored = false;
   for (int target = p.s - 1; target >= 0; --target) {
-    // items 0..target-1: plain sub-steps up to the one being reversed (recomputed from the observation's initial
-    // state: p.s is 1 unless ||tL|| is large); item target: that sub-step; item target+1 (only when `two`):
-    // recompute of its lower terms.  One forward loop and one reverse loop serve all of them.
+    // items 0..target-1: plain sub-steps up to the one being reversed; item target: that sub-step; item target+1
+    // (only when `two`): recompute of its lower terms
     real ymu[BP_N], yS[BP_S], y0mu[BP_N], y0S[BP_S];
 #pragma unroll
-    for (int i = 0; i < BP_N; ++i) { ymu[i] = z0[i]; y0mu[i] = z0[i]; }
+    for (int i = 0; i < BP_N; ++i) { ymu[i] = imu[i]; y0mu[i] = imu[i]; }
 #pragma unroll
-    for (int q = 0; q < BP_S; ++q) { yS[q] = real(0.0); y0S[q] = real(0.0); }
+    for (int q = 0; q < BP_S; ++q) { yS[q] = iS[q]; y0S[q] = iS[q]; }
     const int nitems = target + (two ? 2 : 1);
     for (int it = 0; it < nitems; ++it) {
       const bool is_main = it == target, is_rec = it > target;
@@ -456,21 +465,11 @@ BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 #pragma unroll
       for (int q = 0; q < BP_S; ++q) sS[q] = is_rec ? y0S[q] : yS[q];
       real cfw;
-      bp_series_fwd<true>(A, H, p.h, is_rec ? kh - 1 : m, smu, sS, !is_rec, ymu, yS, is_rec, soff, stride, cfw);
+      bp_series_fwd<true>(A, H, p.h, is_rec ? kh - 1 : m, smu, sS, !is_rec, ymu, yS, is_rec, st, soff, stride, cfw);
       if (is_main) {
         if (!scored) {
           scored = true;
-#if BP_NOISE
-#pragma unroll
-          for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
-#endif
-          real lpk;
-          if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) { status |= BP_ST_NOT_PD; return; }
-          lp += lpk;
-#if BP_NOISE
-#pragma unroll
-          for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += sigma * bS[bp_sidx(i, i)]; }
-#endif
+          if (!score(ymu, yS, bmu, bS)) return false;
         }
         cser = cfw;   // c_m: the reverse sweep starts from z_m = c_m b
 #pragma unroll
@@ -478,7 +477,7 @@ BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 #pragma unroll
         for (int q = 0; q < BP_S; ++q) zS[q] = cser * bS[q];
       }
-      if (is_main || is_rec) bp_series_bwd(A, H, hinv, is_main ? m - 1 : kh - 1, is_main ? kh : 0, soff, stride, bmu, bS, zmu, zS, cser, gA, gH);
+      if (is_main || is_rec) bp_series_bwd(A, H, hinv, is_main ? m - 1 : kh - 1, is_main ? kh : 0, st, soff, stride, bmu, bS, zmu, zS, cser, gA, gH);
     }
     // cotangent of this sub-step's input = cotangent of the previous sub-step's result
 #pragma unroll
@@ -486,6 +485,44 @@ BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 #pragma unroll
     for (int q = 0; q < BP_S; ++q) bS[q] = zS[q];
   }
+  return true;
+}
+
+// score of one observation given its moment state: noise term, multi_normal, cotangents
+BP_HD bool bp_score_obs(const real (&xo)[BP_N], real sigma, real (&ymu)[BP_N], real (&yS)[BP_S], real& lp, real& sb, real (&bmu)[BP_N],
+                        real (&bS)[BP_S]) {
+#if BP_NOISE
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
+#endif
+  real lpk;
+  if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) return false;
+  lp += lpk;
+#if BP_NOISE
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += sigma * bS[bp_sidx(i, i)]; }
+#endif
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one observation of the multitype templates: forward series, score, reverse series.
+// Accumulates lp, gA, gH, sb (d/dsigma_obs), apps; ORs status.  soff/stride: this thread's column of the term ring.
+BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
+                         const real (&xo)[BP_N], real t, real sigma, int soff, int stride, real& lp, real (&gA)[BP_N * BP_N],
+                         real (&gH)[BP_N * BP_S], real& sb, int& status, int& apps, int& dhint) {
+  BpPlan p;
+  if (!bp_make_plan(a1, t, p, dhint)) { status |= BP_ST_RATE_NONFINITE; return; }
+  apps += p.s * p.m;   // algorithmic applications of L (and as many of L^T); recomputed terms are not counted
+  real iS[BP_S];
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) iS[q] = real(0.0);
+  const bool ok = bp_series_fwd_bwd(A, H, p, z0, iS,
+                                    [&](real (&ymu)[BP_N], real (&yS)[BP_S], real (&bmu)[BP_N], real (&bS)[BP_S]) {
+                                      return bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS);
+                                    },
+                                    BpRingShared(), soff, stride, gA, gH);
+  if (!ok) status |= BP_ST_NOT_PD;
 }
 
 // forward only: per-observation log_lik with the normalising constant (LOO block)
@@ -501,7 +538,7 @@ BP_HD real bp_obs_loglik(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
 #pragma unroll
   for (int q = 0; q < BP_S; ++q) yS[q] = real(0.0);
   real cfw;
-  for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, 0, 0, cfw);
+  for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, BpRingShared(), 0, 0, cfw);
 #if BP_NOISE
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
@@ -770,6 +807,177 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
   if (status) atomicOr(a.status + c, status);
 }
 
+// ---- grouped two-phase kernel of the multitype templates ------------------------------------------
+// The reference computes single-ancestor moments once per (dependent-variable level, duration) and contracts them
+// with init_pop[k] for every observation (multitype_template.stan:132-149).  When observations share few distinct
+// (level, duration) pairs this kernel does the same: one CTA per chain,
+//   phase A : thread (g,l) runs the forward series from (e_l, 0) for group g  -> moments in shared memory
+//   phase B : all threads sweep the group's observations: y_k = sum_l z0_kl y^(g,l), score, and accumulate the
+//             cotangents ybar^(g,l) += z0_kl ybar_k (block reduction per group, fixed order)
+//   phase A': thread (g,l) reverses its series with that cotangent (terms in a global, L2-resident ring) -> Theta-bar
+// Observations are sorted so that groups are contiguous (gstart).  Dynamic shared memory:
+// 2 * G*n*BP_D doubles (moments, cotangents) + reduction scratch.
+struct BpGroupArgs {
+  const double* theta;   // [C][BP_DIM]
+  const double* z0;      // [BP_N][npad]
+  const double* xo;      // [BP_N][npad]
+  const int* gstart;     // [G + 1]
+  const double* gt;      // [G] duration of the group
+  const double* gx;      // [BP_KDEP][G] dependent variables of the group's level
+  double* ring;          // [C][BP_MSLOT * BP_D * G * BP_N] series terms of phase A'
+  double* part;          // [C][1][BP_NPART]
+  int* status;           // [C]
+  int nobs, npad, ngroups, nchains;
+};
+
+template <int NV>
+__device__ __forceinline__ void bp_block_sum(double (&vals)[NV], double* red, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = bp_warp_sum(vals[i]);
+    if (lane == 0) red[i * nw + warp] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += red[i * nw + w];
+    out[i] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool bp_group_generator(const double (&th)[BP_DIM], const BpGroupArgs& a, int g, double (&xk)[BP_KDEP],
+                                                   double (&A)[BP_N * BP_N], double (&H)[BP_N * BP_S], double& a1) {
+  double r[BP_E];
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = a.gx[(size_t)q * a.ngroups + g];
+  bp_rates(th, xk, r);
+  bool fin = true;
+#pragma unroll
+  for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+  bp_assemble(r, A, H);
+  a1 = bp_norm1(A);
+  return fin;
+}
+
+extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
+  const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int G = a.ngroups, GN = G * BP_N;
+  double* ymom = bp_smem;                  // [GN][BP_D]
+  double* ybar = ymom + (size_t)GN * BP_D; // [GN][BP_D]
+  double* red = ybar + (size_t)GN * BP_D;  // [max(BP_N*BP_D, BP_NPART) * warps]
+  double th[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+#if BP_NOISE
+  const double sigma = th[BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  int status = 0, apps = 0;
+  // ---- phase A: single-ancestor moments of every (group, ancestor type) ----
+  for (int sx = tid; sx < GN; sx += T) {
+    const int g = sx / BP_N, l = sx - g * BP_N;
+    double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1, ymu[BP_N], yS[BP_S];
+    if (!bp_group_generator(th, a, g, xk, A, H, a1)) status |= BP_ST_RATE_NONFINITE;
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) ymu[i] = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) yS[q] = 0.0;
+    BpPlan p;
+    int dh = 1;
+    if (!bp_make_plan(a1, a.gt[g], p, dh)) { status |= BP_ST_RATE_NONFINITE; p.s = 0; }
+    double cfw;
+    for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, BpRingShared(), 0, 0, cfw);
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) ymom[(size_t)sx * BP_D + i] = ymu[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) ymom[(size_t)sx * BP_D + BP_N + q] = yS[q];
+  }
+  __syncthreads();
+  // ---- phase B: observations, group by group ----
+  double lp = 0.0, sb = 0.0;
+  for (int g = 0; g < G; ++g) {
+    double mom[BP_N][BP_D], acc[BP_N * BP_D];
+#pragma unroll
+    for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+      for (int q = 0; q < BP_D; ++q) { mom[l][q] = ymom[(size_t)(g * BP_N + l) * BP_D + q]; acc[l * BP_D + q] = 0.0; }
+    const int k1 = a.gstart[g + 1];
+    for (int k = a.gstart[g] + tid; k < k1; k += T) {
+      double z0[BP_N], xo[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) {
+        double sacc = z0[0] * mom[0][i];
+#pragma unroll
+        for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l][i];
+        ymu[i] = sacc;
+      }
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) {
+        double sacc = z0[0] * mom[0][BP_N + q];
+#pragma unroll
+        for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l][BP_N + q];
+        yS[q] = sacc;
+      }
+      if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; continue; }
+#pragma unroll
+      for (int l = 0; l < BP_N; ++l) {
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) acc[l * BP_D + i] += z0[l] * bmu[i];
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q) acc[l * BP_D + BP_N + q] += z0[l] * bS[q];
+      }
+    }
+    bp_block_sum(acc, red, ybar + (size_t)g * BP_N * BP_D);
+  }
+  // ---- phase A': reverse sweep of every series with the reduced cotangent ----
+  double cb[BP_P];
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
+  BpRingGlobal ring{a.ring + (size_t)c * BP_MSLOT * BP_D * GN};
+  for (int sx = tid; sx < GN; sx += T) {
+    const int g = sx / BP_N, l = sx - g * BP_N;
+    double A[BP_N * BP_N], H[BP_N * BP_S], gA[BP_N * BP_N], gH[BP_N * BP_S], xk[BP_KDEP], a1, imu[BP_N], iS[BP_S], rb[BP_E];
+    if (!bp_group_generator(th, a, g, xk, A, H, a1)) continue;
+#pragma unroll
+    for (int i = 0; i < BP_N * BP_N; ++i) gA[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) imu[i] = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) iS[q] = 0.0;
+    BpPlan p;
+    int dh = 1;
+    if (!bp_make_plan(a1, a.gt[g], p, dh)) continue;
+    apps += p.s * p.m;
+    const double* yb = ybar + (size_t)sx * BP_D;
+    bp_series_fwd_bwd(A, H, p, imu, iS,
+                      [&](double (&)[BP_N], double (&)[BP_S], double (&bmu)[BP_N], double (&bS)[BP_S]) {
+#pragma unroll
+                        for (int i = 0; i < BP_N; ++i) bmu[i] = yb[i];
+#pragma unroll
+                        for (int q = 0; q < BP_S; ++q) bS[q] = yb[BP_N + q];
+                        return true;
+                      },
+                      ring, sx, GN, gA, gH);
+    bp_assemble_vjp(gA, gH, rb);
+    bp_rates_vjp(th, xk, rb, cb);
+  }
+  double vals[BP_NPART];
+  vals[0] = lp;
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) vals[1 + k] = cb[k];
+  vals[BP_P + 1] = sb;
+  vals[BP_P + 2] = (double)apps;
+  bp_block_sum(vals, red, a.part + (size_t)c * BP_NPART);
+  if (status) atomicOr(a.status + c, status);
+}
+
 // ---- per-observation log_lik (LOO block), forward only -----------------------------------------
 extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_loglik(BpObsArgs a) {
   const int c = blockIdx.y;
@@ -825,7 +1033,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_moments(BpObsArgs a)
   int dhint = 1;
   const bool ok = bp_make_plan(a1, a.t[k], p, dhint);
   double cfw;
-  if (ok) for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, 0, 0, cfw);
+  if (ok) for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, BpRingShared(), 0, 0, cfw);
   double* o = a.loglik + ((size_t)c * a.nobs + a.perm[k]) * (BP_N + BP_N * BP_N);
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) o[i] = ok ? ymu[i] : (0.0 / 0.0);

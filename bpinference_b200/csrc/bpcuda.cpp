@@ -299,7 +299,8 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
   // sort: longest duration first (similar series length within a warp; heavy tiles launch first)
   std::vector<int> perm(N);
   std::iota(perm.begin(), perm.end(), 0);
-  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return t[a] > t[b]; });
+  // (ties broken by group so that the observations of one (level, duration) pair are contiguous: the grouped kernel's ranges)
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return t[a] != t[b] ? t[a] > t[b] : gkey[a] < gkey[b]; });
   const int npad = ((N + 31) / 32) * 32;
   dd->npad = npad;
   const int kd = s.kdep;
@@ -328,8 +329,33 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
   if ((rc = up(dd->t, ht.data(), ht.size() * 8))) return rc;
   if ((rc = up(dd->xv, hv.data(), hv.size() * 8))) return rc;
   if ((rc = up(dd->perm, hp.data(), hp.size() * 4))) return rc;
+  // groups = runs of equal (level, duration) in the sorted order
   dd->grouped = false;
-  (void)grouping;
+  if (!simple && N > 0) {
+    std::vector<int> gs;
+    std::vector<double> gtv;
+    std::vector<int> glev;
+    for (int j = 0; j < N; ++j)
+      if (j == 0 || gkey[perm[j]] != gkey[perm[j - 1]]) { gs.push_back(j); gtv.push_back(t[perm[j]]); glev.push_back(d->var_idx[perm[j]] - 1); }
+    const int G = (int)gs.size();
+    gs.push_back(N);
+    const long long GN = (long long)G * n;
+    const int D = n + n * (n + 1) / 2;
+    const size_t smem = (size_t)(2 * GN * D + 4 * std::max(n * D, s.nparams + 3)) * 8;
+    const bool fits = GN <= 4096 && smem <= 200 * 1024;
+    if (grouping == 2 && !fits) return fail(BPC_E_UNSUPPORTED, "too many (level, duration) groups for the grouped kernel");
+    if (fits && (grouping == 2 || (grouping == 0 && GN * 8 <= N))) {
+      std::vector<double> gxv((size_t)kd * G, 0.0);
+      for (int g = 0; g < G; ++g)
+        for (int q = 0; q < kd; ++q) gxv[(size_t)q * G + g] = (q < d->ndep) ? d->function_var[glev[g] + (size_t)d->ndep_levels * q] : 0.0;
+      if ((rc = up(dd->gstart, gs.data(), gs.size() * 4))) return rc;
+      if ((rc = up(dd->gt, gtv.data(), gtv.size() * 8))) return rc;
+      if ((rc = up(dd->gx, gxv.data(), gxv.size() * 8))) return rc;
+      dd->grouped = true;
+      dd->ngroups = G;
+      dd->group_threads = N <= 2048 ? 32 : (N <= 8192 ? 64 : 128);
+    }
+  }
   BPC_CUDA(cudaStreamCreateWithFlags(&dd->stream, cudaStreamNonBlocking));
   *out = dd.release();
   return BPC_OK;
@@ -353,6 +379,7 @@ namespace bpc {
 
 // tile (observations per CTA) so that the grid has a few waves of CTAs when the problem allows it
 static void choose_tiling(bpc_data* d, int nchains) {
+  if (d->grouped) { d->tile = d->N; d->ntiles = 1; return; }
   const int T = d->model->spec.threads;
   const long long total = (long long)d->N * nchains;
   long long per_thread = total / ((long long)148 * 8 * T);
@@ -369,10 +396,20 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     if ((rc = d->theta.alloc((size_t)nchains * s.dim * 8))) return rc;
     if ((rc = d->part.alloc((size_t)nchains * d->ntiles * (s.nparams + 3) * 8))) return rc;
     if ((rc = d->apps.alloc((size_t)nchains * 8))) return rc;
+    if (d->grouped) {
+      const int n = s.ntypes, D = n + n * (n + 1) / 2;
+      if ((rc = d->ring.alloc((size_t)nchains * s.mslot * D * d->ngroups * n * 8))) return rc;
+    }
     d->ws_chains = nchains;
   }
   return BPC_OK;
 }
+
+struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
+  const double* theta; const double* z0; const double* xo; const int* gstart; const double* gt; const double* gx;
+  double* ring; double* part; int* status;
+  int nobs, npad, ngroups, nchains;
+};
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   const double* theta; const double* z0; const double* xo; const double* t; const double* xv;
@@ -406,7 +443,21 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       BPC_CUDA(cudaEventCreate(&e1));
       BPC_CUDA(cudaEventRecord(e0, st));
     }
-    BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, nchains), dim3(s.threads), args, L->obs_smem, st));
+    if (d->grouped) {
+      if (!L->grouped) return fail(BPC_E_UNSUPPORTED, "module has no grouped kernel");
+      const int n = s.ntypes, D = n + n * (n + 1) / 2, T = d->group_threads;
+      const size_t smem = (size_t)(2 * d->ngroups * n * D + (T / 32) * std::max(n * D, s.nparams + 3)) * 8;
+      if (smem > L->grouped_smem) {
+        BPC_CUDA(cudaKernelSetAttributeForDevice(L->grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, d->device));
+        L->grouped_smem = smem;
+      }
+      GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
+                   (const double*)d->gx.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains};
+      void* gargs[] = {(void*)&ga};
+      BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+    } else {
+      BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, nchains), dim3(s.threads), args, L->obs_smem, st));
+    }
     if (d->timing) {
       BPC_CUDA(cudaEventRecord(e1, st));
       d->timing_events.emplace_back(e0, e1);
@@ -579,7 +630,8 @@ int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains,
   const ModelSpec& s = m->spec;
   const FlopModel f = flop_model(s);
   for (int c = 0; c < nchains; ++c)
-    flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N : apps[c] * (f.per_app_fwd + f.per_app_bwd) + f.per_obs * d->N;
+    flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N
+                                                   : apps[c] * (f.per_app_fwd + f.per_app_bwd) + (d->grouped ? f.per_obs_grouped : f.per_obs) * d->N;
   return BPC_OK;
 }
 

@@ -17,6 +17,7 @@ FlopModel flop_model(const ModelSpec& sp) {
     // bp_onetype_obs: value + gradient w.r.t. (b, d)
     f.per_app_fwd = f.per_app_bwd = 0.0;
     f.per_obs = 70.0;
+    f.per_obs_grouped = 70.0;
     return f;
   }
   auto sidx = [n](int i, int j) { if (i > j) std::swap(i, j); return i * n - i * (i - 1) / 2 + (j - i); };
@@ -67,7 +68,10 @@ FlopModel flop_model(const ModelSpec& sp) {
     for (int i = 0; i <= j; ++i) bS += 2 * (n - 1 - j) + 3;
   }
   const double logdet = (n - 1) + 1, W = n * (n - 1) / 2.0;
-  f.per_obs = 4 + D + fac + logdet + linv + quad + 2 + bmu + W + bS + (sp.kind == 1 ? 6 * n : 0);
+  const double score = fac + logdet + linv + quad + 2 + bmu + W + bS + 1 + (sp.kind == 1 ? 6 * n : 0);   // incl. lp accumulation
+  f.per_obs = 3 + D + score;
+  // grouped path: contraction y = sum_l z0_l y^(l) (D (2n - 1)) and cotangent accumulation (2 n D) instead of the plan
+  f.per_obs_grouped = score + D * (2 * n - 1) + 2 * n * D;
   return f;
 }
 

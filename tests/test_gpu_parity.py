@@ -77,3 +77,50 @@ def test_log_lik_matches_sum_and_constants():
             prior = prior - 0.5 * (sig / 0.1) ** 2
         N = cfg["data"]["ndatapts"]
         np.testing.assert_allclose(ll.sum(axis=1) + 0.5 * n * N * np.log(2 * np.pi), lp_o - prior, rtol=1e-11)
+
+
+@pytest.mark.parametrize("name,nobs,chains", [("cfg2", None, 33), ("cfg4", None, 5), ("cfg5G", 5000, 9), ("cfg5K", 700, 3)])
+def test_grouped_kernel_equals_fused_kernel(name, nobs, chains):
+    """the template-shaped two-phase path (moments once per (level, duration) group) and the per-observation fused
+    kernel are two evaluations of the same function: equal to rounding; both match the oracle."""
+    cfg = syn.make_config(name, chains=chains, nobs=nobs)
+    eng, om = _pair(cfg)
+    if name == "cfg5K":          # a few repeated (level, duration) pairs among many distinct ones
+        d = dict(cfg["data"])
+        d["var_idx"] = np.asarray(d["var_idx"]).copy()
+        d["times_idx"] = np.asarray(d["times_idx"]).copy()
+        d["var_idx"][::2] = 1 + (np.arange(len(d["var_idx"][::2])) % 5)
+        d["times_idx"][::2] = 1 + (np.arange(len(d["times_idx"][::2])) % 3)
+        cfg["data"] = d
+    df = eng.data(cfg["data"], grouping=1)
+    dg = eng.data(cfg["data"], grouping=2)
+    assert not df.grouped and dg.grouped and dg.ngroups >= 1
+    lf, gf, sf = eng.log_prob_grad(df, cfg["upars"])
+    lg, gg, sg = eng.log_prob_grad(dg, cfg["upars"])
+    assert (sf == 0).all() and (sg == 0).all()
+    np.testing.assert_allclose(lg, lf, rtol=1e-12)
+    np.testing.assert_allclose(gg, gf, rtol=1e-9, atol=1e-11 * np.abs(gf).max())
+    lp_o, g_o, _ = bo.log_prob(om, cfg["data"], cfg["upars"])
+    np.testing.assert_allclose(lg, lp_o, rtol=1e-11)
+    np.testing.assert_allclose(gg, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+    auto = eng.data(cfg["data"])
+    assert auto.grouped == (name != "cfg5K")
+
+
+def test_grouped_status_and_large_norm():
+    cfg = syn.make_config("cfg2", chains=4, nobs=40)
+    eng, om = _pair(cfg)
+    d = dict(cfg["data"])
+    d["times"] = np.array([9.0])
+    u = cfg["upars"] + 1.5                       # rates ~ 1, ||tL|| ~ 40: many sub-steps in phase A / A'
+    dg = eng.data(d, grouping=2)
+    lg, gg, sg = eng.log_prob_grad(dg, u)
+    lp_o, g_o, st_o = bo.log_prob(om, d, u)
+    assert sg.tolist() == st_o.tolist()
+    ok = st_o == 0
+    np.testing.assert_allclose(lg[ok], lp_o[ok], rtol=1e-10)
+    np.testing.assert_allclose(gg[ok], g_o[ok], rtol=1e-8, atol=1e-9 * np.abs(g_o).max())
+    d0 = dict(cfg["data"])
+    d0["init_pop"] = np.zeros_like(d0["init_pop"])
+    l0, g0, s0 = eng.log_prob_grad(eng.data(d0, grouping=2), cfg["upars"])
+    assert (s0 & 1).all() and np.isneginf(l0).all() and (g0 == 0).all()
