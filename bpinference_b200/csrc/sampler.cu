@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 
@@ -527,6 +528,9 @@ struct bpc_sampler {
   long long passes = 0;
   int* h_counters = nullptr;   // pinned
   cudaStream_t stream = nullptr;
+  cudaGraph_t graph = nullptr;          // POLL passes (4 kernels each) captured once and replayed: the per-pass cost of
+  cudaGraphExec_t graph_exec = nullptr; // small problems is launch latency, not arithmetic
+  bool graph_tried = false;
 };
 
 extern "C" {
@@ -600,9 +604,23 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
 void bpc_sampler_free(bpc_sampler* s) {
   if (!s) return;
   cudaSetDevice(s->d->device);
-  if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->graph) cudaGraphDestroy(s->graph);
+  if (s->stream) cudaStreamDestroy(s->stream);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   delete s;
+}
+
+static int sampler_passes(bpc_sampler* s, int nb) {
+  const Params& P = s->P;
+  for (int b = 0; b < nb; ++b) {
+    int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream);
+    if (rc) return rc;
+    bp_nuts_advance<<<(P.C + 127) / 128, 128, 0, s->stream>>>(P);
+    g_launches += 1;
+  }
+  return BPC_OK;
 }
 
 int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
@@ -612,16 +630,30 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
   const Params& P = s->P;
   *state = 0;
   long long done_passes = 0;
-  // poll the finished / waiting counters every few passes: cheap for large problems, and for small ones the
+  // poll the finished / waiting counters every POLL passes: cheap for large problems, and for small ones the
   // polling interval bounds the tail of idle passes
-  const int poll = 16;
+  const int POLL = 16;
   while (done_passes < max_passes) {
-    const int nb = (int)std::min<long long>(poll, max_passes - done_passes);
-    for (int b = 0; b < nb; ++b) {
-      int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream);
+    const int nb = (int)std::min<long long>(POLL, max_passes - done_passes);
+    if (nb == POLL && s->passes >= POLL && !s->graph_tried) {
+      // the first block ran eagerly (module load, workspace allocation); capture the next one and replay it from now on
+      s->graph_tried = true;
+      if (!getenv("BPC_NO_GRAPH") && cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const long long before = g_launches;
+        const int rc = sampler_passes(s, POLL);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ec = cudaStreamEndCapture(s->stream, &g);
+        g_launches = before;   // nothing ran during capture
+        if (rc == BPC_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&s->graph_exec, g, 0) == cudaSuccess) s->graph = g;
+        else { if (g) cudaGraphDestroy(g); s->graph_exec = nullptr; cudaGetLastError(); }
+      }
+    }
+    if (nb == POLL && s->graph_exec) {
+      if ((e = cudaGraphLaunch(s->graph_exec, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+      g_launches += 4 * POLL;
+    } else {
+      const int rc = sampler_passes(s, nb);
       if (rc) return rc;
-      bp_nuts_advance<<<(P.C + 127) / 128, 128, 0, s->stream>>>(P);
-      g_launches += 1;
     }
     done_passes += nb;
     s->passes += nb;
@@ -730,10 +762,6 @@ int bpc_sample(bpc_model* m, bpc_data* d, const bpc_sample_args* a, double* draw
   if (!rc && s->h_counters[2] > 0) { bpc_sampler_free(s); return fail(BPC_E_INVALID, "initialization failed for some chains: log density or gradient not finite at 100 random initial values"); }
   bpc_sampler_free(s);
   return rc;
-}
-
-int bpc_simulate(int, int, const double*, const int*, const double*, const double*, const double*, int, int, unsigned long long, int, double*) {
-  return fail(BPC_E_UNSUPPORTED, "device simulator not built yet: use bpinference_b200.bpsims");
 }
 
 }  // extern "C"

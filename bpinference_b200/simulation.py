@@ -51,7 +51,23 @@ def bp(e_mat, r_vec, p_vec, z0_vec, times, rng=None):
     return out
 
 
-def bpsims(model, theta, z0_vec, times, reps, c_mat=None, rng=None):
+def bp_cuda(e_mat, r_vec, p_vec, z0_vec, times, nrep, seed=1, device=0):
+    """nrep replicates of bp() on the GPU (libbpcuda's bpc_simulate): returns [nrep, ntimes, ntypes].  Unlike bp(), `times`
+    must be increasing; the first row of every replicate is the initial population, as in the reference."""
+    from . import _ffi
+    e_mat = np.asfortranarray(np.asarray(e_mat, dtype=np.float64))
+    times = np.ascontiguousarray(np.atleast_1d(np.asarray(times, dtype=np.float64)))
+    p = np.ascontiguousarray(np.asarray(p_vec, dtype=np.int32))
+    r = np.ascontiguousarray(np.asarray(r_vec, dtype=np.float64))
+    z0 = np.ascontiguousarray(np.atleast_1d(np.asarray(z0_vec, dtype=np.float64)))
+    out = np.empty((int(nrep), len(times), e_mat.shape[1]))
+    _ffi.check(_ffi.lib().bpc_simulate(e_mat.shape[1], e_mat.shape[0], _ffi.dptr(e_mat), _ffi.iptr(p), _ffi.dptr(r), _ffi.dptr(z0), _ffi.dptr(times),
+                                       len(times), int(nrep), int(seed), int(device), _ffi.dptr(out)))
+    return out
+
+
+def bpsims(model, theta, z0_vec, times, reps, c_mat=None, rng=None, device=None, seed=1):
+    """`device` = a CUDA device index runs the replicates with libbpcuda's Gillespie kernel instead of the host loop."""
     if getattr(model, "r_class", None) != "bp_model":
         raise ValueError("model must be a bp_model object!")
     rng = np.random.default_rng() if rng is None else rng
@@ -71,8 +87,9 @@ def bpsims(model, theta, z0_vec, times, reps, c_mat=None, rng=None):
     frames = []
     if model["ndep"] == 0 and no_c:
         r_vec = [eval_rate(f, theta) for f in model["func_deps"]]
+        batch = bp_cuda(e_mat, r_vec, model["p_vec"], z0_vec, times, int(reps), seed=seed, device=device) if device is not None else None
         for i in range(int(reps)):
-            pop = bp(e_mat, r_vec, model["p_vec"], z0_vec, times, rng)
+            pop = batch[i] if batch is not None else bp(e_mat, r_vec, model["p_vec"], z0_vec, times, rng)
             d = {"times": times, "rep": np.full(len(times), i + 1)}
             d.update({nm: pop[:, j] for j, nm in enumerate(pop_names)})
             frames.append(pd.DataFrame(d))
@@ -86,8 +103,9 @@ def bpsims(model, theta, z0_vec, times, reps, c_mat=None, rng=None):
     curr = 1
     for i in range(cm.shape[0]):
         r_vec = [eval_rate(f, theta, cm[i]) for f in model["func_deps"]]
-        for _ in range(int(reps[i])):
-            pop = bp(e_mat, r_vec, model["p_vec"], z0_vec, times, rng)
+        batch = bp_cuda(e_mat, r_vec, model["p_vec"], z0_vec, times, int(reps[i]), seed=seed + 7919 * i, device=device) if device is not None else None
+        for k in range(int(reps[i])):
+            pop = batch[k] if batch is not None else bp(e_mat, r_vec, model["p_vec"], z0_vec, times, rng)
             d = {"times": times, "rep": np.full(len(times), curr), "variable_state": np.full(len(times), i + 1)}
             d.update({nm: np.full(len(times), cm[i, j]) for j, nm in enumerate(dep_names)})
             d.update({nm: pop[:, j] for j, nm in enumerate(pop_names)})

@@ -109,3 +109,25 @@ def test_pooled_adaptation_and_user_inits():
     flat = fit.draws.reshape(-1, 6)
     net1 = flat[:, 0] - flat[:, 4] - flat[:, 1] * 0    # birth - death of type 1 (transfer terms cancel in expectation)
     assert abs(np.median(net1) - (0.20 - 0.25)) < 0.1
+
+
+def test_device_simulator_matches_analytic_moments():
+    """tests/testthat/test_simulation.R:109-127 at the reference's own size and tolerances (10 000 replicates, |d mean| < 1,
+    |d var|, |d cov| < 7), with the replicates simulated by the Gillespie kernel; plus the host simulator's column layout."""
+    E2 = np.array([[2, 0], [1, 1], [1, 1], [0, 2], [0, 0], [0, 0]], dtype=float)
+    P2 = [1, 1, 2, 2, 1, 2]
+    th = [0.20, 0.10, 0.05, 0.20, 0.25, 0.20]
+    mod = bp.bp_model(E2, P2, ['c[%d]' % k for k in range(1, 7)], 6, 0)
+    sim = bp.bpsims(mod, th, [100, 50], [5], 10000, device=0, seed=3)
+    assert list(sim.columns) == ["times", "rep", "X1", "X2"] and len(sim) == 10000 and (sim["times"] == 5).all()
+    mom = bp.calculate_moments(E2, P2, th, [100, 50], 5)
+    x = sim.iloc[:, 2:4].to_numpy()
+    assert abs(x[:, 0].mean() - mom["mu_mat"][0, 0]) < 1 and abs(x[:, 1].mean() - mom["mu_mat"][1, 0]) < 1
+    c = np.cov(x.T)
+    assert abs(c[0, 0] - mom["sigma_mat"][0, 0]) < 7 and abs(c[1, 1] - mom["sigma_mat"][1, 1]) < 7 and abs(c[0, 1] - mom["sigma_mat"][0, 1]) < 7
+    # trajectories: first row is z0, rows are recorded at every requested time, reproducible by seed
+    tr = bp.bp_cuda(E2, th, P2, [1000, 500], np.arange(6), 64, seed=9)
+    assert tr.shape == (64, 6, 2) and (tr[:, 0] == [1000, 500]).all() and (tr >= 0).all()
+    assert (bp.bp_cuda(E2, th, P2, [1000, 500], np.arange(6), 64, seed=9) == tr).all()
+    dat = bp.stan_data_from_simulation(bp.bpsims(mod, th, [1000, 500], np.arange(6), 50, device=0), mod)
+    assert dat["ndatapts"] == 250 and dat["ntimes_unique"] == 1 and dat["times"][0] == 1
