@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -383,7 +384,9 @@ static void choose_tiling(bpc_data* d, int nchains) {
   const int T = d->model->spec.threads;
   const long long total = (long long)d->N * nchains;
   long long per_thread = total / ((long long)148 * 8 * T);
-  per_thread = std::max(1LL, std::min(8LL, per_thread));
+  long long cap = 8;
+  if (const char* ev = std::getenv("BPC_OBS_PER_THREAD")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 1024) cap = v; }
+  per_thread = std::max(1LL, std::min(cap, per_thread));
   d->tile = (int)(T * per_thread);
   d->ntiles = std::max(1, (d->N + d->tile - 1) / d->tile);
 }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "rexpr.hpp"
@@ -92,14 +93,20 @@ std::string generate_cuda(ModelSpec& m) {
 
   m.dim = P + (m.kind == 1 ? 1 : 0);
   m.kdep = m.ndep > 0 ? m.ndep : 1;
-  m.mcap = 23;   // at most mcap + 1 = 2 * mslot applications per sub-step: the ring is refilled once
+  m.mcap = 23;   // at most mcap + 1 = 24 applications of L per sub-step
   static const int threads_by_n[6] = {0, 256, 192, 128, 64, 32};
   m.threads = (m.kind == 2) ? 256 : threads_by_n[n];
   m.theta_cap = taylor_theta(m.mcap);
-  m.mslot = (m.mcap + 1) / 2;   // terms kept per thread in shared memory; longer series are reversed in two segments
+  // terms kept per thread in shared memory (ring); longer series are reversed in segments.  BPC_MSLOT / BPC_THREADS
+  // override the defaults (tuning experiments).
+  m.mslot = (m.mcap + 1) / 2;
+  if (const char* ev = std::getenv("BPC_MSLOT")) { const int v = std::atoi(ev); if (v >= 2 && v <= m.mcap + 1) m.mslot = v; }
+  if (const char* ev = std::getenv("BPC_THREADS")) { const int v = std::atoi(ev); if (m.kind != 2 && v >= 32 && v <= 256 && v % 32 == 0) m.threads = v; }
   {
     const size_t smem = (size_t)m.mslot * (n + n * (n + 1) / 2) * m.threads * 8 + 1024;
-    m.minblocks = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / smem));
+    m.minblocks = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / smem));
+    while (m.minblocks > 1 && (size_t)m.minblocks * m.threads * 128 > 65536) --m.minblocks;   // never ask for < 128 registers
+    if (const char* ev = std::getenv("BPC_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= m.minblocks) m.minblocks = v; }
   }
 
   // rates
