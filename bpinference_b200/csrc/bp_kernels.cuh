@@ -427,32 +427,36 @@ BP_HD bool bp_make_plan(real a1, real t, BpPlan& p, int& dhint) {
 // bp_grouped (single-ancestor moments, score = the cotangent reduced over the group's observations).
 //
 // The reverse sweep needs the series terms u_0 .. u_{m-1} of a sub-step in reverse order.  The ring keeps the last
-// BP_MSLOT of them: when m > BP_MSLOT the upper terms kh .. m-1 are reversed first and the lower terms 0 .. kh-1 are
-// then recomputed into the ring (kh - 1 extra applications of L; halves the shared memory per thread, which doubles
-// the warps per SM).  With several sub-steps (large ||tL||) only the one being reversed is stored; earlier ones are
-// recomputed from the initial state.  One forward loop and one reverse loop serve all of these cases.
+// BP_MSLOT terms a forward pass produced: the top segment m-BP_MSLOT .. m-1 is reversed first, then for every lower
+// segment lo .. hi the terms 0 .. hi are recomputed into the ring (hi extra applications of L) and reversed.  A small
+// ring means few kilobytes of shared memory per thread, i.e. more warps per SM to hide the fp64 latencies, at the price
+// of recomputed forward terms (tools/sweep.py: 12 slots, 2 CTAs per SM is the optimum for n = 3).  With several
+// sub-steps (large ||tL||) only the one being reversed is stored; earlier ones are recomputed from the initial state.
+// One forward loop and one reverse loop serve all of these cases.
 template <class ST, class SC>
 BP_HD bool bp_series_fwd_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], const BpPlan& p, const real (&imu)[BP_N],
                              const real (&iS)[BP_S], SC&& score, ST st, int soff, int stride, real (&gA)[BP_N * BP_N],
                              real (&gH)[BP_N * BP_S]) {
   const int m = p.m;
-  const bool two = m > BP_MSLOT;
-  const int kh = two ? m - BP_MSLOT : 0;
+  const int nseg = (m + BP_MSLOT - 1) / BP_MSLOT;   // the m terms are reversed in segments of at most BP_MSLOT, top first
   real bmu[BP_N], bS[BP_S], zmu[BP_N], zS[BP_S];
   real cser = real(1.0);
   const real hinv = real(1.0) / p.h;
   bool scored = false;
   for (int target = p.s - 1; target >= 0; --target) {
-    // items 0..target-1: plain sub-steps up to the one being reversed; item target: that sub-step; item target+1
-    // (only when `two`): recompute of its lower terms
+    // items 0..target-1: plain sub-steps up to the one being reversed; item target: that sub-step (its pass leaves the top
+    // segment in the ring); items target+1..: recompute of terms 0..hi of the next lower segment (hi applications)
     real ymu[BP_N], yS[BP_S], y0mu[BP_N], y0S[BP_S];
 #pragma unroll
     for (int i = 0; i < BP_N; ++i) { ymu[i] = imu[i]; y0mu[i] = imu[i]; }
 #pragma unroll
     for (int q = 0; q < BP_S; ++q) { yS[q] = iS[q]; y0S[q] = iS[q]; }
-    const int nitems = target + (two ? 2 : 1);
+    const int nitems = target + nseg;
     for (int it = 0; it < nitems; ++it) {
-      const bool is_main = it == target, is_rec = it > target;
+      const int seg = it - target;
+      const bool is_main = seg == 0, is_rec = seg > 0;
+      const int hi = m - 1 - (is_rec ? seg : 0) * BP_MSLOT;
+      const int lo = hi - BP_MSLOT + 1 > 0 ? hi - BP_MSLOT + 1 : 0;
       if (is_main) {
 #pragma unroll
         for (int i = 0; i < BP_N; ++i) y0mu[i] = ymu[i];
@@ -465,7 +469,7 @@ BP_HD bool bp_series_fwd_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N 
 #pragma unroll
       for (int q = 0; q < BP_S; ++q) sS[q] = is_rec ? y0S[q] : yS[q];
       real cfw;
-      bp_series_fwd<true>(A, H, p.h, is_rec ? kh - 1 : m, smu, sS, !is_rec, ymu, yS, is_rec, st, soff, stride, cfw);
+      bp_series_fwd<true>(A, H, p.h, is_rec ? hi : m, smu, sS, !is_rec, ymu, yS, is_rec, st, soff, stride, cfw);
       if (is_main) {
         if (!scored) {
           scored = true;
@@ -477,7 +481,7 @@ BP_HD bool bp_series_fwd_bwd(const real (&A)[BP_N * BP_N], const real (&H)[BP_N 
 #pragma unroll
         for (int q = 0; q < BP_S; ++q) zS[q] = cser * bS[q];
       }
-      if (is_main || is_rec) bp_series_bwd(A, H, hinv, is_main ? m - 1 : kh - 1, is_main ? kh : 0, st, soff, stride, bmu, bS, zmu, zS, cser, gA, gH);
+      if (seg >= 0) bp_series_bwd(A, H, hinv, hi, lo, st, soff, stride, bmu, bS, zmu, zS, cser, gA, gH);
     }
     // cotangent of this sub-step's input = cotangent of the previous sub-step's result
 #pragma unroll
