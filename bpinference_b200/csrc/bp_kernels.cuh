@@ -717,7 +717,282 @@ struct BpObsArgs {
   double* loglik;        // [C][N] (bp_*_loglik only)
   const int* perm;       // [npad] original index of sorted observation (bp_*_loglik only)
   int nobs, npad, tile, ntiles, nchains;
+  double* wpart;         // [C][ntiles][BP_WFRAG] per-CTA partial sums of the W_j matrices (bp_fusedw / bp_wpost)
+  int wmode;             // 1: chains whose series need a single sub-step are handled by bp_fusedw + bp_wpost
 };
+
+// ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
+// When the rates do not depend on per-observation variables, every observation of a chain shares the operator L and
+// (for a single sub-step) its state is a polynomial in L:  y_k = sum_j c_j(t_k) L^j y0_k,  c_j(t) = t^j / j!.  Its
+// gradient w.r.t. L,  sum_k sum_j c_j(t_k) sum_i (L^T)^(j-1-i) b_k (L^i y0_k)^T,  is LINEAR in the D x n matrices
+//     W_j = sum_k c_j(t_k) b_k y0_k^T          (b_k = d lp_k / d y_k in packed coordinates, j = 1..m_k)
+// so the per-observation reverse sweep (its Horner recurrence with L^T, the term ring in shared memory and the
+// recomputation that ring costs) is replaced by accumulating W_j over observations and ONE per-chain evaluation of
+//     Lbar = sum_i Y_i P^i,   Y_i = W_(i+1) + P Y_(i+1),   P = L^T                       (bp_wpost).
+// The accumulation  W[j][(d,l)] += T[j][k] * B[k][(d,l)]  over the 32 observations of a warp is a 24 x 32 x 32 matrix
+// product in fp64: it runs on the tensor cores' fp64 path (mma.sync m8n8k4, DMMA in SASS), whose accumulators are
+// distributed over the warp's registers, exactly what a per-thread accumulation could not afford (648 doubles).
+// Operands are staged through shared memory ([row][observation], row stride BP_WLD, conflict-free fragment loads).
+// Chains that need sub-steps (2 ||A||_1 t_max > BP_THETA_CAP) are left to bp_fused; the test is a function of the
+// chain's parameters and the longest duration only, so both kernels take the same decision without communicating.
+#define BP_WROWS (BP_MCAP + 1)              // j = 1 .. BP_MCAP + 1
+#define BP_WCOLS (BP_D * BP_N)             // (d, l) pairs
+#define BP_WRT ((BP_WROWS + 7) / 8)        // 8-row tiles
+#define BP_WCT ((BP_WCOLS + 7) / 8)        // 8-column tiles
+#define BP_WFRAG (BP_WRT * BP_WCT * 64)    // accumulator elements of one warp (fragment layout)
+#define BP_WLD 36                          // leading dimension of the staged operands
+#define BP_WSTAGE ((BP_WRT * 8 + BP_WCT * 8) * BP_WLD)   // doubles per warp
+
+BP_HD bool bp_w_path(bool rates_finite, real a1, real tmax) {
+  const real xx = (a1 + a1) * tmax;
+  return rates_finite && xx >= real(0.0) && xx <= real(BP_THETA_CAP);
+}
+
+#if !defined(BP_HOSTSIM) && BP_KIND != 2 && !BP_XDEP
+__device__ __forceinline__ void bp_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_WMINBLOCKS) bp_fusedw(BpObsArgs a) {
+  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double th[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+#if BP_NOISE
+  const double sigma = th[BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
+#pragma unroll
+  for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+  bp_rates(th, xk, r);
+  bool fin = true;
+#pragma unroll
+  for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+  bp_assemble(r, A, H);
+  const double a1 = bp_norm1(A);
+  if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;   // bp_fused handles this chain
+
+  double* sT = bp_smem + (size_t)warp * BP_WSTAGE;   // [BP_WRT*8][BP_WLD]  T[j-1][obs] = c_j(t_obs)
+  double* sB = sT + BP_WRT * 8 * BP_WLD;             // [BP_WCT*8][BP_WLD]  B[(d,l)][obs] = b_d z0_l
+  for (int i = lane; i < BP_WSTAGE; i += 32) sT[i] = 0.0;   // padding rows / columns stay zero
+  __syncwarp();
+  double acc[BP_WRT * BP_WCT][2];
+#pragma unroll
+  for (int i = 0; i < BP_WRT * BP_WCT; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double lp = 0.0, sb = 0.0;
+  int status = 0, apps = 0, dhint = 1;
+  const int k0 = blockIdx.x * a.tile;
+  const int k1 = min(a.nobs, k0 + a.tile);
+  for (int kb = k0 + warp * 32; kb < k1; kb += BP_THREADS) {   // warp-uniform: 32 consecutive observations per pass
+    const int k = kb + lane;
+    bool valid = k < k1;
+    int m = 0;
+    double t = 0.0, z0[BP_N], bmu[BP_N], bS[BP_S];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) { z0[i] = 0.0; bmu[i] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) bS[q] = 0.0;
+    if (valid) {
+      double xo[BP_N], ymu[BP_N], yS[BP_S];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; ymu[i] = z0[i]; }
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) yS[q] = 0.0;
+      t = a.t[k];
+      BpPlan p;
+      if (!bp_make_plan(a1, t, p, dhint)) { status |= BP_ST_RATE_NONFINITE; valid = false; }
+      else {
+        m = p.m;
+        apps += p.m;
+        double cfw;
+        bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, BpRingShared(), 0, 0, cfw);
+        if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; valid = false; }
+      }
+    }
+    // stage this observation's operands: T column (c_j(t), j = 1..m) and B column (packed-coordinate cotangent x z0)
+    {
+      double cj = 1.0;
+#pragma unroll
+      for (int j = 0; j < BP_WROWS; ++j) {
+        cj = cj * (t * bp_rk[j]);
+        sT[j * BP_WLD + lane] = (valid && j < m) ? cj : 0.0;
+      }
+#pragma unroll
+      for (int d = 0; d < BP_D; ++d) {
+        double bd;
+        if (d < BP_N) bd = bmu[d];
+        else {
+          // packed coordinates: an off-diagonal entry stands for both symmetric positions
+          bool diag = false;
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == d - BP_N);
+          bd = diag ? bS[d - BP_N] : bS[d - BP_N] + bS[d - BP_N];
+        }
+        if (!valid) bd = 0.0;
+#pragma unroll
+        for (int l = 0; l < BP_N; ++l) sB[(d * BP_N + l) * BP_WLD + lane] = bd * z0[l];
+      }
+    }
+    __syncwarp();
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int ob = 0; ob < 8; ++ob) {   // 4 observations per mma
+      double af[BP_WRT], bf[BP_WCT];
+#pragma unroll
+      for (int rt = 0; rt < BP_WRT; ++rt) af[rt] = sT[(rt * 8 + g) * BP_WLD + ob * 4 + tg];
+#pragma unroll
+      for (int ct = 0; ct < BP_WCT; ++ct) bf[ct] = sB[(ct * 8 + g) * BP_WLD + ob * 4 + tg];
+#pragma unroll
+      for (int rt = 0; rt < BP_WRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(acc[rt * BP_WCT + ct][0], acc[rt * BP_WCT + ct][1], af[rt], bf[ct]);
+    }
+    __syncwarp();
+  }
+  // CTA partial of W: sum the warps' accumulators in warp order (fragment layout kept; bp_wpost knows it)
+  __syncthreads();
+  double* red = bp_smem;   // [warps][BP_WFRAG]
+#pragma unroll
+  for (int i = 0; i < BP_WRT * BP_WCT; ++i) { red[(size_t)warp * BP_WFRAG + i * 64 + lane * 2] = acc[i][0]; red[(size_t)warp * BP_WFRAG + i * 64 + lane * 2 + 1] = acc[i][1]; }
+  __syncthreads();
+  double* wout = a.wpart + ((size_t)c * a.ntiles + blockIdx.x) * BP_WFRAG;
+  for (int i = tid; i < BP_WFRAG; i += BP_THREADS) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < BP_THREADS / 32; ++w) sacc += red[(size_t)w * BP_WFRAG + i];
+    wout[i] = sacc;
+  }
+  __syncthreads();
+  double vals[BP_NPART];
+  vals[0] = lp;
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) vals[1 + k] = 0.0;
+  vals[BP_P + 1] = sb;
+  vals[BP_P + 2] = (double)apps;
+  bp_block_reduce_store(vals, bp_smem, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
+  if (status) atomicOr(a.status + c, status);
+}
+
+// per chain: W_j summed over tiles -> Lbar -> (gA, gH) -> Theta-bar, added to the chain's first tile partial
+extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArgs a) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  __shared__ double W[BP_WROWS][BP_WCOLS];      // W_(j+1); then Y_j in place
+  __shared__ double P[BP_D][BP_D];              // L^T in packed coordinates
+  __shared__ double Z[2][BP_D][BP_D];
+  double th[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+  double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
+#pragma unroll
+  for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+  bp_rates(th, xk, r);
+  bool fin = true;
+#pragma unroll
+  for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+  bp_assemble(r, A, H);
+  const double a1 = bp_norm1(A);
+  if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
+  // 1. sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
+  for (int i = tid; i < BP_WFRAG; i += blockDim.x) {
+    double sacc = 0.0;
+    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * BP_WFRAG + i];
+    const int tile = i >> 6, ln = (i & 63) >> 1, e = i & 1;
+    const int row = (tile / BP_WCT) * 8 + (ln >> 2), col = (tile % BP_WCT) * 8 + (ln & 3) * 2 + e;
+    if (row < BP_WROWS && col < BP_WCOLS) W[row][col] = sacc;
+  }
+  // 2. P = L^T: column cc of L is L applied to the packed unit vector e_cc
+  if (tid < BP_D) {
+    double umu[BP_N], uS[BP_S], omu[BP_N], oS[BP_S];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) umu[i] = (tid == i) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) uS[q] = (tid == BP_N + q) ? 1.0 : 0.0;
+    bp_L_apply(A, H, umu, uS, omu, oS);
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) P[tid][i] = omu[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) P[tid][BP_N + q] = oS[q];
+  }
+  __syncthreads();
+  // 3. Y_i = W_(i+1) + P Y_(i+1), i descending (in place in W: row i holds Y_i, columns (d, l))
+  for (int i = BP_WROWS - 2; i >= 0; --i) {
+    double y = 0.0;
+    if (tid < BP_WCOLS) {
+      const int d = tid / BP_N, l = tid - d * BP_N;
+      y = W[i][tid];
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) y += P[d][rr] * W[i + 1][rr * BP_N + l];
+    }
+    __syncthreads();
+    if (tid < BP_WCOLS) W[i][tid] = y;
+    __syncthreads();
+  }
+  // 4. Lbar = sum_i Y_i P^i by Horner on the right; Y_i is D x n (zero beyond the first n columns)
+  int cur = 0;
+  if (tid < BP_D * BP_D) {
+    const int d = tid / BP_D, e = tid - d * BP_D;
+    Z[0][d][e] = (e < BP_N) ? W[BP_WROWS - 1][d * BP_N + e] : 0.0;
+  }
+  __syncthreads();
+  for (int i = BP_WROWS - 2; i >= 0; --i) {
+    if (tid < BP_D * BP_D) {
+      const int d = tid / BP_D, e = tid - d * BP_D;
+      double z = (e < BP_N) ? W[i][d * BP_N + e] : 0.0;
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) z += Z[cur][d][rr] * P[rr][e];
+      Z[cur ^ 1][d][e] = z;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  // 5. Lbar[rr][cc] = d lp / d L[rr][cc] -> (gA, gH) with the accumulation rule of the reverse sweep, input u = e_cc,
+  // output cotangent = column cc of Lbar (packed coordinates -> full symmetric convention: halve off-diagonals)
+  if (tid == 0) {
+    double gA[BP_N * BP_N], gH[BP_N * BP_S], rb[BP_E], cb[BP_P];
+#pragma unroll
+    for (int i = 0; i < BP_N * BP_N; ++i) gA[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
+    for (int cc = 0; cc < BP_D; ++cc) {
+      double umu[BP_N], uS[BP_S], zmu[BP_N], zS[BP_S];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { umu[i] = (cc == i) ? 1.0 : 0.0; zmu[i] = Z[cur][i][cc]; }
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+        for (int j = i; j < BP_N; ++j) {
+          const int q = bp_sidx(i, j);
+          uS[q] = (cc == BP_N + q) ? 1.0 : 0.0;
+          zS[q] = (i == j) ? Z[cur][BP_N + q][cc] : 0.5 * Z[cur][BP_N + q][cc];
+        }
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+        for (int j = 0; j < BP_N; ++j)
+          if (BP_ANZ(i, j)) {
+            double s2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < BP_N; ++q) s2 += uS[bp_sidx(i, q)] * zS[bp_sidx(q, j)];
+            gA[i * BP_N + j] += umu[i] * zmu[j] + 2.0 * s2;
+          }
+#pragma unroll
+      for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q)
+          if (BP_HNZ(l, q)) gH[l * BP_S + q] += umu[l] * zS[q];
+    }
+    bp_assemble_vjp(gA, gH, rb);
+    bp_rates_vjp(th, xk, rb, cb);
+    double* p0 = a.part + (size_t)c * a.ntiles * BP_NPART;
+#pragma unroll
+    for (int k = 0; k < BP_P; ++k) p0[1 + k] += cb[k];
+  }
+}
+#endif  // W path
 
 #if BP_KIND != 2
 // ---- fused per-(chain, observation) kernel of the multitype templates ---------------------------
@@ -760,6 +1035,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
     if (!fin) status |= BP_ST_RATE_NONFINITE;
     bp_assemble(r, A, H);
     a1 = bp_norm1(A);
+    if (a.wmode && bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;   // this chain belongs to bp_fusedw / bp_wpost
   }
 #endif
   const int k0 = blockIdx.x * a.tile;

@@ -91,6 +91,11 @@ int model_load(bpc_model* m, int device, Loaded** out) {
     BPC_CUDA(cudaKernelSetAttributeForDevice(L.obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.obs_smem, device));
     if (cudaLibraryGetKernel(&L.grouped, L.lib, "bp_grouped") != cudaSuccess) { L.grouped = nullptr; cudaGetLastError(); }
     BPC_CUDA(cudaLibraryGetKernel(&L.moments, L.lib, "bp_moments"));
+    if (!m->spec.xdep) {
+      BPC_CUDA(cudaLibraryGetKernel(&L.fusedw, L.lib, "bp_fusedw"));
+      BPC_CUDA(cudaLibraryGetKernel(&L.wpost, L.lib, "bp_wpost"));
+      BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->spec.w_smem, device));
+    }
   }
   auto ins = m->loaded.emplace(device, L);
   *out = &ins.first->second;
@@ -332,6 +337,7 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
   if ((rc = up(dd->perm, hp.data(), hp.size() * 4))) return rc;
   // groups = runs of equal (level, duration) in the sorted order
   dd->grouped = false;
+  dd->wmode = false;
   if (!simple && N > 0) {
     std::vector<int> gs;
     std::vector<double> gtv;
@@ -357,6 +363,8 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
       dd->group_threads = N <= 2048 ? 32 : (N <= 8192 ? 64 : 128);
     }
   }
+  // W path (bp_fusedw + bp_wpost): rates independent of per-observation variables, ungrouped data, n <= 3
+  dd->wmode = !simple && N > 0 && !dd->grouped && !s.xdep && n <= 3 && !std::getenv("BPC_NO_WPATH");
   BPC_CUDA(cudaStreamCreateWithFlags(&dd->stream, cudaStreamNonBlocking));
   *out = dd.release();
   return BPC_OK;
@@ -384,7 +392,7 @@ static void choose_tiling(bpc_data* d, int nchains) {
   const int T = d->model->spec.threads;
   const long long total = (long long)d->N * nchains;
   long long per_thread = total / ((long long)148 * 8 * T);
-  long long cap = 8;
+  long long cap = d->wmode ? 32 : 8;
   if (const char* ev = std::getenv("BPC_OBS_PER_THREAD")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 1024) cap = v; }
   per_thread = std::max(1LL, std::min(cap, per_thread));
   d->tile = (int)(T * per_thread);
@@ -403,6 +411,11 @@ static int ensure_workspace(bpc_data* d, int nchains) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
       if ((rc = d->ring.alloc((size_t)nchains * s.mslot * D * d->ngroups * n * 8))) return rc;
     }
+    if (d->wmode) {
+      const int n = s.ntypes, D = n + n * (n + 1) / 2;
+      const size_t wfrag = (size_t)((s.mcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64;
+      if ((rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
+    }
     d->ws_chains = nchains;
   }
   return BPC_OK;
@@ -418,6 +431,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   const double* theta; const double* z0; const double* xo; const double* t; const double* xv;
   double* part; int* status; double* loglik; const int* perm;
   int nobs, npad, tile, ntiles, nchains;
+  double* wpart; int wmode;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -438,7 +452,8 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   }
   {
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
-              part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains};
+              part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains,
+              (double*)d->wpart.p, d->wmode ? 1 : 0};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -459,6 +474,13 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       void* gargs[] = {(void*)&ga};
       BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
     } else {
+      if (d->wmode) {
+        // chains whose series need one sub-step: W accumulation on the fp64 tensor path + one per-chain matrix polynomial;
+        // bp_fused (below) only works on the chains that need sub-steps
+        BPC_CUDA(cudaLaunchKernel((const void*)L->fusedw, dim3(d->ntiles, nchains), dim3(s.threads), args, s.w_smem, st));
+        BPC_CUDA(cudaLaunchKernel((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
+        g_launches += 2;
+      }
       BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, nchains), dim3(s.threads), args, L->obs_smem, st));
     }
     if (d->timing) {
@@ -537,7 +559,7 @@ int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, dou
   }
   {
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
-              nullptr, status_dev, (double*)ll.p, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains};
+              nullptr, status_dev, (double*)ll.p, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains, nullptr, 0};
     void* args[] = {(void*)&a};
     BPC_CUDA(cudaLaunchKernel((const void*)L->loglik, dim3((d->N + s.threads - 1) / s.threads, nchains), dim3(s.threads), args, 0, st));
   }
@@ -574,7 +596,7 @@ int bpc_moments(bpc_model* m, bpc_data* d, const double* upars, int nchains, dou
   }
   {
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
-              nullptr, status_dev, (double*)out.p, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains};
+              nullptr, status_dev, (double*)out.p, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains, nullptr, 0};
     void* args[] = {(void*)&a};
     BPC_CUDA(cudaLaunchKernel((const void*)L->moments, dim3((d->N + s.threads - 1) / s.threads, nchains), dim3(s.threads), args, 0, st));
   }
@@ -633,8 +655,10 @@ int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains,
   const ModelSpec& s = m->spec;
   const FlopModel f = flop_model(s);
   for (int c = 0; c < nchains; ++c)
+    // (a W-path chain that fell back to the ring kernel is counted with the W-path constants: a lower bound)
     flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N
-                                                   : apps[c] * (f.per_app_fwd + f.per_app_bwd) + (d->grouped ? f.per_obs_grouped : f.per_obs) * d->N;
+                         : d->wmode              ? apps[c] * (f.per_app_fwd + f.per_app_w) + f.per_obs_w * d->N
+                                                 : apps[c] * (f.per_app_fwd + f.per_app_bwd) + (d->grouped ? f.per_obs_grouped : f.per_obs) * d->N;
   return BPC_OK;
 }
 

@@ -38,12 +38,12 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr;
   size_t obs_smem = 0, grouped_smem = 0;
 };
 
 // algorithmic flop constants of the shipped kernels (SURVEY.md §8(d) convention: FMA = 2, div/sqrt/exp/log = 1)
-struct FlopModel { double per_app_fwd, per_app_bwd, per_obs, per_obs_grouped; };
+struct FlopModel { double per_app_fwd, per_app_bwd, per_obs, per_obs_grouped, per_app_w, per_obs_w; };
 FlopModel flop_model(const ModelSpec& s);
 
 }  // namespace bpc
@@ -61,6 +61,8 @@ struct bpc_data {
   int N = 0, npad = 0, ngroups = 0;
   bool grouped = false;
   bpc::DevBuf z0, xo, t, xv, perm;
+  bpc::DevBuf wpart;   // W path: per-CTA partial sums of the W_j matrices
+  bool wmode = false;
   bpc::DevBuf gstart, gt, gx, ring;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;
   // workspace sized for ws_chains chains

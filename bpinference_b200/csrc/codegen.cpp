@@ -170,6 +170,16 @@ std::string generate_cuda(ModelSpec& m) {
   s += buf;
   std::snprintf(buf, sizeof buf, "#define BP_AMASK 0x%llxull\n#define BP_HMASK 0x%llxull\n", amask, hmask);
   s += buf;
+  {
+    // W path (bp_fusedw): staging area per CTA and the CTAs per SM it allows
+    const int D = n + S, wrt = (m.mcap + 1 + 7) / 8, wct = (D * n + 7) / 8;
+    m.w_smem = (size_t)(m.threads / 32) * (wrt * 8 + wct * 8) * 36 * 8;
+    m.w_post_threads = std::max(128, ((D * D + 31) / 32) * 32);
+    int wmin = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (m.w_smem + 1024)));
+    if (const char* ev = std::getenv("BPC_WMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 8) wmin = v; }
+    std::snprintf(buf, sizeof buf, "#define BP_WMINBLOCKS %d\n#define BP_WPOST_THREADS %d\n", wmin, m.w_post_threads);
+    s += buf;
+  }
   s += "#ifdef BP_HOSTSIM\n#define BP_HD inline\n#define BP_GLOBAL_CONST static const\n#else\n"
        "#define BP_HD __device__ __forceinline__\n#define BP_GLOBAL_CONST __constant__ const\ntypedef double real;\n#endif\n";
   // Taylor tables

@@ -18,6 +18,8 @@ FlopModel flop_model(const ModelSpec& sp) {
     f.per_app_fwd = f.per_app_bwd = 0.0;
     f.per_obs = 70.0;
     f.per_obs_grouped = 70.0;
+    f.per_app_w = 0.0;
+    f.per_obs_w = 70.0;
     return f;
   }
   auto sidx = [n](int i, int j) { if (i > j) std::swap(i, j); return i * n - i * (i - 1) / 2 + (j - i); };
@@ -72,6 +74,10 @@ FlopModel flop_model(const ModelSpec& sp) {
   f.per_obs = 3 + D + score;
   // grouped path: contraction y = sum_l z0_l y^(l) (D (2n - 1)) and cotangent accumulation (2 n D) instead of the plan
   f.per_obs_grouped = score + D * (2 * n - 1) + 2 * n * D;
+  // W path: per series term one row of the W update (2 D n); per observation the plan, the staged coefficients c_j (2 per
+  // row), the packed-coordinate cotangent (S - n doublings) and the outer product b z0^T (D n)
+  f.per_app_w = 2.0 * D * n;
+  f.per_obs_w = 2 + score + 2.0 * (sp.mcap + 1) + (S - n) + D * n;
   return f;
 }
 

@@ -124,3 +124,31 @@ def test_grouped_status_and_large_norm():
     d0["init_pop"] = np.zeros_like(d0["init_pop"])
     l0, g0, s0 = eng.log_prob_grad(eng.data(d0, grouping=2), cfg["upars"])
     assert (s0 & 1).all() and np.isneginf(l0).all() and (g0 == 0).all()
+
+
+def test_w_path_and_ring_fallback_in_one_call():
+    """per-observation data with chain-level rates: chains whose series fit one sub-step take the W path (tensor-core
+    accumulation + per-chain matrix polynomial), chains with large ||tL|| fall back to the ring kernel — in the same call."""
+    cfg = syn.make_config("cfg5U", chains=10, nobs=1500)
+    eng, om = _pair(cfg)
+    u = cfg["upars"].copy()
+    u[::2] += 2.2                      # every other chain: rates ~ 9x larger -> 2 ||A|| t_max > theta_cap -> sub-steps
+    d = eng.data(cfg["data"], grouping=1)
+    lp, g, st = eng.log_prob_grad(d, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
+    assert st.tolist() == st_o.tolist()
+    ok = st_o == 0
+    assert ok.sum() >= 5
+    np.testing.assert_allclose(lp[ok], lp_o[ok], rtol=1e-11)
+    np.testing.assert_allclose(g[ok], g_o[ok], rtol=1e-9, atol=1e-10 * np.abs(g_o[ok]).max())
+    # the two paths agree with each other chain by chain as well
+    import os
+    os.environ["BPC_NO_WPATH"] = "1"
+    try:
+        d2 = eng.data(cfg["data"], grouping=1)
+        lp2, g2, st2 = eng.log_prob_grad(d2, u)
+    finally:
+        del os.environ["BPC_NO_WPATH"]
+    assert st2.tolist() == st.tolist()
+    np.testing.assert_allclose(lp[ok], lp2[ok], rtol=1e-12)
+    np.testing.assert_allclose(g[ok], g2[ok], rtol=1e-9, atol=1e-11 * np.abs(g2[ok]).max())
