@@ -393,14 +393,14 @@ struct BpPlan { int s; int m; real h; };
 // sub-steps and series degree for duration t: scaled norm th = 2 ||A||_1 t / s <= BP_THETA_CAP,
 // applications m = 1 + min{ d : th <= bp_th[d] }  (bp_th[d]^d / d! = 2^-55).  `dhint` carries the degree found for
 // the previous observation of this thread: observations are sorted by duration, so the search usually moves by 0 or 1.
-BP_HD bool bp_make_plan(real a1, real t, BpPlan& p, int& dhint) {
+BP_HD bool bp_make_plan(real a1, real t, BpPlan& p, int& dhint, int dcap = BP_MCAP, double theta_cap = BP_THETA_CAP) {
   const real xx = (a1 + a1) * t;
   if (!(xx >= real(0.0)) || !bp_finite(xx)) return false;
   real th = xx;
   p.s = 1;
   p.h = t;
-  if (xx > real(BP_THETA_CAP)) {
-    const real sr = ceil(xx / real(BP_THETA_CAP));
+  if (xx > real(theta_cap)) {
+    const real sr = ceil(xx / real(theta_cap));
     if (sr > real((double)BP_SMAX)) return false;
 #ifdef BP_HOSTSIM
     p.s = (int)bp_val(sr);
@@ -412,7 +412,7 @@ BP_HD bool bp_make_plan(real a1, real t, BpPlan& p, int& dhint) {
   }
   int d = dhint;
   while (d > 1 && !(th > real(bp_th[d - 1]))) --d;
-  while (d < BP_MCAP && th > real(bp_th[d])) ++d;
+  while (d < dcap && th > real(bp_th[d])) ++d;
   dhint = d;
   p.m = d + 1;
   return true;
@@ -735,7 +735,7 @@ struct BpObsArgs {
 // Operands are staged through shared memory ([row][observation], row stride BP_WLD, conflict-free fragment loads).
 // Chains that need sub-steps (2 ||A||_1 t_max > BP_THETA_CAP) are left to bp_fused; the test is a function of the
 // chain's parameters and the longest duration only, so both kernels take the same decision without communicating.
-#define BP_WROWS (BP_MCAP + 1)              // j = 1 .. BP_MCAP + 1
+#define BP_WROWS (BP_WCAP + 1)              // j = 1 .. BP_WCAP + 1: without a term ring the series may be longer than bp_fused's
 #define BP_WCOLS (BP_D * BP_N)             // (d, l) pairs
 #define BP_WRT ((BP_WROWS + 7) / 8)        // 8-row tiles
 #define BP_WCT ((BP_WCOLS + 7) / 8)        // 8-column tiles
@@ -745,7 +745,7 @@ struct BpObsArgs {
 
 BP_HD bool bp_w_path(bool rates_finite, real a1, real tmax) {
   const real xx = (a1 + a1) * tmax;
-  return rates_finite && xx >= real(0.0) && xx <= real(BP_THETA_CAP);
+  return rates_finite && xx >= real(0.0) && xx <= real(BP_WTHETA_CAP);
 }
 
 #if !defined(BP_HOSTSIM) && BP_KIND != 2 && !BP_XDEP
@@ -802,7 +802,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_WMINBLOCKS) bp_fused
       for (int q = 0; q < BP_S; ++q) yS[q] = 0.0;
       t = a.t[k];
       BpPlan p;
-      if (!bp_make_plan(a1, t, p, dhint)) { status |= BP_ST_RATE_NONFINITE; valid = false; }
+      if (!bp_make_plan(a1, t, p, dhint, BP_WCAP, BP_WTHETA_CAP)) { status |= BP_ST_RATE_NONFINITE; valid = false; }
       else {
         m = p.m;
         apps += p.m;
@@ -836,18 +836,21 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_WMINBLOCKS) bp_fused
       }
     }
     __syncwarp();
+    const int mmax = __reduce_max_sync(0xffffffffu, m);   // row tiles above the warp's longest series hold zeros: skip them
     const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
     for (int ob = 0; ob < 8; ++ob) {   // 4 observations per mma
-      double af[BP_WRT], bf[BP_WCT];
-#pragma unroll
-      for (int rt = 0; rt < BP_WRT; ++rt) af[rt] = sT[(rt * 8 + g) * BP_WLD + ob * 4 + tg];
+      double bf[BP_WCT];
 #pragma unroll
       for (int ct = 0; ct < BP_WCT; ++ct) bf[ct] = sB[(ct * 8 + g) * BP_WLD + ob * 4 + tg];
 #pragma unroll
-      for (int rt = 0; rt < BP_WRT; ++rt)
+      for (int rt = 0; rt < BP_WRT; ++rt) {
+        if (rt * 8 < mmax) {
+          const double af = sT[(rt * 8 + g) * BP_WLD + ob * 4 + tg];
 #pragma unroll
-        for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(acc[rt * BP_WCT + ct][0], acc[rt * BP_WCT + ct][1], af[rt], bf[ct]);
+          for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(acc[rt * BP_WCT + ct][0], acc[rt * BP_WCT + ct][1], af, bf[ct]);
+        }
+      }
     }
     __syncwarp();
   }

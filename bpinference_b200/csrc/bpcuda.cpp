@@ -413,7 +413,7 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     }
     if (d->wmode) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
-      const size_t wfrag = (size_t)((s.mcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64;
+      const size_t wfrag = (size_t)((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64;
       if ((rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
     }
     d->ws_chains = nchains;

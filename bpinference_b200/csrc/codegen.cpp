@@ -172,7 +172,7 @@ std::string generate_cuda(ModelSpec& m) {
   s += buf;
   {
     // W path (bp_fusedw): staging area per CTA and the CTAs per SM it allows
-    const int D = n + S, wrt = (m.mcap + 1 + 7) / 8, wct = (D * n + 7) / 8;
+    const int D = n + S, wrt = (m.wcap + 1 + 7) / 8, wct = (D * n + 7) / 8;
     m.w_smem = (size_t)(m.threads / 32) * (wrt * 8 + wct * 8) * 36 * 8;
     m.w_post_threads = std::max(128, ((D * D + 31) / 32) * 32);
     int wmin = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (m.w_smem + 1024)));
@@ -183,12 +183,15 @@ std::string generate_cuda(ModelSpec& m) {
   s += "#ifdef BP_HOSTSIM\n#define BP_HD inline\n#define BP_GLOBAL_CONST static const\n#else\n"
        "#define BP_HD __device__ __forceinline__\n#define BP_GLOBAL_CONST __constant__ const\ntypedef double real;\n#endif\n";
   // Taylor tables
-  s += "BP_GLOBAL_CONST double bp_th[BP_MCAP + 1] = {0.0";
-  for (int d = 1; d <= m.mcap; ++d) s += ", " + lit(taylor_theta(d));
-  s += "};\nBP_GLOBAL_CONST double bp_rk[BP_MCAP + 1] = {";
-  for (int k = 0; k <= m.mcap; ++k) s += (k ? ", " : "") + lit(1.0 / (k + 1));
-  s += "};\nBP_GLOBAL_CONST double bp_kp1[BP_MCAP + 1] = {";
-  for (int k = 0; k <= m.mcap; ++k) s += (k ? ", " : "") + lit((double)(k + 1));
+  // (tables cover the longer series of the W path: BP_WCAP >= BP_MCAP)
+  std::snprintf(buf, sizeof buf, "#define BP_WCAP %d\n#define BP_WTHETA_CAP %s\n", m.wcap, lit(taylor_theta(m.wcap)).c_str());
+  s += buf;
+  s += "BP_GLOBAL_CONST double bp_th[BP_WCAP + 1] = {0.0";
+  for (int d = 1; d <= m.wcap; ++d) s += ", " + lit(taylor_theta(d));
+  s += "};\nBP_GLOBAL_CONST double bp_rk[BP_WCAP + 1] = {";
+  for (int k = 0; k <= m.wcap; ++k) s += (k ? ", " : "") + lit(1.0 / (k + 1));
+  s += "};\nBP_GLOBAL_CONST double bp_kp1[BP_WCAP + 1] = {";
+  for (int k = 0; k <= m.wcap; ++k) s += (k ? ", " : "") + lit((double)(k + 1));
   s += "};\n";
   // prior table
   s += "BP_GLOBAL_CONST int bp_prior_id[BP_P] = {";

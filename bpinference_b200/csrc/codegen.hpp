@@ -28,6 +28,7 @@ struct ModelSpec {
   bool xdep = false;  // some rate reads x[k]
   int threads = 128;  // CTA size of the per-observation kernels
   int mcap = 23;      // the series has at most mcap + 1 applications of L per sub-step
+  int wcap = 31;      // W path: at most wcap + 1 applications of L (no ring, so longer single-step series are affordable)
   int mslot = 12;     // Taylor terms kept per thread in shared memory
   int minblocks = 1;  // CTAs per SM the shared-memory footprint allows
   double theta_cap = 0;

@@ -77,7 +77,7 @@ FlopModel flop_model(const ModelSpec& sp) {
   // W path: per series term one row of the W update (2 D n); per observation the plan, the staged coefficients c_j (2 per
   // row), the packed-coordinate cotangent (S - n doublings) and the outer product b z0^T (D n)
   f.per_app_w = 2.0 * D * n;
-  f.per_obs_w = 2 + score + 2.0 * (sp.mcap + 1) + (S - n) + D * n;
+  f.per_obs_w = 2 + score + 2.0 * (sp.wcap + 1) + (S - n) + D * n;
   return f;
 }
 
