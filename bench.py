@@ -271,8 +271,9 @@ def main():
         except Exception:
             peaks = {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        kernel_name, ntiles, scratch_bytes = data.path(chains)
         obs_bytes = N * 8 * ((2 * cfg["data"].get("ntypes", 1)) + 1 + (cfg["ndep"] or 0))
-        alg_bytes = obs_bytes + chains * (2 * dim + 1) * 8 + chains * data_ntiles(chains, N, eng) * (cfg["nparams"] + 3) * 8
+        alg_bytes = obs_bytes + chains * (2 * dim + 1) * 8 + scratch_bytes
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -282,7 +283,7 @@ def main():
                                                "re-read by every chain of a step and is L2-resident by design",
                        "rejected_chains": bad},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "kernel": "bp_onetype" if cfg["kind"] == "simple_bd" else "bp_fused",
+                         "traffic": None, "kernel": kernel_name, "ctas_per_chain": ntiles,
                          "kernel_ms": k_avg_ms, "flops_per_launch": flops_launch, "flops_per_eval": flops_launch / (chains * N),
                          "peak_source": "DFMA loop measured in this run (bpc_fp64_peak): MEASURED_PEAKS.json has no FP64 figure; "
                                         "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
@@ -303,12 +304,6 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def data_ntiles(chains, N, eng):
-    T = {1: 256, 2: 192, 3: 128, 4: 64, 5: 32}[eng.ntypes] if eng.kind != 2 else 256
-    per_thread = max(1, min(8, (N * chains) // (148 * 8 * T)))
-    return max(1, -(-N // (T * per_thread)))
 
 
 if __name__ == "__main__":

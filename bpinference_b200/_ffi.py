@@ -68,6 +68,7 @@ SYMBOLS = {
     "bpc_data_free": (None, [_vp]),
     "bpc_data_ngroups": (C.c_int, [_vp]),
     "bpc_data_is_grouped": (C.c_int, [_vp]),
+    "bpc_data_path": (C.c_int, [_vp, C.c_int, _ip, _ip, C.POINTER(C.c_ulonglong)]),
     "bpc_log_prob": (C.c_int, [_vp, _vp, _dp, C.c_int, C.c_int, _dp, _dp, _ip]),
     "bpc_log_prob_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "bpc_log_lik": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp]),

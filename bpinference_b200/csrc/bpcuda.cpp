@@ -502,6 +502,25 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
 
 extern "C" {
 
+int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned long long* scratch_bytes) {
+  if (!d || !path || !ntiles || nchains < 1) return fail(BPC_E_INVALID, "bad argument");
+  const ModelSpec& s = d->model->spec;
+  const int keep = d->ws_chains;
+  d->ws_chains = -1;           // tiling only; no allocation
+  choose_tiling(d, nchains);
+  d->ws_chains = -1;
+  (void)keep;
+  *path = s.kind == BPC_SIMPLE_BD ? 3 : (d->grouped ? 1 : (d->wmode ? 2 : 0));
+  *ntiles = d->ntiles;
+  if (scratch_bytes) {
+    const int n = s.ntypes, D = n + n * (n + 1) / 2;
+    unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
+    if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
+    *scratch_bytes = b;
+  }
+  return BPC_OK;
+}
+
 int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nchains, int jacobian, double* lp_dev,
                      double* grad_dev, int* status_dev, void* stream) {
   if (!m || !d || !upars_dev || !lp_dev || !status_dev) return fail(BPC_E_INVALID, "null argument");

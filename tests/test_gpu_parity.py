@@ -152,3 +152,47 @@ def test_w_path_and_ring_fallback_in_one_call():
     assert st2.tolist() == st.tolist()
     np.testing.assert_allclose(lp[ok], lp2[ok], rtol=1e-12)
     np.testing.assert_allclose(g[ok], g2[ok], rtol=1e-9, atol=1e-11 * np.abs(g2[ok]).max())
+
+
+@pytest.mark.parametrize("n", [4, 5])
+def test_four_and_five_type_models(n):
+    """ntypes = 4, 5 (the oracle's and the kernels' upper range): ring kernel, grouped kernel, moments and log_lik."""
+    rng = np.random.default_rng(3)
+    E = 3 * n
+    e_mat = np.zeros((E, n))
+    p_vec = np.zeros(E, dtype=np.int64)
+    for i in range(n):
+        e_mat[3 * i, i] = 2.0
+        e_mat[3 * i + 1, (i + 1) % n] = 1.0
+        e_mat[3 * i + 1, i] = 1.0 if i % 2 else 0.0     # some asymmetric division events
+        p_vec[3 * i: 3 * i + 3] = i + 1
+    theta = rng.uniform(0.03, 0.3, size=E)
+    N = 240
+    z0 = np.rint(rng.uniform(300, 3000, size=(N, n)))
+    tu = np.array([0.7, 1.5, 3.0])
+    tidx = rng.integers(1, 4, size=N).astype(np.int32)
+    mu, S = syn.gaussian_moments(e_mat, p_vec, theta, z0, tu[tidx - 1])
+    data = dict(ntypes=n, nevents=E, ndatapts=N, ntimes_unique=3, ndep_levels=1, ndep=1, nparams=E, e_mat=e_mat, p_vec=p_vec,
+                pop_vec=syn._draw(rng, mu, S), init_pop=z0, times=tu, times_idx=tidx, function_var=np.zeros((1, 1)),
+                var_idx=np.ones(N, dtype=np.int32))
+    priors = [dict(name="normal", params=[0.0, 0.25], bounds=[0.0, 5.0]) for _ in range(E)]
+    cfg = dict(kind="multitype", e_mat=e_mat, p_vec=p_vec, func_deps=["c[%d]" % (k + 1) for k in range(E)], nparams=E, ndep=0, priors=priors)
+    eng, om = _pair(cfg)
+    u = syn.unconstrain(theta, priors)[None, :] + 0.1 * rng.standard_normal((5, E))
+    lp_o, g_o, st_o = bo.log_prob(om, data, u)
+    assert (st_o == 0).all()
+    for grouping in (1, 2):
+        lp, g, st = eng.log_prob_grad(eng.data(data, grouping=grouping), u)
+        assert (st == 0).all()
+        np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
+        np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+    mu_d, sig_d = eng.moments(data, u[:1])
+    th0 = eng.constrain_pars(u[0])
+    mu_h, S_h = syn.gaussian_moments(e_mat, p_vec, th0, z0, tu[tidx - 1], substeps=16, terms=30)
+    np.testing.assert_allclose(mu_d[0], mu_h, rtol=1e-10)
+    np.testing.assert_allclose(sig_d[0], S_h, rtol=1e-8, atol=1e-8 * np.abs(S_h).max())
+    ll = eng.log_lik(data, u)
+    lp_nj, _, _ = bo.log_prob(om, data, u, jacobian=False)
+    th, *_ = bo.constrain(om, u)
+    prior = sum(bo.prior_logpdf(pr["name"], pr["params"], th[:, k])[0] for k, pr in enumerate(om.priors))
+    np.testing.assert_allclose(ll.sum(axis=1) + 0.5 * n * N * np.log(2 * np.pi), lp_nj - prior, rtol=1e-11)
