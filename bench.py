@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--nobs", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline / reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the short NUTS run that reports ESS/s (rank 0, N = 1 only)")
     return ap.parse_args()
 
 
@@ -140,6 +141,28 @@ def cpu_port_rate(cfg, seconds, nthreads=0):
         bo.log_prob(om, sub(nobs), u, grouped=False if cfg["name"] in ("cfg5U", "cfg5K") else None, nthreads=cores)
     dt = time.perf_counter() - t0
     return chains * nobs * reps / dt, cores, "%d chains x first %d of %d observations x %d passes, %d OpenMP threads, %.1f s" % (chains, nobs, N, reps, cores, dt)
+
+
+def sampling_report(bp, syn):
+    """the second half of BASELINE.json's metric: ESS/s of the device-resident NUTS sampler on the two-type example
+    (BASELINE.json configs[1]: examples/two_type.R shape, 250 observations, 1024 parallel chains; adapt_delta 0.8 as in the example)."""
+    import subprocess as sp
+    cfg = syn.make_config("cfg2", seed=1, chains=1024)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"])
+    d = eng.data(cfg["data"])
+    t0 = time.perf_counter()
+    fit = eng.sampling(d, chains=1024, iter=300, warmup=150, control=dict(adapt_delta=0.8, max_treedepth=10), seed=1)
+    dt = time.perf_counter() - t0
+    ess = fit.ess_bulk()
+    try:
+        have_rstan = sp.run(["Rscript", "-e", "library(rstan)"], capture_output=True, timeout=60).returncode == 0
+    except Exception:
+        have_rstan = False
+    return {"workload": "cfg2: two-type model, 250 observations, 1024 chains x 300 iterations (150 warm-up), NUTS, adapt_delta 0.8",
+            "seconds": dt, "min_ess_per_s": float(ess.min() / dt), "min_ess": float(ess.min()), "leapfrogs_per_s": fit.info["leapfrogs"] / dt,
+            "leapfrogs": fit.info["leapfrogs"], "passes": fit.info["passes"], "max_rhat": float(fit.rhat.max()),
+            "divergent": int(fit.divergent__.sum()), "rstan": "installed" if have_rstan else "rstan: not installed"}
 
 
 def run_reference(args, rank):
@@ -295,6 +318,8 @@ def main():
                             "data handle, as the data stays inside the stanfit in rstan::log_prob"},
             "gpu_launches": launches, "clocks": clk,
         }
+        if not args.no_sampling and world == 1:
+            out["sampling"] = sampling_report(bp, syn)
         if not args.no_cpu_baseline:
             v, cores, sample = cpu_port_rate(cfg, args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
