@@ -878,12 +878,107 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_WMINBLOCKS) bp_fused
   if (status) atomicOr(a.status + c, status);
 }
 
+#endif  // W path
+
+#if !defined(BP_HOSTSIM) && BP_KIND != 2
+// ---- cooperative (whole CTA) pieces of the per-chain matrix polynomial, shared by bp_wpost and bp_grouped ----------
+// column cc of L in packed coordinates = L applied to the packed unit vector e_cc; Lm[r * BP_D + cc]
+__device__ __forceinline__ void bp_coop_build_L(const double (&A)[BP_N * BP_N], const double (&H)[BP_N * BP_S], double* Lm) {
+  for (int cc = threadIdx.x; cc < BP_D; cc += blockDim.x) {
+    double umu[BP_N], uS[BP_S], omu[BP_N], oS[BP_S];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) umu[i] = (cc == i) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) uS[q] = (cc == BP_N + q) ? 1.0 : 0.0;
+    bp_L_apply(A, H, umu, uS, omu, oS);
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) Lm[i * BP_D + cc] = omu[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) Lm[(BP_N + q) * BP_D + cc] = oS[q];
+  }
+}
+
+// Lbar = sum_i Y_i P^i with Y_i = W_(i+1) + P Y_(i+1), P = L^T.  W: M rows of D x n ([d * n + l]) in shared memory
+// (overwritten by Y), Lm: [D][D], Z: 2 * D * D scratch.  All threads of the CTA must call; returns the index (0/1) of the
+// Z buffer that holds Lbar[r * D + c] = d lp / d L[r][c].
+__device__ __forceinline__ int bp_coop_lbar(double* W, int M, const double* Lm, double* Z) {
+  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, MAXO = (DD + 31) / 32;
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int i = M - 2; i >= 0; --i) {
+    double tmp[MAXO];
+    int cnt = 0;
+    for (int o = tid; o < DN; o += T, ++cnt) {
+      const int d = o / BP_N, l = o - d * BP_N;
+      double y = W[i * DN + o];
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) y += Lm[rr * BP_D + d] * W[(i + 1) * DN + rr * BP_N + l];
+      tmp[cnt] = y;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int o = tid; o < DN; o += T, ++cnt) W[i * DN + o] = tmp[cnt];
+    __syncthreads();
+  }
+  int cur = 0;
+  for (int o = tid; o < DD; o += T) {
+    const int d = o / BP_D, e = o - d * BP_D;
+    Z[o] = (e < BP_N && M > 0) ? W[(M - 1) * DN + d * BP_N + e] : 0.0;
+  }
+  __syncthreads();
+  for (int i = M - 2; i >= 0; --i) {
+    for (int o = tid; o < DD; o += T) {
+      const int d = o / BP_D, e = o - d * BP_D;
+      double z = (e < BP_N) ? W[i * DN + d * BP_N + e] : 0.0;
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) z += Z[cur * DD + d * BP_D + rr] * Lm[e * BP_D + rr];
+      Z[(cur ^ 1) * DD + o] = z;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// Lbar (packed coordinates) -> (gA, gH) with the accumulation rule of the reverse sweep: input u = e_cc, output
+// cotangent = column cc of Lbar converted to the full symmetric convention (off-diagonals halved).  One thread.
+__device__ __forceinline__ void bp_lbar_to_grad(const double* Zc, double (&gA)[BP_N * BP_N], double (&gH)[BP_N * BP_S]) {
+  for (int cc = 0; cc < BP_D; ++cc) {
+    double umu[BP_N], uS[BP_S], zmu[BP_N], zS[BP_S];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) { umu[i] = (cc == i) ? 1.0 : 0.0; zmu[i] = Zc[i * BP_D + cc]; }
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+      for (int j = i; j < BP_N; ++j) {
+        const int q = bp_sidx(i, j);
+        uS[q] = (cc == BP_N + q) ? 1.0 : 0.0;
+        zS[q] = (i == j) ? Zc[(BP_N + q) * BP_D + cc] : 0.5 * Zc[(BP_N + q) * BP_D + cc];
+      }
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+      for (int j = 0; j < BP_N; ++j)
+        if (BP_ANZ(i, j)) {
+          double s2 = 0.0;
+#pragma unroll
+          for (int q = 0; q < BP_N; ++q) s2 += uS[bp_sidx(i, q)] * zS[bp_sidx(q, j)];
+          gA[i * BP_N + j] += umu[i] * zmu[j] + 2.0 * s2;
+        }
+#pragma unroll
+    for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q)
+        if (BP_HNZ(l, q)) gH[l * BP_S + q] += umu[l] * zS[q];
+  }
+}
+
 // per chain: W_j summed over tiles -> Lbar -> (gA, gH) -> Theta-bar, added to the chain's first tile partial
+#if !BP_XDEP
 extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArgs a) {
   const int c = blockIdx.x, tid = threadIdx.x;
-  __shared__ double W[BP_WROWS][BP_WCOLS];      // W_(j+1); then Y_j in place
-  __shared__ double P[BP_D][BP_D];              // L^T in packed coordinates
-  __shared__ double Z[2][BP_D][BP_D];
+  __shared__ double W[BP_WROWS * BP_WCOLS];   // W_(j+1) as [j][d * n + l]; then Y_j in place
+  __shared__ double Lm[BP_D * BP_D];
+  __shared__ double Z[2 * BP_D * BP_D];
   double th[BP_DIM];
 #pragma unroll
   for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
@@ -897,61 +992,17 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
   bp_assemble(r, A, H);
   const double a1 = bp_norm1(A);
   if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
-  // 1. sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
+  // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
   for (int i = tid; i < BP_WFRAG; i += blockDim.x) {
     double sacc = 0.0;
     for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * BP_WFRAG + i];
     const int tile = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = (tile / BP_WCT) * 8 + (ln >> 2), col = (tile % BP_WCT) * 8 + (ln & 3) * 2 + e;
-    if (row < BP_WROWS && col < BP_WCOLS) W[row][col] = sacc;
+    if (row < BP_WROWS && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
   }
-  // 2. P = L^T: column cc of L is L applied to the packed unit vector e_cc
-  if (tid < BP_D) {
-    double umu[BP_N], uS[BP_S], omu[BP_N], oS[BP_S];
-#pragma unroll
-    for (int i = 0; i < BP_N; ++i) umu[i] = (tid == i) ? 1.0 : 0.0;
-#pragma unroll
-    for (int q = 0; q < BP_S; ++q) uS[q] = (tid == BP_N + q) ? 1.0 : 0.0;
-    bp_L_apply(A, H, umu, uS, omu, oS);
-#pragma unroll
-    for (int i = 0; i < BP_N; ++i) P[tid][i] = omu[i];
-#pragma unroll
-    for (int q = 0; q < BP_S; ++q) P[tid][BP_N + q] = oS[q];
-  }
+  bp_coop_build_L(A, H, Lm);
   __syncthreads();
-  // 3. Y_i = W_(i+1) + P Y_(i+1), i descending (in place in W: row i holds Y_i, columns (d, l))
-  for (int i = BP_WROWS - 2; i >= 0; --i) {
-    double y = 0.0;
-    if (tid < BP_WCOLS) {
-      const int d = tid / BP_N, l = tid - d * BP_N;
-      y = W[i][tid];
-#pragma unroll
-      for (int rr = 0; rr < BP_D; ++rr) y += P[d][rr] * W[i + 1][rr * BP_N + l];
-    }
-    __syncthreads();
-    if (tid < BP_WCOLS) W[i][tid] = y;
-    __syncthreads();
-  }
-  // 4. Lbar = sum_i Y_i P^i by Horner on the right; Y_i is D x n (zero beyond the first n columns)
-  int cur = 0;
-  if (tid < BP_D * BP_D) {
-    const int d = tid / BP_D, e = tid - d * BP_D;
-    Z[0][d][e] = (e < BP_N) ? W[BP_WROWS - 1][d * BP_N + e] : 0.0;
-  }
-  __syncthreads();
-  for (int i = BP_WROWS - 2; i >= 0; --i) {
-    if (tid < BP_D * BP_D) {
-      const int d = tid / BP_D, e = tid - d * BP_D;
-      double z = (e < BP_N) ? W[i][d * BP_N + e] : 0.0;
-#pragma unroll
-      for (int rr = 0; rr < BP_D; ++rr) z += Z[cur][d][rr] * P[rr][e];
-      Z[cur ^ 1][d][e] = z;
-    }
-    __syncthreads();
-    cur ^= 1;
-  }
-  // 5. Lbar[rr][cc] = d lp / d L[rr][cc] -> (gA, gH) with the accumulation rule of the reverse sweep, input u = e_cc,
-  // output cotangent = column cc of Lbar (packed coordinates -> full symmetric convention: halve off-diagonals)
+  const int cur = bp_coop_lbar(W, BP_WROWS, Lm, Z);
   if (tid == 0) {
     double gA[BP_N * BP_N], gH[BP_N * BP_S], rb[BP_E], cb[BP_P];
 #pragma unroll
@@ -960,34 +1011,7 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
     for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
 #pragma unroll
     for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
-    for (int cc = 0; cc < BP_D; ++cc) {
-      double umu[BP_N], uS[BP_S], zmu[BP_N], zS[BP_S];
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i) { umu[i] = (cc == i) ? 1.0 : 0.0; zmu[i] = Z[cur][i][cc]; }
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i)
-#pragma unroll
-        for (int j = i; j < BP_N; ++j) {
-          const int q = bp_sidx(i, j);
-          uS[q] = (cc == BP_N + q) ? 1.0 : 0.0;
-          zS[q] = (i == j) ? Z[cur][BP_N + q][cc] : 0.5 * Z[cur][BP_N + q][cc];
-        }
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i)
-#pragma unroll
-        for (int j = 0; j < BP_N; ++j)
-          if (BP_ANZ(i, j)) {
-            double s2 = 0.0;
-#pragma unroll
-            for (int q = 0; q < BP_N; ++q) s2 += uS[bp_sidx(i, q)] * zS[bp_sidx(q, j)];
-            gA[i * BP_N + j] += umu[i] * zmu[j] + 2.0 * s2;
-          }
-#pragma unroll
-      for (int l = 0; l < BP_N; ++l)
-#pragma unroll
-        for (int q = 0; q < BP_S; ++q)
-          if (BP_HNZ(l, q)) gH[l * BP_S + q] += umu[l] * zS[q];
-    }
+    bp_lbar_to_grad(Z + cur * BP_D * BP_D, gA, gH);
     bp_assemble_vjp(gA, gH, rb);
     bp_rates_vjp(th, xk, rb, cb);
     double* p0 = a.part + (size_t)c * a.ntiles * BP_NPART;
@@ -995,7 +1019,8 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
     for (int k = 0; k < BP_P; ++k) p0[1 + k] += cb[k];
   }
 }
-#endif  // W path
+#endif
+#endif
 
 #if BP_KIND != 2
 // ---- fused per-(chain, observation) kernel of the multitype templates ---------------------------
@@ -1098,8 +1123,14 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
 //   phase B : all threads sweep the group's observations: y_k = sum_l z0_kl y^(g,l), score, and accumulate the
 //             cotangents ybar^(g,l) += z0_kl ybar_k (block reduction per group, fixed order)
 //   phase A': thread (g,l) reverses its series with that cotangent (terms in a global, L2-resident ring) -> Theta-bar
-// Observations are sorted so that groups are contiguous (gstart).  Dynamic shared memory:
-// 2 * G*n*BP_D doubles (moments, cotangents) + reduction scratch.
+// When every group of the chain needs a single sub-step (the usual case) phases A and A' are done COOPERATIVELY by
+// the whole CTA as small dense linear algebra per dependent-variable level (all groups of a level share L):
+//   A : Krylov blocks U_j = L^j [e_1 .. e_n] once per level, moments of group g = sum_j c_j(t_g) U_j
+//   A': W_j = sum_g c_j(t_g) Ybar_g, then Lbar = sum_i Y_i P^i exactly as in bp_wpost
+// which replaces two long single-thread recurrences (the latency of a sampler pass on small data) by ~2 m steps of
+// D x n and D x D updates spread over the threads.
+// Observations are sorted so that groups are contiguous (gstart).  Dynamic shared memory: 2 * G*n*BP_D doubles (moments,
+// cotangents), reduction scratch, and for the cooperative path L, U, W, Z and the per-group series lengths.
 struct BpGroupArgs {
   const double* theta;   // [C][BP_DIM]
   const double* z0;      // [BP_N][npad]
@@ -1107,10 +1138,11 @@ struct BpGroupArgs {
   const int* gstart;     // [G + 1]
   const double* gt;      // [G] duration of the group
   const double* gx;      // [BP_KDEP][G] dependent variables of the group's level
+  const int* glev;       // [G] level id of the group, 0 .. nlevels-1
   double* ring;          // [C][BP_MSLOT * BP_D * G * BP_N] series terms of phase A'
   double* part;          // [C][1][BP_NPART]
   int* status;           // [C]
-  int nobs, npad, ngroups, nchains;
+  int nobs, npad, ngroups, nchains, nlevels;
 };
 
 template <int NV>
@@ -1159,6 +1191,58 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   const double sigma = 0.0;
 #endif
   int status = 0, apps = 0;
+  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
+  const int nwarp = T >> 5;
+  double* Lm = red + (size_t)(BP_N * BP_D > BP_NPART ? BP_N * BP_D : BP_NPART) * nwarp;   // [D][D]
+  double* Uk = Lm + DD;                         // [BP_WROWS + 1][D * n]
+  double* Wm = Uk + (size_t)(BP_WROWS + 1) * DN; // [BP_WROWS][D * n]
+  double* Zb = Wm + (size_t)BP_WROWS * DN;       // [2][D][D]
+  int* gm = (int*)(Zb + 2 * DD);                 // [G] series length of each group
+  // cooperative path iff every group has finite rates and fits one sub-step
+  bool okc = true;
+  for (int g = tid; g < G; g += T) {
+    double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1;
+    const bool fin = bp_group_generator(th, a, g, xk, A, H, a1);
+    BpPlan p;
+    int dh = 1;
+    const bool ok = bp_w_path(fin, a1, a.gt[g]) && bp_make_plan(a1, a.gt[g], p, dh, BP_WCAP, BP_WTHETA_CAP);
+    gm[g] = ok ? p.m : 0;
+    okc = okc && ok;
+  }
+  const bool coop = __syncthreads_and(okc) != 0;
+  if (coop) {
+    // ---- phase A, cooperative: per level, Krylov blocks and the groups' moments ----
+    for (int v = 0; v < a.nlevels; ++v) {
+      int gv = 0, mlev = 0;
+      for (int g = G - 1; g >= 0; --g) if (a.glev[g] == v) { gv = g; mlev = gm[g] > mlev ? gm[g] : mlev; }
+      double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1;
+      bp_group_generator(th, a, gv, xk, A, H, a1);
+      __syncthreads();   // previous level's readers of Lm / Uk are done
+      bp_coop_build_L(A, H, Lm);
+      for (int o = tid; o < DN; o += T) { const int d = o / BP_N, l = o - d * BP_N; Uk[o] = (d == l) ? 1.0 : 0.0; }
+      __syncthreads();
+      for (int j = 1; j <= mlev; ++j) {
+        for (int o = tid; o < DN; o += T) {
+          const int d = o / BP_N, l = o - d * BP_N;
+          double u = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) u += Lm[d * BP_D + rr] * Uk[(j - 1) * DN + rr * BP_N + l];
+          Uk[j * DN + o] = u;
+        }
+        __syncthreads();
+      }
+      for (int g = 0; g < G; ++g) {
+        if (a.glev[g] != v) continue;
+        const double tg = a.gt[g];
+        for (int o = tid; o < DN; o += T) {
+          const int d = o / BP_N, l = o - d * BP_N;
+          double y = Uk[o], cj = 1.0;
+          for (int j = 1; j <= gm[g]; ++j) { cj = cj * (tg * bp_rk[j - 1]); y += cj * Uk[j * DN + o]; }
+          ymom[(size_t)(g * BP_N + l) * BP_D + d] = y;
+        }
+      }
+    }
+  } else {
   // ---- phase A: single-ancestor moments of every (group, ancestor type) ----
   for (int sx = tid; sx < GN; sx += T) {
     const int g = sx / BP_N, l = sx - g * BP_N;
@@ -1177,6 +1261,7 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
     for (int i = 0; i < BP_N; ++i) ymom[(size_t)sx * BP_D + i] = ymu[i];
 #pragma unroll
     for (int q = 0; q < BP_S; ++q) ymom[(size_t)sx * BP_D + BP_N + q] = yS[q];
+  }
   }
   __syncthreads();
   // ---- phase B: observations, group by group ----
@@ -1221,6 +1306,45 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   double cb[BP_P];
 #pragma unroll
   for (int k = 0; k < BP_P; ++k) cb[k] = 0.0;
+  if (coop) {
+    for (int v = 0; v < a.nlevels; ++v) {
+      int gv = 0, mlev = 0;
+      for (int g = G - 1; g >= 0; --g) if (a.glev[g] == v) { gv = g; mlev = gm[g] > mlev ? gm[g] : mlev; }
+      double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1;
+      bp_group_generator(th, a, gv, xk, A, H, a1);
+      __syncthreads();
+      bp_coop_build_L(A, H, Lm);
+      // W_(j+1)[d][l] = sum over the level's groups of c_(j+1)(t_g) * (packed-coordinate cotangent of y^(g,l))_d
+      for (int o = tid; o < DN; o += T) {
+        const int d = o / BP_N, l = o - d * BP_N;
+        bool offdiag = d >= BP_N;
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) if (d == BP_N + bp_sidx(i, i)) offdiag = false;
+        for (int j = 0; j < mlev; ++j) Wm[j * DN + o] = 0.0;
+        for (int g = 0; g < G; ++g) {
+          if (a.glev[g] != v) continue;
+          const double tg = a.gt[g];
+          double yb = ybar[(size_t)(g * BP_N + l) * BP_D + d];
+          if (offdiag) yb += yb;
+          double cj = 1.0;
+          for (int j = 0; j < gm[g]; ++j) { cj = cj * (tg * bp_rk[j]); Wm[j * DN + o] += cj * yb; }
+        }
+      }
+      __syncthreads();
+      const int cur = bp_coop_lbar(Wm, mlev, Lm, Zb);
+      if (tid == 0) {
+        double gA[BP_N * BP_N], gH[BP_N * BP_S], rb[BP_E];
+#pragma unroll
+        for (int i = 0; i < BP_N * BP_N; ++i) gA[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
+        bp_lbar_to_grad(Zb + cur * DD, gA, gH);
+        bp_assemble_vjp(gA, gH, rb);
+        bp_rates_vjp(th, xk, rb, cb);
+        for (int g = 0; g < G; ++g) if (a.glev[g] == v) apps += BP_N * gm[g];
+      }
+    }
+  } else {
   BpRingGlobal ring{a.ring + (size_t)c * BP_MSLOT * BP_D * GN};
   for (int sx = tid; sx < GN; sx += T) {
     const int g = sx / BP_N, l = sx - g * BP_N;
@@ -1250,6 +1374,7 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
                       ring, sx, GN, gA, gH);
     bp_assemble_vjp(gA, gH, rb);
     bp_rates_vjp(th, xk, rb, cb);
+  }
   }
   double vals[BP_NPART];
   vals[0] = lp;

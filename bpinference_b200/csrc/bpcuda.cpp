@@ -348,7 +348,7 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
     gs.push_back(N);
     const long long GN = (long long)G * n;
     const int D = n + n * (n + 1) / 2;
-    const size_t smem = (size_t)(2 * GN * D + 4 * std::max(n * D, s.nparams + 3)) * 8;
+    const size_t smem = (size_t)(2 * GN * D + 4 * std::max(n * D, s.nparams + 3) + 3 * D * D + (2 * (s.wcap + 1) + 1) * D * n) * 8 + (size_t)G * 4 + 16;
     const bool fits = GN <= 4096 && smem <= 200 * 1024;
     if (grouping == 2 && !fits) return fail(BPC_E_UNSUPPORTED, "too many (level, duration) groups for the grouped kernel");
     if (fits && (grouping == 2 || (grouping == 0 && GN * 8 <= N))) {
@@ -358,6 +358,16 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
       if ((rc = up(dd->gstart, gs.data(), gs.size() * 4))) return rc;
       if ((rc = up(dd->gt, gtv.data(), gtv.size() * 8))) return rc;
       if ((rc = up(dd->gx, gxv.data(), gxv.size() * 8))) return rc;
+      // compact level ids (groups of one level share the generator)
+      std::vector<int> lev_ids, gl(G);
+      for (int g = 0; g < G; ++g) {
+        int id = -1;
+        for (size_t q = 0; q < lev_ids.size(); ++q) if (lev_ids[q] == glev[g]) id = (int)q;
+        if (id < 0) { id = (int)lev_ids.size(); lev_ids.push_back(glev[g]); }
+        gl[g] = id;
+      }
+      if ((rc = up(dd->glev, gl.data(), gl.size() * 4))) return rc;
+      dd->nlevels = (int)lev_ids.size();
       dd->grouped = true;
       dd->ngroups = G;
       dd->group_threads = N <= 2048 ? 32 : (N <= 8192 ? 64 : 128);
@@ -422,9 +432,9 @@ static int ensure_workspace(bpc_data* d, int nchains) {
 }
 
 struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
-  const double* theta; const double* z0; const double* xo; const int* gstart; const double* gt; const double* gx;
+  const double* theta; const double* z0; const double* xo; const int* gstart; const double* gt; const double* gx; const int* glev;
   double* ring; double* part; int* status;
-  int nobs, npad, ngroups, nchains;
+  int nobs, npad, ngroups, nchains, nlevels;
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
@@ -463,14 +473,21 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
     }
     if (d->grouped) {
       if (!L->grouped) return fail(BPC_E_UNSUPPORTED, "module has no grouped kernel");
-      const int n = s.ntypes, D = n + n * (n + 1) / 2, T = d->group_threads;
-      const size_t smem = (size_t)(2 * d->ngroups * n * D + (T / 32) * std::max(n * D, s.nparams + 3)) * 8;
+      const int n = s.ntypes, D = n + n * (n + 1) / 2;
+      // CTA size: as many threads as keep all chains resident in one wave (the kernel needs ~240 registers per thread),
+      // never more than the observations can use
+      int T = d->group_threads;
+      while (T < 128 && (long long)nchains * 2 <= 148LL * (65536 / (256 * T * 2)) * 2 && d->N > 2 * T) T *= 2;
+      const size_t wrows = s.wcap + 1;
+      const size_t smem = (size_t)(2 * d->ngroups * n * D + (T / 32) * std::max(n * D, s.nparams + 3) + 3 * D * D + (2 * wrows + 1) * D * n) * 8 +
+                          (size_t)d->ngroups * 4 + 16;
       if (smem > L->grouped_smem) {
         BPC_CUDA(cudaKernelSetAttributeForDevice(L->grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, d->device));
         L->grouped_smem = smem;
       }
       GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
-                   (const double*)d->gx.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains};
+                   (const double*)d->gx.p, (const int*)d->glev.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains,
+                   d->nlevels};
       void* gargs[] = {(void*)&ga};
       BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
     } else {

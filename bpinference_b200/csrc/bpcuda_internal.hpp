@@ -63,7 +63,8 @@ struct bpc_data {
   bpc::DevBuf z0, xo, t, xv, perm;
   bpc::DevBuf wpart;   // W path: per-CTA partial sums of the W_j matrices
   bool wmode = false;
-  bpc::DevBuf gstart, gt, gx, ring;   // grouped path: first observation, duration and dependent variables of each group; term ring
+  bpc::DevBuf gstart, gt, gx, glev, ring;
+  int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;
   // workspace sized for ws_chains chains
   int ws_chains = -1, tile = 0, ntiles = 0;
