@@ -196,3 +196,51 @@ def test_four_and_five_type_models(n):
     th, *_ = bo.constrain(om, u)
     prior = sum(bo.prior_logpdf(pr["name"], pr["params"], th[:, k])[0] for k, pr in enumerate(om.priors))
     np.testing.assert_allclose(ll.sum(axis=1) + 0.5 * n * N * np.log(2 * np.pi), lp_nj - prior, rtol=1e-11)
+
+
+def test_full_size_properties_cfg5U():
+    """BASELINE.json's full observation count (100 000 observations, 3-type model; 32 of the 512 chains per GPU to keep the
+    test short): size-independent properties instead of an oracle pass that would take minutes on the CPU —
+    additivity over a split of the observations, invariance under a permutation of the observations, the sum of the
+    per-observation log_lik, a directional finite difference of the gradient, and a sampled oracle comparison."""
+    cfg = syn.make_config("cfg5U", chains=32, nobs=100000)
+    eng, om = _pair(cfg)
+    d = cfg["data"]
+    u = cfg["upars"]
+    N = d["ndatapts"]
+    lp, g, st = eng.log_prob_grad(d, u, adjust_transform=False)
+    assert (st == 0).all() and np.isfinite(lp).all() and np.isfinite(g).all()
+    theta, *_ = bo.constrain(om, u)
+    prior = sum(bo.prior_logpdf(pr["name"], pr["params"], theta[:, k])[0] for k, pr in enumerate(om.priors))
+    dth = theta * (1 - theta / 5.0)                       # d theta / d u of the (0, 5) bound transform
+    pgrad = np.stack([bo.prior_logpdf(pr["name"], pr["params"], theta[:, k])[1] for k, pr in enumerate(om.priors)], axis=1) * dth
+
+    def subset(idx):
+        s = dict(d)
+        s["ndatapts"] = len(idx)
+        for k in ("pop_vec", "init_pop"):
+            s[k] = np.asarray(d[k])[idx]
+        s["var_idx"] = np.asarray(d["var_idx"])[idx]
+        s["times_idx"] = np.asarray(d["times_idx"])[idx]
+        return s
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(N)
+    a, b = perm[: N // 3], perm[N // 3:]
+    la, ga, _ = eng.log_prob_grad(subset(a), u, adjust_transform=False)
+    lb, gb, _ = eng.log_prob_grad(subset(b), u, adjust_transform=False)
+    np.testing.assert_allclose(la + lb - prior, lp, rtol=1e-12)                  # likelihood is a sum over observations
+    np.testing.assert_allclose(ga + gb - pgrad, g, rtol=1e-9, atol=1e-10 * np.abs(g).max())
+    lq, gq, _ = eng.log_prob_grad(subset(perm), u, adjust_transform=False)       # order of the data list is irrelevant
+    np.testing.assert_allclose(lq, lp, rtol=1e-13)
+    np.testing.assert_allclose(gq, g, rtol=1e-10, atol=1e-11 * np.abs(g).max())
+    ll = eng.log_lik(d, u[:4])
+    np.testing.assert_allclose(ll.sum(axis=1) + 0.5 * 3 * N * np.log(2 * np.pi), (lp - prior)[:4], rtol=1e-12)
+    v = rng.standard_normal(u.shape)
+    h = 1e-6
+    fd = (eng.log_prob(d, u + h * v, adjust_transform=False) - eng.log_prob(d, u - h * v, adjust_transform=False)) / (2 * h)
+    np.testing.assert_allclose((g * v).sum(axis=1), fd, rtol=2e-6)
+    idx = np.sort(rng.choice(N, 2000, replace=False))                            # sampled oracle comparison, 2 chains
+    lo, go, so = bo.log_prob(om, subset(idx), u[:2], jacobian=False)
+    ls, gs, ss = eng.log_prob_grad(subset(idx), u[:2], adjust_transform=False)
+    np.testing.assert_allclose(ls, lo, rtol=1e-11)
+    np.testing.assert_allclose(gs, go, rtol=1e-9, atol=1e-10 * np.abs(go).max())
