@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "fused logp+grad (chain x observation) evaluations per second"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one `ncu --set full` capture of the default
+# workload (profiles/r01_ncu_bp_fusedw_cfg5U.txt: 5.857 MB read + 50.744 MB written, the W partial sums spilling out of L2)
+NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 5.857e6 + 50.744e6}
 UNIT = "evals/s"
 DEFAULT_CHAINS = {"cfg5U": 512, "cfg5K": 512, "cfg5G": 512, "cfg2": 1024, "cfg1": 4, "cfg3": 4, "cfg4": 4}
 
@@ -306,7 +309,8 @@ def main():
                                                "re-read by every chain of a step and is L2-resident by design",
                        "rejected_chains": bad},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "kernel": kernel_name, "ctas_per_chain": ntiles,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, chains, N)), "traffic_unit": "bytes per launch (ncu, profiles/)",
+                         "kernel": kernel_name, "ctas_per_chain": ntiles,
                          "kernel_ms": k_avg_ms, "flops_per_launch": flops_launch, "flops_per_eval": flops_launch / (chains * N),
                          "peak_source": "DFMA loop measured in this run (bpc_fp64_peak): MEASURED_PEAKS.json has no FP64 figure; "
                                         "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
