@@ -133,6 +133,7 @@ def test_w_path_and_ring_fallback_in_one_call():
     eng, om = _pair(cfg)
     u = cfg["upars"].copy()
     u[::2] += 2.2                      # every other chain: rates ~ 9x larger -> 2 ||A|| t_max > theta_cap -> sub-steps
+    u[1::4] += 0.75                    # rates ~ 2x larger: 2 ||A|| t_max ~ 3.3, the long (up to 32 terms) single-step series of the W path
     d = eng.data(cfg["data"], grouping=1)
     lp, g, st = eng.log_prob_grad(d, u)
     lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
