@@ -53,3 +53,27 @@ def calculate_moments(e_mat, p_vec, r_vec, z0_vec, tf):
         dat = create_stan_data(mod, z0_vec.reshape(1, -1), z0_vec.reshape(1, -1), [float(tf)])
     mu, sig = eng.moments(dat, r_vec.reshape(1, -1))
     return dict(mu_mat=mu[0, 0].reshape(-1, 1), sigma_mat=sig[0, 0])
+
+
+def template_moments(e_mat, p_vec, r_vec, tf):
+    """the Stan template's own state at duration tf (multitype_template.stan:85-94, 137-140): m_t [n, n] with
+    m_t[l, j] = E[Z_j | one type-l ancestor] and d_t [n, n*n] with d_t[l, j + n*k] = E[Z_j Z_k | one type-l ancestor]
+    (raw second moments, column-major to_matrix layout).  Evaluated on the device: one unit-ancestor observation per type."""
+    e_mat = np.asarray(e_mat, dtype=float)
+    if e_mat.ndim == 1:
+        e_mat = e_mat.reshape(-1, 1)
+    E, n = e_mat.shape
+    from .engine import stan_model
+    from .model import bp_model
+    from .stan_data import create_stan_data
+    mod = bp_model(e_mat, np.asarray(p_vec, dtype=float), ["c[%d]" % (e + 1) for e in range(E)], E, 0)
+    eng = stan_model(mod, [dict(name="normal", params=[0.0, 1.0], bounds=None)] * E)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dat = create_stan_data(mod, np.eye(n), np.eye(n), [float(tf)] * n)
+    mu, sig = eng.moments(dat, np.asarray(r_vec, dtype=float).reshape(1, -1))
+    m_t = mu[0]                                                     # row l: mean vector from one type-l ancestor
+    d_t = np.empty((n, n * n))
+    for l in range(n):
+        d_t[l] = (sig[0, l] + np.outer(m_t[l], m_t[l])).reshape(-1, order="F")
+    return m_t, d_t

@@ -29,6 +29,24 @@ def test_vignette_golden_moments_on_gpu():
     np.testing.assert_allclose(m1["sigma_mat"].ravel(), [438.72398464468], rtol=1e-12)
 
 
+def test_template_state_matches_literal_ode():
+    """the device moments in the template's own layout (m_t, d_t of multitype_template.stan:137-140) against the literal numpy
+    restatement of the template's ODE integrated at 1e-13 (oracle/stan_template_ref.py)."""
+    from oracle import stan_template_ref as ref
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 3):
+        E = 2 * n + 2
+        e_mat = rng.integers(0, 3, size=(E, n)).astype(float)
+        p_vec = rng.integers(1, n + 1, size=E)
+        r = rng.uniform(0.02, 0.6, size=E)
+        t = float(rng.uniform(0.4, 4.0))
+        m_t, d_t = bp.template_moments(e_mat, p_vec, r, t)
+        row = ref.exact(e_mat, p_vec, r, [t])[0]
+        np.testing.assert_allclose(m_t, row[:n * n].reshape((n, n), order="F"), rtol=1e-9, atol=1e-11)
+        ode_d = row[n * n:].reshape((n, n * n), order="F")
+        np.testing.assert_allclose(d_t, ode_d, rtol=1e-8, atol=1e-9 * max(1.0, np.abs(ode_d).max()))
+
+
 def test_one_type_closed_form_equals_multitype_kernel():
     """one_type_template.stan:42-43 against the n = 1 moment kernel (two template families, one answer)."""
     for b, d, t, z0 in [(0.25, 0.10, 1.0, 1000.0), (0.1, 0.3, 4.0, 50.0), (2.0, 1.5, 0.7, 7.0), (4.5, 4.0, 5.0, 3.0)]:
