@@ -717,8 +717,17 @@ struct BpObsArgs {
   double* loglik;        // [C][N] (bp_*_loglik only)
   const int* perm;       // [npad] original index of sorted observation (bp_*_loglik only)
   int nobs, npad, tile, ntiles, nchains;
-  double* wpart;         // [C][ntiles][BP_WFRAG] per-CTA partial sums of the W_j matrices (bp_fusedw / bp_wpost)
-  int wmode;             // 1: chains whose series need a single sub-step are handled by bp_fusedw + bp_wpost
+  double* wpart;         // [C][ntiles][BP_WFRAG | BP_CFRAG] per-CTA partial sums of the W_j matrices (bp_fusedw / bp_fusedc -> bp_wpost)
+  int wmode;             // 1: chains whose series need a single sub-step are handled by bp_fusedw + bp_wpost; 2: by bp_ctable + bp_fusedc + bp_wpost
+  // centred W path (wmode 2): groups of consecutive 32-observation chunks of the sorted table that share a series centre
+  int cgroups, cgpc;     // number of groups; groups per CTA
+  const int* cg_chunk0;  // [cgroups + 1] first chunk of each group
+  const int* cg_idx;     // [cgroups] centre of the group on the fine time grid: tau_g = cg_idx * cdelta
+  const double* cg_tau;  // [cgroups] tau_g
+  const double* cg_hmax; // [cgroups] max |t_k - tau_g| over the group's observations
+  double cdelta;         // fine grid spacing = longest duration / (BP_CGA * BP_CGB)
+  double* ctab_m1;       // [C][BP_CGA + 1][D * n]  single-ancestor moments exp(a * BP_CGB * cdelta * L) [e_1 .. e_n]
+  double* ctab_e2;       // [C][BP_CGB][D * D]      exp(b * cdelta * L)
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -742,6 +751,11 @@ struct BpObsArgs {
 #define BP_WFRAG (BP_WRT * BP_WCT * 64)    // accumulator elements of one warp (fragment layout)
 #define BP_WLD 36                          // leading dimension of the staged operands
 #define BP_WSTAGE ((BP_WRT * 8 + BP_WCT * 8) * BP_WLD)   // doubles per warp
+// centred W path (bp_fusedc, below): short series of BP_CJ terms around a group centre
+#define BP_CJ 8                                 // rows of the short series: j = 0 .. 7
+#define BP_CROWS (BP_WCAP + 1 + BP_CJ)          // powers n = 1 .. BP_WCAP + 1 + (BP_CJ - 1), rounded to the row tile
+#define BP_CRT ((BP_CROWS + 7) / 8)
+#define BP_CFRAG (BP_CRT * BP_WCT * 64)
 
 BP_HD bool bp_w_path(bool rates_finite, real a1, real tmax) {
   const real xx = (a1 + a1) * tmax;
@@ -976,7 +990,7 @@ __device__ __forceinline__ void bp_lbar_to_grad(const double* Zc, double (&gA)[B
 #if !BP_XDEP
 extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArgs a) {
   const int c = blockIdx.x, tid = threadIdx.x;
-  __shared__ double W[BP_WROWS * BP_WCOLS];   // W_(j+1) as [j][d * n + l]; then Y_j in place
+  __shared__ double W[BP_CROWS * BP_WCOLS];   // W_(j+1) as [j][d * n + l]; then Y_j in place (BP_WROWS rows from bp_fusedw, BP_CROWS from bp_fusedc)
   __shared__ double Lm[BP_D * BP_D];
   __shared__ double Z[2 * BP_D * BP_D];
   double th[BP_DIM];
@@ -993,16 +1007,17 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
   const double a1 = bp_norm1(A);
   if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
   // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
-  for (int i = tid; i < BP_WFRAG; i += blockDim.x) {
+  const int frag = a.wmode == 2 ? BP_CFRAG : BP_WFRAG, rows = a.wmode == 2 ? BP_CROWS : BP_WROWS;
+  for (int i = tid; i < frag; i += blockDim.x) {
     double sacc = 0.0;
-    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * BP_WFRAG + i];
+    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * frag + i];
     const int tile = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = (tile / BP_WCT) * 8 + (ln >> 2), col = (tile % BP_WCT) * 8 + (ln & 3) * 2 + e;
-    if (row < BP_WROWS && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
+    if (row < rows && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
   }
   bp_coop_build_L(A, H, Lm);
   __syncthreads();
-  const int cur = bp_coop_lbar(W, BP_WROWS, Lm, Z);
+  const int cur = bp_coop_lbar(W, rows, Lm, Z);
   if (tid == 0) {
     double gA[BP_N * BP_N], gH[BP_N * BP_S], rb[BP_E], cb[BP_P];
 #pragma unroll
@@ -1019,6 +1034,292 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
     for (int k = 0; k < BP_P; ++k) p0[1 + k] += cb[k];
   }
 }
+
+// ---- centred W path: bp_ctable + bp_fusedc -----------------------------------------------------------
+// The observation table is sorted by duration, so the 32 observations of a warp pass -- and a few consecutive
+// passes -- have almost the same duration.  For a GROUP of such passes with centre tau_g (a point of a fine time
+// grid) write t_k = tau_g + h_k.  Then, by the binomial theorem c_n(tau + h) = sum_j c_(n-j)(tau) c_j(h),
+//     y_k = exp(t_k L) y0_k = sum_(j <= J) c_j(h_k) N_j z0_k,      N_j = L^j M(tau_g),   M(tau) = exp(tau L) [e_1 .. e_n]
+// where J is the SHORT series length |h| needs (<= BP_CJ - 1 because |h_k| is a small fraction of the longest
+// duration) instead of the long one t_k needs, and the W matrices of bp_fusedw factor the same way:
+//     W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j,        S^g_j = sum_(k in g) c_j(h_k) b_k z0_k^T      (j = 0 .. J).
+// So per observation: J + 1 terms of a D x n matrix-vector product (N_j from shared memory), the score, and ONE 8-row
+// tile of the S update on the fp64 tensor path; per group: M(tau_g) = E2[b] M1[a] from two small per-chain tables
+// (bp_ctable; tau_g = (a BP_CGB + b) cdelta), the chain N_(j+1) = L N_j, and the Toeplitz product W += C(tau_g) S^g,
+// again as DMMAs.  bp_wpost turns W into the gradient exactly as for bp_fusedw (with BP_CROWS rows).
+#if BP_N <= 3
+#define BP_CNLD (BP_WCOLS + (BP_WCOLS & 1))     // row stride of the staged N_j
+#define BP_CCTAB (BP_CRT * 8 + 16)              // coefficient table c_i(tau_g), index i + 8, zero outside 0 .. m_g
+#define BP_CSLD (BP_WCT * 8 + 4)                // row stride of the staged S^g
+#define BP_CGA 64                               // coarse grid intervals
+#define BP_CGB 64                               // fine points per coarse interval
+#define BP_CPMAX 14                             // longest series of the fine table E2 (durations <= tmax / BP_CGA)
+#define BP_CWARP (BP_CJ * BP_CNLD + BP_CCTAB + (8 + BP_WCT * 8) * BP_WLD)   // doubles of shared memory per warp
+
+// per chain: the two tables M(tau) is assembled from.  One CTA per chain; Krylov blocks U_j = L^j [e_1 .. e_n] and powers
+// P_j = L^j in shared memory, then every table entry is a short dot product with the coefficients c_j(time).
+extern "C" __global__ void __launch_bounds__(128) bp_ctable(BpObsArgs a) {
+  const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
+  __shared__ double Lm[DD];
+  __shared__ double U[(BP_WROWS + 1) * DN];
+  __shared__ double Pw[(BP_CPMAX + 1) * DD];
+  double th[BP_DIM];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+  double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
+#pragma unroll
+  for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+  bp_rates(th, xk, r);
+  bool fin = true;
+#pragma unroll
+  for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+  bp_assemble(r, A, H);
+  const double a1 = bp_norm1(A);
+  const double tmax = a.nobs > 0 ? a.t[0] : 0.0;
+  if (!bp_w_path(fin, a1, tmax)) return;
+  BpPlan p;
+  int dh = 1;
+  bp_make_plan(a1, tmax, p, dh, BP_WCAP, BP_WTHETA_CAP);
+  const int mtop = p.m;
+  const double d1 = a.cdelta * BP_CGB;
+  dh = 1;
+  bp_make_plan(a1, d1, p, dh, BP_CPMAX - 1, BP_WTHETA_CAP);
+  const int mfine = p.m;
+  bp_coop_build_L(A, H, Lm);
+  for (int o = tid; o < DN; o += T) { const int d = o / BP_N, l = o - d * BP_N; U[o] = (d == l) ? 1.0 : 0.0; }
+  for (int o = tid; o < DD; o += T) { const int d = o / BP_D, e = o - d * BP_D; Pw[o] = (d == e) ? 1.0 : 0.0; }
+  __syncthreads();
+  for (int j = 1; j <= mtop; ++j) {
+    for (int o = tid; o < DN; o += T) {
+      const int d = o / BP_N, l = o - d * BP_N;
+      double u = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) u += Lm[d * BP_D + rr] * U[(j - 1) * DN + rr * BP_N + l];
+      U[j * DN + o] = u;
+    }
+    if (j <= mfine)
+      for (int o = tid; o < DD; o += T) {
+        const int d = o / BP_D, e = o - d * BP_D;
+        double u = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < BP_D; ++rr) u += Lm[d * BP_D + rr] * Pw[(j - 1) * DD + rr * BP_D + e];
+        Pw[j * DD + o] = u;
+      }
+    __syncthreads();
+  }
+  double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
+  for (int i = tid; i < (BP_CGA + 1) * DN; i += T) {
+    const int ai = i / DN, o = i - ai * DN;
+    const double ta = ai * d1;
+    BpPlan q;
+    int dq = 1;
+    bp_make_plan(a1, ta, q, dq, BP_WCAP, BP_WTHETA_CAP);
+    double y = U[o], cj = 1.0;
+    for (int j = 1; j <= q.m; ++j) { cj = cj * (ta * bp_rk[j - 1]); y += cj * U[j * DN + o]; }
+    m1[i] = y;
+  }
+  double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
+  for (int i = tid; i < BP_CGB * DD; i += T) {
+    const int bi = i / DD, o = i - bi * DD;
+    const double tb = bi * a.cdelta;
+    BpPlan q;
+    int dq = 1;
+    bp_make_plan(a1, tb, q, dq, BP_CPMAX - 1, BP_WTHETA_CAP);
+    double y = Pw[o], cj = 1.0;
+    for (int j = 1; j <= q.m; ++j) { cj = cj * (tb * bp_rk[j - 1]); y += cj * Pw[j * DD + o]; }
+    e2[i] = y;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fusedc(BpObsArgs a) {
+  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NW = BP_THREADS / 32;
+  double a1;
+#if BP_NOISE
+  const double sigma = a.theta[(size_t)c * BP_DIM + BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  double* Lm = bp_smem + (size_t)NW * BP_CWARP;   // [D][D], after the warps' areas
+  {
+    double th[BP_DIM];
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+    double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
+#pragma unroll
+    for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+    bp_rates(th, xk, r);
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+    bp_assemble(r, A, H);
+    a1 = bp_norm1(A);
+    if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;   // bp_fused handles this chain
+    bp_coop_build_L(A, H, Lm);
+  }
+  double* sN = bp_smem + (size_t)warp * BP_CWARP;   // [BP_CJ][BP_CNLD]   N_j[(d, l)]
+  double* sC = sN + BP_CJ * BP_CNLD;                // [BP_CCTAB]         c_i(tau_g) at index i + 8
+  double* sT = sC + BP_CCTAB;                       // [8][BP_WLD]        T[j][obs] = c_j(h_obs)
+  double* sB = sT + 8 * BP_WLD;                     // [BP_WCT*8][BP_WLD] B[(d,l)][obs] = b_d z0_l ; also S^g [8][BP_CSLD]
+  for (int i = lane; i < BP_CWARP; i += 32) sN[i] = 0.0;   // padding rows / columns stay zero
+  __syncthreads();
+  const double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
+  const double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
+  double accW[BP_CRT * BP_WCT][2], accS[BP_WCT][2];
+#pragma unroll
+  for (int i = 0; i < BP_CRT * BP_WCT; ++i) { accW[i][0] = 0.0; accW[i][1] = 0.0; }
+  double lp = 0.0, sb = 0.0;
+  int status = 0, apps = 0, dhint = 1, dhh = 1;
+  const int g = lane >> 2, tg = lane & 3;
+  const int od = lane / BP_N, ol = lane - od * BP_N;   // this lane's (d, l) entry of the D x n blocks (lanes < DN)
+  const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
+  for (int grp = g0 + warp; grp < g1; grp += NW) {   // warp-uniform
+    const double tau = a.cg_tau[grp];
+    const int gi = a.cg_idx[grp];
+    BpPlan pc, ph;
+    const bool okc = bp_make_plan(a1, tau, pc, dhint, BP_WCAP, BP_WTHETA_CAP);
+    const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, dhh, BP_CJ - 1, BP_WTHETA_CAP);
+    if (!okc || !okh || pc.s != 1 || ph.s != 1 || ph.m > BP_CJ - 1) { status |= BP_ST_RATE_NONFINITE; continue; }
+    const int mg = pc.m, J = ph.m;   // centre series: powers 0 .. mg; short series: j = 0 .. J
+    // ---- group prologue: N_0 = E2[b] M1[a], N_(j+1) = L N_j, coefficient table c_i(tau_g) ----
+    {
+      const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
+      double nj = 0.0;
+      if (lane < DN) {
+#pragma unroll
+        for (int rr = 0; rr < BP_D; ++rr) nj += e2[(size_t)bi * DD + od * BP_D + rr] * m1[(size_t)ai * DN + rr * BP_N + ol];
+        sN[lane] = nj;
+      }
+      __syncwarp();
+      for (int j = 1; j <= J; ++j) {
+        if (lane < DN) {
+          nj = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) nj += Lm[od * BP_D + rr] * sN[(j - 1) * BP_CNLD + rr * BP_N + ol];
+          sN[j * BP_CNLD + lane] = nj;
+        }
+        __syncwarp();
+      }
+      double ci = 1.0;
+      for (int i = 0; i < BP_CRT * 8 + 8; ++i) {   // indices i + 8; entries below 8 stay zero
+        if (i > 0) ci = ci * (tau * bp_rk[i - 1 < BP_WCAP ? i - 1 : BP_WCAP]);
+        if (lane == (i & 31)) sC[i + 8] = (i <= mg) ? ci : 0.0;
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < BP_WCT; ++ct) { accS[ct][0] = 0.0; accS[ct][1] = 0.0; }
+    __syncwarp();
+    // ---- the group's observations, 32 per pass ----
+    const int ch1 = a.cg_chunk0[grp + 1];
+    for (int ch = a.cg_chunk0[grp]; ch < ch1; ++ch) {
+      const int k = ch * 32 + lane;
+      bool valid = k < a.nobs;
+      double z0[BP_N], xo[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S], w[BP_CJ];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; ymu[i] = 0.0; bmu[i] = 0.0; }
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) { yS[q] = 0.0; bS[q] = 0.0; }
+      const double h = valid ? a.t[k] - tau : 0.0;
+      w[0] = 1.0;
+#pragma unroll
+      for (int j = 1; j < BP_CJ; ++j) w[j] = w[j - 1] * (h * bp_rk[j - 1]);
+#pragma unroll
+      for (int j = 0; j < BP_CJ; ++j) {
+        if (j <= J) {
+          double wz[BP_N];
+#pragma unroll
+          for (int l = 0; l < BP_N; ++l) wz[l] = w[j] * z0[l];
+          const double* nrow = sN + j * BP_CNLD;
+#pragma unroll
+          for (int d = 0; d < BP_D; ++d) {
+            double s = (d < BP_N) ? ymu[d] : yS[d - BP_N];
+#pragma unroll
+            for (int l = 0; l < BP_N; ++l) s += nrow[d * BP_N + l] * wz[l];
+            if (d < BP_N) ymu[d] = s; else yS[d - BP_N] = s;
+          }
+        }
+      }
+      if (valid) {
+        apps += J + 1;
+        if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; valid = false; }
+      }
+      // stage this observation's operands: T column (c_j(h), j = 0..J) and B column (packed-coordinate cotangent x z0)
+#pragma unroll
+      for (int j = 0; j < BP_CJ; ++j) sT[j * BP_WLD + lane] = (valid && j <= J) ? w[j] : 0.0;
+#pragma unroll
+      for (int d = 0; d < BP_D; ++d) {
+        double bd;
+        if (d < BP_N) bd = bmu[d];
+        else {
+          bool diag = false;
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == d - BP_N);
+          bd = diag ? bS[d - BP_N] : bS[d - BP_N] + bS[d - BP_N];
+        }
+        if (!valid) bd = 0.0;
+#pragma unroll
+        for (int l = 0; l < BP_N; ++l) sB[(d * BP_N + l) * BP_WLD + lane] = bd * z0[l];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int ob = 0; ob < 8; ++ob) {   // 4 observations per mma
+        const double af = sT[g * BP_WLD + ob * 4 + tg];
+#pragma unroll
+        for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accS[ct][0], accS[ct][1], af, sB[(ct * 8 + g) * BP_WLD + ob * 4 + tg]);
+      }
+      __syncwarp();
+    }
+    // ---- W += C(tau_g) S^g : rows n - 1 (n = 1 .. mg + J), k = j (8), columns (d, l) ----
+#pragma unroll
+    for (int ct = 0; ct < BP_WCT; ++ct) { sB[g * BP_CSLD + ct * 8 + 2 * tg] = accS[ct][0]; sB[g * BP_CSLD + ct * 8 + 2 * tg + 1] = accS[ct][1]; }
+    __syncwarp();
+    {
+      double bf[2][BP_WCT];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int ct = 0; ct < BP_WCT; ++ct) bf[ks][ct] = sB[(ks * 4 + tg) * BP_CSLD + ct * 8 + g];
+#pragma unroll
+      for (int rt = 0; rt < BP_CRT; ++rt) {
+        if (rt * 8 < mg + J) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const double af = sC[(rt * 8 + g + 1) - (ks * 4 + tg) + 8];   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg
+#pragma unroll
+            for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accW[rt * BP_WCT + ct][0], accW[rt * BP_WCT + ct][1], af, bf[ks][ct]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < 8 * BP_CSLD; i += 32) sB[i] = 0.0;   // the S staging area overlaps B: its padding rows must read zero again
+    __syncwarp();
+  }
+  // CTA partial of W: sum the warps' accumulators in warp order (fragment layout kept; bp_wpost knows it)
+  __syncthreads();
+  double* red = bp_smem;   // [warps][BP_CFRAG]
+#pragma unroll
+  for (int i = 0; i < BP_CRT * BP_WCT; ++i) { red[(size_t)warp * BP_CFRAG + i * 64 + lane * 2] = accW[i][0]; red[(size_t)warp * BP_CFRAG + i * 64 + lane * 2 + 1] = accW[i][1]; }
+  __syncthreads();
+  double* wout = a.wpart + ((size_t)c * a.ntiles + blockIdx.x) * BP_CFRAG;
+  for (int i = tid; i < BP_CFRAG; i += BP_THREADS) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sacc += red[(size_t)w * BP_CFRAG + i];
+    wout[i] = sacc;
+  }
+  __syncthreads();
+  double vals[BP_NPART];
+  vals[0] = lp;
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) vals[1 + k] = 0.0;
+  vals[BP_P + 1] = sb;
+  vals[BP_P + 2] = (double)apps;
+  bp_block_reduce_store(vals, bp_smem, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
+  if (status) atomicOr(a.status + c, status);
+}
+#endif  // BP_N <= 3
 #endif
 #endif
 

@@ -95,6 +95,11 @@ int model_load(bpc_model* m, int device, Loaded** out) {
       BPC_CUDA(cudaLibraryGetKernel(&L.fusedw, L.lib, "bp_fusedw"));
       BPC_CUDA(cudaLibraryGetKernel(&L.wpost, L.lib, "bp_wpost"));
       BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->spec.w_smem, device));
+      if (n <= 3) {
+        BPC_CUDA(cudaLibraryGetKernel(&L.fusedc, L.lib, "bp_fusedc"));
+        BPC_CUDA(cudaLibraryGetKernel(&L.ctable, L.lib, "bp_ctable"));
+        BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->spec.c_smem, device));
+      }
     }
   }
   auto ins = m->loaded.emplace(device, L);
@@ -375,6 +380,55 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
   }
   // W path (bp_fusedw + bp_wpost): rates independent of per-observation variables, ungrouped data, n <= 3
   dd->wmode = !simple && N > 0 && !dd->grouped && !s.xdep && n <= 3 && !std::getenv("BPC_NO_WPATH");
+  // centred W path (bp_ctable + bp_fusedc): the sorted table is cut into groups of consecutive 32-observation chunks whose
+  // durations lie within hcap of a point tau_g of the fine time grid (spacing tmax / 4096).  hcap is chosen so that the short
+  // series in h = t - tau_g needs at most BP_CJ - 1 = 7 applications for EVERY chain the W path accepts
+  // (2 ||A|| tmax <= theta(wcap)  =>  2 ||A|| hcap <= theta(6)).  Data whose chunks are wider than that (few observations spread
+  // over a long range) stay on bp_fusedw.
+  if (dd->wmode && ht[0] > 0.0 && !std::getenv("BPC_NO_CPATH")) {
+    const double tmax = ht[0];
+    const int FG = 64 * 64;
+    const double delta = tmax / FG;
+    const double hcap = 0.999 * tmax * taylor_theta(6) / taylor_theta(s.wcap);
+    int gmax = 8;
+    if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) gmax = v; }
+    const int nchunks = (N + 31) / 32;
+    std::vector<int> c0, idx;
+    std::vector<double> tau, hm;
+    bool ok = true;
+    auto centre = [&](double hi, double lo, int& ig, double& tg, double& hg) {
+      ig = (int)std::llround(0.5 * (hi + lo) / delta);
+      ig = std::max(0, std::min(FG, ig));
+      tg = ig * delta;
+      hg = std::max(std::fabs(hi - tg), std::fabs(lo - tg));
+    };
+    for (int ch = 0; ch < nchunks && ok;) {
+      const double hi = ht[(size_t)ch * 32];   // sorted, longest first
+      int end = ch + 1, ig;
+      double tg, hg;
+      centre(hi, ht[std::min(N, end * 32) - 1], ig, tg, hg);
+      if (!(hg <= hcap)) { ok = false; break; }
+      while (end < nchunks && end - ch < gmax) {
+        int ig2;
+        double tg2, hg2;
+        centre(hi, ht[std::min(N, (end + 1) * 32) - 1], ig2, tg2, hg2);
+        if (!(hg2 <= hcap)) break;
+        ig = ig2; tg = tg2; hg = hg2; ++end;
+      }
+      c0.push_back(ch); idx.push_back(ig); tau.push_back(tg); hm.push_back(hg);
+      ch = end;
+    }
+    if (ok) {
+      c0.push_back(nchunks);
+      dd->cgroups = (int)idx.size();
+      dd->cdelta = delta;
+      if ((rc = up(dd->cg_chunk0, c0.data(), c0.size() * 4))) return rc;
+      if ((rc = up(dd->cg_idx, idx.data(), idx.size() * 4))) return rc;
+      if ((rc = up(dd->cg_tau, tau.data(), tau.size() * 8))) return rc;
+      if ((rc = up(dd->cg_hmax, hm.data(), hm.size() * 8))) return rc;
+      dd->cmode = true;
+    }
+  }
   BPC_CUDA(cudaStreamCreateWithFlags(&dd->stream, cudaStreamNonBlocking));
   *out = dd.release();
   return BPC_OK;
@@ -400,6 +454,19 @@ namespace bpc {
 static void choose_tiling(bpc_data* d, int nchains) {
   if (d->grouped) { d->tile = d->N; d->ntiles = 1; return; }
   const int T = d->model->spec.threads;
+  if (d->cmode) {
+    // CTA = cgpc consecutive groups (a multiple of the warps per CTA); aim at >= 4 waves of 3 CTAs per SM
+    const int nw = T / 32;
+    long long gpc = ((long long)d->cgroups * nchains) / (148LL * 3 * 4);
+    long long cap = 4LL * nw;
+    if (const char* ev = std::getenv("BPC_CGROUPS_PER_CTA")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 4096) cap = v; }
+    gpc = std::max<long long>(nw, std::min(cap, gpc));
+    gpc = (gpc / nw) * nw;
+    d->cgpc = (int)gpc;
+    d->ntiles = std::max(1, (d->cgroups + d->cgpc - 1) / d->cgpc);
+    d->tile = ((d->N + d->ntiles - 1) / d->ntiles + 31) / 32 * 32;   // bp_fused's tiles (chains that need sub-steps) over the same ntiles
+    return;
+  }
   const long long total = (long long)d->N * nchains;
   long long per_thread = total / ((long long)148 * 8 * T);
   long long cap = d->wmode ? 32 : 8;
@@ -423,8 +490,12 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     }
     if (d->wmode) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
-      const size_t wfrag = (size_t)((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64;
+      const size_t wfrag = (size_t)((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64;
       if ((rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
+      if (d->cmode) {
+        if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
+        if ((rc = d->ctab_e2.alloc((size_t)nchains * 64 * D * D * 8))) return rc;
+      }
     }
     d->ws_chains = nchains;
   }
@@ -442,6 +513,8 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   double* part; int* status; double* loglik; const int* perm;
   int nobs, npad, tile, ntiles, nchains;
   double* wpart; int wmode;
+  int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; double cdelta;
+  double* ctab_m1; double* ctab_e2;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -463,7 +536,9 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   {
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
               part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains,
-              (double*)d->wpart.p, d->wmode ? 1 : 0};
+              (double*)d->wpart.p, d->wmode ? (d->cmode ? 2 : 1) : 0,
+              d->cgroups, d->cgpc, (const int*)d->cg_chunk0.p, (const int*)d->cg_idx.p, (const double*)d->cg_tau.p,
+              (const double*)d->cg_hmax.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -494,7 +569,14 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       if (d->wmode) {
         // chains whose series need one sub-step: W accumulation on the fp64 tensor path + one per-chain matrix polynomial;
         // bp_fused (below) only works on the chains that need sub-steps
-        BPC_CUDA(cudaLaunchKernel((const void*)L->fusedw, dim3(d->ntiles, nchains), dim3(s.threads), args, s.w_smem, st));
+        if (d->cmode) {
+          // centred W path: per-chain tables of exp(tau L), then short series around the groups' centres
+          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(128), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedc, dim3(d->ntiles, nchains), dim3(s.threads), args, s.c_smem, st));
+          g_launches += 1;
+        } else {
+          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedw, dim3(d->ntiles, nchains), dim3(s.threads), args, s.w_smem, st));
+        }
         BPC_CUDA(cudaLaunchKernel((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
         g_launches += 2;
       }
@@ -527,12 +609,13 @@ int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned lon
   choose_tiling(d, nchains);
   d->ws_chains = -1;
   (void)keep;
-  *path = s.kind == BPC_SIMPLE_BD ? 3 : (d->grouped ? 1 : (d->wmode ? 2 : 0));
+  *path = s.kind == BPC_SIMPLE_BD ? 3 : (d->grouped ? 1 : (d->wmode ? (d->cmode ? 4 : 2) : 0));
   *ntiles = d->ntiles;
   if (scratch_bytes) {
     const int n = s.ntypes, D = n + n * (n + 1) / 2;
     unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
-    if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
+    if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
+    if (d->cmode) b += 2ull * nchains * (65ull * D * n + 64ull * D * D) * 8;   // per-chain tables, written then read
     *scratch_bytes = b;
   }
   return BPC_OK;
@@ -693,6 +776,7 @@ int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains,
   for (int c = 0; c < nchains; ++c)
     // (a W-path chain that fell back to the ring kernel is counted with the W-path constants: a lower bound)
     flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N
+                         : d->cmode              ? apps[c] * f.per_term_c + f.per_obs_c * d->N
                          : d->wmode              ? apps[c] * (f.per_app_fwd + f.per_app_w) + f.per_obs_w * d->N
                                                  : apps[c] * (f.per_app_fwd + f.per_app_bwd) + (d->grouped ? f.per_obs_grouped : f.per_obs) * d->N;
   return BPC_OK;

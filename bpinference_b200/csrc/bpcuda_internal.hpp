@@ -38,12 +38,12 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr;
   size_t obs_smem = 0, grouped_smem = 0;
 };
 
 // algorithmic flop constants of the shipped kernels (SURVEY.md §8(d) convention: FMA = 2, div/sqrt/exp/log = 1)
-struct FlopModel { double per_app_fwd, per_app_bwd, per_obs, per_obs_grouped, per_app_w, per_obs_w; };
+struct FlopModel { double per_app_fwd, per_app_bwd, per_obs, per_obs_grouped, per_app_w, per_obs_w, per_term_c, per_obs_c; };
 FlopModel flop_model(const ModelSpec& s);
 
 }  // namespace bpc
@@ -63,6 +63,11 @@ struct bpc_data {
   bpc::DevBuf z0, xo, t, xv, perm;
   bpc::DevBuf wpart;   // W path: per-CTA partial sums of the W_j matrices
   bool wmode = false;
+  // centred W path (bp_ctable + bp_fusedc): groups of consecutive 32-observation chunks sharing a series centre
+  bool cmode = false;
+  int cgroups = 0, cgpc = 4;
+  double cdelta = 0.0;
+  bpc::DevBuf cg_chunk0, cg_idx, cg_tau, cg_hmax, ctab_m1, ctab_e2;
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;

@@ -33,6 +33,7 @@ struct ModelSpec {
   int minblocks = 1;  // CTAs per SM the shared-memory footprint allows
   double theta_cap = 0;
   size_t w_smem = 0;        // dynamic shared memory of bp_fusedw
+  size_t c_smem = 0;        // dynamic shared memory of bp_fusedc
   int w_post_threads = 128; // CTA size of bp_wpost
   std::vector<bool> a_nz, h_nz;   // structural non-zeros of A [n*n] and H [n*s]
   std::vector<std::string> warnings;

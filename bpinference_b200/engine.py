@@ -63,7 +63,8 @@ class StanData:
         """(kernel path name, CTAs per chain, partial-sum bytes per launch) of bpc_log_prob for `nchains` chains."""
         p, nt, sb = C.c_int(), C.c_int(), C.c_ulonglong()
         _ffi.check(_ffi.lib().bpc_data_path(self.handle, int(nchains), C.byref(p), C.byref(nt), C.byref(sb)))
-        names = {0: "bp_fused", 1: "bp_grouped", 2: "bp_fusedw + bp_wpost (bp_fused for chains that need sub-steps)", 3: "bp_onetype"}
+        names = {0: "bp_fused", 1: "bp_grouped", 2: "bp_fusedw + bp_wpost (bp_fused for chains that need sub-steps)", 3: "bp_onetype",
+                 4: "bp_ctable + bp_fusedc + bp_wpost (bp_fused for chains that need sub-steps)"}
         return names[p.value], nt.value, sb.value
 
     def close(self):

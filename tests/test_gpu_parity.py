@@ -245,3 +245,40 @@ def test_full_size_properties_cfg5U():
     ls, gs, ss = eng.log_prob_grad(subset(idx), u[:2], adjust_transform=False)
     np.testing.assert_allclose(ls, lo, rtol=1e-11)
     np.testing.assert_allclose(gs, go, rtol=1e-9, atol=1e-10 * np.abs(go).max())
+
+
+@pytest.mark.parametrize("nobs,chunks", [(20000, None), (60000, None), (60000, "3")])
+def test_centred_w_path_matches_oracle_and_w_path(nobs, chunks):
+    """dense sorted durations: the centred W path (bp_ctable + bp_fusedc: short series around shared centres, Toeplitz
+    product into the W matrices) against the oracle, against bp_fusedw on the same data, with chains of small and large
+    ||A|| t (long centre series) and one chain that needs sub-steps (ring fallback) in the same call."""
+    import os
+    cfg = syn.make_config("cfg5U", chains=6, nobs=nobs)
+    eng, om = _pair(cfg)
+    u = cfg["upars"].copy()
+    u[1] += 0.75                       # 2 ||A|| t_max ~ 3.3: centre series of up to 32 terms
+    u[2] -= 1.5                        # small rates: short series everywhere
+    u[3] += 2.2                        # sub-steps: bp_fused
+    if chunks:
+        os.environ["BPC_CGROUP_CHUNKS"] = chunks
+    try:
+        d = eng.data(cfg["data"])
+    finally:
+        os.environ.pop("BPC_CGROUP_CHUNKS", None)
+    assert d.path(6)[0].startswith("bp_ctable")
+    lp, g, st = eng.log_prob_grad(d, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
+    assert st.tolist() == st_o.tolist() and (st == 0).all()
+    np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
+    np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+    os.environ["BPC_NO_CPATH"] = "1"
+    try:
+        d2 = eng.data(cfg["data"])
+    finally:
+        del os.environ["BPC_NO_CPATH"]
+    assert d2.path(6)[0].startswith("bp_fusedw")
+    lp2, g2, st2 = eng.log_prob_grad(d2, u)
+    np.testing.assert_allclose(lp, lp2, rtol=1e-12)
+    np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
+    b = eng.log_prob_grad(d, u)        # deterministic
+    assert (b[0] == lp).all() and (b[1] == g).all()
