@@ -717,7 +717,8 @@ struct BpObsArgs {
   double* loglik;        // [C][N] (bp_*_loglik only)
   const int* perm;       // [npad] original index of sorted observation (bp_*_loglik only)
   int nobs, npad, tile, ntiles, nchains;
-  double* wpart;         // [C][ntiles][BP_WFRAG | BP_CFRAG] per-CTA partial sums of the W_j matrices (bp_fusedw / bp_fusedc -> bp_wpost)
+  double* wpart;         // bp_fusedw -> bp_wpost: [C][ntiles][BP_WFRAG] per-CTA partial sums of the W_j matrices;
+                         // bp_fusedc -> bp_wpost: [C][cgroups][BP_CSG] the groups' S^g matrices
   int wmode;             // 1: chains whose series need a single sub-step are handled by bp_fusedw + bp_wpost; 2: by bp_ctable + bp_fusedc + bp_wpost
   // centred W path (wmode 2): groups of consecutive 32-observation chunks of the sorted table that share a series centre
   int cgroups, cgpc;     // number of groups; groups per CTA
@@ -755,7 +756,13 @@ struct BpObsArgs {
 #define BP_CJ 8                                 // rows of the short series: j = 0 .. 7
 #define BP_CROWS (BP_WCAP + 1 + BP_CJ)          // powers n = 1 .. BP_WCAP + 1 + (BP_CJ - 1), rounded to the row tile
 #define BP_CRT ((BP_CROWS + 7) / 8)
-#define BP_CFRAG (BP_CRT * BP_WCT * 64)
+#define BP_CNLD (BP_WCOLS + (BP_WCOLS & 1))     // row stride of the staged N_j
+#define BP_CCTAB (BP_CRT * 8 + 16)              // coefficient table c_i(tau_g), index i + 8, zero outside 0 .. m_g
+#define BP_CGA 64                               // coarse grid intervals
+#define BP_CGB 64                               // fine points per coarse interval
+#define BP_CPMAX 14                             // longest series of the fine table E2 (durations <= tmax / BP_CGA)
+#define BP_CWARP (BP_CJ * BP_CNLD + (8 + BP_WCT * 8) * BP_WLD)   // doubles of shared memory per warp
+#define BP_CSG (8 * BP_WCT * 8)                 // doubles of one stored S^g: [j][8 BP_WCT columns]
 
 BP_HD bool bp_w_path(bool rates_finite, real a1, real tmax) {
   const real xx = (a1 + a1) * tmax;
@@ -1007,13 +1014,75 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
   const double a1 = bp_norm1(A);
   if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
   // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
-  const int frag = a.wmode == 2 ? BP_CFRAG : BP_WFRAG, rows = a.wmode == 2 ? BP_CROWS : BP_WROWS;
-  for (int i = tid; i < frag; i += blockDim.x) {
+  const int rows = a.wmode == 2 ? BP_CROWS : BP_WROWS;
+#if BP_N <= 3
+  if (a.wmode == 2) {
+    // centred W path: W_n = sum over groups of sum_j c_(n-j)(tau_g) S^g_j  (rows n - 1, n = 1 .. m_g + J; k = j; columns (d, l)),
+    // a Toeplitz product per group on the fp64 tensor path.  Warps take groups round-robin; their accumulators are added
+    // in warp order.
+    __shared__ double sCt[BP_WPOST_THREADS / 32][BP_CCTAB];
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, g = lane >> 2, tg = lane & 3;
+    double* sC = sCt[warp];
+    for (int i = lane; i < BP_CCTAB; i += 32) sC[i] = 0.0;
+    for (int i = tid; i < BP_CROWS * BP_WCOLS; i += blockDim.x) W[i] = 0.0;
+    double accW[BP_CRT * BP_WCT][2];
+#pragma unroll
+    for (int i = 0; i < BP_CRT * BP_WCT; ++i) { accW[i][0] = 0.0; accW[i][1] = 0.0; }
+    int dhint = 1, dhh = 1;
+    for (int grp = warp; grp < a.cgroups; grp += nw) {
+      const double tau = a.cg_tau[grp];
+      BpPlan pc, ph;
+      const bool okc = bp_make_plan(a1, tau, pc, dhint, BP_WCAP, BP_WTHETA_CAP);
+      const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, dhh, BP_CJ - 1, BP_WTHETA_CAP);
+      if (!okc || !okh || pc.s != 1 || ph.s != 1 || ph.m > BP_CJ - 1) continue;   // bp_fusedc flagged the chain
+      const int mg = pc.m, J = ph.m;
+      __syncwarp();
+      double ci = 1.0;
+      for (int i = 0; i <= BP_WCAP + 1; ++i) {   // c_i(tau_g) at index i + 8; entries outside 0 .. m_g are zero
+        if (i > 0) ci = ci * (tau * bp_rk[i - 1]);
+        if (lane == (i & 31)) sC[i + 8] = (i <= mg) ? ci : 0.0;
+      }
+      __syncwarp();
+      const double* sg = a.wpart + ((size_t)c * a.cgroups + grp) * BP_CSG;
+      double bf[2][BP_WCT];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int ct = 0; ct < BP_WCT; ++ct) bf[ks][ct] = sg[(ks * 4 + tg) * (BP_WCT * 8) + ct * 8 + g];
+#pragma unroll
+      for (int rt = 0; rt < BP_CRT; ++rt) {
+        if (rt * 8 < mg + J) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const double af = sC[(rt * 8 + g + 1) - (ks * 4 + tg) + 8];   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg
+#pragma unroll
+            for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accW[rt * BP_WCT + ct][0], accW[rt * BP_WCT + ct][1], af, bf[ks][ct]);
+          }
+        }
+      }
+    }
+    for (int w = 0; w < nw; ++w) {
+      __syncthreads();
+      if (warp == w) {
+#pragma unroll
+        for (int rt = 0; rt < BP_CRT; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < BP_WCT; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int row = rt * 8 + g, col = ct * 8 + 2 * tg + e;
+              if (row < BP_CROWS && col < BP_WCOLS) W[row * BP_WCOLS + col] += accW[rt * BP_WCT + ct][e];
+            }
+      }
+    }
+  } else
+#endif
+  for (int i = tid; i < BP_WFRAG; i += blockDim.x) {
     double sacc = 0.0;
-    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * frag + i];
+    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * BP_WFRAG + i];
     const int tile = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = (tile / BP_WCT) * 8 + (ln >> 2), col = (tile % BP_WCT) * 8 + (ln & 3) * 2 + e;
-    if (row < rows && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
+    if (row < BP_WROWS && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
   }
   bp_coop_build_L(A, H, Lm);
   __syncthreads();
@@ -1048,13 +1117,6 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
 // (bp_ctable; tau_g = (a BP_CGB + b) cdelta), the chain N_(j+1) = L N_j, and the Toeplitz product W += C(tau_g) S^g,
 // again as DMMAs.  bp_wpost turns W into the gradient exactly as for bp_fusedw (with BP_CROWS rows).
 #if BP_N <= 3
-#define BP_CNLD (BP_WCOLS + (BP_WCOLS & 1))     // row stride of the staged N_j
-#define BP_CCTAB (BP_CRT * 8 + 16)              // coefficient table c_i(tau_g), index i + 8, zero outside 0 .. m_g
-#define BP_CSLD (BP_WCT * 8 + 4)                // row stride of the staged S^g
-#define BP_CGA 64                               // coarse grid intervals
-#define BP_CGB 64                               // fine points per coarse interval
-#define BP_CPMAX 14                             // longest series of the fine table E2 (durations <= tmax / BP_CGA)
-#define BP_CWARP (BP_CJ * BP_CNLD + BP_CCTAB + (8 + BP_WCT * 8) * BP_WLD)   // doubles of shared memory per warp
 
 // per chain: the two tables M(tau) is assembled from.  One CTA per chain; Krylov blocks U_j = L^j [e_1 .. e_n] and powers
 // P_j = L^j in shared memory, then every table entry is a short dot product with the coefficients c_j(time).
@@ -1159,16 +1221,13 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     bp_coop_build_L(A, H, Lm);
   }
   double* sN = bp_smem + (size_t)warp * BP_CWARP;   // [BP_CJ][BP_CNLD]   N_j[(d, l)]
-  double* sC = sN + BP_CJ * BP_CNLD;                // [BP_CCTAB]         c_i(tau_g) at index i + 8
-  double* sT = sC + BP_CCTAB;                       // [8][BP_WLD]        T[j][obs] = c_j(h_obs)
-  double* sB = sT + 8 * BP_WLD;                     // [BP_WCT*8][BP_WLD] B[(d,l)][obs] = b_d z0_l ; also S^g [8][BP_CSLD]
+  double* sT = sN + BP_CJ * BP_CNLD;                // [8][BP_WLD]        T[j][obs] = c_j(h_obs)
+  double* sB = sT + 8 * BP_WLD;                     // [BP_WCT*8][BP_WLD] B[(d,l)][obs] = b_d z0_l
   for (int i = lane; i < BP_CWARP; i += 32) sN[i] = 0.0;   // padding rows / columns stay zero
   __syncthreads();
   const double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
   const double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
-  double accW[BP_CRT * BP_WCT][2], accS[BP_WCT][2];
-#pragma unroll
-  for (int i = 0; i < BP_CRT * BP_WCT; ++i) { accW[i][0] = 0.0; accW[i][1] = 0.0; }
+  double accS[BP_WCT][2];
   double lp = 0.0, sb = 0.0;
   int status = 0, apps = 0, dhint = 1, dhh = 1;
   const int g = lane >> 2, tg = lane & 3;
@@ -1180,8 +1239,13 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     BpPlan pc, ph;
     const bool okc = bp_make_plan(a1, tau, pc, dhint, BP_WCAP, BP_WTHETA_CAP);
     const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, dhh, BP_CJ - 1, BP_WTHETA_CAP);
-    if (!okc || !okh || pc.s != 1 || ph.s != 1 || ph.m > BP_CJ - 1) { status |= BP_ST_RATE_NONFINITE; continue; }
-    const int mg = pc.m, J = ph.m;   // centre series: powers 0 .. mg; short series: j = 0 .. J
+    double* sg = a.wpart + ((size_t)c * a.cgroups + grp) * BP_CSG;   // this group's S^g, row-major [j][8 BP_WCT]
+    if (!okc || !okh || pc.s != 1 || ph.s != 1 || ph.m > BP_CJ - 1) {
+      status |= BP_ST_RATE_NONFINITE;
+      for (int i = lane; i < BP_CSG; i += 32) sg[i] = 0.0;
+      continue;
+    }
+    const int J = ph.m;   // short series: j = 0 .. J
     // ---- group prologue: N_0 = E2[b] M1[a], N_(j+1) = L N_j, coefficient table c_i(tau_g) ----
     {
       const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
@@ -1200,11 +1264,6 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
           sN[j * BP_CNLD + lane] = nj;
         }
         __syncwarp();
-      }
-      double ci = 1.0;
-      for (int i = 0; i < BP_CRT * 8 + 8; ++i) {   // indices i + 8; entries below 8 stay zero
-        if (i > 0) ci = ci * (tau * bp_rk[i - 1 < BP_WCAP ? i - 1 : BP_WCAP]);
-        if (lane == (i & 31)) sC[i + 8] = (i <= mg) ? ci : 0.0;
       }
     }
 #pragma unroll
@@ -1270,44 +1329,9 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
       }
       __syncwarp();
     }
-    // ---- W += C(tau_g) S^g : rows n - 1 (n = 1 .. mg + J), k = j (8), columns (d, l) ----
+    // ---- hand S^g to bp_wpost (W += C(tau_g) S^g there): accumulator fragment -> row-major, 16-byte stores ----
 #pragma unroll
-    for (int ct = 0; ct < BP_WCT; ++ct) { sB[g * BP_CSLD + ct * 8 + 2 * tg] = accS[ct][0]; sB[g * BP_CSLD + ct * 8 + 2 * tg + 1] = accS[ct][1]; }
-    __syncwarp();
-    {
-      double bf[2][BP_WCT];
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-        for (int ct = 0; ct < BP_WCT; ++ct) bf[ks][ct] = sB[(ks * 4 + tg) * BP_CSLD + ct * 8 + g];
-#pragma unroll
-      for (int rt = 0; rt < BP_CRT; ++rt) {
-        if (rt * 8 < mg + J) {
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const double af = sC[(rt * 8 + g + 1) - (ks * 4 + tg) + 8];   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg
-#pragma unroll
-            for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accW[rt * BP_WCT + ct][0], accW[rt * BP_WCT + ct][1], af, bf[ks][ct]);
-          }
-        }
-      }
-    }
-    __syncwarp();
-    for (int i = lane; i < 8 * BP_CSLD; i += 32) sB[i] = 0.0;   // the S staging area overlaps B: its padding rows must read zero again
-    __syncwarp();
-  }
-  // CTA partial of W: sum the warps' accumulators in warp order (fragment layout kept; bp_wpost knows it)
-  __syncthreads();
-  double* red = bp_smem;   // [warps][BP_CFRAG]
-#pragma unroll
-  for (int i = 0; i < BP_CRT * BP_WCT; ++i) { red[(size_t)warp * BP_CFRAG + i * 64 + lane * 2] = accW[i][0]; red[(size_t)warp * BP_CFRAG + i * 64 + lane * 2 + 1] = accW[i][1]; }
-  __syncthreads();
-  double* wout = a.wpart + ((size_t)c * a.ntiles + blockIdx.x) * BP_CFRAG;
-  for (int i = tid; i < BP_CFRAG; i += BP_THREADS) {
-    double sacc = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) sacc += red[(size_t)w * BP_CFRAG + i];
-    wout[i] = sacc;
+    for (int ct = 0; ct < BP_WCT; ++ct) *reinterpret_cast<double2*>(sg + g * (BP_WCT * 8) + ct * 8 + 2 * tg) = make_double2(accS[ct][0], accS[ct][1]);
   }
   __syncthreads();
   double vals[BP_NPART];

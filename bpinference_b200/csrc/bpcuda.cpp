@@ -490,8 +490,10 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     }
     if (d->wmode) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
-      const size_t wfrag = (size_t)((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64;
-      if ((rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
+      const size_t wfrag = (size_t)((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64;
+      // bp_fusedw: per-CTA partial W matrices; bp_fusedc: one 8-row S matrix per group
+      const size_t wbytes = d->cmode ? (size_t)nchains * d->cgroups * 8 * ((D * n + 7) / 8) * 8 * 8 : (size_t)nchains * d->ntiles * wfrag * 8;
+      if ((rc = d->wpart.alloc(wbytes))) return rc;
       if (d->cmode) {
         if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
         if ((rc = d->ctab_e2.alloc((size_t)nchains * 64 * D * D * 8))) return rc;
@@ -614,8 +616,8 @@ int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned lon
   if (scratch_bytes) {
     const int n = s.ntypes, D = n + n * (n + 1) / 2;
     unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
-    if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
-    if (d->cmode) b += 2ull * nchains * (65ull * D * n + 64ull * D * D) * 8;   // per-chain tables, written then read
+    if (d->wmode && !d->cmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
+    if (d->cmode) b += 2ull * nchains * ((unsigned long long)d->cgroups * 8 * ((D * n + 7) / 8) * 8 + 65ull * D * n + 64ull * D * D) * 8;   // S^g per group and the per-chain tables, written then read
     *scratch_bytes = b;
   }
   return BPC_OK;

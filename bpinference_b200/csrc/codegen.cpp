@@ -179,12 +179,12 @@ std::string generate_cuda(ModelSpec& m) {
     if (const char* ev = std::getenv("BPC_WMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 8) wmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_WMINBLOCKS %d\n#define BP_WPOST_THREADS %d\n", wmin, m.w_post_threads);
     s += buf;
-    // centred W path (bp_fusedc): per warp N_j, the coefficient table and the T / B staging; the CTA's dense L; the
-    // area is reused for the end-of-kernel reduction of the W accumulators
+    // centred W path (bp_fusedc): per warp N_j and the T / B staging; the CTA's dense L
     const int crt = (m.wcap + 1 + 8 + 7) / 8, dn = D * n, nw = m.threads / 32;
-    const size_t cwarp = (size_t)8 * (dn + (dn & 1)) + (crt * 8 + 16) + (size_t)(8 + wct * 8) * 36;
-    m.c_smem = std::max<size_t>(nw * cwarp + D * D, (size_t)nw * crt * wct * 64) * 8;
-    int cmin = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (m.c_smem + 1024)));
+    const size_t cwarp = (size_t)8 * (dn + (dn & 1)) + (size_t)(8 + wct * 8) * 36;
+    (void)crt;
+    m.c_smem = (nw * cwarp + D * D) * 8;
+    int cmin = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (m.c_smem + 1024)));
     if (const char* ev = std::getenv("BPC_CMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 8) cmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_CMINBLOCKS %d\n", cmin);
     s += buf;
