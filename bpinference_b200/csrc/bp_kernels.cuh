@@ -717,8 +717,7 @@ struct BpObsArgs {
   double* loglik;        // [C][N] (bp_*_loglik only)
   const int* perm;       // [npad] original index of sorted observation (bp_*_loglik only)
   int nobs, npad, tile, ntiles, nchains;
-  double* wpart;         // bp_fusedw -> bp_wpost: [C][ntiles][BP_WFRAG] per-CTA partial sums of the W_j matrices;
-                         // bp_fusedc -> bp_wpost: [C][cgroups][BP_CSG] the groups' S^g matrices
+  double* wpart;         // [C][ntiles][BP_WFRAG | BP_CFRAG] per-CTA partial sums of the W_j matrices (bp_fusedw / bp_fusedc -> bp_wpost)
   int wmode;             // 1: chains whose series need a single sub-step are handled by bp_fusedw + bp_wpost; 2: by bp_ctable + bp_fusedc + bp_wpost
   // centred W path (wmode 2): groups of consecutive 32-observation chunks of the sorted table that share a series centre
   int cgroups, cgpc;     // number of groups; groups per CTA
@@ -726,9 +725,11 @@ struct BpObsArgs {
   const int* cg_idx;     // [cgroups] centre of the group on the fine time grid: tau_g = cg_idx * cdelta
   const double* cg_tau;  // [cgroups] tau_g
   const double* cg_hmax; // [cgroups] max |t_k - tau_g| over the group's observations
+  const double* cg_coef; // [cgroups][BP_CCTAB] c_i(tau_g) = tau_g^i / i! at index i + 8 (i = 0 .. BP_WCAP + 1), zero elsewhere
   double cdelta;         // fine grid spacing = longest duration / (BP_CGA * BP_CGB)
   double* ctab_m1;       // [C][BP_CGA + 1][D * n]  single-ancestor moments exp(a * BP_CGB * cdelta * L) [e_1 .. e_n]
   double* ctab_e2;       // [C][BP_CGB][D * D]      exp(b * cdelta * L)
+  double* csg;           // [C][cgroups][BP_CSG]    scratch: the groups' S^g between a warp's main loop and its Toeplitz products
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -756,6 +757,7 @@ struct BpObsArgs {
 #define BP_CJ 8                                 // rows of the short series: j = 0 .. 7
 #define BP_CROWS (BP_WCAP + 1 + BP_CJ)          // powers n = 1 .. BP_WCAP + 1 + (BP_CJ - 1), rounded to the row tile
 #define BP_CRT ((BP_CROWS + 7) / 8)
+#define BP_CFRAG (BP_CRT * BP_WCT * 64)
 #define BP_CNLD (BP_WCOLS + (BP_WCOLS & 1))     // row stride of the staged N_j
 #define BP_CCTAB (BP_CRT * 8 + 16)              // coefficient table c_i(tau_g), index i + 8, zero outside 0 .. m_g
 #define BP_CGA 64                               // coarse grid intervals
@@ -1014,75 +1016,14 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
   const double a1 = bp_norm1(A);
   if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
   // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
-  const int rows = a.wmode == 2 ? BP_CROWS : BP_WROWS;
-#if BP_N <= 3
-  if (a.wmode == 2) {
-    // centred W path: W_n = sum over groups of sum_j c_(n-j)(tau_g) S^g_j  (rows n - 1, n = 1 .. m_g + J; k = j; columns (d, l)),
-    // a Toeplitz product per group on the fp64 tensor path.  Warps take groups round-robin; their accumulators are added
-    // in warp order.
-    __shared__ double sCt[BP_WPOST_THREADS / 32][BP_CCTAB];
-    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, g = lane >> 2, tg = lane & 3;
-    double* sC = sCt[warp];
-    for (int i = lane; i < BP_CCTAB; i += 32) sC[i] = 0.0;
-    for (int i = tid; i < BP_CROWS * BP_WCOLS; i += blockDim.x) W[i] = 0.0;
-    double accW[BP_CRT * BP_WCT][2];
-#pragma unroll
-    for (int i = 0; i < BP_CRT * BP_WCT; ++i) { accW[i][0] = 0.0; accW[i][1] = 0.0; }
-    int dhint = 1, dhh = 1;
-    for (int grp = warp; grp < a.cgroups; grp += nw) {
-      const double tau = a.cg_tau[grp];
-      BpPlan pc, ph;
-      const bool okc = bp_make_plan(a1, tau, pc, dhint, BP_WCAP, BP_WTHETA_CAP);
-      const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, dhh, BP_CJ - 1, BP_WTHETA_CAP);
-      if (!okc || !okh || pc.s != 1 || ph.s != 1 || ph.m > BP_CJ - 1) continue;   // bp_fusedc flagged the chain
-      const int mg = pc.m, J = ph.m;
-      __syncwarp();
-      double ci = 1.0;
-      for (int i = 0; i <= BP_WCAP + 1; ++i) {   // c_i(tau_g) at index i + 8; entries outside 0 .. m_g are zero
-        if (i > 0) ci = ci * (tau * bp_rk[i - 1]);
-        if (lane == (i & 31)) sC[i + 8] = (i <= mg) ? ci : 0.0;
-      }
-      __syncwarp();
-      const double* sg = a.wpart + ((size_t)c * a.cgroups + grp) * BP_CSG;
-      double bf[2][BP_WCT];
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-        for (int ct = 0; ct < BP_WCT; ++ct) bf[ks][ct] = sg[(ks * 4 + tg) * (BP_WCT * 8) + ct * 8 + g];
-#pragma unroll
-      for (int rt = 0; rt < BP_CRT; ++rt) {
-        if (rt * 8 < mg + J) {
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const double af = sC[(rt * 8 + g + 1) - (ks * 4 + tg) + 8];   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg
-#pragma unroll
-            for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accW[rt * BP_WCT + ct][0], accW[rt * BP_WCT + ct][1], af, bf[ks][ct]);
-          }
-        }
-      }
-    }
-    for (int w = 0; w < nw; ++w) {
-      __syncthreads();
-      if (warp == w) {
-#pragma unroll
-        for (int rt = 0; rt < BP_CRT; ++rt)
-#pragma unroll
-          for (int ct = 0; ct < BP_WCT; ++ct)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int row = rt * 8 + g, col = ct * 8 + 2 * tg + e;
-              if (row < BP_CROWS && col < BP_WCOLS) W[row * BP_WCOLS + col] += accW[rt * BP_WCT + ct][e];
-            }
-      }
-    }
-  } else
-#endif
-  for (int i = tid; i < BP_WFRAG; i += blockDim.x) {
+  // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
+  const int frag = a.wmode == 2 ? BP_CFRAG : BP_WFRAG, rows = a.wmode == 2 ? BP_CROWS : BP_WROWS;
+  for (int i = tid; i < frag; i += blockDim.x) {
     double sacc = 0.0;
-    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * BP_WFRAG + i];
+    for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * frag + i];
     const int tile = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = (tile / BP_WCT) * 8 + (ln >> 2), col = (tile % BP_WCT) * 8 + (ln & 3) * 2 + e;
-    if (row < BP_WROWS && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
+    if (row < rows && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
   }
   bp_coop_build_L(A, H, Lm);
   __syncthreads();
@@ -1239,13 +1180,16 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     BpPlan pc, ph;
     const bool okc = bp_make_plan(a1, tau, pc, dhint, BP_WCAP, BP_WTHETA_CAP);
     const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, dhh, BP_CJ - 1, BP_WTHETA_CAP);
-    double* sg = a.wpart + ((size_t)c * a.cgroups + grp) * BP_CSG;   // this group's S^g, row-major [j][8 BP_WCT]
-    if (!okc || !okh || pc.s != 1 || ph.s != 1 || ph.m > BP_CJ - 1) {
+    double* sg = a.csg + ((size_t)c * a.cgroups + grp) * BP_CSG;   // this group's S^g, row-major [j][8 BP_WCT]
+    if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[grp] <= bp_th[ph.m - 1])) {   // (never for data bpc_data_create accepted)
       status |= BP_ST_RATE_NONFINITE;
       for (int i = lane; i < BP_CSG; i += 32) sg[i] = 0.0;
       continue;
     }
-    const int J = ph.m;   // short series: j = 0 .. J
+    // short series: j = 0 .. J with J = the degree d of the plan (theta_h^d / d! <= 2^-55), not d + 1 as for the long
+    // series: theta_h <= bp_th[BP_CJ - 1] << 1, so each further term is smaller by theta_h / j and the coupling factor
+    // (j ||H|| / 2||A||) of the block-triangular operator cannot bring term d + 1 back above the threshold
+    const int J = ph.m - 1;
     // ---- group prologue: N_0 = E2[b] M1[a], N_(j+1) = L N_j, coefficient table c_i(tau_g) ----
     {
       const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
@@ -1282,7 +1226,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
       const double h = valid ? a.t[k] - tau : 0.0;
       w[0] = 1.0;
 #pragma unroll
-      for (int j = 1; j < BP_CJ; ++j) w[j] = w[j - 1] * (h * bp_rk[j - 1]);
+      for (int j = 1; j < BP_CJ; ++j) w[j] = w[j - 1] * (h * (j <= J ? bp_rk[j - 1] : 0.0));   // zero beyond J
 #pragma unroll
       for (int j = 0; j < BP_CJ; ++j) {
         if (j <= J) {
@@ -1305,7 +1249,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
       }
       // stage this observation's operands: T column (c_j(h), j = 0..J) and B column (packed-coordinate cotangent x z0)
 #pragma unroll
-      for (int j = 0; j < BP_CJ; ++j) sT[j * BP_WLD + lane] = (valid && j <= J) ? w[j] : 0.0;
+      for (int j = 0; j < BP_CJ; ++j) sT[j * BP_WLD + lane] = valid ? w[j] : 0.0;   // a zero T column removes the observation from S
 #pragma unroll
       for (int d = 0; d < BP_D; ++d) {
         double bd;
@@ -1316,7 +1260,6 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
           for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == d - BP_N);
           bd = diag ? bS[d - BP_N] : bS[d - BP_N] + bS[d - BP_N];
         }
-        if (!valid) bd = 0.0;
 #pragma unroll
         for (int l = 0; l < BP_N; ++l) sB[(d * BP_N + l) * BP_WLD + lane] = bd * z0[l];
       }
@@ -1329,9 +1272,55 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
       }
       __syncwarp();
     }
-    // ---- hand S^g to bp_wpost (W += C(tau_g) S^g there): accumulator fragment -> row-major, 16-byte stores ----
+    // ---- park S^g (accumulator fragment -> row-major, 16-byte stores; L2-resident until the Toeplitz products below) ----
 #pragma unroll
     for (int ct = 0; ct < BP_WCT; ++ct) *reinterpret_cast<double2*>(sg + g * (BP_WCT * 8) + ct * 8 + 2 * tg) = make_double2(accS[ct][0], accS[ct][1]);
+  }
+  // ---- W += C(tau_g) S^g for this warp's groups: rows n - 1 (n = 1 .. m_g + J), k = j (8), columns (d, l).  Deferred to here so
+  // that the 2 BP_CRT BP_WCT accumulator registers do not live through the observation loop. ----
+  __syncwarp();
+  double accW[BP_CRT * BP_WCT][2];
+#pragma unroll
+  for (int i = 0; i < BP_CRT * BP_WCT; ++i) { accW[i][0] = 0.0; accW[i][1] = 0.0; }
+  dhint = 1; dhh = 1;
+  for (int grp = g0 + warp; grp < g1; grp += NW) {
+    BpPlan pc, ph;
+    const bool okc = bp_make_plan(a1, a.cg_tau[grp], pc, dhint, BP_WCAP, BP_WTHETA_CAP);
+    const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, dhh, BP_CJ - 1, BP_WTHETA_CAP);
+    if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[grp] <= bp_th[ph.m - 1])) continue;   // flagged above
+    const int mg = pc.m, J = ph.m - 1;
+    const double* sg = a.csg + ((size_t)c * a.cgroups + grp) * BP_CSG;
+    const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
+    double bf[2][BP_WCT];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int ct = 0; ct < BP_WCT; ++ct) bf[ks][ct] = __ldcg(sg + (ks * 4 + tg) * (BP_WCT * 8) + ct * 8 + g);
+#pragma unroll
+    for (int rt = 0; rt < BP_CRT; ++rt) {
+      if (rt * 8 < mg + J) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg
+          const double af = (ix <= mg) ? cf[ix] : 0.0;
+#pragma unroll
+          for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accW[rt * BP_WCT + ct][0], accW[rt * BP_WCT + ct][1], af, bf[ks][ct]);
+        }
+      }
+    }
+  }
+  // CTA partial of W: sum the warps' accumulators in warp order (fragment layout kept; bp_wpost knows it)
+  __syncthreads();
+  double* red = bp_smem;   // [warps][BP_CFRAG]
+#pragma unroll
+  for (int i = 0; i < BP_CRT * BP_WCT; ++i) { red[(size_t)warp * BP_CFRAG + i * 64 + lane * 2] = accW[i][0]; red[(size_t)warp * BP_CFRAG + i * 64 + lane * 2 + 1] = accW[i][1]; }
+  __syncthreads();
+  double* wout = a.wpart + ((size_t)c * a.ntiles + blockIdx.x) * BP_CFRAG;
+  for (int i = tid; i < BP_CFRAG; i += BP_THREADS) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sacc += red[(size_t)w * BP_CFRAG + i];
+    wout[i] = sacc;
   }
   __syncthreads();
   double vals[BP_NPART];

@@ -382,14 +382,14 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
   dd->wmode = !simple && N > 0 && !dd->grouped && !s.xdep && n <= 3 && !std::getenv("BPC_NO_WPATH");
   // centred W path (bp_ctable + bp_fusedc): the sorted table is cut into groups of consecutive 32-observation chunks whose
   // durations lie within hcap of a point tau_g of the fine time grid (spacing tmax / 4096).  hcap is chosen so that the short
-  // series in h = t - tau_g needs at most BP_CJ - 1 = 7 applications for EVERY chain the W path accepts
-  // (2 ||A|| tmax <= theta(wcap)  =>  2 ||A|| hcap <= theta(6)).  Data whose chunks are wider than that (few observations spread
+  // series in h = t - tau_g has degree at most BP_CJ - 1 = 7 for EVERY chain the W path accepts
+  // (2 ||A|| tmax <= theta(wcap)  =>  2 ||A|| hcap <= theta(7)).  Data whose chunks are wider than that (few observations spread
   // over a long range) stay on bp_fusedw.
   if (dd->wmode && ht[0] > 0.0 && !std::getenv("BPC_NO_CPATH")) {
     const double tmax = ht[0];
     const int FG = 64 * 64;
     const double delta = tmax / FG;
-    const double hcap = 0.999 * tmax * taylor_theta(6) / taylor_theta(s.wcap);
+    const double hcap = 0.999 * tmax * taylor_theta(7) / taylor_theta(s.wcap);
     int gmax = 8;
     if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) gmax = v; }
     const int nchunks = (N + 31) / 32;
@@ -426,6 +426,17 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
       if ((rc = up(dd->cg_idx, idx.data(), idx.size() * 4))) return rc;
       if ((rc = up(dd->cg_tau, tau.data(), tau.size() * 8))) return rc;
       if ((rc = up(dd->cg_hmax, hm.data(), hm.size() * 8))) return rc;
+      // c_i(tau_g) = tau_g^i / i! at index i + 8, i = 0 .. wcap + 1 (the A operand of bp_wpost's Toeplitz products)
+      const int ctab = ((s.wcap + 1 + 8 + 7) / 8) * 8 + 16;
+      std::vector<double> coef((size_t)dd->cgroups * ctab, 0.0);
+      for (int gI = 0; gI < dd->cgroups; ++gI) {
+        double ci = 1.0;
+        for (int i = 0; i <= s.wcap + 1; ++i) {
+          if (i > 0) ci = ci * (tau[gI] * (1.0 / i));
+          coef[(size_t)gI * ctab + i + 8] = ci;
+        }
+      }
+      if ((rc = up(dd->cg_coef, coef.data(), coef.size() * 8))) return rc;
       dd->cmode = true;
     }
   }
@@ -490,11 +501,10 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     }
     if (d->wmode) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
-      const size_t wfrag = (size_t)((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64;
-      // bp_fusedw: per-CTA partial W matrices; bp_fusedc: one 8-row S matrix per group
-      const size_t wbytes = d->cmode ? (size_t)nchains * d->cgroups * 8 * ((D * n + 7) / 8) * 8 * 8 : (size_t)nchains * d->ntiles * wfrag * 8;
-      if ((rc = d->wpart.alloc(wbytes))) return rc;
+      const size_t wfrag = (size_t)((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64;
+      if ((rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
       if (d->cmode) {
+        if ((rc = d->csg.alloc((size_t)nchains * d->cgroups * 8 * ((D * n + 7) / 8) * 8 * 8))) return rc;   // one 8-row S matrix per group
         if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
         if ((rc = d->ctab_e2.alloc((size_t)nchains * 64 * D * D * 8))) return rc;
       }
@@ -515,8 +525,8 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   double* part; int* status; double* loglik; const int* perm;
   int nobs, npad, tile, ntiles, nchains;
   double* wpart; int wmode;
-  int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; double cdelta;
-  double* ctab_m1; double* ctab_e2;
+  int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; const double* cg_coef; double cdelta;
+  double* ctab_m1; double* ctab_e2; double* csg;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -540,7 +550,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains,
               (double*)d->wpart.p, d->wmode ? (d->cmode ? 2 : 1) : 0,
               d->cgroups, d->cgpc, (const int*)d->cg_chunk0.p, (const int*)d->cg_idx.p, (const double*)d->cg_tau.p,
-              (const double*)d->cg_hmax.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p};
+              (const double*)d->cg_hmax.p, (const double*)d->cg_coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -616,7 +626,7 @@ int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned lon
   if (scratch_bytes) {
     const int n = s.ntypes, D = n + n * (n + 1) / 2;
     unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
-    if (d->wmode && !d->cmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
+    if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
     if (d->cmode) b += 2ull * nchains * ((unsigned long long)d->cgroups * 8 * ((D * n + 7) / 8) * 8 + 65ull * D * n + 64ull * D * D) * 8;   // S^g per group and the per-chain tables, written then read
     *scratch_bytes = b;
   }

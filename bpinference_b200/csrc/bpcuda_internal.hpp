@@ -67,7 +67,7 @@ struct bpc_data {
   bool cmode = false;
   int cgroups = 0, cgpc = 4;
   double cdelta = 0.0;
-  bpc::DevBuf cg_chunk0, cg_idx, cg_tau, cg_hmax, ctab_m1, ctab_e2;
+  bpc::DevBuf cg_chunk0, cg_idx, cg_tau, cg_hmax, cg_coef, ctab_m1, ctab_e2, csg;
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;
