@@ -1135,6 +1135,26 @@ extern "C" __global__ void __launch_bounds__(128) bp_ctable(BpObsArgs a) {
   }
 }
 
+// y = sum_(j < NT) N_j (w_j z0): NT terms of a D x n matrix-vector product, N_j broadcast from shared memory
+template <int NT>
+__device__ __forceinline__ void bp_c_forward(const double* __restrict__ sN, const double (&w)[BP_CJ], const double (&z0)[BP_N],
+                                             double (&ymu)[BP_N], double (&yS)[BP_S]) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    double wz[BP_N];
+#pragma unroll
+    for (int l = 0; l < BP_N; ++l) wz[l] = w[j] * z0[l];
+    const double* nrow = sN + j * BP_CNLD;
+#pragma unroll
+    for (int d = 0; d < BP_D; ++d) {
+      double s = (d < BP_N) ? ymu[d] : yS[d - BP_N];
+#pragma unroll
+      for (int l = 0; l < BP_N; ++l) s += nrow[d * BP_N + l] * wz[l];
+      if (d < BP_N) ymu[d] = s; else yS[d - BP_N] = s;
+    }
+  }
+}
+
 extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fusedc(BpObsArgs a) {
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NW = BP_THREADS / 32;
@@ -1170,7 +1190,8 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
   const double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
   double accS[BP_WCT][2];
   double lp = 0.0, sb = 0.0;
-  int status = 0, apps = 0, dhint = 1, dhh = 1;
+  int status = 0, dhint = 1, dhh = 1;
+  double flops = 0.0;   // algorithmic flops of the series terms and of the per-group work (bpc_count_flops adds the per-observation constant)
   const int g = lane >> 2, tg = lane & 3;
   const int od = lane / BP_N, ol = lane - od * BP_N;   // this lane's (d, l) entry of the D x n blocks (lanes < DN)
   const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
@@ -1190,6 +1211,8 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     // series: theta_h <= bp_th[BP_CJ - 1] << 1, so each further term is smaller by theta_h / j and the coupling factor
     // (j ||H|| / 2||A||) of the block-triangular operator cannot bring term d + 1 back above the threshold
     const int J = ph.m - 1;
+    // N_0 and the chain N_1 .. N_J (2 D^2 n each), and the Toeplitz product ((J + 1)(m_g + 1) - 1 coefficient x row updates of 2 D n)
+    if (lane == 0) flops += 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (pc.m + 1) - 1);
     // ---- group prologue: N_0 = E2[b] M1[a], N_(j+1) = L N_j, coefficient table c_i(tau_g) ----
     {
       const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
@@ -1227,24 +1250,12 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
       w[0] = 1.0;
 #pragma unroll
       for (int j = 1; j < BP_CJ; ++j) w[j] = w[j - 1] * (h * (j <= J ? bp_rk[j - 1] : 0.0));   // zero beyond J
-#pragma unroll
-      for (int j = 0; j < BP_CJ; ++j) {
-        if (j <= J) {
-          double wz[BP_N];
-#pragma unroll
-          for (int l = 0; l < BP_N; ++l) wz[l] = w[j] * z0[l];
-          const double* nrow = sN + j * BP_CNLD;
-#pragma unroll
-          for (int d = 0; d < BP_D; ++d) {
-            double s = (d < BP_N) ? ymu[d] : yS[d - BP_N];
-#pragma unroll
-            for (int l = 0; l < BP_N; ++l) s += nrow[d * BP_N + l] * wz[l];
-            if (d < BP_N) ymu[d] = s; else yS[d - BP_N] = s;
-          }
-        }
-      }
+      // branch-free variants by number of terms (terms beyond J have w_j = 0 and read stale but finite rows of sN)
+      if (J <= 5) bp_c_forward<6>(sN, w, z0, ymu, yS);
+      else if (J == 6) bp_c_forward<7>(sN, w, z0, ymu, yS);
+      else bp_c_forward<8>(sN, w, z0, ymu, yS);
       if (valid) {
-        apps += J + 1;
+        flops += (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);   // per term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
         if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; valid = false; }
       }
       // stage this observation's operands: T column (c_j(h), j = 0..J) and B column (packed-coordinate cotangent x z0)
@@ -1328,7 +1339,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 #pragma unroll
   for (int k = 0; k < BP_P; ++k) vals[1 + k] = 0.0;
   vals[BP_P + 1] = sb;
-  vals[BP_P + 2] = (double)apps;
+  vals[BP_P + 2] = flops;
   bp_block_reduce_store(vals, bp_smem, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
   if (status) atomicOr(a.status + c, status);
 }

@@ -469,7 +469,7 @@ static void choose_tiling(bpc_data* d, int nchains) {
     // CTA = cgpc consecutive groups (a multiple of the warps per CTA); aim at >= 4 waves of 3 CTAs per SM
     const int nw = T / 32;
     long long gpc = ((long long)d->cgroups * nchains) / (148LL * 3 * 4);
-    long long cap = 4LL * nw;
+    long long cap = 8LL * nw;
     if (const char* ev = std::getenv("BPC_CGROUPS_PER_CTA")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 4096) cap = v; }
     gpc = std::max<long long>(nw, std::min(cap, gpc));
     gpc = (gpc / nw) * nw;
@@ -788,7 +788,7 @@ int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains,
   for (int c = 0; c < nchains; ++c)
     // (a W-path chain that fell back to the ring kernel is counted with the W-path constants: a lower bound)
     flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N
-                         : d->cmode              ? apps[c] * f.per_term_c + f.per_obs_c * d->N
+                         : d->cmode              ? apps[c] + f.per_obs_c * d->N   // (bp_fusedc counts the flops of its terms and groups itself)
                          : d->wmode              ? apps[c] * (f.per_app_fwd + f.per_app_w) + f.per_obs_w * d->N
                                                  : apps[c] * (f.per_app_fwd + f.per_app_bwd) + (d->grouped ? f.per_obs_grouped : f.per_obs) * d->N;
   return BPC_OK;

@@ -81,8 +81,9 @@ FlopModel flop_model(const ModelSpec& sp) {
   f.per_app_w = 2.0 * D * n;
   f.per_obs_w = 2 + score + 2.0 * (sp.wcap + 1) + (S - n) + D * n;
   // centred W path: per term of the short series the coefficient c_j(h) (2), w_j z0 (n), N_j (w_j z0) (2 D n) and one row of the
-  // S update (2 D n); per observation h (1), the score, the packed-coordinate cotangent and the outer product b z0^T.  The
-  // per-group work (N_j chain, Toeplitz product) is not counted.
+  // S update (2 D n) -- bp_fusedc accumulates these and the per-group work (N_j chain, Toeplitz product) itself; per
+  // observation h (1), the score, the packed-coordinate cotangent and the outer product b z0^T.  The per-chain tables
+  // (bp_ctable) and the matrix polynomial (bp_wpost) are not counted.
   f.per_term_c = 2.0 + n + 4.0 * D * n;
   f.per_obs_c = 1 + score + (S - n) + D * n;
   return f;
