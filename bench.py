@@ -30,8 +30,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fused logp+grad (chain x observation) evaluations per second"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one `ncu --set full` capture of the default
-# workload (profiles/r01_ncu_bp_fusedw_cfg5U.txt: 5.857 MB read + 50.744 MB written, the W partial sums spilling out of L2)
-NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 5.857e6 + 50.744e6}
+# workload (profiles/r01_ncu_bp_fusedc_cfg5U.txt: 33.8 MB read + 426.0 MB written — the per-group S matrices (410 MB of scratch per
+# launch) are written once, read back from L2 by the same warp and evicted later; the observation table itself is 5.6 MB)
+NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 33.795e6 + 426.030e6}
 UNIT = "evals/s"
 DEFAULT_CHAINS = {"cfg5U": 512, "cfg5K": 512, "cfg5G": 512, "cfg2": 1024, "cfg1": 4, "cfg3": 4, "cfg4": 4}
 

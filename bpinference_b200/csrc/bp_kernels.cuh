@@ -763,7 +763,11 @@ struct BpObsArgs {
 #define BP_CGA 64                               // coarse grid intervals
 #define BP_CGB 64                               // fine points per coarse interval
 #define BP_CPMAX 14                             // longest series of the fine table E2 (durations <= tmax / BP_CGA)
-#define BP_CWARP (BP_CJ * BP_CNLD + (8 + BP_WCT * 8) * BP_WLD)   // doubles of shared memory per warp
+#ifndef BP_CSPLIT
+#define BP_CSPLIT 1                              // the B operand is staged in BP_CSPLIT column blocks (less shared memory per warp)
+#endif
+#define BP_CHCT (BP_WCT / BP_CSPLIT)            // column tiles per staged block
+#define BP_CWARP (BP_CJ * BP_CNLD + (8 + BP_CHCT * 8) * BP_WLD)   // doubles of shared memory per warp
 #define BP_CSG (8 * BP_WCT * 8)                 // doubles of one stored S^g: [j][8 BP_WCT columns]
 
 BP_HD bool bp_w_path(bool rates_finite, real a1, real tmax) {
@@ -1183,7 +1187,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
   }
   double* sN = bp_smem + (size_t)warp * BP_CWARP;   // [BP_CJ][BP_CNLD]   N_j[(d, l)]
   double* sT = sN + BP_CJ * BP_CNLD;                // [8][BP_WLD]        T[j][obs] = c_j(h_obs)
-  double* sB = sT + 8 * BP_WLD;                     // [BP_WCT*8][BP_WLD] B[(d,l)][obs] = b_d z0_l
+  double* sB = sT + 8 * BP_WLD;                     // [BP_CHCT*8][BP_WLD] B[(d,l)][obs] = b_d z0_l, one column block at a time
   for (int i = lane; i < BP_CWARP; i += 32) sN[i] = 0.0;   // padding rows / columns stay zero
   __syncthreads();
   const double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
@@ -1262,26 +1266,32 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 #pragma unroll
       for (int j = 0; j < BP_CJ; ++j) sT[j * BP_WLD + lane] = valid ? w[j] : 0.0;   // a zero T column removes the observation from S
 #pragma unroll
-      for (int d = 0; d < BP_D; ++d) {
-        double bd;
-        if (d < BP_N) bd = bmu[d];
-        else {
-          bool diag = false;
+      for (int hb = 0; hb < BP_CSPLIT; ++hb) {   // column blocks of the B operand (stale padding columns of a later block are
+                                                 // harmless: columns >= D n of S and W are never read)
 #pragma unroll
-          for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == d - BP_N);
-          bd = diag ? bS[d - BP_N] : bS[d - BP_N] + bS[d - BP_N];
+        for (int d = 0; d < BP_D; ++d) {
+          double bd;
+          if (d < BP_N) bd = bmu[d];
+          else {
+            bool diag = false;
+#pragma unroll
+            for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == d - BP_N);
+            bd = diag ? bS[d - BP_N] : bS[d - BP_N] + bS[d - BP_N];
+          }
+#pragma unroll
+          for (int l = 0; l < BP_N; ++l)
+            if ((d * BP_N + l) / (BP_CHCT * 8) == hb) sB[((d * BP_N + l) - hb * BP_CHCT * 8) * BP_WLD + lane] = bd * z0[l];
         }
+        __syncwarp();
 #pragma unroll
-        for (int l = 0; l < BP_N; ++l) sB[(d * BP_N + l) * BP_WLD + lane] = bd * z0[l];
+        for (int ob = 0; ob < 8; ++ob) {   // 4 observations per mma
+          const double af = sT[g * BP_WLD + ob * 4 + tg];
+#pragma unroll
+          for (int ct = 0; ct < BP_CHCT; ++ct)
+            bp_dmma(accS[hb * BP_CHCT + ct][0], accS[hb * BP_CHCT + ct][1], af, sB[(ct * 8 + g) * BP_WLD + ob * 4 + tg]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-#pragma unroll
-      for (int ob = 0; ob < 8; ++ob) {   // 4 observations per mma
-        const double af = sT[g * BP_WLD + ob * 4 + tg];
-#pragma unroll
-        for (int ct = 0; ct < BP_WCT; ++ct) bp_dmma(accS[ct][0], accS[ct][1], af, sB[(ct * 8 + g) * BP_WLD + ob * 4 + tg]);
-      }
-      __syncwarp();
     }
     // ---- park S^g (accumulator fragment -> row-major, 16-byte stores; L2-resident until the Toeplitz products below) ----
 #pragma unroll

@@ -181,9 +181,13 @@ std::string generate_cuda(ModelSpec& m) {
     s += buf;
     // centred W path (bp_fusedc): per warp N_j and the T / B staging; the CTA's dense L
     const int crt = (m.wcap + 1 + 8 + 7) / 8, dn = D * n, nw = m.threads / 32;
-    const size_t cwarp = (size_t)8 * (dn + (dn & 1)) + (size_t)(8 + wct * 8) * 36;
+    int csplit = 1;
+    if (const char* ev = std::getenv("BPC_CSPLIT")) { const int v = std::atoi(ev); if (v >= 1 && v <= wct && wct % v == 0) csplit = v; }
+    const size_t cwarp = (size_t)8 * (dn + (dn & 1)) + (size_t)(8 + wct / csplit * 8) * 36;
     m.c_smem = std::max<size_t>(nw * cwarp + D * D, (size_t)nw * crt * wct * 64) * 8;   // (also holds the end-of-kernel reduction of W)
     int cmin = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (m.c_smem + 1024)));
+    std::snprintf(buf, sizeof buf, "#define BP_CSPLIT %d\n", csplit);
+    s += buf;
     if (const char* ev = std::getenv("BPC_CMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 8) cmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_CMINBLOCKS %d\n", cmin);
     s += buf;

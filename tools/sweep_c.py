@@ -9,7 +9,9 @@ combos = [(128, 3, 8, 16), (128, 3, 4, 16), (128, 3, 16, 16), (128, 3, 8, 8), (1
           (64, 6, 8, 8), (64, 4, 8, 8), (256, 1, 8, 32), (256, 2, 8, 32), (128, 3, 6, 16), (128, 3, 12, 16)]
 if len(sys.argv) > 1:
     combos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
-for thr, cmin, chunks, gpc in combos:
+for combo in combos:
+    thr, cmin, chunks, gpc = combo[:4]
+    os.environ["BPC_CSPLIT"] = str(combo[4]) if len(combo) > 4 else "1"
     os.environ["BPC_THREADS"] = str(thr); os.environ["BPC_CMINBLOCKS"] = str(cmin)
     os.environ["BPC_CGROUP_CHUNKS"] = str(chunks); os.environ["BPC_CGROUPS_PER_CTA"] = str(gpc)
     try:
@@ -20,7 +22,7 @@ for thr, cmin, chunks, gpc in combos:
             lp, g, st = eng.log_prob_grad(d, cfg["upars"])
         ms, n = _ffi.C.c_double(), _ffi.C.c_longlong()
         _ffi.lib().bpc_kernel_time_ms(d.handle, 1, _ffi.C.byref(ms), _ffi.C.byref(n))
-        print("threads %3d cminblocks %d chunks/group %2d groups/CTA %2d (%s tiles): %.3f ms  evals/s %.3e  lp0 %.6f bad %d" % (thr, cmin, chunks, gpc, d.path(512)[1], ms.value / n.value, 512 * 100000 / (ms.value / n.value * 1e-3), lp[0], int((st != 0).sum())), flush=True)
+        print("split %s " % os.environ["BPC_CSPLIT"] + "threads %3d cminblocks %d chunks/group %2d groups/CTA %2d (%s tiles): %.3f ms  evals/s %.3e  lp0 %.6f bad %d" % (thr, cmin, chunks, gpc, d.path(512)[1], ms.value / n.value, 512 * 100000 / (ms.value / n.value * 1e-3), lp[0], int((st != 0).sum())), flush=True)
         d.close(); eng.close()
     except Exception as e:
         print("threads", thr, "cmin", cmin, "chunks", chunks, "gpc", gpc, "FAILED", str(e)[:300], flush=True)
