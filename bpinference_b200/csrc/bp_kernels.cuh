@@ -769,6 +769,21 @@ struct BpObsArgs {
 #define BP_CHCT (BP_WCT / BP_CSPLIT)            // column tiles per staged block
 #define BP_CWARP (BP_CJ * BP_CNLD + (8 + BP_CHCT * 8) * BP_WLD)   // doubles of shared memory per warp
 #define BP_CSG (8 * BP_WCT * 8)                 // doubles of one stored S^g: [j][8 BP_WCT columns]
+// X formulation of bp_fusedc (BP_CX, default): BOTH products of an observation pass run on the fp64 tensor path.  With
+// X[(j, l)][k] = c_j(h_k) z0_kl (staged once per pass):  forward  Y[d][k] = sum_(j,l) N_j[d][l] X[(j,l)][k]  (components d < 8; a
+// ninth component, n = 3, is a short DFMA dot product), and  S'[(j,l)][d] += sum_k X[(j,l)][k] b_k[d]  (the same X as the A operand;
+// the ninth component as T[j][k] x (b_k[8] z0_kl)).  S^g is parked with columns (l, d) instead of (d, l); bp_wpost undoes that.
+#ifndef BP_CX
+#define BP_CX 1
+#endif
+#define BP_XR (BP_CJ * BP_N)                    // rows of X: (j, l), j-major
+#define BP_XKS (BP_XR / 4)                      // k-steps of the forward product
+#define BP_XRT (BP_XR / 8)                      // row tiles of the S' update
+#define BP_XDM (BP_D < 8 ? BP_D : 8)            // components on the tensor path
+#define BP_XDR (BP_D - BP_XDM)                  // remaining components (1 for n = 3)
+#define BP_XNLD 12                              // row stride of the staged N: [(j, l)][d < 8]  (conflict-free A fragments)
+#define BP_XYLD 40                              // row stride of Y[d][obs] (conflict-free 16-byte stores of the accumulator fragments)
+#define BP_XWARP (BP_XR * BP_XNLD + BP_XR * (BP_XDR ? BP_XDR : 1) + BP_XR * BP_WLD + 8 * BP_XYLD)   // doubles per warp
 
 BP_HD bool bp_w_path(bool rates_finite, real a1, real tmax) {
   const real xx = (a1 + a1) * tmax;
@@ -1027,6 +1042,15 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
     for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * frag + i];
     const int tile = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = (tile / BP_WCT) * 8 + (ln >> 2), col = (tile % BP_WCT) * 8 + (ln & 3) * 2 + e;
+#if BP_CX && BP_N <= 3
+    if (a.wmode == 2) {   // bp_fusedc (X formulation) parks columns as (l, d) for d < BP_XDM, then (q, l) for the remaining components
+      int dd = -1, ll = 0;
+      if (col < BP_N * 8) { ll = col >> 3; dd = (col & 7) < BP_XDM ? (col & 7) : -1; }
+      else { const int rem = col - BP_N * 8, q = rem / BP_N; ll = rem - q * BP_N; dd = q < BP_XDR ? BP_XDM + q : -1; }
+      if (row < rows && dd >= 0) W[row * BP_WCOLS + dd * BP_N + ll] = sacc;
+      continue;
+    }
+#endif
     if (row < rows && col < BP_WCOLS) W[row * BP_WCOLS + col] = sacc;
   }
   bp_coop_build_L(A, H, Lm);
@@ -1168,7 +1192,12 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 #else
   const double sigma = 0.0;
 #endif
-  double* Lm = bp_smem + (size_t)NW * BP_CWARP;   // [D][D], after the warps' areas
+#if BP_CX
+  constexpr int WARPD = BP_XWARP;
+#else
+  constexpr int WARPD = BP_CWARP;
+#endif
+  double* Lm = bp_smem + (size_t)NW * WARPD;   // [D][D], after the warps' areas
   {
     double th[BP_DIM];
 #pragma unroll
@@ -1185,10 +1214,17 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;   // bp_fused handles this chain
     bp_coop_build_L(A, H, Lm);
   }
-  double* sN = bp_smem + (size_t)warp * BP_CWARP;   // [BP_CJ][BP_CNLD]   N_j[(d, l)]
+#if BP_CX
+  double* sN = bp_smem + (size_t)warp * WARPD;      // [BP_XR][BP_XNLD]   N_j[d][l] at [(j, l)][d], d < BP_XDM
+  double* sN9 = sN + BP_XR * BP_XNLD;               // [BP_XR][BP_XDR]    the remaining components of N_j
+  double* sX = sN9 + BP_XR * (BP_XDR ? BP_XDR : 1); // [BP_XR][BP_WLD]    X[(j, l)][obs] = c_j(h_obs) z0_obs,l
+  double* sBm = sX + BP_XR * BP_WLD;                // [8][BP_XYLD]       Y[d][obs] out of the forward product, then b[d][obs] (row stride BP_WLD)
+#else
+  double* sN = bp_smem + (size_t)warp * WARPD;      // [BP_CJ][BP_CNLD]   N_j[(d, l)]
   double* sT = sN + BP_CJ * BP_CNLD;                // [8][BP_WLD]        T[j][obs] = c_j(h_obs)
   double* sB = sT + 8 * BP_WLD;                     // [BP_CHCT*8][BP_WLD] B[(d,l)][obs] = b_d z0_l, one column block at a time
-  for (int i = lane; i < BP_CWARP; i += 32) sN[i] = 0.0;   // padding rows / columns stay zero
+#endif
+  for (int i = lane; i < WARPD; i += 32) sN[i] = 0.0;   // padding rows / columns stay zero
   __syncthreads();
   const double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
   const double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
@@ -1217,6 +1253,165 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     const int J = ph.m - 1;
     // N_0 and the chain N_1 .. N_J (2 D^2 n each), and the Toeplitz product ((J + 1)(m_g + 1) - 1 coefficient x row updates of 2 D n)
     if (lane == 0) flops += 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (pc.m + 1) - 1);
+#if BP_CX
+    // ---- group prologue: N_0 = E2[b] M1[a], N_(j+1) = L N_j; stored transposed, [(j, l)][d] ----
+    {
+      const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
+      double nj = 0.0;
+      if (lane < DN) {
+#pragma unroll
+        for (int rr = 0; rr < BP_D; ++rr) nj += e2[(size_t)bi * DD + od * BP_D + rr] * m1[(size_t)ai * DN + rr * BP_N + ol];
+        if (od < BP_XDM) sN[ol * BP_XNLD + od] = nj; else sN9[ol * BP_XDR + (od - BP_XDM)] = nj;
+      }
+      __syncwarp();
+      for (int j = 1; j <= J; ++j) {
+        if (lane < DN) {
+          const double* pn = sN + ((j - 1) * BP_N + ol) * BP_XNLD;
+          nj = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < BP_XDM; ++rr) nj += Lm[od * BP_D + rr] * pn[rr];
+#pragma unroll
+          for (int rr = BP_XDM; rr < BP_D; ++rr) nj += Lm[od * BP_D + rr] * sN9[((j - 1) * BP_N + ol) * BP_XDR + (rr - BP_XDM)];
+          if (od < BP_XDM) sN[(j * BP_N + ol) * BP_XNLD + od] = nj; else sN9[(j * BP_N + ol) * BP_XDR + (od - BP_XDM)] = nj;
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < BP_WCT; ++ct) { accS[ct][0] = 0.0; accS[ct][1] = 0.0; }
+    // the A fragments of the forward product (N, shared by the group's passes) stay in registers
+    double nf[BP_XKS];
+#pragma unroll
+    for (int kk = 0; kk < BP_XKS; ++kk) nf[kk] = sN[(kk * 4 + tg) * BP_XNLD + g];
+#if BP_XDR
+    // S update of the components beyond the tensor tile: per-lane accumulators over the group's passes, summed over lanes once per group
+    double acc9[BP_XDR][BP_XR];
+#pragma unroll
+    for (int q = 0; q < BP_XDR; ++q)
+#pragma unroll
+      for (int r = 0; r < BP_XR; ++r) acc9[q][r] = 0.0;
+#endif
+    // ---- the group's observations, 32 per pass ----
+    const int ch1 = a.cg_chunk0[grp + 1];
+    for (int ch = a.cg_chunk0[grp]; ch < ch1; ++ch) {
+      const int k = ch * 32 + lane;
+      bool valid = k < a.nobs;
+      double z0[BP_N], xo[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S], w[BP_CJ];
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; bmu[i] = 0.0; }
+#pragma unroll
+      for (int q = 0; q < BP_S; ++q) bS[q] = 0.0;
+      const double h = valid ? a.t[k] - tau : 0.0;
+      // X[(j, l)] = c_j(h) z0_l (zero beyond J); the components beyond the tensor tile as a dot product on the way
+      double yr[BP_XDR ? BP_XDR : 1][BP_N];   // (one partial sum per l: independent chains)
+#pragma unroll
+      for (int q = 0; q < (BP_XDR ? BP_XDR : 1); ++q)
+#pragma unroll
+        for (int l = 0; l < BP_N; ++l) yr[q][l] = 0.0;
+      w[0] = 1.0;
+#pragma unroll
+      for (int j = 0; j < BP_CJ; ++j) {
+        if (j > 0) w[j] = w[j - 1] * (h * (j <= J ? bp_rk[j - 1] : 0.0));
+#pragma unroll
+        for (int l = 0; l < BP_N; ++l) {
+          const double x = w[j] * z0[l];
+          sX[(j * BP_N + l) * BP_WLD + lane] = x;
+#pragma unroll
+          for (int q = 0; q < BP_XDR; ++q) yr[q][l] += sN9[(j * BP_N + l) * BP_XDR + q] * x;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < BP_XDR; ++q)
+#pragma unroll
+        for (int l = 1; l < BP_N; ++l) yr[q][0] += yr[q][l];
+      __syncwarp();
+      // forward product on the tensor path: Y[d][obs] = sum_r N[r][d] X[r][obs], d < BP_XDM, four 8-observation tiles
+      {
+        double accY[4][2];
+#pragma unroll
+        for (int ot = 0; ot < 4; ++ot) { accY[ot][0] = 0.0; accY[ot][1] = 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < BP_XKS; ++kk)
+#pragma unroll
+          for (int ot = 0; ot < 4; ++ot) bp_dmma(accY[ot][0], accY[ot][1], nf[kk], sX[(kk * 4 + tg) * BP_WLD + ot * 8 + g]);
+#pragma unroll
+        for (int ot = 0; ot < 4; ++ot) *reinterpret_cast<double2*>(sBm + g * BP_XYLD + ot * 8 + 2 * tg) = make_double2(accY[ot][0], accY[ot][1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < BP_D; ++d) {
+        const double yd = d < BP_XDM ? sBm[(d < BP_XDM ? d : 0) * BP_XYLD + lane] : yr[d < BP_XDM ? 0 : d - BP_XDM][0];
+        if (d < BP_N) ymu[d] = yd; else yS[d - BP_N] = yd;
+      }
+      __syncwarp();
+      if (valid) {
+        flops += (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);   // per term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
+        if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; valid = false; }
+      }
+      // stage the cotangent in packed coordinates (zero for an observation that does not count)
+#pragma unroll
+      for (int d = 0; d < BP_D; ++d) {
+        double bd;
+        if (d < BP_N) bd = bmu[d];
+        else {
+          bool diag = false;
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == d - BP_N);
+          bd = diag ? bS[d - BP_N] : bS[d - BP_N] + bS[d - BP_N];
+        }
+        bd = valid ? bd : 0.0;
+        if (d < BP_XDM) sBm[d * BP_WLD + lane] = bd;
+#if BP_XDR
+        else {
+#pragma unroll
+          for (int j = 0; j < BP_CJ; ++j) {
+            const double wb = w[j] * bd;
+#pragma unroll
+            for (int l = 0; l < BP_N; ++l) acc9[d < BP_XDM ? 0 : d - BP_XDM][j * BP_N + l] += wb * z0[l];
+          }
+        }
+#endif
+      }
+      __syncwarp();
+#pragma unroll
+      for (int ob = 0; ob < 8; ++ob) {   // 4 observations per mma
+        const double bf = sBm[g * BP_WLD + ob * 4 + tg];
+#pragma unroll
+        for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][0], accS[rt][1], sX[(rt * 8 + g) * BP_WLD + ob * 4 + tg], bf);
+      }
+      __syncwarp();
+    }
+    // ---- park S^g: row j, columns (l, d) for d < BP_XDM, then the remaining components (q, l) ----
+#pragma unroll
+    for (int rt = 0; rt < BP_XRT; ++rt) {
+      const int r = rt * 8 + g, jj = r / BP_N, ll = r - jj * BP_N;
+      *reinterpret_cast<double2*>(sg + jj * (BP_WCT * 8) + ll * 8 + 2 * tg) = make_double2(accS[rt][0], accS[rt][1]);
+    }
+#if BP_XDR
+    // sum the per-lane accumulators over the warp's lanes: one product with a matrix of ones (rows (j, l) x lanes)
+#pragma unroll
+    for (int q = 0; q < BP_XDR; ++q) {
+#pragma unroll
+      for (int r = 0; r < BP_XR; ++r) sX[r * BP_WLD + lane] = acc9[q][r];
+      __syncwarp();
+      double red9[BP_XRT][2];
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt) { red9[rt][0] = 0.0; red9[rt][1] = 0.0; }
+#pragma unroll
+      for (int ob = 0; ob < 8; ++ob)
+#pragma unroll
+        for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(red9[rt][0], red9[rt][1], sX[(rt * 8 + g) * BP_WLD + ob * 4 + tg], 1.0);
+      if (tg == 0) {
+#pragma unroll
+        for (int rt = 0; rt < BP_XRT; ++rt) {
+          const int r = rt * 8 + g, jj = r / BP_N, ll = r - jj * BP_N;
+          sg[jj * (BP_WCT * 8) + BP_N * 8 + q * BP_N + ll] = red9[rt][0];
+        }
+      }
+      __syncwarp();
+    }
+#endif
+#else
     // ---- group prologue: N_0 = E2[b] M1[a], N_(j+1) = L N_j, coefficient table c_i(tau_g) ----
     {
       const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
@@ -1296,6 +1491,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
     // ---- park S^g (accumulator fragment -> row-major, 16-byte stores; L2-resident until the Toeplitz products below) ----
 #pragma unroll
     for (int ct = 0; ct < BP_WCT; ++ct) *reinterpret_cast<double2*>(sg + g * (BP_WCT * 8) + ct * 8 + 2 * tg) = make_double2(accS[ct][0], accS[ct][1]);
+#endif
   }
   // ---- W += C(tau_g) S^g for this warp's groups: rows n - 1 (n = 1 .. m_g + J), k = j (8), columns (d, l).  Deferred to here so
   // that the 2 BP_CRT BP_WCT accumulator registers do not live through the observation loop. ----

@@ -390,7 +390,7 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
     const int FG = 64 * 64;
     const double delta = tmax / FG;
     const double hcap = 0.999 * tmax * taylor_theta(7) / taylor_theta(s.wcap);
-    int gmax = 8;
+    int gmax = 16;   // (tools/perf_c.py: 8 -> 3.03 ms, 12 -> 3.13, 16 -> 2.78, 20 -> 2.99 on cfg5U; wider groups need a longer short series)
     if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) gmax = v; }
     const int nchunks = (N + 31) / 32;
     std::vector<int> c0, idx;

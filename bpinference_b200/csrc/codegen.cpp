@@ -183,9 +183,17 @@ std::string generate_cuda(ModelSpec& m) {
     const int crt = (m.wcap + 1 + 8 + 7) / 8, dn = D * n, nw = m.threads / 32;
     int csplit = 1;
     if (const char* ev = std::getenv("BPC_CSPLIT")) { const int v = std::atoi(ev); if (v >= 1 && v <= wct && wct % v == 0) csplit = v; }
-    const size_t cwarp = (size_t)8 * (dn + (dn & 1)) + (size_t)(8 + wct / csplit * 8) * 36;
+    int cx = 1;   // X formulation: both products of a pass on the fp64 tensor path (bp_kernels.cuh, BP_CX)
+    if (const char* ev = std::getenv("BPC_CX")) cx = std::atoi(ev) ? 1 : 0;
+    const int xr = 8 * n, xdr = D > 8 ? D - 8 : 0;
+    const size_t cwarp = cx ? (size_t)xr * 12 + (size_t)xr * (xdr ? xdr : 1) + (size_t)xr * 36 + (size_t)8 * 40
+                            : (size_t)8 * (dn + (dn & 1)) + (size_t)(8 + wct / csplit * 8) * 36;
+    std::snprintf(buf, sizeof buf, "#define BP_CX %d\n", cx);
+    s += buf;
     m.c_smem = std::max<size_t>(nw * cwarp + D * D, (size_t)nw * crt * wct * 64) * 8;   // (also holds the end-of-kernel reduction of W)
-    int cmin = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (m.c_smem + 1024)));
+    // (X formulation: per-lane accumulators of the ninth component need the registers of 3 CTAs per SM; the kernel is bound by the
+    // shared-memory and FP64 pipes, not by occupancy)
+    int cmin = (int)std::max<size_t>(1, std::min<size_t>(cx ? 3 : 4, (227 * 1024) / (m.c_smem + 1024)));
     std::snprintf(buf, sizeof buf, "#define BP_CSPLIT %d\n", csplit);
     s += buf;
     if (const char* ev = std::getenv("BPC_CMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 8) cmin = v; }
