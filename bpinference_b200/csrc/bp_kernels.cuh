@@ -730,6 +730,13 @@ struct BpObsArgs {
   double* ctab_m1;       // [C][BP_CGA + 1][D * n]  single-ancestor moments exp(a * BP_CGB * cdelta * L) [e_1 .. e_n]
   double* ctab_e2;       // [C][BP_CGB][D * D]      exp(b * cdelta * L)
   double* csg;           // [C][cgroups][BP_CSG]    scratch: the groups' S^g between a warp's main loop and its Toeplitz products
+  // octet path (wmode 3, bp_ntable + bp_fusedo + bp_toep + bp_wpost): eight chains share the tensor tiles of a pass
+  int noct;              // octets = ceil(C / 8)
+  double* ntab;          // [noct][cgroups][BP_XR][8 BP_D]  N_j(tau_g) of the octet's chains: row (j, l), column cc * BP_D + d
+  int* cg_jm;            // [noct * 8][cgroups]             J | m << 8 of (chain, group); -1: the chain is not on this path
+  double* cg_flops;      // [noct * 8][cgroups]             algorithmic flops of (chain, group)
+  double* osg;           // [noct][cgroups][BP_XR][8 BP_D]  S'^g of the octet: row (j, l), column cc * BP_D + d
+  double* wplain;        // [C][BP_CROWS][BP_WCOLS]         W_n of each chain, row n - 1, column d * BP_N + l
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -1036,7 +1043,12 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
   if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
   // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
   // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
-  const int frag = a.wmode == 2 ? BP_CFRAG : BP_WFRAG, rows = a.wmode == 2 ? BP_CROWS : BP_WROWS;
+  const int frag = a.wmode == 1 ? BP_WFRAG : BP_CFRAG, rows = a.wmode == 1 ? BP_WROWS : BP_CROWS;
+#if BP_N <= 3
+  if (a.wmode == 3) {   // octet path: bp_toep wrote W of this chain in place
+    for (int i = tid; i < BP_CROWS * BP_WCOLS; i += blockDim.x) W[i] = a.wplain[(size_t)c * BP_CROWS * BP_WCOLS + i];
+  } else
+#endif
   for (int i = tid; i < frag; i += blockDim.x) {
     double sacc = 0.0;
     for (int tI = 0; tI < a.ntiles; ++tI) sacc += a.wpart[((size_t)c * a.ntiles + tI) * frag + i];
@@ -1548,6 +1560,321 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
   vals[BP_P + 2] = flops;
   bp_block_reduce_store(vals, bp_smem, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
   if (status) atomicOr(a.status + c, status);
+}
+
+// ---- octet path: bp_ntable + bp_fusedo + bp_toep ---------------------------------------------------------------
+// X[(j, l)][k] = c_j(h_k) z0_kl does not depend on the chain, and 8 chains x D components fill the 8-wide tensor tiles exactly
+// (for every n).  So a warp takes one pass of 32 observations for EIGHT chains at once:
+//     forward   Y[(cc, d)][k]  = sum_(j,l) N^cc_j[d][l] X[(j,l)][k]          D row tiles x 4 observation tiles x BP_XKS k-steps
+//     score     per (chain, observation), one observation per lane, the 8 chains one after the other (independent work)
+//     S update  S'[(j,l)][(cc, d)] += sum_k X[(j,l)][k] b^cc_k[d]              BP_XRT x D tiles x 8 k-steps
+// with X staged once per pass, its fragments shared by all column tiles, no padded tile rows and no ninth-component side path.
+// The short series is never masked in the hot loop: N rows beyond a chain's own degree J are zero (bp_ntable), and the rows of
+// S' beyond it are dropped by bp_toep.  bp_ntable builds N_j(tau_g) for every (chain, group) (what bp_fusedc does in its group
+// prologue), bp_toep is the Toeplitz product W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for all groups at once, bp_wpost finishes.
+#define BP_OU (8 * BP_D)                         // columns of an octet: (cc, d)
+#define BP_ONLD (BP_OU + 4)                      // row stride of the staged N (conflict-free A fragments: stride = 12 mod 16)
+#define BP_OWARPS 2
+#define BP_OWARP (BP_XR * BP_WLD + BP_OU * BP_WLD)   // doubles per warp: X[(j,l)][obs], Y / b[(cc,d)][obs]
+#define BP_OSMEM ((BP_XR * BP_ONLD + BP_OWARPS * BP_OWARP) * 8)
+
+extern "C" __global__ void __launch_bounds__(128) bp_ntable(BpObsArgs a) {
+  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
+  __shared__ double Lm[DD];
+  __shared__ double sNw[4][BP_XR * BP_D];
+  const int grp = blockIdx.x * 4 + warp;
+  const int o = c >> 3, cc = c & 7;
+  bool okpath = false;
+  double a1 = 0.0;
+  if (c < a.nchains) {
+    double th[BP_DIM];
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+    double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
+#pragma unroll
+    for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+    bp_rates(th, xk, r);
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+    bp_assemble(r, A, H);
+    a1 = bp_norm1(A);
+    okpath = bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0);
+    if (okpath) bp_coop_build_L(A, H, Lm);
+  }
+  __syncthreads();
+  if (grp >= a.cgroups) return;
+  double* out = a.ntab + (((size_t)o * a.cgroups + grp) * BP_XR) * BP_OU + cc * BP_D;
+  double* sN = sNw[warp];
+  int J = -1, mg = 0;
+  if (okpath) {
+    BpPlan pc, ph;
+    int d1 = 1, d2 = 1;
+    const bool okc = bp_make_plan(a1, a.cg_tau[grp], pc, d1, BP_WCAP, BP_WTHETA_CAP);
+    const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, d2, BP_CJ - 1, BP_WTHETA_CAP);
+    if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[grp] <= bp_th[ph.m - 1])) {   // (never for data bpc_data_create accepted)
+      if (lane == 0) atomicOr(a.status + c, BP_ST_RATE_NONFINITE);
+    } else {
+      J = ph.m - 1;
+      mg = pc.m;
+    }
+  }
+  for (int i = lane; i < BP_XR * BP_D; i += 32) sN[i] = 0.0;
+  __syncwarp();
+  if (J >= 0) {
+    const double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
+    const double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
+    const int gi = a.cg_idx[grp];
+    const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
+    const int od = lane / BP_N, ol = lane - od * BP_N;
+    double nj = 0.0;
+    if (lane < DN) {
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) nj += e2[(size_t)bi * DD + od * BP_D + rr] * m1[(size_t)ai * DN + rr * BP_N + ol];
+      sN[ol * BP_D + od] = nj;
+    }
+    __syncwarp();
+    for (int j = 1; j <= J; ++j) {
+      if (lane < DN) {
+        nj = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < BP_D; ++rr) nj += Lm[od * BP_D + rr] * sN[((j - 1) * BP_N + ol) * BP_D + rr];
+        sN[(j * BP_N + ol) * BP_D + od] = nj;
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < BP_XR * BP_D; i += 32) { const int r = i / BP_D, d = i - r * BP_D; out[(size_t)r * BP_OU + d] = sN[i]; }
+  if (lane == 0) {
+    a.cg_jm[(size_t)c * a.cgroups + grp] = J < 0 ? -1 : (J | (mg << 8));
+    double fl = 0.0;
+    if (J >= 0) {
+      const int k0 = a.cg_chunk0[grp] * 32, k1 = min(a.nobs, a.cg_chunk0[grp + 1] * 32);
+      fl = 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (mg + 1) - 1)      // N_0 .. N_J and the Toeplitz product (as bp_fusedc counts them)
+           + (double)max(0, k1 - k0) * (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);               // per observation and term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
+    }
+    a.cg_flops[(size_t)c * a.cgroups + grp] = fl;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(32 * BP_OWARPS, 3) bp_fusedo(BpObsArgs a) {
+  const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  double* sN = bp_smem;                                              // [BP_XR][BP_ONLD]
+  double* sX = bp_smem + BP_XR * BP_ONLD + (size_t)warp * BP_OWARP;  // [BP_XR][BP_WLD]
+  double* sY = sX + BP_XR * BP_WLD;                                  // [BP_OU][BP_WLD]
+  __shared__ int sjm[8];
+  __shared__ double sred[BP_OWARPS][8][3];
+  double lp[8], sb[8];
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) { lp[cc] = 0.0; sb[cc] = 0.0; }
+  int notpd = 0;   // bit cc: an observation of chain cc had a covariance that is not positive definite
+  const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
+  for (int grp = g0; grp < g1; ++grp) {
+    __syncthreads();   // the previous group's N and reduction scratch are free
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.ntab + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU);
+      for (int i = tid; i < BP_XR * BP_OU / 2; i += 32 * BP_OWARPS) {
+        const int r = i / (BP_OU / 2), q = i - r * (BP_OU / 2);
+        *reinterpret_cast<double2*>(sN + r * BP_ONLD + 2 * q) = src[i];
+      }
+      if (tid < 8) sjm[tid] = (o * 8 + tid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + tid) * a.cgroups + grp] : -1;
+    }
+    __syncthreads();
+    const double tau = a.cg_tau[grp];
+    double accS[BP_XRT][BP_D][2];
+#pragma unroll
+    for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < BP_D; ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
+    const int ch1 = a.cg_chunk0[grp + 1];
+    for (int ch = a.cg_chunk0[grp] + warp; ch < ch1; ch += BP_OWARPS) {
+      const int k = ch * 32 + lane;
+      const bool valid = k < a.nobs;
+      double xo[BP_N];
+      {
+        double z0[BP_N];
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+        const double h = valid ? a.t[k] - tau : 0.0;
+        double w = 1.0;
+#pragma unroll
+        for (int j = 0; j < BP_CJ; ++j) {
+          if (j > 0) w = w * (h * bp_rk[j - 1]);
+#pragma unroll
+          for (int l = 0; l < BP_N; ++l) sX[(j * BP_N + l) * BP_WLD + lane] = w * z0[l];
+        }
+      }
+      __syncwarp();
+      // forward product, three row tiles (24 columns of the octet) at a time
+#pragma unroll
+      for (int t0 = 0; t0 < BP_D; t0 += 3) {
+        double accY[3][4][2];
+#pragma unroll
+        for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+          for (int ot = 0; ot < 4; ++ot) { accY[t3][ot][0] = 0.0; accY[t3][ot][1] = 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < BP_XKS; ++kk) {
+          double xb[4];
+#pragma unroll
+          for (int ot = 0; ot < 4; ++ot) xb[ot] = sX[(kk * 4 + tg) * BP_WLD + ot * 8 + g];
+#pragma unroll
+          for (int t3 = 0; t3 < 3; ++t3) {
+            if (t0 + t3 < BP_D) {
+              const double af = sN[(kk * 4 + tg) * BP_ONLD + (t0 + t3) * 8 + g];
+#pragma unroll
+              for (int ot = 0; ot < 4; ++ot) bp_dmma(accY[t3][ot][0], accY[t3][ot][1], af, xb[ot]);
+            }
+          }
+        }
+#pragma unroll
+        for (int t3 = 0; t3 < 3; ++t3)
+          if (t0 + t3 < BP_D) {
+#pragma unroll
+            for (int ot = 0; ot < 4; ++ot)
+              *reinterpret_cast<double2*>(sY + ((t0 + t3) * 8 + g) * BP_WLD + ot * 8 + 2 * tg) = make_double2(accY[t3][ot][0], accY[t3][ot][1]);
+          }
+      }
+      __syncwarp();
+      // score: this lane's observation under each of the 8 chains; the cotangent (packed coordinates) replaces Y in place
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        double* yc = sY + (cc * BP_D) * BP_WLD + lane;
+        double ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+        bool ok = valid && sjm[cc] >= 0;
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) { ymu[i] = yc[i * BP_WLD]; bmu[i] = 0.0; }
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q) { yS[q] = yc[(BP_N + q) * BP_WLD]; bS[q] = 0.0; }
+        if (ok) {
+#if BP_NOISE
+          const double sigma = a.theta[(size_t)(o * 8 + cc) * BP_DIM + BP_P];
+#else
+          const double sigma = 0.0;
+#endif
+          if (!bp_score_obs(xo, sigma, ymu, yS, lp[cc], sb[cc], bmu, bS)) { notpd |= 1 << cc; ok = false; }
+        }
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) yc[i * BP_WLD] = ok ? bmu[i] : 0.0;
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q) {
+          bool diag = false;
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == q);
+          const double bd = diag ? bS[q] : bS[q] + bS[q];
+          yc[(BP_N + q) * BP_WLD] = ok ? bd : 0.0;
+        }
+      }
+      __syncwarp();
+      // S' update: X fragments (A) shared by all column tiles, b fragments (B) by all row tiles
+#pragma unroll
+      for (int ob = 0; ob < 8; ++ob) {
+        double xa[BP_XRT];
+#pragma unroll
+        for (int rt = 0; rt < BP_XRT; ++rt) xa[rt] = sX[(rt * 8 + g) * BP_WLD + ob * 4 + tg];
+#pragma unroll
+        for (int ct = 0; ct < BP_D; ++ct) {
+          const double bf = sY[(ct * 8 + g) * BP_WLD + ob * 4 + tg];
+#pragma unroll
+          for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][ct][0], accS[rt][ct][1], xa[rt], bf);
+        }
+      }
+      __syncwarp();
+    }
+    // ---- the group's S' = sum of the warps' accumulators (fixed order), parked row-major [(j, l)][(cc, d)] ----
+    // (each warp's Y area holds BP_OU * BP_WLD >= BP_XRT * BP_D * 64 doubles)
+    if (warp > 0) {
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < BP_D; ++ct) *reinterpret_cast<double2*>(sY + ((rt * BP_D + ct) * 32 + lane) * 2) = make_double2(accS[rt][ct][0], accS[rt][ct][1]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < BP_D; ++ct) {
+          double s0 = accS[rt][ct][0], s1 = accS[rt][ct][1];
+#pragma unroll
+          for (int w = 1; w < BP_OWARPS; ++w) {
+            const double2 v = *reinterpret_cast<const double2*>(sY + (size_t)w * BP_OWARP + ((rt * BP_D + ct) * 32 + lane) * 2);
+            s0 += v.x; s1 += v.y;
+          }
+          *reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + ct * 8 + 2 * tg) = make_double2(s0, s1);
+        }
+    }
+  }
+  // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial ----
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    const double l = bp_warp_sum(lp[cc]), s2 = bp_warp_sum(sb[cc]);
+    if (lane == 0) { sred[warp][cc][0] = l; sred[warp][cc][1] = s2; }
+  }
+  notpd = __reduce_or_sync(0xffffffffu, notpd);
+  __syncthreads();
+  if (tid < 8 && o * 8 + tid < a.nchains) {
+    const int c = o * 8 + tid;
+    double l = 0.0, s2 = 0.0, fl = 0.0;
+    for (int w = 0; w < BP_OWARPS; ++w) { l += sred[w][tid][0]; s2 += sred[w][tid][1]; }
+    bool mine = false;
+    for (int grp = g0; grp < g1; ++grp) { fl += a.cg_flops[(size_t)c * a.cgroups + grp]; mine = mine || a.cg_jm[(size_t)c * a.cgroups + grp] >= 0; }
+    if (mine || g0 >= g1 || a.cg_jm[(size_t)c * a.cgroups] >= 0) {   // chains on the fallback path keep the partials bp_fused writes
+      double* p = a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART;
+      p[0] = l;
+#pragma unroll
+      for (int k = 0; k < BP_P; ++k) p[1 + k] = 0.0;
+      p[BP_P + 1] = s2;
+      p[BP_P + 2] = fl;
+    }
+  }
+  if (lane < 8 && ((notpd >> lane) & 1) && o * 8 + lane < a.nchains) atomicOr(a.status + o * 8 + lane, BP_ST_NOT_PD);
+}
+
+// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
+extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
+  const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+  __shared__ double red[4][BP_CRT * 64];
+  const int u = ct * 8 + g, cc = u / BP_D;        // this lane's column of the B fragments: chain cc of the octet
+  const int c = o * 8 + cc;
+  double accW[BP_CRT][2];
+#pragma unroll
+  for (int rt = 0; rt < BP_CRT; ++rt) { accW[rt][0] = 0.0; accW[rt][1] = 0.0; }
+  for (int grp = warp; grp < a.cgroups; grp += 4) {
+    const int jm = c < a.nchains ? a.cg_jm[(size_t)c * a.cgroups + grp] : -1;
+    const int J = jm < 0 ? -1 : (jm & 255);
+    const double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
+    const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
+    double bf[2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int j = ks * 4 + tg;
+      const double v = __ldcg(sg + (size_t)(j * BP_N + l) * BP_OU + u);
+      bf[ks] = j <= J ? v : 0.0;   // rows beyond the chain's own degree hold X b products of terms the chain does not have
+    }
+#pragma unroll
+    for (int rt = 0; rt < BP_CRT; ++rt)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg (the table is zero outside 0 .. BP_WCAP + 1)
+        bp_dmma(accW[rt][0], accW[rt][1], cf[ix], bf[ks]);
+      }
+  }
+#pragma unroll
+  for (int rt = 0; rt < BP_CRT; ++rt) { red[warp][rt * 64 + lane * 2] = accW[rt][0]; red[warp][rt * 64 + lane * 2 + 1] = accW[rt][1]; }
+  __syncthreads();
+  for (int i = tid; i < BP_CRT * 64; i += 128) {
+    const double sacc = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
+    const int rt = i >> 6, ln = (i & 63) >> 1, e = i & 1;
+    const int row = rt * 8 + (ln >> 2), uu = ct * 8 + (ln & 3) * 2 + e;
+    const int c2 = o * 8 + uu / BP_D, d = uu % BP_D;
+    if (row < BP_CROWS && c2 < a.nchains) a.wplain[((size_t)c2 * BP_CROWS + row) * BP_WCOLS + d * BP_N + l] = sacc;
+  }
 }
 #endif  // BP_N <= 3
 #endif

@@ -99,6 +99,12 @@ int model_load(bpc_model* m, int device, Loaded** out) {
         BPC_CUDA(cudaLibraryGetKernel(&L.fusedc, L.lib, "bp_fusedc"));
         BPC_CUDA(cudaLibraryGetKernel(&L.ctable, L.lib, "bp_ctable"));
         BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->spec.c_smem, device));
+        BPC_CUDA(cudaLibraryGetKernel(&L.ntable, L.lib, "bp_ntable"));
+        BPC_CUDA(cudaLibraryGetKernel(&L.fusedo, L.lib, "bp_fusedo"));
+        BPC_CUDA(cudaLibraryGetKernel(&L.toep, L.lib, "bp_toep"));
+        // bp_fusedo: N of the octet [8 n][8 D + 4] + per warp X [8 n][36] and Y [8 D][36]  (BP_OSMEM in bp_kernels.cuh)
+        L.o_smem = ((size_t)8 * n * (8 * D + 4) + 2 * ((size_t)8 * n * 36 + (size_t)8 * D * 36)) * sizeof(double);
+        BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.o_smem, device));
       }
     }
   }
@@ -465,6 +471,20 @@ namespace bpc {
 static void choose_tiling(bpc_data* d, int nchains) {
   if (d->grouped) { d->tile = d->N; d->ntiles = 1; return; }
   const int T = d->model->spec.threads;
+  // octet path: opt-in (BPC_OPATH=1) until it beats bp_fusedc
+  { const char* ev = std::getenv("BPC_OPATH"); d->omode = d->cmode && nchains >= 8 && ev && std::atoi(ev) != 0; }
+  if (d->omode) {
+    // octet path: CTA = cgpc consecutive groups of one octet of chains; aim at >= 6 waves of 3 CTAs per SM
+    d->noct = (nchains + 7) / 8;
+    long long gpc = ((long long)d->cgroups * d->noct) / (148LL * 3 * 6);
+    long long cap = 16;
+    if (const char* ev = std::getenv("BPC_OGROUPS_PER_CTA")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 4096) cap = v; }
+    gpc = std::max<long long>(1, std::min(cap, gpc));
+    d->cgpc = (int)gpc;
+    d->ntiles = std::max(1, (d->cgroups + d->cgpc - 1) / d->cgpc);
+    d->tile = ((d->N + d->ntiles - 1) / d->ntiles + 31) / 32 * 32;   // bp_fused's tiles (chains that need sub-steps) over the same ntiles
+    return;
+  }
   if (d->cmode) {
     // CTA = cgpc consecutive groups (a multiple of the warps per CTA); aim at >= 4 waves of 3 CTAs per SM
     const int nw = T / 32;
@@ -502,8 +522,17 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     if (d->wmode) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
       const size_t wfrag = (size_t)((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64;
-      if ((rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
-      if (d->cmode) {
+      if (!d->omode && (rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
+      if (d->omode) {
+        const size_t oct = (size_t)d->noct * d->cgroups * (8 * n) * (8 * D) * 8;
+        if ((rc = d->ntab.alloc(oct))) return rc;
+        if ((rc = d->osg.alloc(oct))) return rc;
+        if ((rc = d->cg_jm.alloc((size_t)d->noct * 8 * d->cgroups * 4))) return rc;
+        if ((rc = d->cg_flops.alloc((size_t)d->noct * 8 * d->cgroups * 8))) return rc;
+        if ((rc = d->wplain.alloc((size_t)nchains * (((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n * 8))) return rc;
+        if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
+        if ((rc = d->ctab_e2.alloc((size_t)nchains * 64 * D * D * 8))) return rc;
+      } else if (d->cmode) {
         if ((rc = d->csg.alloc((size_t)nchains * d->cgroups * 8 * ((D * n + 7) / 8) * 8 * 8))) return rc;   // one 8-row S matrix per group
         if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
         if ((rc = d->ctab_e2.alloc((size_t)nchains * 64 * D * D * 8))) return rc;
@@ -527,6 +556,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   double* wpart; int wmode;
   int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; const double* cg_coef; double cdelta;
   double* ctab_m1; double* ctab_e2; double* csg;
+  int noct; double* ntab; int* cg_jm; double* cg_flops; double* osg; double* wplain;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -548,9 +578,10 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   {
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
               part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains,
-              (double*)d->wpart.p, d->wmode ? (d->cmode ? 2 : 1) : 0,
+              (double*)d->wpart.p, d->wmode ? (d->omode ? 3 : (d->cmode ? 2 : 1)) : 0,
               d->cgroups, d->cgpc, (const int*)d->cg_chunk0.p, (const int*)d->cg_idx.p, (const double*)d->cg_tau.p,
-              (const double*)d->cg_hmax.p, (const double*)d->cg_coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p};
+              (const double*)d->cg_hmax.p, (const double*)d->cg_coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
+              d->noct, (double*)d->ntab.p, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -581,7 +612,15 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       if (d->wmode) {
         // chains whose series need one sub-step: W accumulation on the fp64 tensor path + one per-chain matrix polynomial;
         // bp_fused (below) only works on the chains that need sub-steps
-        if (d->cmode) {
+        if (d->omode) {
+          // octet path: per-chain tables, N_j(tau_g) of every (chain, group), the fused passes of 8 chains at a time, the Toeplitz products
+          const int n = s.ntypes, D = n + n * (n + 1) / 2;
+          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(128), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->ntable, dim3((d->cgroups + 3) / 4, d->noct * 8), dim3(128), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(64), args, L->o_smem, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
+          g_launches += 3;
+        } else if (d->cmode) {
           // centred W path: per-chain tables of exp(tau L), then short series around the groups' centres
           BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(128), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->fusedc, dim3(d->ntiles, nchains), dim3(s.threads), args, s.c_smem, st));
@@ -621,13 +660,18 @@ int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned lon
   choose_tiling(d, nchains);
   d->ws_chains = -1;
   (void)keep;
-  *path = s.kind == BPC_SIMPLE_BD ? 3 : (d->grouped ? 1 : (d->wmode ? (d->cmode ? 4 : 2) : 0));
+  *path = s.kind == BPC_SIMPLE_BD ? 3 : (d->grouped ? 1 : (d->wmode ? (d->omode ? 5 : (d->cmode ? 4 : 2)) : 0));
   *ntiles = d->ntiles;
   if (scratch_bytes) {
     const int n = s.ntypes, D = n + n * (n + 1) / 2;
     unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
-    if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
-    if (d->cmode) b += 2ull * nchains * ((unsigned long long)d->cgroups * 8 * ((D * n + 7) / 8) * 8 + 65ull * D * n + 64ull * D * D) * 8;   // S^g per group and the per-chain tables, written then read
+    if (d->omode) {
+      // N and S' of every (octet, group), W of every chain and the per-chain tables, written then read
+      b += 2ull * ((unsigned long long)d->noct * d->cgroups * (8 * n) * (8 * D) * 2 + (unsigned long long)nchains * ((((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n + 65ull * D * n + 64ull * D * D)) * 8;
+    } else {
+      if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
+      if (d->cmode) b += 2ull * nchains * ((unsigned long long)d->cgroups * 8 * ((D * n + 7) / 8) * 8 + 65ull * D * n + 64ull * D * D) * 8;   // S^g per group and the per-chain tables, written then read
+    }
     *scratch_bytes = b;
   }
   return BPC_OK;

@@ -38,8 +38,8 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr;
-  size_t obs_smem = 0, grouped_smem = 0;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, ntable = nullptr, fusedo = nullptr, toep = nullptr;
+  size_t obs_smem = 0, grouped_smem = 0, o_smem = 0;
 };
 
 // algorithmic flop constants of the shipped kernels (SURVEY.md §8(d) convention: FMA = 2, div/sqrt/exp/log = 1)
@@ -68,6 +68,10 @@ struct bpc_data {
   int cgroups = 0, cgpc = 4;
   double cdelta = 0.0;
   bpc::DevBuf cg_chunk0, cg_idx, cg_tau, cg_hmax, cg_coef, ctab_m1, ctab_e2, csg;
+  // octet path (bp_ntable + bp_fusedo + bp_toep): eight chains per tensor tile; chosen per chain count (choose_tiling)
+  bool omode = false;
+  int noct = 0;
+  bpc::DevBuf ntab, cg_jm, cg_flops, osg, wplain;
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;
