@@ -737,6 +737,7 @@ struct BpObsArgs {
   double* cg_flops;      // [noct * 8][cgroups]             algorithmic flops of (chain, group)
   double* osg;           // [noct][cgroups][BP_XR][8 BP_D]  S'^g of the octet: row (j, l), column cc * BP_D + d
   double* wplain;        // [C][BP_CROWS][BP_WCOLS]         W_n of each chain, row n - 1, column d * BP_N + l
+  int* fb;               // [1 + C]  wmode >= 2: number and ids of the chains left to bp_fused (written by bp_ctable)
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -1120,7 +1121,10 @@ extern "C" __global__ void __launch_bounds__(128) bp_ctable(BpObsArgs a) {
   bp_assemble(r, A, H);
   const double a1 = bp_norm1(A);
   const double tmax = a.nobs > 0 ? a.t[0] : 0.0;
-  if (!bp_w_path(fin, a1, tmax)) return;
+  if (!bp_w_path(fin, a1, tmax)) {   // bp_fused takes this chain
+    if (tid == 0) a.fb[1 + atomicAdd(a.fb, 1)] = c;
+    return;
+  }
   BpPlan p;
   int dh = 1;
   bp_make_plan(a1, tmax, p, dh, BP_WCAP, BP_WTHETA_CAP);
@@ -1574,9 +1578,22 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 // prologue), bp_toep is the Toeplitz product W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for all groups at once, bp_wpost finishes.
 #define BP_OU (8 * BP_D)                         // columns of an octet: (cc, d)
 #define BP_ONLD (BP_OU + 4)                      // row stride of the staged N (conflict-free A fragments: stride = 12 mod 16)
-#define BP_OWARPS 2
-#define BP_OWARP (BP_XR * BP_WLD + BP_OU * BP_WLD)   // doubles per warp: X[(j,l)][obs], Y / b[(cc,d)][obs]
-#define BP_OSMEM ((BP_XR * BP_ONLD + BP_OWARPS * BP_OWARP) * 8)
+#define BP_OTHREADS 128                          // one CTA = four warps on the same pass
+#ifndef BP_OMINBLOCKS
+#define BP_OMINBLOCKS 4
+#endif
+#define BP_OYLD 40                               // row stride of Y / b; element (r, k) lives at column k ^ ((r & 2) << 1): the 16-byte
+                                                 // accumulator stores, the per-lane column reads and the B fragments are all conflict-free
+#define BP_OY(r, k) ((r) * BP_OYLD + ((k) ^ (((r) & 2) << 1)))
+#define BP_OOBS ((2 * BP_N + 1) * 32)             // one chunk of the observation table: z0[n], xo[n], t, 32 doubles each
+#define BP_OSMEM ((BP_XR * BP_ONLD + 2 * BP_XR * BP_WLD + BP_OU * BP_OYLD + 2 * BP_OOBS) * 8)
+
+// 16-byte asynchronous copy global -> shared (LDGSTS), used to stage the next chunk of the observation table
+__device__ __forceinline__ void bp_cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void bp_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 extern "C" __global__ void __launch_bounds__(128) bp_ntable(BpObsArgs a) {
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1658,181 +1675,257 @@ extern "C" __global__ void __launch_bounds__(128) bp_ntable(BpObsArgs a) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(32 * BP_OWARPS, 3) bp_fusedo(BpObsArgs a) {
+// One CTA (four warps) per pass of 32 observations x 8 chains; every phase is split four ways, three barriers per pass:
+//   stage    warp w writes the rows of X of terms j = 2w, 2w + 1 (X is double-buffered: staging pass p + 1 overlaps the S update of p);
+//            the chunk of the observation table of pass p + 1 arrives by cp.async while pass p runs
+//   forward  warp w = (wlo, whi): observation tiles 2 wlo, 2 wlo + 1 x the (cc, d) tiles BP_OHT whi .. BP_OHT whi + BP_OHT - 1, plus
+//            (BP_D odd) the last (cc, d) tile x observation tile 2 wlo + whi
+//   score    thread (w, lane): observation `lane` under chains 2w and 2w + 1; the cotangent replaces Y in place
+//   S update warp w: observations 16 wlo .. 16 wlo + 15 x the same BP_OHT tiles of (cc, d), plus the last tile x observations
+//            16 wlo + 8 whi .. + 7; the partial sums over k are added per group
+// so that every warp carries the same number of tensor products without a predicate in the loops; all shared-memory addresses are a
+// per-lane base plus a compile-time offset.  The FP64 datapath (DMMA and DFMA share it) is kept busy by the other CTAs of the SM
+// while one waits at a barrier.
+#define BP_OHT (BP_D / 2)                         // (cc, d) tiles of a warp pair
+#define BP_OEX (BP_D & 1)                         // one more tile shared by the four warps
+#define BP_OACC (BP_OHT + BP_OEX)
+extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fusedo(BpObsArgs a) {
   const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
-  double* sN = bp_smem;                                              // [BP_XR][BP_ONLD]
-  double* sX = bp_smem + BP_XR * BP_ONLD + (size_t)warp * BP_OWARP;  // [BP_XR][BP_WLD]
-  double* sY = sX + BP_XR * BP_WLD;                                  // [BP_OU][BP_WLD]
+  double* sN = bp_smem;                         // [BP_XR][BP_ONLD]     N_j[d][l] of chain cc at [(j, l)][cc * BP_D + d]
+  double* sXb = sN + BP_XR * BP_ONLD;           // [2][BP_XR][BP_WLD]   X[(j, l)][obs]
+  double* sY = sXb + 2 * BP_XR * BP_WLD;        // [BP_OU][BP_OYLD]     Y, then b: [(cc, d)][obs] (swizzled, BP_OY)
+  double* sOb = sY + BP_OU * BP_OYLD;           // [2][2 BP_N + 1][32]  the pass's chunk of the observation table (z0, xo, t), double-buffered
   __shared__ int sjm[8];
-  __shared__ double sred[BP_OWARPS][8][3];
-  double lp[8], sb[8];
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc) { lp[cc] = 0.0; sb[cc] = 0.0; }
-  int notpd = 0;   // bit cc: an observation of chain cc had a covariance that is not positive definite
+  const int wlo = warp & 1, whi = warp >> 1;
+  const int swz = (g >> 1) & 1;                 // rows r of Y with bit 1 set keep column k at k ^ 4 (r & 2 == g & 2 for tile rows 8 t + g)
+  // per-lane bases (doubles)
+  const int fN = tg * BP_ONLD + whi * (BP_OHT * 8) + g;            // A fragments of the forward product: + kk * 4 * BP_ONLD + t * 8
+  const int fNx = tg * BP_ONLD + 2 * BP_OHT * 8 + g;               // ... of the last tile
+  const int fX = tg * BP_WLD + wlo * 16 + g;                       // B fragments: + kk * 4 * BP_WLD + q * 8
+  const int fXx = tg * BP_WLD + (2 * wlo + whi) * 8 + g;           // ... for the last tile's observation tile
+  const int fY = (whi * (BP_OHT * 8) + g) * BP_OYLD + wlo * 16 + ((2 * tg) ^ (swz << 2));   // accumulator stores: + t * 8 * BP_OYLD + q * 8
+  const int fYx = (2 * BP_OHT * 8 + g) * BP_OYLD + (2 * wlo + whi) * 8 + ((2 * tg) ^ (swz << 2));
+  const int uX = g * BP_WLD + wlo * 16 + tg;                       // A fragments of the S update: + rt * 8 * BP_WLD + ob * 4
+  const int uY = (whi * (BP_OHT * 8) + g) * BP_OYLD + wlo * 16 + tg;   // B fragments: + ct * 8 * BP_OYLD + (ob ^ swz) * 4
+  const int uYx = (2 * BP_OHT * 8 + g) * BP_OYLD + wlo * 16 + whi * 8 + tg;
+  // score: row r = (2 warp + i2) BP_D + d; r & 2 = ((9 i2 + d) & 2) ^ (2 wlo) for BP_D = 9 (18 warp = 2 wlo mod 4), computed generally below
+  double lp[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
+  int notpd = 0;                                // bit i: an observation of chain 2 warp + i had a covariance that is not positive definite
+  int pass = 0;
   const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
+  // the chunks of this CTA's groups are consecutive: chunk `ch` of pass p is copied into sOb[p & 1] while pass p - 1 runs
+  // (thread = one 16-byte piece of one array; complete before the barrier that follows the score of pass p - 1)
+  const int chend = g0 < g1 ? a.cg_chunk0[g1] : 0;
+  const double* osrc = nullptr;
+  {
+    const int ai = tid >> 4, q = tid & 15;
+    if (ai < 2 * BP_N + 1) osrc = (ai < BP_N ? a.z0 + (size_t)ai * a.npad : (ai < 2 * BP_N ? a.xo + (size_t)(ai - BP_N) * a.npad : a.t)) + 2 * q;
+    if (osrc && g0 < g1) bp_cp_async16(sOb + tid * 2, osrc + (size_t)a.cg_chunk0[g0] * 32);
+    bp_cp_async_commit();
+    bp_cp_async_wait_all();
+    __syncthreads();
+  }
   for (int grp = g0; grp < g1; ++grp) {
-    __syncthreads();   // the previous group's N and reduction scratch are free
-    {
+    {   // N of (octet, group); the previous group's last forward product is behind a barrier
       const double2* src = reinterpret_cast<const double2*>(a.ntab + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU);
-      for (int i = tid; i < BP_XR * BP_OU / 2; i += 32 * BP_OWARPS) {
+      for (int i = tid; i < BP_XR * BP_OU / 2; i += BP_OTHREADS) {
         const int r = i / (BP_OU / 2), q = i - r * (BP_OU / 2);
-        *reinterpret_cast<double2*>(sN + r * BP_ONLD + 2 * q) = src[i];
+        *reinterpret_cast<double2*>(sN + r * BP_ONLD + 2 * q) = __ldcg(src + i);
       }
       if (tid < 8) sjm[tid] = (o * 8 + tid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + tid) * a.cgroups + grp] : -1;
     }
-    __syncthreads();
     const double tau = a.cg_tau[grp];
-    double accS[BP_XRT][BP_D][2];
+    double accS[BP_XRT][BP_OACC][2];
 #pragma unroll
     for (int rt = 0; rt < BP_XRT; ++rt)
 #pragma unroll
-      for (int ct = 0; ct < BP_D; ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
+      for (int ct = 0; ct < BP_OACC; ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
     const int ch1 = a.cg_chunk0[grp + 1];
-    for (int ch = a.cg_chunk0[grp] + warp; ch < ch1; ch += BP_OWARPS) {
-      const int k = ch * 32 + lane;
-      const bool valid = k < a.nobs;
-      double xo[BP_N];
-      {
+    for (int ch = a.cg_chunk0[grp]; ch < ch1; ++ch, ++pass) {
+      double* sX = sXb + (pass & 1) * (BP_XR * BP_WLD);
+      const double* sO = sOb + (pass & 1) * BP_OOBS;
+      const bool valid = ch * 32 + lane < a.nobs;
+      if (osrc && ch + 1 < chend) bp_cp_async16(sOb + ((pass + 1) & 1) * BP_OOBS + tid * 2, osrc + (size_t)(ch + 1) * 32);
+      bp_cp_async_commit();
+      {   // stage: terms j = 2 warp, 2 warp + 1 of this lane's observation
         double z0[BP_N];
 #pragma unroll
-        for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
-        const double h = valid ? a.t[k] - tau : 0.0;
-        double w = 1.0;
+        for (int i = 0; i < BP_N; ++i) z0[i] = sO[i * 32 + lane];
+        const double h = valid ? sO[2 * BP_N * 32 + lane] - tau : 0.0;
+        double we = 1.0;
+        for (int j = 1; j <= 2 * warp; ++j) we = we * (h * bp_rk[j - 1]);   // warp-uniform trip count
+        const double wo = we * (h * bp_rk[2 * warp]);
+        double* xs = sX + (2 * warp * BP_N) * BP_WLD + lane;
 #pragma unroll
-        for (int j = 0; j < BP_CJ; ++j) {
-          if (j > 0) w = w * (h * bp_rk[j - 1]);
-#pragma unroll
-          for (int l = 0; l < BP_N; ++l) sX[(j * BP_N + l) * BP_WLD + lane] = w * z0[l];
+        for (int l = 0; l < BP_N; ++l) {
+          xs[l * BP_WLD] = we * z0[l];
+          xs[(BP_N + l) * BP_WLD] = wo * z0[l];
         }
       }
-      __syncwarp();
-      // forward product, three row tiles (24 columns of the octet) at a time
+      __syncthreads();   // X (and, for the first pass, N) staged; every warp is done with the previous pass
+      {   // forward: Y[(cc, d)][obs] = sum_(j,l) N[(j,l)][(cc,d)] X[(j,l)][obs]
+        double accY[BP_OHT][2][2];
+        double accE[2] = {0.0, 0.0};
 #pragma unroll
-      for (int t0 = 0; t0 < BP_D; t0 += 3) {
-        double accY[3][4][2];
+        for (int t = 0; t < BP_OHT; ++t)
 #pragma unroll
-        for (int t3 = 0; t3 < 3; ++t3)
-#pragma unroll
-          for (int ot = 0; ot < 4; ++ot) { accY[t3][ot][0] = 0.0; accY[t3][ot][1] = 0.0; }
+          for (int q = 0; q < 2; ++q) { accY[t][q][0] = 0.0; accY[t][q][1] = 0.0; }
+        const double* pn = sN + fN;
+        const double* px = sX + fX;
 #pragma unroll
         for (int kk = 0; kk < BP_XKS; ++kk) {
-          double xb[4];
+          const double xb0 = px[kk * 4 * BP_WLD], xb1 = px[kk * 4 * BP_WLD + 8];
 #pragma unroll
-          for (int ot = 0; ot < 4; ++ot) xb[ot] = sX[(kk * 4 + tg) * BP_WLD + ot * 8 + g];
-#pragma unroll
-          for (int t3 = 0; t3 < 3; ++t3) {
-            if (t0 + t3 < BP_D) {
-              const double af = sN[(kk * 4 + tg) * BP_ONLD + (t0 + t3) * 8 + g];
-#pragma unroll
-              for (int ot = 0; ot < 4; ++ot) bp_dmma(accY[t3][ot][0], accY[t3][ot][1], af, xb[ot]);
-            }
+          for (int t = 0; t < BP_OHT; ++t) {
+            const double af = pn[kk * 4 * BP_ONLD + t * 8];
+            bp_dmma(accY[t][0][0], accY[t][0][1], af, xb0);
+            bp_dmma(accY[t][1][0], accY[t][1][1], af, xb1);
           }
-        }
-#pragma unroll
-        for (int t3 = 0; t3 < 3; ++t3)
-          if (t0 + t3 < BP_D) {
-#pragma unroll
-            for (int ot = 0; ot < 4; ++ot)
-              *reinterpret_cast<double2*>(sY + ((t0 + t3) * 8 + g) * BP_WLD + ot * 8 + 2 * tg) = make_double2(accY[t3][ot][0], accY[t3][ot][1]);
-          }
-      }
-      __syncwarp();
-      // score: this lane's observation under each of the 8 chains; the cotangent (packed coordinates) replaces Y in place
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        double* yc = sY + (cc * BP_D) * BP_WLD + lane;
-        double ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
-        bool ok = valid && sjm[cc] >= 0;
-#pragma unroll
-        for (int i = 0; i < BP_N; ++i) { ymu[i] = yc[i * BP_WLD]; bmu[i] = 0.0; }
-#pragma unroll
-        for (int q = 0; q < BP_S; ++q) { yS[q] = yc[(BP_N + q) * BP_WLD]; bS[q] = 0.0; }
-        if (ok) {
-#if BP_NOISE
-          const double sigma = a.theta[(size_t)(o * 8 + cc) * BP_DIM + BP_P];
-#else
-          const double sigma = 0.0;
+#if BP_OEX
+          bp_dmma(accE[0], accE[1], sN[fNx + kk * 4 * BP_ONLD], sX[fXx + kk * 4 * BP_WLD]);
 #endif
-          if (!bp_score_obs(xo, sigma, ymu, yS, lp[cc], sb[cc], bmu, bS)) { notpd |= 1 << cc; ok = false; }
         }
+        double* py = sY + fY;
 #pragma unroll
-        for (int i = 0; i < BP_N; ++i) yc[i * BP_WLD] = ok ? bmu[i] : 0.0;
+        for (int t = 0; t < BP_OHT; ++t)
 #pragma unroll
-        for (int q = 0; q < BP_S; ++q) {
-          bool diag = false;
-#pragma unroll
-          for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == q);
-          const double bd = diag ? bS[q] : bS[q] + bS[q];
-          yc[(BP_N + q) * BP_WLD] = ok ? bd : 0.0;
-        }
+          for (int q = 0; q < 2; ++q) *reinterpret_cast<double2*>(py + t * 8 * BP_OYLD + q * 8) = make_double2(accY[t][q][0], accY[t][q][1]);
+#if BP_OEX
+        *reinterpret_cast<double2*>(sY + fYx) = make_double2(accE[0], accE[1]);
+#endif
       }
-      __syncwarp();
-      // S' update: X fragments (A) shared by all column tiles, b fragments (B) by all row tiles
+      __syncthreads();
+      // score: this lane's observation under chains 2 warp and 2 warp + 1 (independent work); the cotangent in packed coordinates replaces Y
+      {
+        double xo[BP_N];
 #pragma unroll
-      for (int ob = 0; ob < 8; ++ob) {
-        double xa[BP_XRT];
+        for (int i = 0; i < BP_N; ++i) xo[i] = sO[(BP_N + i) * 32 + lane];
+        const int rbase = 2 * warp * BP_D;
+        const int kA = lane ^ ((rbase & 2) << 1), kB = kA ^ 4;   // column of this lane in rows r with ((r - rbase) & 2) == 0 / != 0
+        double* yrow = sY + rbase * BP_OYLD;
 #pragma unroll
-        for (int rt = 0; rt < BP_XRT; ++rt) xa[rt] = sX[(rt * 8 + g) * BP_WLD + ob * 4 + tg];
+        for (int i2 = 0; i2 < 2; ++i2) {
+          double ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+          bool ok = valid && sjm[2 * warp + i2] >= 0;
 #pragma unroll
-        for (int ct = 0; ct < BP_D; ++ct) {
-          const double bf = sY[(ct * 8 + g) * BP_WLD + ob * 4 + tg];
+          for (int i = 0; i < BP_N; ++i) { ymu[i] = yrow[(i2 * BP_D + i) * BP_OYLD + (((i2 * BP_D + i) & 2) ? kB : kA)]; bmu[i] = 0.0; }
 #pragma unroll
-          for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][ct][0], accS[rt][ct][1], xa[rt], bf);
-        }
-      }
-      __syncwarp();
-    }
-    // ---- the group's S' = sum of the warps' accumulators (fixed order), parked row-major [(j, l)][(cc, d)] ----
-    // (each warp's Y area holds BP_OU * BP_WLD >= BP_XRT * BP_D * 64 doubles)
-    if (warp > 0) {
-#pragma unroll
-      for (int rt = 0; rt < BP_XRT; ++rt)
-#pragma unroll
-        for (int ct = 0; ct < BP_D; ++ct) *reinterpret_cast<double2*>(sY + ((rt * BP_D + ct) * 32 + lane) * 2) = make_double2(accS[rt][ct][0], accS[rt][ct][1]);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
-#pragma unroll
-      for (int rt = 0; rt < BP_XRT; ++rt)
-#pragma unroll
-        for (int ct = 0; ct < BP_D; ++ct) {
-          double s0 = accS[rt][ct][0], s1 = accS[rt][ct][1];
-#pragma unroll
-          for (int w = 1; w < BP_OWARPS; ++w) {
-            const double2 v = *reinterpret_cast<const double2*>(sY + (size_t)w * BP_OWARP + ((rt * BP_D + ct) * 32 + lane) * 2);
-            s0 += v.x; s1 += v.y;
+          for (int q = 0; q < BP_S; ++q) { yS[q] = yrow[(i2 * BP_D + BP_N + q) * BP_OYLD + (((i2 * BP_D + BP_N + q) & 2) ? kB : kA)]; bS[q] = 0.0; }
+          if (ok) {
+#if BP_NOISE
+            const double sigma = a.theta[(size_t)(o * 8 + 2 * warp + i2) * BP_DIM + BP_P];
+#else
+            const double sigma = 0.0;
+#endif
+            if (!bp_score_obs(xo, sigma, ymu, yS, lp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
           }
-          *reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + ct * 8 + 2 * tg) = make_double2(s0, s1);
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) yrow[(i2 * BP_D + i) * BP_OYLD + (((i2 * BP_D + i) & 2) ? kB : kA)] = ok ? bmu[i] : 0.0;
+#pragma unroll
+          for (int q = 0; q < BP_S; ++q) {
+            bool diag = false;
+#pragma unroll
+            for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == q);
+            const double bd = diag ? bS[q] : bS[q] + bS[q];
+            yrow[(i2 * BP_D + BP_N + q) * BP_OYLD + (((i2 * BP_D + BP_N + q) & 2) ? kB : kA)] = ok ? bd : 0.0;
+          }
+        }
+      }
+      bp_cp_async_wait_all();   // the next pass's chunk has landed (this thread's piece; the barrier publishes all of them)
+      __syncthreads();
+      {   // S' update over this warp's 16 observations: X fragments (A) shared by the column tiles, b fragments (B) by the row tiles
+        const double* px = sX + uX;
+        const double* pbE = sY + uY + (swz << 2);   // k-steps ob even: column block ob ^ swz = ob + swz
+        const double* pbO = sY + uY - (swz << 2);   // k-steps ob odd:  ob - swz
+#pragma unroll
+        for (int ob = 0; ob < 4; ++ob) {
+          double xa[BP_XRT];
+#pragma unroll
+          for (int rt = 0; rt < BP_XRT; ++rt) xa[rt] = px[rt * 8 * BP_WLD + ob * 4];
+#pragma unroll
+          for (int ct = 0; ct < BP_OHT; ++ct) {
+            const double bf = ((ob & 1) ? pbO : pbE)[ct * 8 * BP_OYLD + ob * 4];
+#pragma unroll
+            for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][ct][0], accS[rt][ct][1], xa[rt], bf);
+          }
+#if BP_OEX
+          if ((ob >> 1) == 0) {   // the last tile: k-steps 2 whi, 2 whi + 1 of this half (compile-time ob2 = ob, runtime offset 8 whi)
+            const double bf = sY[uYx + ((ob & 1) ? -(swz << 2) : (swz << 2)) + ob * 4];
+#pragma unroll
+            for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][BP_OHT][0], accS[rt][BP_OHT][1], px[rt * 8 * BP_WLD + whi * 8 + ob * 4], bf);
+          }
+#endif
+        }
+      }
+    }
+    // ---- the group's S' = sum of the partial sums over k (fixed order), row-major [(j, l)][(cc, d)] ----
+    __syncthreads();   // all S updates have read Y
+    double* scr = sY;                                         // [2][BP_XRT][BP_OHT][64], then [3][BP_XRT][64] for the last tile
+    double* scrx = sY + 2 * BP_XRT * BP_OHT * 64;
+    if (wlo) {
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < BP_OHT; ++ct)
+          *reinterpret_cast<double2*>(scr + ((whi * BP_XRT + rt) * BP_OHT + ct) * 64 + lane * 2) = make_double2(accS[rt][ct][0], accS[rt][ct][1]);
+    }
+#if BP_OEX
+    if (warp) {
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+        *reinterpret_cast<double2*>(scrx + ((warp - 1) * BP_XRT + rt) * 64 + lane * 2) = make_double2(accS[rt][BP_OHT][0], accS[rt][BP_OHT][1]);
+    }
+#endif
+    __syncthreads();
+    double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
+    if (!wlo) {
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < BP_OHT; ++ct) {
+          const double2 v = *reinterpret_cast<const double2*>(scr + ((whi * BP_XRT + rt) * BP_OHT + ct) * 64 + lane * 2);
+          __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (whi * BP_OHT + ct) * 8 + 2 * tg),
+                 make_double2(accS[rt][ct][0] + v.x, accS[rt][ct][1] + v.y));
         }
     }
-  }
-  // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial ----
-  __syncthreads();
+#if BP_OEX
+    if (!warp) {
 #pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
-    const double l = bp_warp_sum(lp[cc]), s2 = bp_warp_sum(sb[cc]);
-    if (lane == 0) { sred[warp][cc][0] = l; sred[warp][cc][1] = s2; }
+      for (int rt = 0; rt < BP_XRT; ++rt) {
+        double s0 = accS[rt][BP_OHT][0], s1 = accS[rt][BP_OHT][1];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const double2 v = *reinterpret_cast<const double2*>(scrx + (w * BP_XRT + rt) * 64 + lane * 2);
+          s0 += v.x; s1 += v.y;
+        }
+        __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + 2 * BP_OHT * 8 + 2 * tg), make_double2(s0, s1));
+      }
+    }
+#endif
+    // (the next group's first barrier separates these reads of the scratch from the next forward product)
+  }
+  // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial; chain 2 warp + i belongs to this warp alone ----
+#pragma unroll
+  for (int i2 = 0; i2 < 2; ++i2) {
+    const double l = bp_warp_sum(lp[i2]), s2 = bp_warp_sum(sb[i2]);
+    const int c = o * 8 + 2 * warp + i2;
+    if (lane == 0 && c < a.nchains) {
+      double fl = 0.0;
+      bool mine = false;
+      for (int grp = g0; grp < g1; ++grp) { fl += a.cg_flops[(size_t)c * a.cgroups + grp]; mine = mine || a.cg_jm[(size_t)c * a.cgroups + grp] >= 0; }
+      if (mine || g0 >= g1 || a.cg_jm[(size_t)c * a.cgroups] >= 0) {   // chains on the fallback path keep the partials bp_fused writes
+        double* p = a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART;
+        p[0] = l;
+#pragma unroll
+        for (int k = 0; k < BP_P; ++k) p[1 + k] = 0.0;
+        p[BP_P + 1] = s2;
+        p[BP_P + 2] = fl;
+      }
+    }
   }
   notpd = __reduce_or_sync(0xffffffffu, notpd);
-  __syncthreads();
-  if (tid < 8 && o * 8 + tid < a.nchains) {
-    const int c = o * 8 + tid;
-    double l = 0.0, s2 = 0.0, fl = 0.0;
-    for (int w = 0; w < BP_OWARPS; ++w) { l += sred[w][tid][0]; s2 += sred[w][tid][1]; }
-    bool mine = false;
-    for (int grp = g0; grp < g1; ++grp) { fl += a.cg_flops[(size_t)c * a.cgroups + grp]; mine = mine || a.cg_jm[(size_t)c * a.cgroups + grp] >= 0; }
-    if (mine || g0 >= g1 || a.cg_jm[(size_t)c * a.cgroups] >= 0) {   // chains on the fallback path keep the partials bp_fused writes
-      double* p = a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART;
-      p[0] = l;
-#pragma unroll
-      for (int k = 0; k < BP_P; ++k) p[1 + k] = 0.0;
-      p[BP_P + 1] = s2;
-      p[BP_P + 2] = fl;
-    }
-  }
-  if (lane < 8 && ((notpd >> lane) & 1) && o * 8 + lane < a.nchains) atomicOr(a.status + o * 8 + lane, BP_ST_NOT_PD);
+  if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 
 // W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
@@ -1885,8 +1978,7 @@ extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
 // grid (ntiles, C); CTA = BP_THREADS threads = one tile of one chain; thread i takes observations
 // tile*T + i, + BP_THREADS, ... (coalesced SoA loads).  Dynamic shared memory: the Taylor-term store,
 // BP_MSLOT * BP_D doubles per thread (a ring of series terms), laid out [slot][component][thread] (conflict-free).
-extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(BpObsArgs a) {
-  const int c = blockIdx.y;
+__device__ __forceinline__ void bp_fused_chain(const BpObsArgs& a, const int c) {
   const int tid = threadIdx.x;
 
   double th[BP_DIM];
@@ -1971,6 +2063,20 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
   __syncthreads();   // the term store is dead: reuse its first words as reduction scratch
   bp_block_reduce_store(vals, bp_smem, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
   if (status) atomicOr(a.status + c, status);
+}
+
+// grid (tiles, chains).  On the centred / octet W paths (wmode >= 2) the chains that need sub-steps are rare: bp_ctable lists them
+// (fb[0] = count, fb[1 ..] = chain ids) and a few rows of CTAs walk the list instead of one row per chain exiting at once.
+extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(BpObsArgs a) {
+  if (a.wmode >= 2) {
+    const int nfb = a.fb[0];
+    for (int i = blockIdx.y; i < nfb; i += gridDim.y) {
+      bp_fused_chain(a, a.fb[1 + i]);
+      __syncthreads();
+    }
+  } else {
+    bp_fused_chain(a, blockIdx.y);
+  }
 }
 
 // ---- grouped two-phase kernel of the multitype templates ------------------------------------------

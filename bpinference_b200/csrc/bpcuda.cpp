@@ -102,8 +102,8 @@ int model_load(bpc_model* m, int device, Loaded** out) {
         BPC_CUDA(cudaLibraryGetKernel(&L.ntable, L.lib, "bp_ntable"));
         BPC_CUDA(cudaLibraryGetKernel(&L.fusedo, L.lib, "bp_fusedo"));
         BPC_CUDA(cudaLibraryGetKernel(&L.toep, L.lib, "bp_toep"));
-        // bp_fusedo: N of the octet [8 n][8 D + 4] + per warp X [8 n][36] and Y [8 D][36]  (BP_OSMEM in bp_kernels.cuh)
-        L.o_smem = ((size_t)8 * n * (8 * D + 4) + 2 * ((size_t)8 * n * 36 + (size_t)8 * D * 36)) * sizeof(double);
+        // bp_fusedo: N of the octet [8 n][8 D + 4], X [2][8 n][36], Y [8 D][40], two chunks of the table [2][2 n + 1][32]  (BP_OSMEM in bp_kernels.cuh)
+        L.o_smem = ((size_t)8 * n * (8 * D + 4) + 2 * (size_t)8 * n * 36 + (size_t)8 * D * 40 + 2 * (size_t)(2 * n + 1) * 32) * sizeof(double);
         BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.o_smem, device));
       }
     }
@@ -471,13 +471,13 @@ namespace bpc {
 static void choose_tiling(bpc_data* d, int nchains) {
   if (d->grouped) { d->tile = d->N; d->ntiles = 1; return; }
   const int T = d->model->spec.threads;
-  // octet path: opt-in (BPC_OPATH=1) until it beats bp_fusedc
-  { const char* ev = std::getenv("BPC_OPATH"); d->omode = d->cmode && nchains >= 8 && ev && std::atoi(ev) != 0; }
+  // octet path: eight chains per tensor tile once there are at least two octets (BPC_OPATH=0 keeps bp_fusedc, =1 forces the octet path from 8 chains)
+  { const char* ev = std::getenv("BPC_OPATH"); d->omode = d->cmode && nchains >= 8 && (ev ? std::atoi(ev) != 0 : nchains >= 16); }
   if (d->omode) {
-    // octet path: CTA = cgpc consecutive groups of one octet of chains; aim at >= 6 waves of 3 CTAs per SM
+    // octet path: CTA = cgpc consecutive groups of one octet of chains; aim at >= 8 waves of 4 CTAs per SM
     d->noct = (nchains + 7) / 8;
-    long long gpc = ((long long)d->cgroups * d->noct) / (148LL * 3 * 6);
-    long long cap = 16;
+    long long gpc = ((long long)d->cgroups * d->noct) / (148LL * 4 * 8);
+    long long cap = 2;
     if (const char* ev = std::getenv("BPC_OGROUPS_PER_CTA")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 4096) cap = v; }
     gpc = std::max<long long>(1, std::min(cap, gpc));
     d->cgpc = (int)gpc;
@@ -523,6 +523,7 @@ static int ensure_workspace(bpc_data* d, int nchains) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
       const size_t wfrag = (size_t)((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64;
       if (!d->omode && (rc = d->wpart.alloc((size_t)nchains * d->ntiles * wfrag * 8))) return rc;
+      if (d->cmode && (rc = d->fb.alloc((size_t)(nchains + 1) * 4))) return rc;
       if (d->omode) {
         const size_t oct = (size_t)d->noct * d->cgroups * (8 * n) * (8 * D) * 8;
         if ((rc = d->ntab.alloc(oct))) return rc;
@@ -557,6 +558,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; const double* cg_coef; double cdelta;
   double* ctab_m1; double* ctab_e2; double* csg;
   int noct; double* ntab; int* cg_jm; double* cg_flops; double* osg; double* wplain;
+  int* fb;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -581,7 +583,8 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               (double*)d->wpart.p, d->wmode ? (d->omode ? 3 : (d->cmode ? 2 : 1)) : 0,
               d->cgroups, d->cgpc, (const int*)d->cg_chunk0.p, (const int*)d->cg_idx.p, (const double*)d->cg_tau.p,
               (const double*)d->cg_hmax.p, (const double*)d->cg_coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
-              d->noct, (double*)d->ntab.p, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p};
+              d->noct, (double*)d->ntab.p, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
+              (int*)d->fb.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -612,12 +615,13 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       if (d->wmode) {
         // chains whose series need one sub-step: W accumulation on the fp64 tensor path + one per-chain matrix polynomial;
         // bp_fused (below) only works on the chains that need sub-steps
+        if (d->cmode) BPC_CUDA(cudaMemsetAsync(d->fb.p, 0, sizeof(int), st));
         if (d->omode) {
           // octet path: per-chain tables, N_j(tau_g) of every (chain, group), the fused passes of 8 chains at a time, the Toeplitz products
           const int n = s.ntypes, D = n + n * (n + 1) / 2;
           BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(128), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->ntable, dim3((d->cgroups + 3) / 4, d->noct * 8), dim3(128), args, 0, st));
-          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(64), args, L->o_smem, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
           g_launches += 3;
         } else if (d->cmode) {
@@ -631,7 +635,8 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
         BPC_CUDA(cudaLaunchKernel((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
         g_launches += 2;
       }
-      BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, nchains), dim3(s.threads), args, L->obs_smem, st));
+      // (centred / octet W paths: bp_ctable listed the chains that need sub-steps; a few rows of CTAs walk that list)
+      BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, d->cmode ? std::min(nchains, 8) : nchains), dim3(s.threads), args, L->obs_smem, st));
     }
     if (d->timing) {
       BPC_CUDA(cudaEventRecord(e1, st));
