@@ -738,6 +738,7 @@ struct BpObsArgs {
   double* osg;           // [noct][cgroups][BP_XR][8 BP_D]  S'^g of the octet: row (j, l), column cc * BP_D + d
   double* wplain;        // [C][BP_CROWS][BP_WCOLS]         W_n of each chain, row n - 1, column d * BP_N + l
   int* fb;               // [1 + C]  wmode >= 2: number and ids of the chains left to bp_fused (written by bp_ctable)
+  double* ctab_l;        // [noct * 8][BP_D * BP_D + 1]  octet path: L of the chain, then ||A||_1 (-1: the chain is not on this path)
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -1122,7 +1123,10 @@ extern "C" __global__ void __launch_bounds__(128) bp_ctable(BpObsArgs a) {
   const double a1 = bp_norm1(A);
   const double tmax = a.nobs > 0 ? a.t[0] : 0.0;
   if (!bp_w_path(fin, a1, tmax)) {   // bp_fused takes this chain
-    if (tid == 0) a.fb[1 + atomicAdd(a.fb, 1)] = c;
+    if (tid == 0) {
+      a.fb[1 + atomicAdd(a.fb, 1)] = c;
+      if (a.wmode == 3) a.ctab_l[(size_t)c * (DD + 1) + DD] = -1.0;
+    }
     return;
   }
   BpPlan p;
@@ -1134,6 +1138,11 @@ extern "C" __global__ void __launch_bounds__(128) bp_ctable(BpObsArgs a) {
   bp_make_plan(a1, d1, p, dh, BP_CPMAX - 1, BP_WTHETA_CAP);
   const int mfine = p.m;
   bp_coop_build_L(A, H, Lm);
+  if (a.wmode == 3) {
+    __syncthreads();
+    for (int o = tid; o < DD; o += T) a.ctab_l[(size_t)c * (DD + 1) + o] = Lm[o];
+    if (tid == 0) a.ctab_l[(size_t)c * (DD + 1) + DD] = a1;
+  }
   for (int o = tid; o < DN; o += T) { const int d = o / BP_N, l = o - d * BP_N; U[o] = (d == l) ? 1.0 : 0.0; }
   for (int o = tid; o < DD; o += T) { const int d = o / BP_D, e = o - d * BP_D; Pw[o] = (d == e) ? 1.0 : 0.0; }
   __syncthreads();
@@ -1596,83 +1605,34 @@ __device__ __forceinline__ void bp_cp_async_commit() { asm volatile("cp.async.co
 __device__ __forceinline__ void bp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 extern "C" __global__ void __launch_bounds__(128) bp_ntable(BpObsArgs a) {
-  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
-  __shared__ double Lm[DD];
-  __shared__ double sNw[4][BP_XR * BP_D];
-  const int grp = blockIdx.x * 4 + warp;
-  const int o = c >> 3, cc = c & 7;
-  bool okpath = false;
-  double a1 = 0.0;
-  if (c < a.nchains) {
-    double th[BP_DIM];
-#pragma unroll
-    for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
-    double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
-#pragma unroll
-    for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
-    bp_rates(th, xk, r);
-    bool fin = true;
-#pragma unroll
-    for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
-    bp_assemble(r, A, H);
-    a1 = bp_norm1(A);
-    okpath = bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0);
-    if (okpath) bp_coop_build_L(A, H, Lm);
-  }
-  __syncthreads();
+  // series lengths of every (chain, group): J (short series in h = t - tau_g) and m (centre series), and the algorithmic flops
+  const int grp = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y;
+  constexpr int DD = BP_D * BP_D;
   if (grp >= a.cgroups) return;
-  double* out = a.ntab + (((size_t)o * a.cgroups + grp) * BP_XR) * BP_OU + cc * BP_D;
-  double* sN = sNw[warp];
   int J = -1, mg = 0;
-  if (okpath) {
-    BpPlan pc, ph;
-    int d1 = 1, d2 = 1;
-    const bool okc = bp_make_plan(a1, a.cg_tau[grp], pc, d1, BP_WCAP, BP_WTHETA_CAP);
-    const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, d2, BP_CJ - 1, BP_WTHETA_CAP);
-    if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[grp] <= bp_th[ph.m - 1])) {   // (never for data bpc_data_create accepted)
-      if (lane == 0) atomicOr(a.status + c, BP_ST_RATE_NONFINITE);
-    } else {
-      J = ph.m - 1;
-      mg = pc.m;
-    }
-  }
-  for (int i = lane; i < BP_XR * BP_D; i += 32) sN[i] = 0.0;
-  __syncwarp();
-  if (J >= 0) {
-    const double* m1 = a.ctab_m1 + (size_t)c * (BP_CGA + 1) * DN;
-    const double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
-    const int gi = a.cg_idx[grp];
-    const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
-    const int od = lane / BP_N, ol = lane - od * BP_N;
-    double nj = 0.0;
-    if (lane < DN) {
-#pragma unroll
-      for (int rr = 0; rr < BP_D; ++rr) nj += e2[(size_t)bi * DD + od * BP_D + rr] * m1[(size_t)ai * DN + rr * BP_N + ol];
-      sN[ol * BP_D + od] = nj;
-    }
-    __syncwarp();
-    for (int j = 1; j <= J; ++j) {
-      if (lane < DN) {
-        nj = 0.0;
-#pragma unroll
-        for (int rr = 0; rr < BP_D; ++rr) nj += Lm[od * BP_D + rr] * sN[((j - 1) * BP_N + ol) * BP_D + rr];
-        sN[(j * BP_N + ol) * BP_D + od] = nj;
+  if (c < a.nchains) {
+    const double a1 = a.ctab_l[(size_t)c * (DD + 1) + DD];
+    if (a1 >= 0.0) {
+      BpPlan pc, ph;
+      int d1 = 1, d2 = 1;
+      const bool okc = bp_make_plan(a1, a.cg_tau[grp], pc, d1, BP_WCAP, BP_WTHETA_CAP);
+      const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, d2, BP_CJ - 1, BP_WTHETA_CAP);
+      if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[grp] <= bp_th[ph.m - 1])) {   // (never for data bpc_data_create accepted)
+        atomicOr(a.status + c, BP_ST_RATE_NONFINITE);
+      } else {
+        J = ph.m - 1;
+        mg = pc.m;
       }
-      __syncwarp();
     }
   }
-  for (int i = lane; i < BP_XR * BP_D; i += 32) { const int r = i / BP_D, d = i - r * BP_D; out[(size_t)r * BP_OU + d] = sN[i]; }
-  if (lane == 0) {
-    a.cg_jm[(size_t)c * a.cgroups + grp] = J < 0 ? -1 : (J | (mg << 8));
-    double fl = 0.0;
-    if (J >= 0) {
-      const int k0 = a.cg_chunk0[grp] * 32, k1 = min(a.nobs, a.cg_chunk0[grp + 1] * 32);
-      fl = 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (mg + 1) - 1)      // N_0 .. N_J and the Toeplitz product (as bp_fusedc counts them)
-           + (double)max(0, k1 - k0) * (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);               // per observation and term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
-    }
-    a.cg_flops[(size_t)c * a.cgroups + grp] = fl;
+  a.cg_jm[(size_t)c * a.cgroups + grp] = J < 0 ? -1 : (J | (mg << 8));
+  double fl = 0.0;
+  if (J >= 0) {
+    const int k0 = a.cg_chunk0[grp] * 32, k1 = min(a.nobs, a.cg_chunk0[grp + 1] * 32);
+    fl = 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (mg + 1) - 1)      // N_0 .. N_J and the Toeplitz product (as bp_fusedc counts them)
+         + (double)max(0, k1 - k0) * (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);               // per observation and term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
   }
+  a.cg_flops[(size_t)c * a.cgroups + grp] = fl;
 }
 
 // One CTA (four warps) per pass of 32 observations x 8 chains; every phase is split four ways, three barriers per pass:
@@ -1727,13 +1687,55 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
     __syncthreads();
   }
   for (int grp = g0; grp < g1; ++grp) {
-    {   // N of (octet, group); the previous group's last forward product is behind a barrier
-      const double2* src = reinterpret_cast<const double2*>(a.ntab + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU);
-      for (int i = tid; i < BP_XR * BP_OU / 2; i += BP_OTHREADS) {
-        const int r = i / (BP_OU / 2), q = i - r * (BP_OU / 2);
-        *reinterpret_cast<double2*>(sN + r * BP_ONLD + 2 * q) = __ldcg(src + i);
+    // ---- N_j(tau_g) of the octet's chains: N_0 = E2[b] M1[a] (tables of bp_ctable), N_(j+1) = L N_j; thread = entries (cc, d, l).
+    // Rows beyond a chain's own degree J are zero.  (The previous group's last forward product is behind a barrier.) ----
+    if (tid < 8) sjm[tid] = (o * 8 + tid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + tid) * a.cgroups + grp] : -1;
+    __syncthreads();
+    {
+      constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NQ = (8 * DN + BP_OTHREADS - 1) / BP_OTHREADS;
+      const int gi = a.cg_idx[grp];
+      const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
+      double Lr[NQ][BP_D];
+      int Jq[NQ], eo[NQ], dq[NQ];   // degree of the entry's chain (-1: not on this path, -2: no entry), offset of (row (0, l), column (cc, 0)) in sN, d
+      int Jmax = -1;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) Jmax = max(Jmax, sjm[cc] < 0 ? -1 : (sjm[cc] & 255));
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e = tid + q * BP_OTHREADS;
+        const int cc = e / DN, rem = e - cc * DN, d = rem / BP_N, l = rem - d * BP_N;
+        Jq[q] = e < 8 * DN ? (sjm[cc & 7] < 0 ? -1 : (sjm[cc & 7] & 255)) : -2;
+        eo[q] = l * BP_ONLD + cc * BP_D;
+        dq[q] = d;
+        double n0 = 0.0;
+        if (Jq[q] >= 0) {
+          const size_t c = (size_t)o * 8 + cc;
+          const double* lrow = a.ctab_l + c * (DD + 1) + d * BP_D;
+          const double* e2 = a.ctab_e2 + (c * BP_CGB + bi) * DD + d * BP_D;
+          const double* m1 = a.ctab_m1 + (c * (BP_CGA + 1) + ai) * DN + l;
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) { Lr[q][rr] = lrow[rr]; n0 += e2[rr] * m1[rr * BP_N]; }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = 0.0;
+        }
+        if (Jq[q] >= -1) sN[eo[q] + d] = n0;
       }
-      if (tid < 8) sjm[tid] = (o * 8 + tid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + tid) * a.cgroups + grp] : -1;
+      for (int j = 1; j < BP_CJ; ++j) {
+        if (j <= Jmax) __syncthreads();   // row j - 1 complete (uniform: Jmax comes from shared memory)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          if (Jq[q] >= -1) {
+            double v = 0.0;
+            if (j <= Jq[q]) {
+              const double* prev = sN + (j - 1) * BP_N * BP_ONLD + eo[q];
+#pragma unroll
+              for (int rr = 0; rr < BP_D; ++rr) v += Lr[q][rr] * prev[rr];
+            }
+            sN[j * BP_N * BP_ONLD + eo[q] + dq[q]] = v;
+          }
+        }
+      }
     }
     const double tau = a.cg_tau[grp];
     double accS[BP_XRT][BP_OACC][2];

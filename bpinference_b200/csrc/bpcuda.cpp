@@ -526,8 +526,8 @@ static int ensure_workspace(bpc_data* d, int nchains) {
       if (d->cmode && (rc = d->fb.alloc((size_t)(nchains + 1) * 4))) return rc;
       if (d->omode) {
         const size_t oct = (size_t)d->noct * d->cgroups * (8 * n) * (8 * D) * 8;
-        if ((rc = d->ntab.alloc(oct))) return rc;
         if ((rc = d->osg.alloc(oct))) return rc;
+        if ((rc = d->ctab_l.alloc((size_t)d->noct * 8 * (D * D + 1) * 8))) return rc;
         if ((rc = d->cg_jm.alloc((size_t)d->noct * 8 * d->cgroups * 4))) return rc;
         if ((rc = d->cg_flops.alloc((size_t)d->noct * 8 * d->cgroups * 8))) return rc;
         if ((rc = d->wplain.alloc((size_t)nchains * (((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n * 8))) return rc;
@@ -558,7 +558,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; const double* cg_coef; double cdelta;
   double* ctab_m1; double* ctab_e2; double* csg;
   int noct; double* ntab; int* cg_jm; double* cg_flops; double* osg; double* wplain;
-  int* fb;
+  int* fb; double* ctab_l;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -584,7 +584,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               d->cgroups, d->cgpc, (const int*)d->cg_chunk0.p, (const int*)d->cg_idx.p, (const double*)d->cg_tau.p,
               (const double*)d->cg_hmax.p, (const double*)d->cg_coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
               d->noct, (double*)d->ntab.p, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
-              (int*)d->fb.p};
+              (int*)d->fb.p, (double*)d->ctab_l.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -620,7 +620,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
           // octet path: per-chain tables, N_j(tau_g) of every (chain, group), the fused passes of 8 chains at a time, the Toeplitz products
           const int n = s.ntypes, D = n + n * (n + 1) / 2;
           BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(128), args, 0, st));
-          BPC_CUDA(cudaLaunchKernel((const void*)L->ntable, dim3((d->cgroups + 3) / 4, d->noct * 8), dim3(128), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->ntable, dim3((d->cgroups + 127) / 128, d->noct * 8), dim3(128), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
           g_launches += 3;
@@ -671,8 +671,8 @@ int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned lon
     const int n = s.ntypes, D = n + n * (n + 1) / 2;
     unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
     if (d->omode) {
-      // N and S' of every (octet, group), W of every chain and the per-chain tables, written then read
-      b += 2ull * ((unsigned long long)d->noct * d->cgroups * (8 * n) * (8 * D) * 2 + (unsigned long long)nchains * ((((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n + 65ull * D * n + 64ull * D * D)) * 8;
+      // S' of every (octet, group), W of every chain and the per-chain tables, written then read
+      b += 2ull * ((unsigned long long)d->noct * d->cgroups * (8 * n) * (8 * D) + (unsigned long long)nchains * ((((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n + 65ull * D * n + 64ull * D * D)) * 8;
     } else {
       if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
       if (d->cmode) b += 2ull * nchains * ((unsigned long long)d->cgroups * 8 * ((D * n + 7) / 8) * 8 + 65ull * D * n + 64ull * D * D) * 8;   // S^g per group and the per-chain tables, written then read

@@ -282,3 +282,42 @@ def test_centred_w_path_matches_oracle_and_w_path(nobs, chunks):
     np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
     b = eng.log_prob_grad(d, u)        # deterministic
     assert (b[0] == lp).all() and (b[1] == g).all()
+
+
+@pytest.mark.parametrize("name,nobs,chains,grouping", [("cfg5U", 20000, 19, None), ("cfg5U", 60000, 16, None), ("cfg2", None, 24, 1),
+                                                       ("cfg4", None, 17, 1)])
+def test_octet_path_matches_oracle_and_centred_path(name, nobs, chains, grouping):
+    """octet path (bp_ctable + bp_ntable + bp_fusedo + bp_toep: eight chains share the tensor tiles of a pass) against the
+    oracle and against bp_fusedc on the same data; a ragged last octet, chains with long and short centre series, one chain
+    that needs sub-steps (ring fallback, listed by bp_ctable) in the same call; two-type and noise models on ungrouped data."""
+    import os
+    cfg = syn.make_config(name, chains=chains, nobs=nobs)
+    eng, om = _pair(cfg)
+    u = cfg["upars"].copy()
+    if name == "cfg5U":
+        u[1] += 0.75                   # 2 ||A|| t_max ~ 3.3: centre series of up to 32 terms
+        u[2] -= 1.5                    # small rates: short series everywhere
+        u[11] += 2.2                   # sub-steps: bp_fused
+    kw = {} if grouping is None else {"grouping": grouping}
+    d = eng.data(cfg["data"], **kw)
+    assert "bp_fusedo" in d.path(chains)[0]
+    lp, g, st = eng.log_prob_grad(d, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
+    assert st.tolist() == st_o.tolist() and (st == 0).all()
+    np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
+    np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+    os.environ["BPC_OPATH"] = "0"
+    try:
+        d2 = eng.data(cfg["data"], **kw)
+        assert "bp_fusedc" in d2.path(chains)[0]
+        lp2, g2, st2 = eng.log_prob_grad(d2, u)
+    finally:
+        del os.environ["BPC_OPATH"]
+    np.testing.assert_allclose(lp, lp2, rtol=1e-12)
+    np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
+    b = eng.log_prob_grad(d, u)        # deterministic
+    assert (b[0] == lp).all() and (b[1] == g).all()
+    # fewer chains than the octet threshold on the same handle: back to bp_fusedc, same numbers
+    lp3, g3, st3 = eng.log_prob_grad(d, u[:5])
+    np.testing.assert_allclose(lp3, lp[:5], rtol=1e-12)
+    np.testing.assert_allclose(g3, g[:5], rtol=1e-9, atol=1e-11 * np.abs(g).max())
