@@ -1641,14 +1641,15 @@ extern "C" __global__ void __launch_bounds__(128) bp_ntable(BpObsArgs a) {
 //   forward  warp w = (wlo, whi): observation tiles 2 wlo, 2 wlo + 1 x the (cc, d) tiles BP_OHT whi .. BP_OHT whi + BP_OHT - 1, plus
 //            (BP_D odd) the last (cc, d) tile x observation tile 2 wlo + whi
 //   score    thread (w, lane): observation `lane` under chains 2w and 2w + 1; the cotangent replaces Y in place
-//   S update warp w: observations 16 wlo .. 16 wlo + 15 x the same BP_OHT tiles of (cc, d), plus the last tile x observations
-//            16 wlo + 8 whi .. + 7; the partial sums over k are added per group
+//   S update warp w: all 32 observations x the (cc, d) tiles BP_OTW w .. BP_OTW w + BP_OTW - 1 x all row tiles, plus one
+//            (row tile, remaining (cc, d) tile) pair: every tile of S' belongs to one warp (no reduction between warps)
 // so that every warp carries the same number of tensor products without a predicate in the loops; all shared-memory addresses are a
 // per-lane base plus a compile-time offset.  The FP64 datapath (DMMA and DFMA share it) is kept busy by the other CTAs of the SM
 // while one waits at a barrier.
 #define BP_OHT (BP_D / 2)                         // (cc, d) tiles of a warp pair
 #define BP_OEX (BP_D & 1)                         // one more tile shared by the four warps
-#define BP_OACC (BP_OHT + BP_OEX)
+#define BP_OTW (BP_D / 4)                         // S update: (cc, d) tiles owned by each warp with all their row tiles
+#define BP_OREM (BP_D - 4 * BP_OTW)               // remaining (cc, d) tiles: their BP_OREM * BP_XRT (<= 4) tiles go to warps 0, 1, ..
 extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fusedo(BpObsArgs a) {
   const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
@@ -1666,9 +1667,12 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   const int fXx = tg * BP_WLD + (2 * wlo + whi) * 8 + g;           // ... for the last tile's observation tile
   const int fY = (whi * (BP_OHT * 8) + g) * BP_OYLD + wlo * 16 + ((2 * tg) ^ (swz << 2));   // accumulator stores: + t * 8 * BP_OYLD + q * 8
   const int fYx = (2 * BP_OHT * 8 + g) * BP_OYLD + (2 * wlo + whi) * 8 + ((2 * tg) ^ (swz << 2));
-  const int uX = g * BP_WLD + wlo * 16 + tg;                       // A fragments of the S update: + rt * 8 * BP_WLD + ob * 4
-  const int uY = (whi * (BP_OHT * 8) + g) * BP_OYLD + wlo * 16 + tg;   // B fragments: + ct * 8 * BP_OYLD + (ob ^ swz) * 4
-  const int uYx = (2 * BP_OHT * 8 + g) * BP_OYLD + wlo * 16 + whi * 8 + tg;
+  const int uX = g * BP_WLD + tg;                                  // A fragments of the S update: + rt * 8 * BP_WLD + ob * 4
+  const int uY = (warp * (BP_OTW * 8) + g) * BP_OYLD + tg;         // B fragments: + ct * 8 * BP_OYLD + (ob ^ swz) * 4
+  const int wx = min(warp, BP_OREM * BP_XRT - 1);                  // this warp's remaining tile (warps beyond the last one repeat it and drop the result)
+  const int xct = 4 * BP_OTW + wx / BP_XRT, xrt = wx % BP_XRT;
+  const int uXx = (xrt * 8 + g) * BP_WLD + tg;
+  const int uYx = (xct * 8 + g) * BP_OYLD + tg;
   // score: row r = (2 warp + i2) BP_D + d; r & 2 = ((9 i2 + d) & 2) ^ (2 wlo) for BP_D = 9 (18 warp = 2 wlo mod 4), computed generally below
   double lp[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
   int notpd = 0;                                // bit i: an observation of chain 2 warp + i had a covariance that is not positive definite
@@ -1738,11 +1742,11 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
       }
     }
     const double tau = a.cg_tau[grp];
-    double accS[BP_XRT][BP_OACC][2];
+    double accS[BP_XRT][BP_OTW ? BP_OTW : 1][2], accX[2] = {0.0, 0.0};
 #pragma unroll
     for (int rt = 0; rt < BP_XRT; ++rt)
 #pragma unroll
-      for (int ct = 0; ct < BP_OACC; ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
+      for (int ct = 0; ct < (BP_OTW ? BP_OTW : 1); ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
     const int ch1 = a.cg_chunk0[grp + 1];
     for (int ch = a.cg_chunk0[grp]; ch < ch1; ++ch, ++pass) {
       double* sX = sXb + (pass & 1) * (BP_XR * BP_WLD);
@@ -1836,76 +1840,38 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
       }
       bp_cp_async_wait_all();   // the next pass's chunk has landed (this thread's piece; the barrier publishes all of them)
       __syncthreads();
-      {   // S' update over this warp's 16 observations: X fragments (A) shared by the column tiles, b fragments (B) by the row tiles
+      {   // S' update over the 32 observations: X fragments (A) shared by the column tiles, b fragments (B) by the row tiles
         const double* px = sX + uX;
         const double* pbE = sY + uY + (swz << 2);   // k-steps ob even: column block ob ^ swz = ob + swz
         const double* pbO = sY + uY - (swz << 2);   // k-steps ob odd:  ob - swz
 #pragma unroll
-        for (int ob = 0; ob < 4; ++ob) {
+        for (int ob = 0; ob < 8; ++ob) {
+#if BP_OTW
           double xa[BP_XRT];
 #pragma unroll
           for (int rt = 0; rt < BP_XRT; ++rt) xa[rt] = px[rt * 8 * BP_WLD + ob * 4];
 #pragma unroll
-          for (int ct = 0; ct < BP_OHT; ++ct) {
+          for (int ct = 0; ct < BP_OTW; ++ct) {
             const double bf = ((ob & 1) ? pbO : pbE)[ct * 8 * BP_OYLD + ob * 4];
 #pragma unroll
             for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][ct][0], accS[rt][ct][1], xa[rt], bf);
           }
-#if BP_OEX
-          if ((ob >> 1) == 0) {   // the last tile: k-steps 2 whi, 2 whi + 1 of this half (compile-time ob2 = ob, runtime offset 8 whi)
-            const double bf = sY[uYx + ((ob & 1) ? -(swz << 2) : (swz << 2)) + ob * 4];
-#pragma unroll
-            for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][BP_OHT][0], accS[rt][BP_OHT][1], px[rt * 8 * BP_WLD + whi * 8 + ob * 4], bf);
-          }
 #endif
+          bp_dmma(accX[0], accX[1], sX[uXx + ob * 4], sY[uYx + ((ob & 1) ? -(swz << 2) : (swz << 2)) + ob * 4]);
         }
       }
     }
-    // ---- the group's S' = sum of the partial sums over k (fixed order), row-major [(j, l)][(cc, d)] ----
-    __syncthreads();   // all S updates have read Y
-    double* scr = sY;                                         // [2][BP_XRT][BP_OHT][64], then [3][BP_XRT][64] for the last tile
-    double* scrx = sY + 2 * BP_XRT * BP_OHT * 64;
-    if (wlo) {
-#pragma unroll
-      for (int rt = 0; rt < BP_XRT; ++rt)
-#pragma unroll
-        for (int ct = 0; ct < BP_OHT; ++ct)
-          *reinterpret_cast<double2*>(scr + ((whi * BP_XRT + rt) * BP_OHT + ct) * 64 + lane * 2) = make_double2(accS[rt][ct][0], accS[rt][ct][1]);
-    }
-#if BP_OEX
-    if (warp) {
-#pragma unroll
-      for (int rt = 0; rt < BP_XRT; ++rt)
-        *reinterpret_cast<double2*>(scrx + ((warp - 1) * BP_XRT + rt) * 64 + lane * 2) = make_double2(accS[rt][BP_OHT][0], accS[rt][BP_OHT][1]);
-    }
-#endif
-    __syncthreads();
+    // ---- the group's S', row-major [(j, l)][(cc, d)]: every tile from the warp that owns it ----
     double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
-    if (!wlo) {
+#if BP_OTW
 #pragma unroll
-      for (int rt = 0; rt < BP_XRT; ++rt)
+    for (int rt = 0; rt < BP_XRT; ++rt)
 #pragma unroll
-        for (int ct = 0; ct < BP_OHT; ++ct) {
-          const double2 v = *reinterpret_cast<const double2*>(scr + ((whi * BP_XRT + rt) * BP_OHT + ct) * 64 + lane * 2);
-          __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (whi * BP_OHT + ct) * 8 + 2 * tg),
-                 make_double2(accS[rt][ct][0] + v.x, accS[rt][ct][1] + v.y));
-        }
-    }
-#if BP_OEX
-    if (!warp) {
-#pragma unroll
-      for (int rt = 0; rt < BP_XRT; ++rt) {
-        double s0 = accS[rt][BP_OHT][0], s1 = accS[rt][BP_OHT][1];
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-          const double2 v = *reinterpret_cast<const double2*>(scrx + (w * BP_XRT + rt) * 64 + lane * 2);
-          s0 += v.x; s1 += v.y;
-        }
-        __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + 2 * BP_OHT * 8 + 2 * tg), make_double2(s0, s1));
-      }
-    }
+      for (int ct = 0; ct < BP_OTW; ++ct)
+        __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (warp * BP_OTW + ct) * 8 + 2 * tg), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
 #endif
-    // (the next group's first barrier separates these reads of the scratch from the next forward product)
+    if (warp < BP_OREM * BP_XRT) __stcg(reinterpret_cast<double2*>(sg + (size_t)(xrt * 8 + g) * BP_OU + xct * 8 + 2 * tg), make_double2(accX[0], accX[1]));
+    // (the next group's prologue barrier separates this group's last S update from the next writes of N and Y)
   }
   // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial; chain 2 warp + i belongs to this warp alone ----
 #pragma unroll
@@ -2487,23 +2453,26 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_loglik(BpObsArgs a) 
 }
 #endif  // BP_KIND
 
-// ---- epilogue: one thread per chain ---------------------------------------------------------------
-// sums the tile partials in tile order, adds priors and the log-Jacobian, applies the chain rule of the
-// bound transform, and rejects the chain (lp = -inf, grad = 0) when any status bit is set.
+// ---- epilogue: one warp per chain -----------------------------------------------------------------
+// sums the tile partials in a fixed order (lane i takes tiles i, i + 32, ..., then a shuffle tree), adds priors and the
+// log-Jacobian, applies the chain rule of the bound transform, and rejects the chain (lp = -inf, grad = 0) when any status bit is set.
 extern "C" __global__ void bp_epilogue(const double* __restrict__ u, const double* __restrict__ theta,
                                        const double* __restrict__ part, int ntiles, int nchains, int jacobian,
                                        double* __restrict__ lp_out, double* __restrict__ grad_out, int* __restrict__ status,
                                        double* __restrict__ apps_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nchains) return;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= nchains) return;   // (warp-uniform)
   double acc[BP_NPART];
 #pragma unroll
   for (int i = 0; i < BP_NPART; ++i) acc[i] = 0.0;
-  for (int tI = 0; tI < ntiles; ++tI) {
+  for (int tI = lane; tI < ntiles; tI += 32) {
     const double* p = part + ((size_t)c * ntiles + tI) * BP_NPART;
 #pragma unroll
     for (int i = 0; i < BP_NPART; ++i) acc[i] += p[i];
   }
+#pragma unroll
+  for (int i = 0; i < BP_NPART; ++i) acc[i] = bp_warp_sum(acc[i]);
+  if (lane) return;
   double lp = acc[0];
   int st = status[c];
   double grad[BP_DIM];

@@ -647,7 +647,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
     int ntiles = d->ntiles;
     void* args[] = {(void*)&u_dev, (void*)&theta, (void*)&part, (void*)&ntiles, (void*)&nchains, (void*)&jacobian,
                     (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps};
-    BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
+    BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
   g_launches += 3;
   return BPC_OK;

@@ -199,9 +199,9 @@ std::string generate_cuda(ModelSpec& m) {
     if (const char* ev = std::getenv("BPC_CMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 8) cmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_CMINBLOCKS %d\n", cmin);
     s += buf;
-    // octet path (bp_fusedo): three CTAs of four warps per SM (168 registers per thread: the two scores of a thread interleave
-    // without spills; tools/perf_c.py: 2.44 ms against 2.49 ms with four CTAs at 128 registers on cfg5U)
-    int omin = 3;
+    // octet path (bp_fusedo): four CTAs of four warps per SM (128 registers per thread, no spills: every tile of S' has one owner warp,
+    // 14 accumulator doubles per thread; tools/perf_c.py: 2.24 ms against 2.33 ms with three CTAs on cfg5U)
+    int omin = 4;
     if (const char* ev = std::getenv("BPC_OMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 4) omin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_OMINBLOCKS %d\n", omin);
     s += buf;

@@ -321,3 +321,35 @@ def test_octet_path_matches_oracle_and_centred_path(name, nobs, chains, grouping
     lp3, g3, st3 = eng.log_prob_grad(d, u[:5])
     np.testing.assert_allclose(lp3, lp[:5], rtol=1e-12)
     np.testing.assert_allclose(g3, g[:5], rtol=1e-9, atol=1e-11 * np.abs(g).max())
+
+
+def test_octet_path_one_type_multitype_template():
+    """ntypes = 1 under the multitype template with per-observation durations: the octet path's smallest shape
+    (D = 2: two (cc, d) tiles, one row tile) against the oracle and against bp_fusedc."""
+    import os
+    rng = np.random.default_rng(7)
+    N, chains = 5000, 16
+    t = rng.uniform(0.5, 3.0, N)
+    z0 = np.rint(rng.uniform(500, 2000, N))
+    x = np.rint(z0 * np.exp(0.05 * t) + rng.standard_normal(N) * np.sqrt(0.15 * z0 * t))
+    mod = bp.bp_model([[2], [0]], [1, 1], ["c[1]", "c[2]"], 2, 0)
+    priors = [bp.prior_dist("uniform", [0, 1], [0, 2])] * 2
+    data = bp.create_stan_data(mod, x, z0, t)
+    eng = bp.stan_model(mod, priors)
+    om = bo.OracleModel("multitype", [[2.0], [0.0]], [1, 1], ["c[1]", "c[2]"], 2, 0, priors)
+    u = np.log(np.array([0.1, 0.05]) / (2 - np.array([0.1, 0.05])))[None, :] + 0.1 * rng.standard_normal((chains, 2))
+    d = eng.data(data)
+    assert "bp_fusedo" in d.path(chains)[0]
+    lp, g, st = eng.log_prob_grad(d, u)
+    lp_o, g_o, st_o = bo.log_prob(om, data, u)
+    assert (st == 0).all() and (st_o == 0).all()
+    np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
+    np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+    os.environ["BPC_OPATH"] = "0"
+    try:
+        d2 = eng.data(data)
+        lp2, g2, st2 = eng.log_prob_grad(d2, u)
+    finally:
+        del os.environ["BPC_OPATH"]
+    np.testing.assert_allclose(lp, lp2, rtol=1e-12)
+    np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
