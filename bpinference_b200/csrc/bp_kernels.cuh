@@ -1103,7 +1103,7 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
 
 // per chain: the two tables M(tau) is assembled from.  One CTA per chain; Krylov blocks U_j = L^j [e_1 .. e_n] and powers
 // P_j = L^j in shared memory, then every table entry is a short dot product with the coefficients c_j(time).
-extern "C" __global__ void __launch_bounds__(128) bp_ctable(BpObsArgs a) {
+extern "C" __global__ void __launch_bounds__(512) bp_ctable(BpObsArgs a) {
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
   __shared__ double Lm[DD];
@@ -1862,6 +1862,7 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
       }
     }
     // ---- the group's S', row-major [(j, l)][(cc, d)]: every tile from the warp that owns it ----
+    // (a layout that bp_toep could stream, [tile][l][group][j][8], scatters these stores and costs more here than it saves there)
     double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
 #if BP_OTW
 #pragma unroll
@@ -1896,41 +1897,62 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 
-// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
-extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
+// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups,
+// four groups in flight per warp (the loads of S' come from DRAM: their latency, not the arithmetic, is the cost).
+#define BP_TOEP_WARPS 8
+#define BP_TOEP_UNROLL 4
+extern "C" __global__ void __launch_bounds__(32 * BP_TOEP_WARPS) bp_toep(BpObsArgs a) {
   const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
-  __shared__ double red[4][BP_CRT * 64];
+  __shared__ double red[BP_TOEP_WARPS][BP_CRT * 64];
   const int u = ct * 8 + g, cc = u / BP_D;        // this lane's column of the B fragments: chain cc of the octet
   const int c = o * 8 + cc;
   double accW[BP_CRT][2];
 #pragma unroll
   for (int rt = 0; rt < BP_CRT; ++rt) { accW[rt][0] = 0.0; accW[rt][1] = 0.0; }
-  for (int grp = warp; grp < a.cgroups; grp += 4) {
-    const int jm = c < a.nchains ? a.cg_jm[(size_t)c * a.cgroups + grp] : -1;
-    const int J = jm < 0 ? -1 : (jm & 255);
-    const double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
-    const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
-    double bf[2];
+  for (int grp0 = warp; grp0 < a.cgroups; grp0 += BP_TOEP_WARPS * BP_TOEP_UNROLL) {
+    double bf[BP_TOEP_UNROLL][2];
+    int rows[BP_TOEP_UNROLL];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int j = ks * 4 + tg;
-      const double v = __ldcg(sg + (size_t)(j * BP_N + l) * BP_OU + u);
-      bf[ks] = j <= J ? v : 0.0;   // rows beyond the chain's own degree hold X b products of terms the chain does not have
-    }
-#pragma unroll
-    for (int rt = 0; rt < BP_CRT; ++rt)
+    for (int q = 0; q < BP_TOEP_UNROLL; ++q) {
+      const int grp = grp0 + q * BP_TOEP_WARPS;
+      const bool on = grp < a.cgroups;
+      const int jm = (on && c < a.nchains) ? a.cg_jm[(size_t)c * a.cgroups + grp] : -1;
+      const int J = jm < 0 ? -1 : (jm & 255);
+      const double* sg = a.osg + ((size_t)o * a.cgroups + (on ? grp : 0)) * BP_XR * BP_OU;
+      // rows n = 1 .. m_g + J of W get a contribution from this group: row tiles beyond that are skipped (warp-uniform bound)
+      rows[q] = __reduce_max_sync(0xffffffffu, jm < 0 ? 0 : (jm >> 8) + J);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg (the table is zero outside 0 .. BP_WCAP + 1)
-        bp_dmma(accW[rt][0], accW[rt][1], cf[ix], bf[ks]);
+        const int j = ks * 4 + tg;
+        // rows beyond the chain's own degree hold X b products of terms the chain does not have
+        bf[q][ks] = j <= J ? __ldcs(sg + (size_t)(j * BP_N + l) * BP_OU + u) : 0.0;
       }
+    }
+#pragma unroll
+    for (int q = 0; q < BP_TOEP_UNROLL; ++q) {
+      const int grp = grp0 + q * BP_TOEP_WARPS;
+      if (grp < a.cgroups) {   // (warp-uniform)
+        const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
+#pragma unroll
+        for (int rt = 0; rt < BP_CRT; ++rt)
+          if (rt * 8 < rows[q]) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg (the table is zero outside 0 .. BP_WCAP + 1)
+              bp_dmma(accW[rt][0], accW[rt][1], cf[ix], bf[q][ks]);
+            }
+          }
+      }
+    }
   }
 #pragma unroll
   for (int rt = 0; rt < BP_CRT; ++rt) { red[warp][rt * 64 + lane * 2] = accW[rt][0]; red[warp][rt * 64 + lane * 2 + 1] = accW[rt][1]; }
   __syncthreads();
-  for (int i = tid; i < BP_CRT * 64; i += 128) {
-    const double sacc = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
+  for (int i = tid; i < BP_CRT * 64; i += 32 * BP_TOEP_WARPS) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < BP_TOEP_WARPS; ++w) sacc += red[w][i];
     const int rt = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = rt * 8 + (ln >> 2), uu = ct * 8 + (ln & 3) * 2 + e;
     const int c2 = o * 8 + uu / BP_D, d = uu % BP_D;
