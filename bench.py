@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fused logp+grad (chain x observation) evaluations per second"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one `ncu --set full` capture of the default
-# workload (profiles/r01_ncu_bp_fusedc_cfg5U.txt: 33.8 MB read + 426.0 MB written — the per-group S matrices (410 MB of scratch per
-# launch) are written once, read back from L2 by the same warp and evicted later; the observation table itself is 5.6 MB)
-NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 33.795e6 + 426.030e6}
+# workload (profiles/r01_ncu_bp_fusedo_cfg5U.txt: 34.7 MB read + 125.5 MB written — the per-(octet, group) S' matrices, 173 MB of
+# scratch per launch, are written once and streamed back by bp_toep; the per-chain tables are 28 MB, the observation table 5.6 MB)
+NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 34.682e6 + 125.513e6}
 UNIT = "evals/s"
 DEFAULT_CHAINS = {"cfg5U": 512, "cfg5K": 512, "cfg5G": 512, "cfg2": 1024, "cfg1": 4, "cfg3": 4, "cfg4": 4}
 
@@ -40,7 +40,7 @@ DEFAULT_CHAINS = {"cfg5U": 512, "cfg5K": 512, "cfg5G": 512, "cfg2": 1024, "cfg1"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5U")
@@ -63,15 +63,40 @@ def workload_description(name, chains, N):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every 5 ms from a
+    thread (a timed region of tens of milliseconds sees many samples); `nvidia-smi -lms 100` when NVML cannot be loaded."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stopflag = index, [], None, None, False
+
+    def _poll_nvml(self):
+        n, h = self.nvml
+        bits = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        while not self.stopflag:
+            try:
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append("%d, %d, %.2f, %s" % (n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, n.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                                       ", ".join("Active" if r & b else "Not Active" for _, b in bits)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            self.nvml = (n, n.nvmlDeviceGetHandleByIndex(self.index))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            self.proc = True
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -87,11 +112,15 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml:
+            self.stopflag = True
+            self.thread.join(timeout=1)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -233,10 +262,14 @@ def main():
     stream = torch.cuda.Stream(device=dev)      # the stream every kernel of the timed region is launched on
     torch.cuda.set_stream(stream)
 
-    def step_dev():
-        flush.zero_()                                                    # L2 flush between timed iterations
+    def step_dev(ev=None):
+        flush.zero_()                                                    # L2 flush between timed iterations (not part of a step)
+        if ev is not None:
+            ev[0].record(stream)
         _ffi.check(L.bpc_log_prob_dev(eng.handle, data.handle, u_dev.data_ptr(), chains, 1, lp_dev.data_ptr(), g_dev.data_ptr(),
                                       st_dev.data_ptr(), stream.cuda_stream))
+        if ev is not None:
+            ev[1].record(stream)
 
     def sync_all():
         if world > 1:
@@ -253,13 +286,12 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_dev()
-    e1.record(stream)
+    # every step between its own pair of events on the launching stream; the L2 flush runs between the steps, outside the pairs
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for ev in evs:
+        step_dev(ev)
     sync_all()
-    ms = e0.elapsed_time(e1)
+    ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
     clk = clocks.stop()
     launches = int(L.bpc_launch_count(0))
     kms, kl = _ffi.C.c_double(), _ffi.C.c_longlong()
@@ -306,8 +338,8 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + workload_description(args.workload, chains, N), "chains_per_gpu": chains,
-                       "observations": N, "l2": "256 MiB buffer rewritten before every timed step (L2 flush); the 5.6 MB observation table is "
-                                               "re-read by every chain of a step and is L2-resident by design",
+                       "observations": N, "l2": "256 MiB buffer rewritten between the timed steps (L2 flush, outside each step's event pair); the 5.6 MB "
+                                               "observation table is re-read by every chain of a step and is L2-resident by design",
                        "rejected_chains": bad},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": NCU_TRAFFIC_BYTES.get((args.workload, chains, N)), "traffic_unit": "bytes per launch (ncu, profiles/)",

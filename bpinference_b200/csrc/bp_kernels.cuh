@@ -1145,6 +1145,14 @@ extern "C" __global__ void __launch_bounds__(512) bp_ctable(BpObsArgs a) {
   }
   for (int o = tid; o < DN; o += T) { const int d = o / BP_N, l = o - d * BP_N; U[o] = (d == l) ? 1.0 : 0.0; }
   for (int o = tid; o < DD; o += T) { const int d = o / BP_D, e = o - d * BP_D; Pw[o] = (d == e) ? 1.0 : 0.0; }
+  // series lengths of the table points, once per point (not per entry)
+  __shared__ int mA[BP_CGA + 1], mB[BP_CGB];
+  for (int i = tid; i < BP_CGA + 1 + BP_CGB; i += T) {
+    BpPlan q;
+    int dq = 1;
+    if (i <= BP_CGA) { bp_make_plan(a1, i * d1, q, dq, BP_WCAP, BP_WTHETA_CAP); mA[i] = q.m; }
+    else { bp_make_plan(a1, (i - BP_CGA - 1) * a.cdelta, q, dq, BP_CPMAX - 1, BP_WTHETA_CAP); mB[i - BP_CGA - 1] = q.m; }
+  }
   __syncthreads();
   for (int j = 1; j <= mtop; ++j) {
     for (int o = tid; o < DN; o += T) {
@@ -1168,22 +1176,18 @@ extern "C" __global__ void __launch_bounds__(512) bp_ctable(BpObsArgs a) {
   for (int i = tid; i < (BP_CGA + 1) * DN; i += T) {
     const int ai = i / DN, o = i - ai * DN;
     const double ta = ai * d1;
-    BpPlan q;
-    int dq = 1;
-    bp_make_plan(a1, ta, q, dq, BP_WCAP, BP_WTHETA_CAP);
+    const int qm = mA[ai];
     double y = U[o], cj = 1.0;
-    for (int j = 1; j <= q.m; ++j) { cj = cj * (ta * bp_rk[j - 1]); y += cj * U[j * DN + o]; }
+    for (int j = 1; j <= qm; ++j) { cj = cj * (ta * bp_rk[j - 1]); y += cj * U[j * DN + o]; }
     m1[i] = y;
   }
   double* e2 = a.ctab_e2 + (size_t)c * BP_CGB * DD;
   for (int i = tid; i < BP_CGB * DD; i += T) {
     const int bi = i / DD, o = i - bi * DD;
     const double tb = bi * a.cdelta;
-    BpPlan q;
-    int dq = 1;
-    bp_make_plan(a1, tb, q, dq, BP_CPMAX - 1, BP_WTHETA_CAP);
+    const int qm = mB[bi];
     double y = Pw[o], cj = 1.0;
-    for (int j = 1; j <= q.m; ++j) { cj = cj * (tb * bp_rk[j - 1]); y += cj * Pw[j * DD + o]; }
+    for (int j = 1; j <= qm; ++j) { cj = cj * (tb * bp_rk[j - 1]); y += cj * Pw[j * DD + o]; }
     e2[i] = y;
   }
 }
@@ -1897,62 +1901,47 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 
-// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups,
-// four groups in flight per warp (the loads of S' come from DRAM: their latency, not the arithmetic, is the cost).
-#define BP_TOEP_WARPS 8
-#define BP_TOEP_UNROLL 4
-extern "C" __global__ void __launch_bounds__(32 * BP_TOEP_WARPS) bp_toep(BpObsArgs a) {
+// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
+// (Variants measured on cfg5U and not kept: eight warps with four groups in flight, software-pipelined loads, a group-major
+// layout of S' that this kernel could stream -- all within a few microseconds of this one, 82 .. 93 us; ncu: tensor path 39 % busy.)
+extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
   const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
-  __shared__ double red[BP_TOEP_WARPS][BP_CRT * 64];
+  __shared__ double red[4][BP_CRT * 64];
   const int u = ct * 8 + g, cc = u / BP_D;        // this lane's column of the B fragments: chain cc of the octet
   const int c = o * 8 + cc;
   double accW[BP_CRT][2];
 #pragma unroll
   for (int rt = 0; rt < BP_CRT; ++rt) { accW[rt][0] = 0.0; accW[rt][1] = 0.0; }
-  for (int grp0 = warp; grp0 < a.cgroups; grp0 += BP_TOEP_WARPS * BP_TOEP_UNROLL) {
-    double bf[BP_TOEP_UNROLL][2];
-    int rows[BP_TOEP_UNROLL];
+  for (int grp = warp; grp < a.cgroups; grp += 4) {
+    const int jm = c < a.nchains ? a.cg_jm[(size_t)c * a.cgroups + grp] : -1;
+    const int J = jm < 0 ? -1 : (jm & 255);
+    // rows n = 1 .. m_g + J of W get a contribution from this group: row tiles beyond that are skipped (warp-uniform bound)
+    const int rows = __reduce_max_sync(0xffffffffu, jm < 0 ? 0 : (jm >> 8) + J);
+    const double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
+    const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
+    double bf[2];
 #pragma unroll
-    for (int q = 0; q < BP_TOEP_UNROLL; ++q) {
-      const int grp = grp0 + q * BP_TOEP_WARPS;
-      const bool on = grp < a.cgroups;
-      const int jm = (on && c < a.nchains) ? a.cg_jm[(size_t)c * a.cgroups + grp] : -1;
-      const int J = jm < 0 ? -1 : (jm & 255);
-      const double* sg = a.osg + ((size_t)o * a.cgroups + (on ? grp : 0)) * BP_XR * BP_OU;
-      // rows n = 1 .. m_g + J of W get a contribution from this group: row tiles beyond that are skipped (warp-uniform bound)
-      rows[q] = __reduce_max_sync(0xffffffffu, jm < 0 ? 0 : (jm >> 8) + J);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const int j = ks * 4 + tg;
-        // rows beyond the chain's own degree hold X b products of terms the chain does not have
-        bf[q][ks] = j <= J ? __ldcs(sg + (size_t)(j * BP_N + l) * BP_OU + u) : 0.0;
-      }
+    for (int ks = 0; ks < 2; ++ks) {
+      const int j = ks * 4 + tg;
+      const double v = __ldcs(sg + (size_t)(j * BP_N + l) * BP_OU + u);
+      bf[ks] = j <= J ? v : 0.0;   // rows beyond the chain's own degree hold X b products of terms the chain does not have
     }
 #pragma unroll
-    for (int q = 0; q < BP_TOEP_UNROLL; ++q) {
-      const int grp = grp0 + q * BP_TOEP_WARPS;
-      if (grp < a.cgroups) {   // (warp-uniform)
-        const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
+    for (int rt = 0; rt < BP_CRT; ++rt)
+      if (rt * 8 < rows) {
 #pragma unroll
-        for (int rt = 0; rt < BP_CRT; ++rt)
-          if (rt * 8 < rows[q]) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg (the table is zero outside 0 .. BP_WCAP + 1)
-              bp_dmma(accW[rt][0], accW[rt][1], cf[ix], bf[q][ks]);
-            }
-          }
+        for (int ks = 0; ks < 2; ++ks) {
+          const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg (the table is zero outside 0 .. BP_WCAP + 1)
+          bp_dmma(accW[rt][0], accW[rt][1], cf[ix], bf[ks]);
+        }
       }
-    }
   }
 #pragma unroll
   for (int rt = 0; rt < BP_CRT; ++rt) { red[warp][rt * 64 + lane * 2] = accW[rt][0]; red[warp][rt * 64 + lane * 2 + 1] = accW[rt][1]; }
   __syncthreads();
-  for (int i = tid; i < BP_CRT * 64; i += 32 * BP_TOEP_WARPS) {
-    double sacc = 0.0;
-#pragma unroll
-    for (int w = 0; w < BP_TOEP_WARPS; ++w) sacc += red[w][i];
+  for (int i = tid; i < BP_CRT * 64; i += 128) {
+    const double sacc = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
     const int rt = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = rt * 8 + (ln >> 2), uu = ct * 8 + (ln & 3) * 2 + e;
     const int c2 = o * 8 + uu / BP_D, d = uu % BP_D;

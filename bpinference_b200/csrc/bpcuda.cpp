@@ -619,14 +619,14 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
         if (d->omode) {
           // octet path: per-chain tables, N_j(tau_g) of every (chain, group), the fused passes of 8 chains at a time, the Toeplitz products
           const int n = s.ntypes, D = n + n * (n + 1) / 2;
-          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(nchains >= 1024 ? 256 : 512), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(256), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->ntable, dim3((d->cgroups + 127) / 128, d->noct * 8), dim3(128), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
-          BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(256), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
           g_launches += 3;
         } else if (d->cmode) {
           // centred W path: per-chain tables of exp(tau L), then short series around the groups' centres
-          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(nchains >= 1024 ? 256 : 512), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(256), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->fusedc, dim3(d->ntiles, nchains), dim3(s.threads), args, s.c_smem, st));
           g_launches += 1;
         } else {
