@@ -396,53 +396,62 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
     const int FG = 64 * 64;
     const double delta = tmax / FG;
     const double hcap = 0.999 * tmax * taylor_theta(7) / taylor_theta(s.wcap);
-    int gmax = 16;   // (tools/perf_c.py: 8 -> 3.03 ms, 12 -> 3.13, 16 -> 2.78, 20 -> 2.99 on cfg5U; wider groups need a longer short series)
-    if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) gmax = v; }
+    // runs of at most gmax chunks: 16 for bp_fusedc (tools/perf_c.py: 8 -> 3.03 ms, 12 -> 3.13, 16 -> 2.78, 20 -> 2.99 on cfg5U; wider groups
+    // need a longer short series), 32 for the octet path, whose passes always carry all BP_CJ terms (8 -> 2.37 ms, 16 -> 2.23, 24 -> 2.17,
+    // 32 -> 2.17: fewer groups, less per-group work).  Both groupings are built; choose_tiling picks one by chain count.
+    int gmaxs[2] = {16, 32};
+    if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) gmaxs[0] = gmaxs[1] = v; }
     const int nchunks = (N + 31) / 32;
-    std::vector<int> c0, idx;
-    std::vector<double> tau, hm;
-    bool ok = true;
     auto centre = [&](double hi, double lo, int& ig, double& tg, double& hg) {
       ig = (int)std::llround(0.5 * (hi + lo) / delta);
       ig = std::max(0, std::min(FG, ig));
       tg = ig * delta;
       hg = std::max(std::fabs(hi - tg), std::fabs(lo - tg));
     };
-    for (int ch = 0; ch < nchunks && ok;) {
-      const double hi = ht[(size_t)ch * 32];   // sorted, longest first
-      int end = ch + 1, ig;
-      double tg, hg;
-      centre(hi, ht[std::min(N, end * 32) - 1], ig, tg, hg);
-      if (!(hg <= hcap)) { ok = false; break; }
-      while (end < nchunks && end - ch < gmax) {
-        int ig2;
-        double tg2, hg2;
-        centre(hi, ht[std::min(N, (end + 1) * 32) - 1], ig2, tg2, hg2);
-        if (!(hg2 <= hcap)) break;
-        ig = ig2; tg = tg2; hg = hg2; ++end;
+    bool ok = true;
+    for (int set = 0; set < 2 && ok; ++set) {
+      const int gmax = gmaxs[set];
+      std::vector<int> c0, idx;
+      std::vector<double> tau, hm;
+      for (int ch = 0; ch < nchunks && ok;) {
+        const double hi = ht[(size_t)ch * 32];   // sorted, longest first
+        int end = ch + 1, ig;
+        double tg, hg;
+        centre(hi, ht[std::min(N, end * 32) - 1], ig, tg, hg);
+        if (!(hg <= hcap)) { ok = false; break; }
+        while (end < nchunks && end - ch < gmax) {
+          int ig2;
+          double tg2, hg2;
+          centre(hi, ht[std::min(N, (end + 1) * 32) - 1], ig2, tg2, hg2);
+          if (!(hg2 <= hcap)) break;
+          ig = ig2; tg = tg2; hg = hg2; ++end;
+        }
+        c0.push_back(ch); idx.push_back(ig); tau.push_back(tg); hm.push_back(hg);
+        ch = end;
       }
-      c0.push_back(ch); idx.push_back(ig); tau.push_back(tg); hm.push_back(hg);
-      ch = end;
-    }
-    if (ok) {
+      if (!ok) break;
       c0.push_back(nchunks);
-      dd->cgroups = (int)idx.size();
-      dd->cdelta = delta;
-      if ((rc = up(dd->cg_chunk0, c0.data(), c0.size() * 4))) return rc;
-      if ((rc = up(dd->cg_idx, idx.data(), idx.size() * 4))) return rc;
-      if ((rc = up(dd->cg_tau, tau.data(), tau.size() * 8))) return rc;
-      if ((rc = up(dd->cg_hmax, hm.data(), hm.size() * 8))) return rc;
-      // c_i(tau_g) = tau_g^i / i! at index i + 8, i = 0 .. wcap + 1 (the A operand of bp_wpost's Toeplitz products)
+      CGrouping& G = dd->cgs[set];
+      G.n = (int)idx.size();
+      if ((rc = up(G.chunk0, c0.data(), c0.size() * 4))) return rc;
+      if ((rc = up(G.idx, idx.data(), idx.size() * 4))) return rc;
+      if ((rc = up(G.tau, tau.data(), tau.size() * 8))) return rc;
+      if ((rc = up(G.hmax, hm.data(), hm.size() * 8))) return rc;
+      // c_i(tau_g) = tau_g^i / i! at index i + 8, i = 0 .. wcap + 1 (the A operand of the Toeplitz products)
       const int ctab = ((s.wcap + 1 + 8 + 7) / 8) * 8 + 16;
-      std::vector<double> coef((size_t)dd->cgroups * ctab, 0.0);
-      for (int gI = 0; gI < dd->cgroups; ++gI) {
+      std::vector<double> coef((size_t)G.n * ctab, 0.0);
+      for (int gI = 0; gI < G.n; ++gI) {
         double ci = 1.0;
         for (int i = 0; i <= s.wcap + 1; ++i) {
           if (i > 0) ci = ci * (tau[gI] * (1.0 / i));
           coef[(size_t)gI * ctab + i + 8] = ci;
         }
       }
-      if ((rc = up(dd->cg_coef, coef.data(), coef.size() * 8))) return rc;
+      if ((rc = up(G.coef, coef.data(), coef.size() * 8))) return rc;
+    }
+    if (ok) {
+      dd->cgroups = dd->cgs[0].n;
+      dd->cdelta = delta;
       dd->cmode = true;
     }
   }
@@ -473,11 +482,13 @@ static void choose_tiling(bpc_data* d, int nchains) {
   const int T = d->model->spec.threads;
   // octet path: eight chains per tensor tile once there are at least two octets (BPC_OPATH=0 keeps bp_fusedc, =1 forces the octet path from 8 chains)
   { const char* ev = std::getenv("BPC_OPATH"); d->omode = d->cmode && nchains >= 8 && (ev ? std::atoi(ev) != 0 : nchains >= 16); }
+  if (d->cmode) { d->cgsel = d->omode ? 1 : 0; d->cgroups = d->cgs[d->cgsel].n; }
   if (d->omode) {
-    // octet path: CTA = cgpc consecutive groups of one octet of chains; aim at >= 8 waves of 4 CTAs per SM
+    // octet path: CTA = cgpc consecutive groups of one octet of chains; one group per CTA unless that makes more than 16 waves of
+    // 4 CTAs per SM (tools/perf_c.py on cfg5U: 1 -> 2.215 ms, 2 -> 2.230, 3 -> 2.236, 4 -> 2.256)
     d->noct = (nchains + 7) / 8;
-    long long gpc = ((long long)d->cgroups * d->noct) / (148LL * 4 * 8);
-    long long cap = 2;
+    long long gpc = ((long long)d->cgroups * d->noct) / (148LL * 4 * 16);
+    long long cap = 1;
     if (const char* ev = std::getenv("BPC_OGROUPS_PER_CTA")) { const long long v = std::atoll(ev); if (v >= 1 && v <= 4096) cap = v; }
     gpc = std::max<long long>(1, std::min(cap, gpc));
     d->cgpc = (int)gpc;
@@ -581,8 +592,8 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
               part, status_dev, nullptr, (const int*)d->perm.p, d->N, d->npad, d->tile, d->ntiles, nchains,
               (double*)d->wpart.p, d->wmode ? (d->omode ? 3 : (d->cmode ? 2 : 1)) : 0,
-              d->cgroups, d->cgpc, (const int*)d->cg_chunk0.p, (const int*)d->cg_idx.p, (const double*)d->cg_tau.p,
-              (const double*)d->cg_hmax.p, (const double*)d->cg_coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
+              d->cgroups, d->cgpc, (const int*)d->cgs[d->cgsel].chunk0.p, (const int*)d->cgs[d->cgsel].idx.p, (const double*)d->cgs[d->cgsel].tau.p,
+              (const double*)d->cgs[d->cgsel].hmax.p, (const double*)d->cgs[d->cgsel].coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
               d->noct, (double*)d->ntab.p, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
               (int*)d->fb.p, (double*)d->ctab_l.p};
     void* args[] = {(void*)&a};

@@ -55,6 +55,11 @@ struct bpc_model {
   std::map<int, bpc::Loaded> loaded;
 };
 
+struct CGrouping {   // groups of consecutive chunks of the sorted table that share a series centre
+  int n = 0;
+  bpc::DevBuf chunk0, idx, tau, hmax, coef;
+};
+
 struct bpc_data {
   const bpc_model* model = nullptr;
   int device = 0;
@@ -65,9 +70,10 @@ struct bpc_data {
   bool wmode = false;
   // centred W path (bp_ctable + bp_fusedc): groups of consecutive 32-observation chunks sharing a series centre
   bool cmode = false;
-  int cgroups = 0, cgpc = 4;
+  int cgroups = 0, cgpc = 4, cgsel = 0;   // groups of the grouping in use: cgs[cgsel] (0: bp_fusedc, 1: octet path)
   double cdelta = 0.0;
-  bpc::DevBuf cg_chunk0, cg_idx, cg_tau, cg_hmax, cg_coef, ctab_m1, ctab_e2, csg;
+  CGrouping cgs[2];
+  bpc::DevBuf ctab_m1, ctab_e2, csg;
   // octet path (bp_ntable + bp_fusedo + bp_toep): eight chains per tensor tile; chosen per chain count (choose_tiling)
   bool omode = false;
   int noct = 0;
