@@ -30,9 +30,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fused logp+grad (chain x observation) evaluations per second"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one `ncu --set full` capture of the default
-# workload (profiles/r01_ncu_bp_fusedo_cfg5U.txt: 34.7 MB read + 125.5 MB written — the per-(octet, group) S' matrices, 173 MB of
-# scratch per launch, are written once and streamed back by bp_toep; the per-chain tables are 28 MB, the observation table 5.6 MB)
-NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 34.682e6 + 125.513e6}
+# workload (profiles/r01_ncu_bp_fusedo_cfg5U.txt: 27.2 MB read + 56.5 MB written — the per-(octet, group) S' matrices, 102 MB of
+# scratch per launch, are written once and streamed back by bp_toep (part of them still from L2); the per-chain tables are 28 MB, the
+# observation table 5.6 MB)
+NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 27.190e6 + 56.474e6}
 UNIT = "evals/s"
 DEFAULT_CHAINS = {"cfg5U": 512, "cfg5K": 512, "cfg5G": 512, "cfg2": 1024, "cfg1": 4, "cfg3": 4, "cfg4": 4}
 
