@@ -214,7 +214,7 @@ def run_reference(args, rank):
             rates.append(r)
             info = (cores, sample)
     v = float(np.mean(rates))
-    print(json.dumps({
+    _RESULT_LINE.append(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + workload_description(args.workload, chains, N),
@@ -227,6 +227,25 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON; whatever libraries write to fd 1 meanwhile (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION)
+    # goes to stderr: fd 1 points at fd 2 until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[0], flush=True)
+
+
+_RESULT_LINE = []
+
+
+def _main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -363,7 +382,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                    "rstan": "not installed (no R in this image): the CPU restatement in oracle/ stands in; it does less work "
                                             "than rstan's RK45 forward-sensitivity solve"}
-        print(json.dumps(out))
+        _RESULT_LINE.append(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
