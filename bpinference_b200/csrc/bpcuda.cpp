@@ -118,6 +118,72 @@ int model_load(bpc_model* m, int device, Loaded** out) {
 using namespace bpc;
 
 // =============================================================================================
+namespace bpc {
+
+// Cuts the sorted table (d->h_t, longest first) into runs of at most gmax chunks of 32 observations whose durations lie within
+// cg_hcap of a point tau_g of the fine time grid.  store: build and upload the arrays of G; otherwise only count (G.n, G.maxlen).
+// Returns 0, -1 when a single chunk is wider than cg_hcap (no centred path for this data), or a BPC error code (> 0).
+int build_grouping(bpc_data* d, int gmax, CGrouping& G, bool store) {
+  const int N = d->N, nchunks = (N + 31) / 32, FG = 64 * 64;
+  const double delta = d->cdelta, hcap = d->cg_hcap;
+  const std::vector<double>& ht = d->h_t;
+  const ModelSpec& s = d->model->spec;
+  std::vector<int> c0, idx;
+  std::vector<double> tau, hm;
+  auto centre = [&](double hi, double lo, int& ig, double& tg, double& hg) {
+    ig = (int)std::llround(0.5 * (hi + lo) / delta);
+    ig = std::max(0, std::min(FG, ig));
+    tg = ig * delta;
+    hg = std::max(std::fabs(hi - tg), std::fabs(lo - tg));
+  };
+  int ng = 0, maxlen = 0;
+  for (int ch = 0; ch < nchunks;) {
+    const double hi = ht[(size_t)ch * 32];
+    int end = ch + 1, ig;
+    double tg, hg;
+    centre(hi, ht[std::min(N, end * 32) - 1], ig, tg, hg);
+    if (!(hg <= hcap)) return -1;
+    while (end < nchunks && end - ch < gmax) {
+      int ig2;
+      double tg2, hg2;
+      centre(hi, ht[std::min(N, (end + 1) * 32) - 1], ig2, tg2, hg2);
+      if (!(hg2 <= hcap)) break;
+      ig = ig2; tg = tg2; hg = hg2; ++end;
+    }
+    if (store) { c0.push_back(ch); idx.push_back(ig); tau.push_back(tg); hm.push_back(hg); }
+    ++ng;
+    maxlen = std::max(maxlen, end - ch);
+    ch = end;
+  }
+  G.n = ng; G.maxlen = maxlen; G.gmax = gmax;
+  if (!store) return 0;
+  c0.push_back(nchunks);
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+    int rc = b.alloc(bytes);
+    if (rc) return rc;
+    if (bytes && cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return fail(BPC_E_CUDA, "cudaMemcpy (groups)");
+    return BPC_OK;
+  };
+  int rc;
+  if ((rc = up(G.chunk0, c0.data(), c0.size() * 4))) return rc;
+  if ((rc = up(G.idx, idx.data(), idx.size() * 4))) return rc;
+  if ((rc = up(G.tau, tau.data(), tau.size() * 8))) return rc;
+  if ((rc = up(G.hmax, hm.data(), hm.size() * 8))) return rc;
+  // c_i(tau_g) = tau_g^i / i! at index i + 8, i = 0 .. wcap + 1 (the A operand of the Toeplitz products)
+  const int ctab = ((s.wcap + 1 + 8 + 7) / 8) * 8 + 16;
+  std::vector<double> coef((size_t)G.n * ctab, 0.0);
+  for (int gI = 0; gI < G.n; ++gI) {
+    double ci = 1.0;
+    for (int i = 0; i <= s.wcap + 1; ++i) {
+      if (i > 0) ci = ci * (tau[gI] * (1.0 / i));
+      coef[(size_t)gI * ctab + i + 8] = ci;
+    }
+  }
+  return up(G.coef, coef.data(), coef.size() * 8);
+}
+
+}  // namespace bpc
+
 extern "C" {
 
 int bpc_abi_version(void) { return BPC_ABI_VERSION; }
@@ -397,63 +463,23 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
     const double delta = tmax / FG;
     const double hcap = 0.999 * tmax * taylor_theta(7) / taylor_theta(s.wcap);
     // runs of at most gmax chunks: 16 for bp_fusedc (tools/perf_c.py: 8 -> 3.03 ms, 12 -> 3.13, 16 -> 2.78, 20 -> 2.99 on cfg5U; wider groups
-    // need a longer short series), 32 for the octet path, whose passes always carry all BP_CJ terms (8 -> 2.37 ms, 16 -> 2.23, 24 -> 2.17,
-    // 32 -> 2.17: fewer groups, less per-group work).  Both groupings are built; choose_tiling picks one by chain count.
-    int gmaxs[2] = {16, 32};
-    if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) gmaxs[0] = gmaxs[1] = v; }
-    const int nchunks = (N + 31) / 32;
-    auto centre = [&](double hi, double lo, int& ig, double& tg, double& hg) {
-      ig = (int)std::llround(0.5 * (hi + lo) / delta);
-      ig = std::max(0, std::min(FG, ig));
-      tg = ig * delta;
-      hg = std::max(std::fabs(hi - tg), std::fabs(lo - tg));
-    };
-    bool ok = true;
-    for (int set = 0; set < 2 && ok; ++set) {
-      const int gmax = gmaxs[set];
-      std::vector<int> c0, idx;
-      std::vector<double> tau, hm;
-      for (int ch = 0; ch < nchunks && ok;) {
-        const double hi = ht[(size_t)ch * 32];   // sorted, longest first
-        int end = ch + 1, ig;
-        double tg, hg;
-        centre(hi, ht[std::min(N, end * 32) - 1], ig, tg, hg);
-        if (!(hg <= hcap)) { ok = false; break; }
-        while (end < nchunks && end - ch < gmax) {
-          int ig2;
-          double tg2, hg2;
-          centre(hi, ht[std::min(N, (end + 1) * 32) - 1], ig2, tg2, hg2);
-          if (!(hg2 <= hcap)) break;
-          ig = ig2; tg = tg2; hg = hg2; ++end;
-        }
-        c0.push_back(ch); idx.push_back(ig); tau.push_back(tg); hm.push_back(hg);
-        ch = end;
-      }
-      if (!ok) break;
-      c0.push_back(nchunks);
-      CGrouping& G = dd->cgs[set];
-      G.n = (int)idx.size();
-      if ((rc = up(G.chunk0, c0.data(), c0.size() * 4))) return rc;
-      if ((rc = up(G.idx, idx.data(), idx.size() * 4))) return rc;
-      if ((rc = up(G.tau, tau.data(), tau.size() * 8))) return rc;
-      if ((rc = up(G.hmax, hm.data(), hm.size() * 8))) return rc;
-      // c_i(tau_g) = tau_g^i / i! at index i + 8, i = 0 .. wcap + 1 (the A operand of the Toeplitz products)
-      const int ctab = ((s.wcap + 1 + 8 + 7) / 8) * 8 + 16;
-      std::vector<double> coef((size_t)G.n * ctab, 0.0);
-      for (int gI = 0; gI < G.n; ++gI) {
-        double ci = 1.0;
-        for (int i = 0; i <= s.wcap + 1; ++i) {
-          if (i > 0) ci = ci * (tau[gI] * (1.0 / i));
-          coef[(size_t)gI * ctab + i + 8] = ci;
-        }
-      }
-      if ((rc = up(G.coef, coef.data(), coef.size() * 8))) return rc;
-    }
-    if (ok) {
+    // need a longer short series); the octet path, whose passes always carry all BP_CJ terms, takes wider ones (8 -> 2.37 ms, 16 -> 2.23,
+    // 24 -> 2.17, 32 -> 2.17: bp_fusedo's time does not depend on the width, bp_toep's is proportional to the number of groups; a search
+    // for the width that fills the last wave of CTAs best found nothing to gain).  choose_tiling picks the grouping by chain count.
+    dd->h_t.assign(ht.begin(), ht.begin() + N);
+    dd->cg_hcap = hcap;
+    dd->cdelta = delta;
+    dd->cg_fixed = 0;
+    if (const char* ev = std::getenv("BPC_CGROUP_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) dd->cg_fixed = v; }
+    int rcg = bpc::build_grouping(dd.get(), dd->cg_fixed ? dd->cg_fixed : 16, dd->cgs[0], true);
+    if (rcg > 0) return rcg;
+    if (rcg == 0) rcg = bpc::build_grouping(dd.get(), dd->cg_fixed ? dd->cg_fixed : 32, dd->cgs[1], true);
+    if (rcg > 0) return rcg;
+    if (rcg == 0) {
       dd->cgroups = dd->cgs[0].n;
-      dd->cdelta = delta;
       dd->cmode = true;
     }
+    std::vector<double>().swap(dd->h_t);
   }
   BPC_CUDA(cudaStreamCreateWithFlags(&dd->stream, cudaStreamNonBlocking));
   *out = dd.release();

@@ -56,9 +56,12 @@ struct bpc_model {
 };
 
 struct CGrouping {   // groups of consecutive chunks of the sorted table that share a series centre
-  int n = 0;
+  int n = 0, maxlen = 0, gmax = 0;   // groups, chunks of the longest one, the cap they were built with
   bpc::DevBuf chunk0, idx, tau, hmax, coef;
 };
+
+struct bpc_data;
+namespace bpc { int build_grouping(bpc_data* d, int gmax, CGrouping& G, bool store); }
 
 struct bpc_data {
   const bpc_model* model = nullptr;
@@ -71,7 +74,9 @@ struct bpc_data {
   // centred W path (bp_ctable + bp_fusedc): groups of consecutive 32-observation chunks sharing a series centre
   bool cmode = false;
   int cgroups = 0, cgpc = 4, cgsel = 0;   // groups of the grouping in use: cgs[cgsel] (0: bp_fusedc, 1: octet path)
-  double cdelta = 0.0;
+  double cdelta = 0.0, cg_hcap = 0.0;
+  int cg_fixed = 0;                 // BPC_CGROUP_CHUNKS: the same cap for both groupings, no search
+  std::vector<double> h_t;          // sorted durations (host copy while bpc_data_create builds the groupings)
   CGrouping cgs[2];
   bpc::DevBuf ctab_m1, ctab_e2, csg;
   // octet path (bp_ntable + bp_fusedo + bp_toep): eight chains per tensor tile; chosen per chain count (choose_tiling)
