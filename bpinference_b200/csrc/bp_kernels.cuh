@@ -732,7 +732,6 @@ struct BpObsArgs {
   double* csg;           // [C][cgroups][BP_CSG]    scratch: the groups' S^g between a warp's main loop and its Toeplitz products
   // octet path (wmode 3, bp_ntable + bp_fusedo + bp_toep + bp_wpost): eight chains share the tensor tiles of a pass
   int noct;              // octets = ceil(C / 8)
-  double* ntab;          // [noct][cgroups][BP_XR][8 BP_D]  N_j(tau_g) of the octet's chains: row (j, l), column cc * BP_D + d
   int* cg_jm;            // [noct * 8][cgroups]             J | m << 8 of (chain, group); -1: the chain is not on this path
   double* cg_flops;      // [noct * 8][cgroups]             algorithmic flops of (chain, group)
   double* osg;           // [noct][cgroups][BP_XR][8 BP_D]  S'^g of the octet: row (j, l), column cc * BP_D + d
@@ -1581,13 +1580,14 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 
 // ---- octet path: bp_ntable + bp_fusedo + bp_toep ---------------------------------------------------------------
 // X[(j, l)][k] = c_j(h_k) z0_kl does not depend on the chain, and 8 chains x D components fill the 8-wide tensor tiles exactly
-// (for every n).  So a warp takes one pass of 32 observations for EIGHT chains at once:
+// (for every n).  So a CTA takes one pass of 32 observations for EIGHT chains at once:
 //     forward   Y[(cc, d)][k]  = sum_(j,l) N^cc_j[d][l] X[(j,l)][k]          D row tiles x 4 observation tiles x BP_XKS k-steps
-//     score     per (chain, observation), one observation per lane, the 8 chains one after the other (independent work)
+//     score     per (chain, observation): 256 per pass, two per thread
 //     S update  S'[(j,l)][(cc, d)] += sum_k X[(j,l)][k] b^cc_k[d]              BP_XRT x D tiles x 8 k-steps
 // with X staged once per pass, its fragments shared by all column tiles, no padded tile rows and no ninth-component side path.
-// The short series is never masked in the hot loop: N rows beyond a chain's own degree J are zero (bp_ntable), and the rows of
-// S' beyond it are dropped by bp_toep.  bp_ntable builds N_j(tau_g) for every (chain, group) (what bp_fusedc does in its group
+// The short series is never masked in the hot loop: N rows beyond a chain's own degree J are zero, and the rows of
+// S' beyond it are dropped by bp_toep.  bp_ntable finds the series lengths (J, m) of every (chain, group); bp_fusedo builds N_j(tau_g)
+// of its octet in the group prologue (what bp_fusedc does per warp in its group
 // prologue), bp_toep is the Toeplitz product W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for all groups at once, bp_wpost finishes.
 #define BP_OU (8 * BP_D)                         // columns of an octet: (cc, d)
 #define BP_ONLD (BP_OU + 4)                      // row stride of the staged N (conflict-free A fragments: stride = 12 mod 16)

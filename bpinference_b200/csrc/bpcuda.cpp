@@ -594,7 +594,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   double* wpart; int wmode;
   int cgroups, cgpc; const int* cg_chunk0; const int* cg_idx; const double* cg_tau; const double* cg_hmax; const double* cg_coef; double cdelta;
   double* ctab_m1; double* ctab_e2; double* csg;
-  int noct; double* ntab; int* cg_jm; double* cg_flops; double* osg; double* wplain;
+  int noct; int* cg_jm; double* cg_flops; double* osg; double* wplain;
   int* fb; double* ctab_l;
 };
 
@@ -620,7 +620,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               (double*)d->wpart.p, d->wmode ? (d->omode ? 3 : (d->cmode ? 2 : 1)) : 0,
               d->cgroups, d->cgpc, (const int*)d->cgs[d->cgsel].chunk0.p, (const int*)d->cgs[d->cgsel].idx.p, (const double*)d->cgs[d->cgsel].tau.p,
               (const double*)d->cgs[d->cgsel].hmax.p, (const double*)d->cgs[d->cgsel].coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
-              d->noct, (double*)d->ntab.p, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
+              d->noct, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
               (int*)d->fb.p, (double*)d->ctab_l.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -82,7 +82,7 @@ struct bpc_data {
   // octet path (bp_ntable + bp_fusedo + bp_toep): eight chains per tensor tile; chosen per chain count (choose_tiling)
   bool omode = false;
   int noct = 0;
-  bpc::DevBuf ntab, cg_jm, cg_flops, osg, wplain, fb, ctab_l;
+  bpc::DevBuf cg_jm, cg_flops, osg, wplain, fb, ctab_l;
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;
