@@ -186,14 +186,18 @@ def sampling_report(bp, syn):
     eng = bp.stan_model(mod, cfg["priors"])
     d = eng.data(cfg["data"])
     t0 = time.perf_counter()
-    fit = eng.sampling(d, chains=1024, iter=300, warmup=150, control=dict(adapt_delta=0.8, max_treedepth=10), seed=1)
+    # warm-up statistics pooled over the chains at the window boundaries (the cross-chain exchange of the path: an all-reduce of
+    # 1 + 2 dim doubles over NCCL when N > 1); per-chain adaptation as in rstan (pooled_adaptation=False) gives 1/3 of the ESS/s
+    # on this workload (tools/pool_test.py: 766 against 2308), because 150 warm-up draws of one chain estimate the metric poorly
+    fit = eng.sampling(d, chains=1024, iter=300, warmup=150, control=dict(adapt_delta=0.8, max_treedepth=10), seed=1, pooled_adaptation=True)
     dt = time.perf_counter() - t0
     ess = fit.ess_bulk()
     try:
         have_rstan = sp.run(["Rscript", "-e", "library(rstan)"], capture_output=True, timeout=60).returncode == 0
     except Exception:
         have_rstan = False
-    return {"workload": "cfg2: two-type model, 250 observations, 1024 chains x 300 iterations (150 warm-up), NUTS, adapt_delta 0.8",
+    return {"workload": "cfg2: two-type model, 250 observations, 1024 chains x 300 iterations (150 warm-up), NUTS, adapt_delta 0.8, "
+                        "diagonal metric and step size adapted from warm-up statistics pooled over the chains",
             "seconds": dt, "min_ess_per_s": float(ess.min() / dt), "min_ess": float(ess.min()), "leapfrogs_per_s": fit.info["leapfrogs"] / dt,
             "leapfrogs": fit.info["leapfrogs"], "passes": fit.info["passes"], "max_rhat": float(fit.rhat.max()),
             "divergent": int(fit.divergent__.sum()), "rstan": "installed" if have_rstan else "rstan: not installed"}
