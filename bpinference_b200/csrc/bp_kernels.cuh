@@ -662,24 +662,81 @@ __device__ inline bool bp_prior(int id, double p0, double p1, double p2, double 
 
 // ---- prologue: unconstrained -> constrained, one thread per chain -------------------------------
 // theta[c][k] = lo + (hi - lo) inv_logit(u) for bounded parameters, u otherwise; sigma_obs = exp(u).
+// (also called by bp_grouped when it does its own input / output: one launch per evaluation instead of three)
+__device__ __forceinline__ void bp_transform(const double* __restrict__ u, double (&th)[BP_DIM]) {
+#pragma unroll
+  for (int k = 0; k < BP_P; ++k) {
+    const double uk = u[k];
+    double t = uk;
+    if (bp_has_bounds[k]) {
+      const double s = (uk >= 0.0) ? 1.0 / (1.0 + exp(-uk)) : exp(uk) / (1.0 + exp(uk));
+      t = bp_lo[k] + (bp_hi[k] - bp_lo[k]) * s;
+    }
+    th[k] = t;
+  }
+#if BP_NOISE
+  th[BP_P] = exp(u[BP_P]);
+#endif
+}
+
 extern "C" __global__ void bp_prologue(const double* __restrict__ u, int nchains, double* __restrict__ theta,
                                        int* __restrict__ status) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchains) return;
+  double th[BP_DIM];
+  bp_transform(u + (size_t)c * BP_DIM, th);
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) theta[(size_t)c * BP_DIM + k] = th[k];
+  status[c] = 0;
+}
+
+// ---- end of an evaluation: priors, log-Jacobian, chain rule of the bound transform, rejection (bp_epilogue; bp_grouped) ----
+// acc: the chain's sums (BP_NPART); st: its status bits so far.  One thread.
+__device__ __forceinline__ void bp_finish(int c, const double (&acc)[BP_NPART], int st, const double* __restrict__ u,
+                                          const double* __restrict__ theta, int jacobian, double* __restrict__ lp_out,
+                                          double* __restrict__ grad_out, int* __restrict__ status, double* __restrict__ apps_out) {
+  double lp = acc[0];
+  double grad[BP_DIM];
 #pragma unroll
   for (int k = 0; k < BP_P; ++k) {
+    const double th = theta[(size_t)c * BP_DIM + k];
     const double uk = u[(size_t)c * BP_DIM + k];
-    double th = uk;
+    double pl, pg;
+    if (!bp_prior(bp_prior_id[k], bp_prior_par[k][0], bp_prior_par[k][1], bp_prior_par[k][2], th, pl, pg)) { st |= BP_ST_PRIOR_SUPPORT; pl = 0.0; pg = 0.0; }
+    lp += pl;
+    double gth = acc[1 + k] + pg;
     if (bp_has_bounds[k]) {
       const double s = (uk >= 0.0) ? 1.0 / (1.0 + exp(-uk)) : exp(uk) / (1.0 + exp(uk));
-      th = bp_lo[k] + (bp_hi[k] - bp_lo[k]) * s;
+      gth *= (bp_hi[k] - bp_lo[k]) * s * (1.0 - s);
+      if (jacobian) {
+        const double au = fabs(uk);
+        lp += log(bp_hi[k] - bp_lo[k]) - au - 2.0 * log1p(exp(-au));
+        gth += 1.0 - 2.0 * s;
+      }
     }
-    theta[(size_t)c * BP_DIM + k] = th;
+    grad[k] = gth;
   }
 #if BP_NOISE
-  theta[(size_t)c * BP_DIM + BP_P] = exp(u[(size_t)c * BP_DIM + BP_P]);
+  {
+    // sigma_obs ~ normal(0, .1) on sigma_obs > 0 (multitype_noise_template.stan:131); sigma_obs = exp(u)
+    const double sig = theta[(size_t)c * BP_DIM + BP_P];
+    lp += -0.5 * (sig / 0.1) * (sig / 0.1);
+    double g = (acc[BP_P + 1] - sig / 0.01) * sig;
+    if (jacobian) { lp += u[(size_t)c * BP_DIM + BP_P]; g += 1.0; }
+    grad[BP_P] = g;
+  }
 #endif
-  status[c] = 0;
+  bool bad = st != 0 || !isfinite(lp);
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) bad = bad || !isfinite(grad[k]);
+  if (bad && st == 0) st = BP_ST_RATE_NONFINITE;
+  status[c] = st;
+  lp_out[c] = bad ? -(1.0 / 0.0) : lp;
+  if (grad_out) {
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) grad_out[(size_t)c * BP_DIM + k] = bad ? 0.0 : grad[k];
+  }
+  if (apps_out) apps_out[c] = acc[BP_P + 2];
 }
 
 // ---- block reduction of BP_NPART partial sums, fixed order (deterministic) ----------------------
@@ -2075,7 +2132,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(
 // Observations are sorted so that groups are contiguous (gstart).  Dynamic shared memory: 2 * G*n*BP_D doubles (moments,
 // cotangents), reduction scratch, and for the cooperative path L, U, W, Z and the per-group series lengths.
 struct BpGroupArgs {
-  const double* theta;   // [C][BP_DIM]
+  double* theta;         // [C][BP_DIM]  (written when the kernel does its own input / output)
   const double* z0;      // [BP_N][npad]
   const double* xo;      // [BP_N][npad]
   const int* gstart;     // [G + 1]
@@ -2086,6 +2143,10 @@ struct BpGroupArgs {
   double* part;          // [C][1][BP_NPART]
   int* status;           // [C]
   int nobs, npad, ngroups, nchains, nlevels;
+  // own input / output (one launch per evaluation: what a sampler pass on small data is made of): u != nullptr
+  const double* u;       // [C][BP_DIM] unconstrained parameters; theta is written, not read
+  int jacobian;
+  double* lp_out; double* grad_out; double* apps_out;
 };
 
 template <int NV>
@@ -2126,8 +2187,16 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   double* ybar = ymom + (size_t)GN * BP_D; // [GN][BP_D]
   double* red = ybar + (size_t)GN * BP_D;  // [max(BP_N*BP_D, BP_NPART) * warps]
   double th[BP_DIM];
+  if (a.u) {   // the transform of bp_prologue, by every thread (theta is kept for the priors)
+    bp_transform(a.u + (size_t)c * BP_DIM, th);
+    if (tid == 0) {
 #pragma unroll
-  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+      for (int k = 0; k < BP_DIM; ++k) a.theta[(size_t)c * BP_DIM + k] = th[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+  }
 #if BP_NOISE
   const double sigma = th[BP_P];
 #else
@@ -2325,6 +2394,21 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   for (int k = 0; k < BP_P; ++k) vals[1 + k] = cb[k];
   vals[BP_P + 1] = sb;
   vals[BP_P + 2] = (double)apps;
+  if (a.u) {
+    // the chain's status: OR over the CTA; then the work of bp_epilogue by one thread
+    __shared__ int sst;
+    if (tid == 0) sst = 0;
+    __syncthreads();
+    if (status) atomicOr(&sst, status);
+    bp_block_sum(vals, red, a.part + (size_t)c * BP_NPART);   // (ends with a barrier; the sums are also in global memory)
+    if (tid == 0) {
+      double acc[BP_NPART];
+#pragma unroll
+      for (int i = 0; i < BP_NPART; ++i) acc[i] = __ldcg(a.part + (size_t)c * BP_NPART + i);
+      bp_finish(c, acc, sst, a.u, a.theta, a.jacobian, a.lp_out, a.grad_out, a.status, a.apps_out);
+    }
+    return;
+  }
   bp_block_sum(vals, red, a.part + (size_t)c * BP_NPART);
   if (status) atomicOr(a.status + c, status);
 }
@@ -2484,49 +2568,7 @@ extern "C" __global__ void bp_epilogue(const double* __restrict__ u, const doubl
 #pragma unroll
   for (int i = 0; i < BP_NPART; ++i) acc[i] = bp_warp_sum(acc[i]);
   if (lane) return;
-  double lp = acc[0];
-  int st = status[c];
-  double grad[BP_DIM];
-#pragma unroll
-  for (int k = 0; k < BP_P; ++k) {
-    const double th = theta[(size_t)c * BP_DIM + k];
-    const double uk = u[(size_t)c * BP_DIM + k];
-    double pl, pg;
-    if (!bp_prior(bp_prior_id[k], bp_prior_par[k][0], bp_prior_par[k][1], bp_prior_par[k][2], th, pl, pg)) { st |= BP_ST_PRIOR_SUPPORT; pl = 0.0; pg = 0.0; }
-    lp += pl;
-    double gth = acc[1 + k] + pg;
-    if (bp_has_bounds[k]) {
-      const double s = (uk >= 0.0) ? 1.0 / (1.0 + exp(-uk)) : exp(uk) / (1.0 + exp(uk));
-      gth *= (bp_hi[k] - bp_lo[k]) * s * (1.0 - s);
-      if (jacobian) {
-        const double au = fabs(uk);
-        lp += log(bp_hi[k] - bp_lo[k]) - au - 2.0 * log1p(exp(-au));
-        gth += 1.0 - 2.0 * s;
-      }
-    }
-    grad[k] = gth;
-  }
-#if BP_NOISE
-  {
-    // sigma_obs ~ normal(0, .1) on sigma_obs > 0 (multitype_noise_template.stan:131); sigma_obs = exp(u)
-    const double sig = theta[(size_t)c * BP_DIM + BP_P];
-    lp += -0.5 * (sig / 0.1) * (sig / 0.1);
-    double g = (acc[BP_P + 1] - sig / 0.01) * sig;
-    if (jacobian) { lp += u[(size_t)c * BP_DIM + BP_P]; g += 1.0; }
-    grad[BP_P] = g;
-  }
-#endif
-  bool bad = st != 0 || !isfinite(lp);
-#pragma unroll
-  for (int k = 0; k < BP_DIM; ++k) bad = bad || !isfinite(grad[k]);
-  if (bad && st == 0) st = BP_ST_RATE_NONFINITE;
-  status[c] = st;
-  lp_out[c] = bad ? -(1.0 / 0.0) : lp;
-  if (grad_out) {
-#pragma unroll
-    for (int k = 0; k < BP_DIM; ++k) grad_out[(size_t)c * BP_DIM + k] = bad ? 0.0 : grad[k];
-  }
-  if (apps_out) apps_out[c] = acc[BP_P + 2];
+  bp_finish(c, acc, status[c], u, theta, jacobian, lp_out, grad_out, status, apps_out);
 }
 #endif  // !BP_HOSTSIM
 

@@ -582,9 +582,10 @@ static int ensure_workspace(bpc_data* d, int nchains) {
 }
 
 struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
-  const double* theta; const double* z0; const double* xo; const int* gstart; const double* gt; const double* gx; const int* glev;
+  double* theta; const double* z0; const double* xo; const int* gstart; const double* gt; const double* gx; const int* glev;
   double* ring; double* part; int* status;
   int nobs, npad, ngroups, nchains, nlevels;
+  const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
@@ -610,7 +611,9 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   double* theta = (double*)d->theta.p;
   double* part = (double*)d->part.p;
   double* apps = (double*)d->apps.p;
-  {
+  // grouped path: one CTA per chain does the transform, the evaluation and the priors / chain rule itself (one launch)
+  const bool own_io = d->grouped && L->grouped;
+  if (!own_io) {
     void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
     BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
   }
@@ -645,7 +648,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       }
       GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
                    (const double*)d->gx.p, (const int*)d->glev.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains,
-                   d->nlevels};
+                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps};
       void* gargs[] = {(void*)&ga};
       BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
     } else {
@@ -680,13 +683,13 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       d->timing_events.emplace_back(e0, e1);
     }
   }
-  {
+  if (!own_io) {
     int ntiles = d->ntiles;
     void* args[] = {(void*)&u_dev, (void*)&theta, (void*)&part, (void*)&ntiles, (void*)&nchains, (void*)&jacobian,
                     (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps};
     BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
-  g_launches += 3;
+  g_launches += own_io ? 1 : 3;
   return BPC_OK;
 }
 

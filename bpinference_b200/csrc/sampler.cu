@@ -17,7 +17,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <memory>
 #include <vector>
@@ -531,6 +533,9 @@ struct bpc_sampler {
   cudaGraph_t graph = nullptr;          // POLL passes (4 kernels each) captured once and replayed: the per-pass cost of
   cudaGraphExec_t graph_exec = nullptr; // small problems is launch latency, not arithmetic
   bool graph_tried = false;
+  int graph_launches = 0;               // kernels of one replay
+  bool trace = std::getenv("BPC_SAMPLER_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point trace_t0 = std::chrono::steady_clock::now();
 };
 
 extern "C" {
@@ -643,6 +648,7 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
         const int rc = sampler_passes(s, POLL);
         cudaGraph_t g = nullptr;
         const cudaError_t ec = cudaStreamEndCapture(s->stream, &g);
+        s->graph_launches = (int)(g_launches - before);
         g_launches = before;   // nothing ran during capture
         if (rc == BPC_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&s->graph_exec, g, 0) == cudaSuccess) s->graph = g;
         else { if (g) cudaGraphDestroy(g); s->graph_exec = nullptr; cudaGetLastError(); }
@@ -650,13 +656,20 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
     }
     if (nb == POLL && s->graph_exec) {
       if ((e = cudaGraphLaunch(s->graph_exec, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
-      g_launches += 4 * POLL;
+      g_launches += s->graph_launches;
     } else {
       const int rc = sampler_passes(s, nb);
       if (rc) return rc;
     }
     done_passes += nb;
     s->passes += nb;
+    if (s->trace && s->passes / 2048 != (s->passes - nb) / 2048) {   // BPC_SAMPLER_TRACE: wall time per block of passes and where the chains are
+      cudaStreamSynchronize(s->stream);
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[sampler] passes %lld  %.1f us per pass  finished %d waiting %d of %d\n", s->passes,
+                   std::chrono::duration<double, std::micro>(now - s->trace_t0).count() / 2048.0, s->h_counters[0], s->h_counters[1], P.C);
+      s->trace_t0 = now;
+    }
     if ((e = cudaMemcpyAsync(s->h_counters, P.counters, 12, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync");
     if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(e, "sampler pass");
     if (s->h_counters[0] >= P.C) { *state = 1; return BPC_OK; }
