@@ -1046,6 +1046,38 @@ __device__ __forceinline__ int bp_coop_lbar(double* W, int M, const double* Lm, 
   return cur;
 }
 
+// The same polynomial for W_j with D columns (rows of D x D in shared memory, overwritten): the reverse sweep of a series whose
+// inputs are full state vectors, as the sub-steps of bp_grouped's cooperative multi-step path are.
+__device__ __forceinline__ int bp_coop_lbar_full(double* W, int M, const double* Lm, double* Z) {
+  constexpr int DD = BP_D * BP_D;
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int i = M - 2; i >= 0; --i) {
+    for (int o = tid; o < DD; o += T) {
+      const int d = o / BP_D, e = o - d * BP_D;
+      double y = W[i * DD + o];
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) y += Lm[rr * BP_D + d] * W[(i + 1) * DD + rr * BP_D + e];
+      W[i * DD + o] = y;
+    }
+    __syncthreads();
+  }
+  int cur = 0;
+  for (int o = tid; o < DD; o += T) Z[o] = M > 0 ? W[(M - 1) * DD + o] : 0.0;
+  __syncthreads();
+  for (int i = M - 2; i >= 0; --i) {
+    for (int o = tid; o < DD; o += T) {
+      const int d = o / BP_D, e = o - d * BP_D;
+      double z = W[i * DD + o];
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) z += Z[cur * DD + d * BP_D + rr] * Lm[e * BP_D + rr];
+      Z[(cur ^ 1) * DD + o] = z;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
+
 // Lbar (packed coordinates) -> (gA, gH) with the accumulation rule of the reverse sweep: input u = e_cc, output
 // cotangent = column cc of Lbar converted to the full symmetric convention (off-diagonals halved).  One thread.
 __device__ __forceinline__ void bp_lbar_to_grad(const double* Zc, double (&gA)[BP_N * BP_N], double (&gH)[BP_N * BP_S]) {
@@ -2147,6 +2179,7 @@ struct BpGroupArgs {
   const double* u;       // [C][BP_DIM] unconstrained parameters; theta is written, not read
   int jacobian;
   double* lp_out; double* grad_out; double* apps_out;
+  int yscap;             // cooperative multi-step path: D x n blocks of shared memory for the sub-step states (0: path not available)
 };
 
 template <int NV>
@@ -2205,23 +2238,56 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   int status = 0, apps = 0;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
   const int nwarp = T >> 5;
+  // (layout sized by log_prob_dev; BP_GMS: the cooperative multi-step path with its D x D work arrays, n <= 3)
+#if BP_N <= 3
+#define BP_GMS 1
+  const int WK = a.yscap > 0 ? DD : DN;   // (yscap == 0: the host left the multi-step path's arrays out)
+#else
+#define BP_GMS 0
+  constexpr int WK = DN;
+#endif
   double* Lm = red + (size_t)(BP_N * BP_D > BP_NPART ? BP_N * BP_D : BP_NPART) * nwarp;   // [D][D]
-  double* Uk = Lm + DD;                         // [BP_WROWS + 1][D * n]
-  double* Wm = Uk + (size_t)(BP_WROWS + 1) * DN; // [BP_WROWS][D * n]
-  double* Zb = Wm + (size_t)BP_WROWS * DN;       // [2][D][D]
+  double* Uk = Lm + DD;                         // [BP_WROWS + 1][D * n]   (multi-step path: [BP_WROWS + 1][D * D], powers of L)
+  double* Wm = Uk + (size_t)(BP_WROWS + 1) * WK; // [BP_WROWS][D * n]      (multi-step path: [BP_WROWS][D * D])
+  double* Zb = Wm + (size_t)BP_WROWS * WK;       // [2][D][D]
+#if BP_GMS
+  double* Fm = Zb + 2 * DD;                      // [D][D]   exp(h L) of the group at hand
+  double* Qm = Fm + DD;                          // [D][D]   sum over sub-steps of z_(i+1) y_i^T
+  double* Zv = Qm + DD;                          // [2][D * n] cotangent of the sub-step states
+  double* Ys = Zv + 2 * DN;                      // [yscap][D * n] sub-step states Y_0 .. Y_s of every group
+  int* gm = a.yscap > 0 ? (int*)(Ys + (size_t)a.yscap * DN) : (int*)(Zb + 2 * DD);   // [G] series length of each group
+#else
   int* gm = (int*)(Zb + 2 * DD);                 // [G] series length of each group
-  // cooperative path iff every group has finite rates and fits one sub-step
-  bool okc = true;
+#endif
+  int* gs = gm + G;                              // [G] sub-steps of each group
+  int* goff = gs + G;                            // [G] first block of the group in Ys
+  // cooperative path iff every group has finite rates and fits one sub-step; cooperative multi-step path iff the rates are finite
+  // and the sub-step states of all groups fit Ys
+  bool okc = true, okm = true;
   for (int g = tid; g < G; g += T) {
     double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1;
     const bool fin = bp_group_generator(th, a, g, xk, A, H, a1);
     BpPlan p;
     int dh = 1;
-    const bool ok = bp_w_path(fin, a1, a.gt[g]) && bp_make_plan(a1, a.gt[g], p, dh, BP_WCAP, BP_WTHETA_CAP);
-    gm[g] = ok ? p.m : 0;
-    okc = okc && ok;
+    const bool okp = fin && bp_make_plan(a1, a.gt[g], p, dh, BP_WCAP, BP_WTHETA_CAP);
+    gm[g] = okp ? p.m : 0;
+    gs[g] = okp ? p.s : 0;
+    okc = okc && okp && p.s == 1;
+    okm = okm && okp;
   }
   const bool coop = __syncthreads_and(okc) != 0;
+  bool coopm = false;
+#if BP_GMS
+  if (!coop) {
+    coopm = __syncthreads_and(okm) != 0;
+    int tot = 0;
+    for (int g = 0; g < G; ++g) tot += gs[g] + 1;
+    coopm = coopm && tot <= a.yscap;
+    __syncthreads();
+    if (coopm && tid == 0) { int o = 0; for (int g = 0; g < G; ++g) { goff[g] = o; o += gs[g] + 1; } }
+    __syncthreads();
+  }
+#endif
   if (coop) {
     // ---- phase A, cooperative: per level, Krylov blocks and the groups' moments ----
     for (int v = 0; v < a.nlevels; ++v) {
@@ -2254,7 +2320,61 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
         }
       }
     }
-  } else {
+  }
+#if BP_GMS
+  else if (coopm) {
+    // ---- phase A, cooperative with sub-steps: per level the powers of L; per group F = exp(h L) as a D x D matrix and the
+    // sub-step states Y_(i+1) = F Y_i from Y_0 = [e_1 .. e_n] (kept for phase A') ----
+    for (int v = 0; v < a.nlevels; ++v) {
+      int gv = 0, mlev = 0;
+      for (int g = G - 1; g >= 0; --g) if (a.glev[g] == v) { gv = g; mlev = gm[g] > mlev ? gm[g] : mlev; }
+      double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1;
+      bp_group_generator(th, a, gv, xk, A, H, a1);
+      __syncthreads();
+      bp_coop_build_L(A, H, Lm);
+      for (int o = tid; o < DD; o += T) { const int d = o / BP_D, e = o - d * BP_D; Uk[o] = (d == e) ? 1.0 : 0.0; }
+      __syncthreads();
+      for (int j = 1; j <= mlev; ++j) {
+        for (int o = tid; o < DD; o += T) {
+          const int d = o / BP_D, e = o - d * BP_D;
+          double u = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) u += Lm[d * BP_D + rr] * Uk[(j - 1) * DD + rr * BP_D + e];
+          Uk[j * DD + o] = u;
+        }
+        __syncthreads();
+      }
+      for (int g = 0; g < G; ++g) {
+        if (a.glev[g] != v) continue;
+        const double hg = a.gt[g] / gs[g];
+        for (int o = tid; o < DD; o += T) {
+          double y = Uk[o], cj = 1.0;
+          for (int j = 1; j <= gm[g]; ++j) { cj = cj * (hg * bp_rk[j - 1]); y += cj * Uk[j * DD + o]; }
+          Fm[o] = y;
+        }
+        double* Y = Ys + (size_t)goff[g] * DN;
+        for (int o = tid; o < DN; o += T) { const int d = o / BP_N, l = o - d * BP_N; Y[o] = (d == l) ? 1.0 : 0.0; }
+        __syncthreads();
+        for (int i = 0; i < gs[g]; ++i) {
+          for (int o = tid; o < DN; o += T) {
+            const int d = o / BP_N, l = o - d * BP_N;
+            double y = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < BP_D; ++rr) y += Fm[d * BP_D + rr] * Y[i * DN + rr * BP_N + l];
+            Y[(i + 1) * DN + o] = y;
+          }
+          __syncthreads();
+        }
+        for (int o = tid; o < DN; o += T) {
+          const int d = o / BP_N, l = o - d * BP_N;
+          ymom[(size_t)(g * BP_N + l) * BP_D + d] = Y[gs[g] * DN + o];
+        }
+        __syncthreads();   // Fm is rewritten for the next group
+      }
+    }
+  }
+#endif
+  else {
   // ---- phase A: single-ancestor moments of every (group, ancestor type) ----
   for (int sx = tid; sx < GN; sx += T) {
     const int g = sx / BP_N, l = sx - g * BP_N;
@@ -2356,7 +2476,96 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
         for (int g = 0; g < G; ++g) if (a.glev[g] == v) apps += BP_N * gm[g];
       }
     }
-  } else {
+  }
+#if BP_GMS
+  else if (coopm) {
+    // reverse of the sub-steps: z_s = cotangent of Y_s; for i = s - 1 .. 0: Q += z_(i+1) y_i^T, z_i = F^T z_(i+1); every sub-step
+    // applies the same series F = sum_j c_j(h) L^j, so W_j = c_j(h) Q (D x D) and Lbar = the matrix polynomial of bp_coop_lbar_full
+    for (int v = 0; v < a.nlevels; ++v) {
+      int gv = 0, mlev = 0;
+      for (int g = G - 1; g >= 0; --g) if (a.glev[g] == v) { gv = g; mlev = gm[g] > mlev ? gm[g] : mlev; }
+      double A[BP_N * BP_N], H[BP_N * BP_S], xk[BP_KDEP], a1;
+      bp_group_generator(th, a, gv, xk, A, H, a1);
+      __syncthreads();
+      bp_coop_build_L(A, H, Lm);
+      for (int o = tid; o < DD; o += T) {
+        const int d = o / BP_D, e = o - d * BP_D;
+        Uk[o] = (d == e) ? 1.0 : 0.0;
+        for (int j = 0; j < mlev; ++j) Wm[j * DD + o] = 0.0;
+      }
+      __syncthreads();
+      for (int j = 1; j <= mlev; ++j) {
+        for (int o = tid; o < DD; o += T) {
+          const int d = o / BP_D, e = o - d * BP_D;
+          double u = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) u += Lm[d * BP_D + rr] * Uk[(j - 1) * DD + rr * BP_D + e];
+          Uk[j * DD + o] = u;
+        }
+        __syncthreads();
+      }
+      for (int g = 0; g < G; ++g) {
+        if (a.glev[g] != v) continue;
+        const double hg = a.gt[g] / gs[g];
+        for (int o = tid; o < DD; o += T) {
+          double y = Uk[o], cj = 1.0;
+          for (int j = 1; j <= gm[g]; ++j) { cj = cj * (hg * bp_rk[j - 1]); y += cj * Uk[j * DD + o]; }
+          Fm[o] = y;
+          Qm[o] = 0.0;
+        }
+        for (int o = tid; o < DN; o += T) {   // packed-coordinate cotangent of Y_s
+          const int d = o / BP_N, l = o - d * BP_N;
+          bool offdiag = d >= BP_N;
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) if (d == BP_N + bp_sidx(i, i)) offdiag = false;
+          double yb = ybar[(size_t)(g * BP_N + l) * BP_D + d];
+          if (offdiag) yb += yb;
+          Zv[o] = yb;
+        }
+        __syncthreads();
+        const double* Y = Ys + (size_t)goff[g] * DN;
+        int cz = 0;
+        for (int i = gs[g] - 1; i >= 0; --i) {
+          for (int o = tid; o < DD; o += T) {
+            const int d = o / BP_D, e = o - d * BP_D;
+            double q = Qm[o];
+#pragma unroll
+            for (int l = 0; l < BP_N; ++l) q += Zv[cz * DN + d * BP_N + l] * Y[i * DN + e * BP_N + l];
+            Qm[o] = q;
+          }
+          for (int o = tid; o < DN; o += T) {
+            const int d = o / BP_N, l = o - d * BP_N;
+            double z = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < BP_D; ++rr) z += Fm[rr * BP_D + d] * Zv[cz * DN + rr * BP_N + l];
+            Zv[(cz ^ 1) * DN + o] = z;
+          }
+          __syncthreads();
+          cz ^= 1;
+        }
+        for (int o = tid; o < DD; o += T) {
+          const double q = Qm[o];
+          double cj = 1.0;
+          for (int j = 0; j < gm[g]; ++j) { cj = cj * (hg * bp_rk[j]); Wm[j * DD + o] += cj * q; }
+        }
+        __syncthreads();   // Fm, Qm, Zv are rewritten for the next group
+      }
+      const int cur = bp_coop_lbar_full(Wm, mlev, Lm, Zb);
+      if (tid == 0) {
+        double gA[BP_N * BP_N], gH[BP_N * BP_S], rb[BP_E];
+#pragma unroll
+        for (int i = 0; i < BP_N * BP_N; ++i) gA[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < BP_N * BP_S; ++i) gH[i] = 0.0;
+        bp_lbar_to_grad(Zb + cur * DD, gA, gH);
+        bp_assemble_vjp(gA, gH, rb);
+        bp_rates_vjp(th, xk, rb, cb);
+        for (int g = 0; g < G; ++g) if (a.glev[g] == v) apps += BP_N * gs[g] * gm[g];
+      }
+    }
+  }
+#endif
+  else {
   BpRingGlobal ring{a.ring + (size_t)c * BP_MSLOT * BP_D * GN};
   for (int sx = tid; sx < GN; sx += T) {
     const int g = sx / BP_N, l = sx - g * BP_N;

@@ -586,6 +586,7 @@ struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
   double* ring; double* part; int* status;
   int nobs, npad, ngroups, nchains, nlevels;
   const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
+  int yscap;
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
@@ -640,15 +641,23 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       int T = d->group_threads;
       while (T < 128 && (long long)nchains * 2 <= 148LL * (65536 / (256 * T * 2)) * 2 && d->N > 2 * T) T *= 2;
       const size_t wrows = s.wcap + 1;
-      const size_t smem = (size_t)(2 * d->ngroups * n * D + (T / 32) * std::max(n * D, s.nparams + 3) + 3 * D * D + (2 * wrows + 1) * D * n) * 8 +
-                          (size_t)d->ngroups * 4 + 16;
+      // (layout of bp_grouped; n <= 3: the cooperative multi-step path with D x D work arrays and yscap blocks for the sub-step states)
+      const bool gms = n <= 3;
+      const size_t base0 = (size_t)(2 * d->ngroups * n * D + (T / 32) * std::max(n * D, s.nparams + 3) + 3 * D * D + (2 * wrows + 1) * D * n) * 8 +
+                           (size_t)d->ngroups * 12 + 16;
+      const size_t extra = (size_t)((2 * wrows + 1) * D * (D - n) + 2 * D * D + 2 * D * n) * 8;   // D x D work arrays instead of D x n, F, Q, z
+      // sub-step states: 4 G + 12 blocks when everything stays within 64 KB per CTA (data with many groups: the path is left out)
+      int yscap = 0;
+      if (gms && base0 + extra + (size_t)(2 * d->ngroups + 2) * D * n * 8 <= 64 * 1024)
+        yscap = (int)std::min<size_t>(4 * (size_t)d->ngroups + 12, (64 * 1024 - base0 - extra) / ((size_t)D * n * 8));
+      const size_t smem = base0 + (yscap > 0 ? extra + (size_t)yscap * D * n * 8 : 0);
       if (smem > L->grouped_smem) {
         BPC_CUDA(cudaKernelSetAttributeForDevice(L->grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, d->device));
         L->grouped_smem = smem;
       }
       GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
                    (const double*)d->gx.p, (const int*)d->glev.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains,
-                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps};
+                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps, yscap};
       void* gargs[] = {(void*)&ga};
       BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
     } else {

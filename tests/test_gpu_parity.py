@@ -353,3 +353,36 @@ def test_octet_path_one_type_multitype_template():
         del os.environ["BPC_OPATH"]
     np.testing.assert_allclose(lp, lp2, rtol=1e-12)
     np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
+
+
+@pytest.mark.parametrize("name,nobs,chains", [("cfg2", None, 12), ("cfg5G", 1200, 12), ("cfg4", None, 8)])
+def test_grouped_multi_step_cooperative_path(name, nobs, chains):
+    """bp_grouped picks its path per chain: single-step cooperative (rates near the truth), cooperative with sub-steps
+    (F = exp(h L) as a matrix, states Y_i kept, Lbar from the D-column polynomial) for 2 ||A|| t up to a few tens, and the
+    per-thread series beyond what the sub-step states' shared memory holds.  All three against the oracle and against the
+    per-observation kernel in one call (this is what a sampler pass sees during warm-up)."""
+    cfg = syn.make_config(name, chains=chains, nobs=nobs)
+    eng, om = _pair(cfg)
+    u = cfg["upars"].copy()
+    P = cfg["nparams"]
+    u[1, :P] += 1.2      # rates x ~3
+    u[2, :P] += 2.0      # x ~6: sub-steps
+    u[3, :P] += 2.8      # x ~10
+    u[4, :P] += 3.5      # close to the upper bound
+    u[5, :P] = 6.0       # at the bound: many sub-steps
+    u[6, 0] += 3.0       # one large rate
+    dg = eng.data(cfg["data"], grouping=2)
+    df = eng.data(cfg["data"], grouping=1)
+    lg, gg, sg = eng.log_prob_grad(dg, u)
+    lf, gf, sf = eng.log_prob_grad(df, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
+    assert sg.tolist() == st_o.tolist() == sf.tolist()
+    ok = st_o == 0
+    assert ok.sum() >= chains - 3
+    np.testing.assert_allclose(lg[ok], lp_o[ok], rtol=1e-10)
+    np.testing.assert_allclose(lg[ok], lf[ok], rtol=1e-10)
+    for c in np.flatnonzero(ok):     # gradients chain by chain: their scales differ by orders of magnitude
+        np.testing.assert_allclose(gg[c], g_o[c], rtol=1e-8, atol=1e-9 * np.abs(g_o[c]).max(), err_msg="chain %d vs oracle" % c)
+        np.testing.assert_allclose(gg[c], gf[c], rtol=1e-8, atol=1e-9 * np.abs(gf[c]).max(), err_msg="chain %d vs bp_fused" % c)
+    b = eng.log_prob_grad(dg, u)
+    assert (b[0][ok] == lg[ok]).all() and (b[1][ok] == gg[ok]).all()
