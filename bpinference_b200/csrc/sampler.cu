@@ -323,9 +323,12 @@ __device__ void end_transition(const Chain& ch) {
   begin_transition(ch);
 }
 
+// One chain per WARP (lane 0 works): the chains of a pass are at different points of their state machines, and 32 of them in one
+// warp execute the union of all the paths taken, one after the other; alone in its warp a chain executes its own path only, and
+// the 8 x more blocks spread over the SMs.
 __global__ void bp_nuts_advance(Params P) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.C) return;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= P.C || (threadIdx.x & 31)) return;
   Chain ch(P, c);
   const int phase = ch.i(I_PHASE);
   const int dim = P.dim;
@@ -373,44 +376,74 @@ __global__ void bp_nuts_advance(Params P) {
   }
 
   // ---- PH_NUTS: a leapfrog of the sub-tree under construction has just been evaluated ----------
-  const int dir = ch.i(I_DIR);
+  // This is the path of almost every pass.  The vectors it needs are read once, in batches of independent loads, into
+  // local arrays (a loop over a run-time dim that reads and writes the state in HBM pays one L2 round trip per element:
+  // the compiler cannot move the loads of element k + 1 above the stores of element k), and written back once.
+  // (the scalars too: one batch of loads up front, the stores where the original sequence has them)
+  const int dir = ch.i(I_DIR), leaf = ch.i(I_LEAF), depth = ch.i(I_DEPTH), nleap = ch.i(I_NLEAP), rng = ch.i(I_RNG), st_e = P.st_eval[c];
+  const double eps = ch.s(S_EPS), h0 = ch.s(S_H0), sub0 = ch.s(S_SUB_LSW), sacc0 = ch.s(S_SUM_ACC), lp_e = P.lp_eval[c];
   const int fq = dir > 0 ? V_QR : V_QL, fp = dir > 0 ? V_PR : V_PL, fg = dir > 0 ? V_GR : V_GL;
-  double lp_new;
-  const double H = finish_leapfrog(ch, fq, fp, fg, dir, lp_new);
-  ch.i(I_NLEAP) += 1;
-  const double dH = ch.s(S_H0) - H;
-  if (!(H - ch.s(S_H0) <= 1000.0)) {   // divergent (also NaN / rejected points): the sub-tree is discarded
+  double pl[MAXDIM], ql[MAXDIM], gl[MAXDIM], ml[MAXDIM], rl[MAXDIM];
+  for (int k = 0; k < dim; ++k) {
+    gl[k] = P.g_eval[(size_t)c * dim + k];
+    ql[k] = P.q_eval[(size_t)c * dim + k];
+    pl[k] = ch.v(fp, k);
+    ml[k] = ch.v(V_MINV, k);
+    rl[k] = ch.v(V_RHO_SUB, k);
+  }
+  // second half kick with the freshly evaluated gradient (finish_leapfrog): the edge becomes the new leaf
+  const double e = eps * dir;
+  const double lp_new = st_e ? -INFINITY : lp_e;
+  double ke = 0.0;
+  for (int k = 0; k < dim; ++k) {
+    pl[k] += 0.5 * e * gl[k];
+    ke += ml[k] * pl[k] * pl[k];
+  }
+  for (int k = 0; k < dim; ++k) { ch.v(fq, k) = ql[k]; ch.v(fg, k) = gl[k]; ch.v(fp, k) = pl[k]; }
+  double H = -lp_new + 0.5 * ke;
+  if (isnan(H)) H = INFINITY;
+  ch.i(I_NLEAP) = nleap + 1;
+  const double dH = h0 - H;
+  if (!(H - h0 <= 1000.0)) {   // divergent (also NaN / rejected points): the sub-tree is discarded
     ch.i(I_DIVERGENT) = 1;
     end_transition(ch);
     return;
   }
   // multinomial sampling inside the sub-tree: the new leaf replaces the sub-tree's proposal w.p. w_leaf / w_subtree
-  const double sub_lsw = logaddexp(ch.s(S_SUB_LSW), dH);
+  const double sub_lsw = logaddexp(sub0, dH);
   ch.s(S_SUB_LSW) = sub_lsw;
-  ch.s(S_SUM_ACC) += fmin(1.0, exp(dH));
-  const bool take = ch.uniform() < exp(dH - sub_lsw);
+  ch.s(S_SUM_ACC) = sacc0 + fmin(1.0, exp(dH));
+  double u_take;
+  {   // ch.uniform() with the counter already in a register
+    unsigned r[4];
+    philox(P.seed, (unsigned)(P.chain_offset + c), (unsigned)rng, r);
+    ch.i(I_RNG) = rng + 1;
+    u_take = (((unsigned long long)r[0] << 21) ^ (r[1] >> 11)) * (1.0 / 9007199254740992.0) + (0.5 / 9007199254740992.0);
+  }
+  const bool take = u_take < exp(dH - sub_lsw);
   for (int k = 0; k < dim; ++k) {
-    ch.v(V_RHO_SUB, k) += ch.v(fp, k);
-    if (take) { ch.v(V_Q_SP, k) = ch.v(fq, k); ch.v(V_G_SP, k) = ch.v(fg, k); }
+    rl[k] += pl[k];
+    ch.v(V_RHO_SUB, k) = rl[k];
+    if (take) { ch.v(V_Q_SP, k) = ql[k]; ch.v(V_G_SP, k) = gl[k]; }
   }
   if (take) ch.s(S_LP_SP) = lp_new;
   // sub-tree U-turn checks with checkpointed partial sums (leaf index bits select the balanced sub-trees that end here)
-  const int leaf = ch.i(I_LEAF);
   int idx_max = __popc((unsigned)leaf >> 1);
   bool turning = false;
   if ((leaf & 1) == 0) {
-    for (int k = 0; k < dim; ++k) { ch.rck(idx_max, k) = ch.v(fp, k); ch.rsck(idx_max, k) = ch.v(V_RHO_SUB, k); }
+    for (int k = 0; k < dim; ++k) { ch.rck(idx_max, k) = pl[k]; ch.rsck(idx_max, k) = rl[k]; }
   } else {
     int ntrail = 0;
     for (unsigned b = (unsigned)leaf; b & 1u; b >>= 1) ++ntrail;
     const int idx_min = idx_max - ntrail + 1;
     for (int lvl = idx_max; lvl >= idx_min && !turning; --lvl) {
+      double ck[MAXDIM], sk[MAXDIM];
+      for (int k = 0; k < dim; ++k) { ck[k] = ch.rck(lvl, k); sk[k] = ch.rsck(lvl, k); }
       double a = 0.0, b = 0.0;
       for (int k = 0; k < dim; ++k) {
-        const double r = ch.v(V_RHO_SUB, k) - ch.rsck(lvl, k) + ch.rck(lvl, k);
-        const double mi = ch.v(V_MINV, k);
-        a += mi * ch.rck(lvl, k) * r;
-        b += mi * ch.v(fp, k) * r;
+        const double r = rl[k] - sk[k] + ck[k];
+        a += ml[k] * ck[k] * r;
+        b += ml[k] * pl[k] * r;
       }
       turning = !(a > 0.0 && b > 0.0);
     }
@@ -420,9 +453,12 @@ __global__ void bp_nuts_advance(Params P) {
     end_transition(ch);
     return;
   }
-  const int depth = ch.i(I_DEPTH);
-  if (leaf + 1 < (1 << depth)) {   // keep extending the same sub-tree
-    start_leapfrog(ch, fq, fp, fg, dir);
+  if (leaf + 1 < (1 << depth)) {   // keep extending the same sub-tree (start_leapfrog from the local copies)
+    for (int k = 0; k < dim; ++k) {
+      const double ph = pl[k] + 0.5 * e * gl[k];
+      ch.v(fp, k) = ph;
+      P.q_eval[(size_t)c * dim + k] = ql[k] + e * ml[k] * ph;
+    }
     return;
   }
   // sub-tree complete: biased progressive sampling at the top level, merge, tree-level U-turn check
@@ -622,7 +658,7 @@ static int sampler_passes(bpc_sampler* s, int nb) {
   for (int b = 0; b < nb; ++b) {
     int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream);
     if (rc) return rc;
-    bp_nuts_advance<<<(P.C + 127) / 128, 128, 0, s->stream>>>(P);
+    bp_nuts_advance<<<(P.C + 3) / 4, 128, 0, s->stream>>>(P);
     g_launches += 1;
   }
   return BPC_OK;
