@@ -764,7 +764,7 @@ __device__ __forceinline__ void bp_block_reduce_store(double (&vals)[BP_NPART], 
 }
 
 struct BpObsArgs {
-  const double* theta;   // [C][BP_DIM]
+  double* theta;         // [C][BP_DIM]
   const double* z0;      // [BP_N][npad]   init_pop, SoA, sorted
   const double* xo;      // [BP_N][npad]   pop_vec
   const double* t;       // [npad]         duration of each observation
@@ -795,6 +795,10 @@ struct BpObsArgs {
   double* wplain;        // [C][BP_CROWS][BP_WCOLS]         W_n of each chain, row n - 1, column d * BP_N + l
   int* fb;               // [1 + C]  wmode >= 2: number and ids of the chains left to bp_fused (written by bp_ctable)
   double* ctab_l;        // [noct * 8][BP_D * BP_D + 1]  octet path: L of the chain, then ||A||_1 (-1: the chain is not on this path)
+  // own input / output (bp_onetype with one tile per chain: one launch per evaluation): u != nullptr
+  const double* u;       // [C][BP_DIM] unconstrained parameters; theta is written, not read
+  int jacobian;
+  double* lp_out; double* grad_out; double* apps_out;
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -2693,8 +2697,16 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_onetype(BpObsArgs a)
   const int c = blockIdx.y;
   const int tid = threadIdx.x;
   double th[BP_DIM];
+  if (a.u) {   // the transform of bp_prologue, by every thread (theta is kept for the priors)
+    bp_transform(a.u + (size_t)c * BP_DIM, th);
+    if (tid == 0) {
 #pragma unroll
-  for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+      for (int k = 0; k < BP_DIM; ++k) a.theta[(size_t)c * BP_DIM + k] = th[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
+  }
   double lp = 0.0;
   double cb[BP_P], r[BP_E], rb[2] = {0.0, 0.0}, xk[BP_KDEP];
 #pragma unroll
@@ -2732,6 +2744,21 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_onetype(BpObsArgs a)
   for (int k = 0; k < BP_P; ++k) vals[1 + k] = cb[k];
   vals[BP_P + 1] = 0.0;
   vals[BP_P + 2] = 0.0;
+  if (a.u) {   // one tile per chain: the chain's status (OR over the CTA), its sums, then the work of bp_epilogue by one thread
+    __shared__ int sst;
+    if (tid == 0) sst = 0;
+    __syncthreads();
+    if (status) atomicOr(&sst, status);
+    bp_block_reduce_store(vals, scratch, a.part + (size_t)c * BP_NPART);
+    __syncthreads();
+    if (tid == 0) {
+      double acc[BP_NPART];
+#pragma unroll
+      for (int i = 0; i < BP_NPART; ++i) acc[i] = __ldcg(a.part + (size_t)c * BP_NPART + i);
+      bp_finish(c, acc, sst, a.u, a.theta, a.jacobian, a.lp_out, a.grad_out, a.status, a.apps_out);
+    }
+    return;
+  }
   bp_block_reduce_store(vals, scratch, a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART);
   if (status) atomicOr(a.status + c, status);
 }

@@ -535,6 +535,11 @@ static void choose_tiling(bpc_data* d, int nchains) {
     d->tile = ((d->N + d->ntiles - 1) / d->ntiles + 31) / 32 * 32;   // bp_fused's tiles (chains that need sub-steps) over the same ntiles
     return;
   }
+  if (d->model->spec.kind == BPC_SIMPLE_BD && d->N <= 8 * T) {   // small data: one tile per chain, and the kernel does its own input / output
+    d->tile = ((d->N + T - 1) / T) * T;
+    d->ntiles = 1;
+    return;
+  }
   const long long total = (long long)d->N * nchains;
   long long per_thread = total / ((long long)148 * 8 * T);
   long long cap = d->wmode ? 32 : 8;
@@ -590,7 +595,7 @@ struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
-  const double* theta; const double* z0; const double* xo; const double* t; const double* xv;
+  double* theta; const double* z0; const double* xo; const double* t; const double* xv;
   double* part; int* status; double* loglik; const int* perm;
   int nobs, npad, tile, ntiles, nchains;
   double* wpart; int wmode;
@@ -598,6 +603,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   double* ctab_m1; double* ctab_e2; double* csg;
   int noct; int* cg_jm; double* cg_flops; double* osg; double* wplain;
   int* fb; double* ctab_l;
+  const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -612,8 +618,10 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   double* theta = (double*)d->theta.p;
   double* part = (double*)d->part.p;
   double* apps = (double*)d->apps.p;
-  // grouped path: one CTA per chain does the transform, the evaluation and the priors / chain rule itself (one launch)
-  const bool own_io = d->grouped && L->grouped;
+  // grouped path, and the one-type template with one tile per chain: one CTA per chain does the transform, the evaluation and the
+  // priors / chain rule itself (one launch)
+  const bool own_io_1t = s.kind == BPC_SIMPLE_BD && d->ntiles == 1;
+  const bool own_io = (d->grouped && L->grouped) || own_io_1t;
   if (!own_io) {
     void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
     BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
@@ -625,7 +633,8 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               d->cgroups, d->cgpc, (const int*)d->cgs[d->cgsel].chunk0.p, (const int*)d->cgs[d->cgsel].idx.p, (const double*)d->cgs[d->cgsel].tau.p,
               (const double*)d->cgs[d->cgsel].hmax.p, (const double*)d->cgs[d->cgsel].coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
               d->noct, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
-              (int*)d->fb.p, (double*)d->ctab_l.p};
+              (int*)d->fb.p, (double*)d->ctab_l.p,
+              own_io_1t ? u_dev : nullptr, jacobian, lp_dev, grad_dev, apps};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
