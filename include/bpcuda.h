@@ -186,7 +186,7 @@ int bpc_flop_model(const bpc_model* m, double* per_app_fwd, double* per_app_bwd,
 int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* flops_per_chain);
 
 /* ---- sample: replaces rstan::sampling(stan_mod, data, chains, iter, warmup, init, control) ---- */
-/* (examples/two_type.R:26; sampler settings of examples/*.R).  Device-resident NUTS (multinomial, diagonal
+/* (examples/two_type.R:26; sampler settings of examples/<script>.R).  Device-resident NUTS (multinomial, diagonal
  * metric, Stan's windowed warm-up and dual averaging): every chain is a state machine advanced by one leapfrog
  * step per pass; one pass = one fused log-density+gradient evaluation of ALL chains + one bookkeeping kernel.
  * Random numbers are Philox4x32-10 keyed by (seed, global chain id), so a chain's draws do not depend on how
