@@ -787,7 +787,7 @@ struct BpObsArgs {
   double* ctab_m1;       // [C][BP_CGA + 1][D * n]  single-ancestor moments exp(a * BP_CGB * cdelta * L) [e_1 .. e_n]
   double* ctab_e2;       // [C][BP_CGB][D * D]      exp(b * cdelta * L)
   double* csg;           // [C][cgroups][BP_CSG]    scratch: the groups' S^g between a warp's main loop and its Toeplitz products
-  // octet path (wmode 3, bp_ntable + bp_fusedo + bp_toep + bp_wpost): eight chains share the tensor tiles of a pass
+  // octet path (wmode 3, bp_otable + bp_fusedo + bp_toep + bp_wpost): eight chains share the tensor tiles of a pass
   int noct;              // octets = ceil(C / 8)
   int* cg_jm;            // [noct * 8][cgroups]             J | m << 8 of (chain, group); -1: the chain is not on this path
   double* cg_flops;      // [noct * 8][cgroups]             algorithmic flops of (chain, group)
@@ -799,6 +799,7 @@ struct BpObsArgs {
   const double* u;       // [C][BP_DIM] unconstrained parameters; theta is written, not read
   int jacobian;
   double* lp_out; double* grad_out; double* apps_out;
+  double* n0tab;         // [C][cgroups][BP_D * BP_N]  octet path: N_0(tau_g) of every (chain, group), entry d * BP_N + l (bp_otable)
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -1671,7 +1672,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
   if (status) atomicOr(a.status + c, status);
 }
 
-// ---- octet path: bp_ntable + bp_fusedo + bp_toep ---------------------------------------------------------------
+// ---- octet path: bp_otable + bp_fusedo + bp_toep ---------------------------------------------------------------
 // X[(j, l)][k] = c_j(h_k) z0_kl does not depend on the chain, and 8 chains x D components fill the 8-wide tensor tiles exactly
 // (for every n).  So a CTA takes one pass of 32 observations for EIGHT chains at once:
 //     forward   Y[(cc, d)][k]  = sum_(j,l) N^cc_j[d][l] X[(j,l)][k]          D row tiles x 4 observation tiles x BP_XKS k-steps
@@ -1679,9 +1680,8 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 //     S update  S'[(j,l)][(cc, d)] += sum_k X[(j,l)][k] b^cc_k[d]              BP_XRT x D tiles x 8 k-steps
 // with X staged once per pass, its fragments shared by all column tiles, no padded tile rows and no ninth-component side path.
 // The short series is never masked in the hot loop: N rows beyond a chain's own degree J are zero, and the rows of
-// S' beyond it are dropped by bp_toep.  bp_ntable finds the series lengths (J, m) of every (chain, group); bp_fusedo builds N_j(tau_g)
-// of its octet in the group prologue (what bp_fusedc does per warp in its group
-// prologue), bp_toep is the Toeplitz product W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for all groups at once, bp_wpost finishes.
+// S' beyond it are dropped by bp_toep.  bp_otable finds the series lengths (J, m) and N_0(tau_g) of every (chain, group); bp_fusedo
+// builds N_j = L N_(j-1) of its octet in the group prologue, bp_toep is the Toeplitz product W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for all groups at once, bp_wpost finishes.
 #define BP_OU (8 * BP_D)                         // columns of an octet: (cc, d)
 #define BP_ONLD (BP_OU + 4)                      // row stride of the staged N (conflict-free A fragments: stride = 12 mod 16)
 #define BP_OTHREADS 128                          // one CTA = four warps on the same pass
@@ -1701,35 +1701,101 @@ __device__ __forceinline__ void bp_cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void bp_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-extern "C" __global__ void __launch_bounds__(128) bp_ntable(BpObsArgs a) {
-  // series lengths of every (chain, group): J (short series in h = t - tau_g) and m (centre series), and the algorithmic flops
-  const int grp = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y;
-  constexpr int DD = BP_D * BP_D;
-  if (grp >= a.cgroups) return;
-  int J = -1, mg = 0;
-  if (c < a.nchains) {
-    const double a1 = a.ctab_l[(size_t)c * (DD + 1) + DD];
-    if (a1 >= 0.0) {
-      BpPlan pc, ph;
-      int d1 = 1, d2 = 1;
-      const bool okc = bp_make_plan(a1, a.cg_tau[grp], pc, d1, BP_WCAP, BP_WTHETA_CAP);
-      const bool okh = bp_make_plan(a1, a.cg_hmax[grp], ph, d2, BP_CJ - 1, BP_WTHETA_CAP);
-      if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[grp] <= bp_th[ph.m - 1])) {   // (never for data bpc_data_create accepted)
-        atomicOr(a.status + c, BP_ST_RATE_NONFINITE);
-      } else {
-        J = ph.m - 1;
-        mg = pc.m;
-      }
+// per chain, everything the octet path needs before its passes: the bound transform (when the call gives u: no bp_prologue launch),
+// the path decision (chains that need sub-steps go to bp_fused's list), L, the series lengths (J, m) and algorithmic flops of every
+// (chain, group), and N_0(tau_g) = exp(tau_g L) [e_1 .. e_n] = sum_(j <= m_g) c_j(tau_g) U_j from the Krylov blocks U_j = L^j [e_1 .. e_n]
+// (c_j(tau_g): the coefficient table bp_toep uses).  One CTA per chain.
+extern "C" __global__ void __launch_bounds__(256) bp_otable(BpObsArgs a) {
+  const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
+  __shared__ double Lm[DD];
+  __shared__ double U[(BP_WROWS + 1) * DN];
+  double th[BP_DIM];
+  if (a.u) {
+    bp_transform(a.u + (size_t)c * BP_DIM, th);
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < BP_DIM; ++k) a.theta[(size_t)c * BP_DIM + k] = th[k];
+      a.status[c] = 0;
     }
+    __syncthreads();   // the status is reset before anybody ORs into it
+  } else {
+#pragma unroll
+    for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
   }
-  a.cg_jm[(size_t)c * a.cgroups + grp] = J < 0 ? -1 : (J | (mg << 8));
-  double fl = 0.0;
-  if (J >= 0) {
-    const int k0 = a.cg_chunk0[grp] * 32, k1 = min(a.nobs, a.cg_chunk0[grp + 1] * 32);
-    fl = 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (mg + 1) - 1)      // N_0 .. N_J and the Toeplitz product (as bp_fusedc counts them)
-         + (double)max(0, k1 - k0) * (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);               // per observation and term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
+  double A[BP_N * BP_N], H[BP_N * BP_S], r[BP_E], xk[BP_KDEP];
+#pragma unroll
+  for (int k = 0; k < BP_KDEP; ++k) xk[k] = 0.0;
+  bp_rates(th, xk, r);
+  bool fin = true;
+#pragma unroll
+  for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
+  bp_assemble(r, A, H);
+  const double a1 = bp_norm1(A);
+  const double tmax = a.nobs > 0 ? a.t[0] : 0.0;
+  int* jm = a.cg_jm + (size_t)c * a.cgroups;
+  double* fl = a.cg_flops + (size_t)c * a.cgroups;
+  if (!bp_w_path(fin, a1, tmax)) {   // bp_fused takes this chain
+    if (tid == 0) {
+      a.fb[1 + atomicAdd(a.fb, 1)] = c;
+      a.ctab_l[(size_t)c * (DD + 1) + DD] = -1.0;
+    }
+    for (int g = tid; g < a.cgroups; g += T) { jm[g] = -1; fl[g] = 0.0; }
+    return;
   }
-  a.cg_flops[(size_t)c * a.cgroups + grp] = fl;
+  BpPlan p;
+  int dh = 1;
+  bp_make_plan(a1, tmax, p, dh, BP_WCAP, BP_WTHETA_CAP);
+  const int mtop = p.m;
+  bp_coop_build_L(A, H, Lm);
+  for (int o = tid; o < DN; o += T) { const int d = o / BP_N, l = o - d * BP_N; U[o] = (d == l) ? 1.0 : 0.0; }
+  // series lengths and flops of the groups
+  for (int g = tid; g < a.cgroups; g += T) {
+    BpPlan pc, ph;
+    int d1 = 1, d2 = 1, J = -1, mg = 0;
+    const bool okc = bp_make_plan(a1, a.cg_tau[g], pc, d1, BP_WCAP, BP_WTHETA_CAP);
+    const bool okh = bp_make_plan(a1, a.cg_hmax[g], ph, d2, BP_CJ - 1, BP_WTHETA_CAP);
+    if (!okc || !okh || pc.s != 1 || ph.s != 1 || !((a1 + a1) * a.cg_hmax[g] <= bp_th[ph.m - 1])) {   // (never for data bpc_data_create accepted)
+      atomicOr(a.status + c, BP_ST_RATE_NONFINITE);
+    } else {
+      J = ph.m - 1;
+      mg = pc.m;
+    }
+    jm[g] = J < 0 ? -1 : (J | (mg << 8));
+    double f = 0.0;
+    if (J >= 0) {
+      const int k0 = a.cg_chunk0[g] * 32, k1 = min(a.nobs, a.cg_chunk0[g + 1] * 32);
+      f = 2.0 * BP_D * BP_D * BP_N * (J + 1) + 2.0 * BP_D * BP_N * ((J + 1) * (mg + 1) - 1)      // N_0 .. N_J and the Toeplitz product (as bp_fusedc counts them)
+          + (double)max(0, k1 - k0) * (J + 1) * (2.0 + BP_N + 4.0 * BP_D * BP_N);               // per observation and term: c_j(h), w_j z0, N_j (w_j z0), one row of the S update
+    }
+    fl[g] = f;
+  }
+  __syncthreads();   // L, U_0 and the groups' series lengths (global, this CTA's own) are written
+  for (int o = tid; o < DD; o += T) a.ctab_l[(size_t)c * (DD + 1) + o] = Lm[o];
+  if (tid == 0) a.ctab_l[(size_t)c * (DD + 1) + DD] = a1;
+  for (int j = 1; j <= mtop; ++j) {
+    for (int o = tid; o < DN; o += T) {
+      const int d = o / BP_N, l = o - d * BP_N;
+      double u = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < BP_D; ++rr) u += Lm[d * BP_D + rr] * U[(j - 1) * DN + rr * BP_N + l];
+      U[j * DN + o] = u;
+    }
+    __syncthreads();
+  }
+  double* n0 = a.n0tab + (size_t)c * a.cgroups * DN;
+  for (int i = tid; i < a.cgroups * DN; i += T) {
+    const int g = i / DN, o = i - g * DN;
+    const int q = jm[g];
+    double y = 0.0;
+    if (q >= 0) {
+      const int mg = q >> 8;
+      const double* cf = a.cg_coef + (size_t)g * BP_CCTAB + 8;
+      y = U[o];
+      for (int j = 1; j <= mg; ++j) y += cf[j] * U[j * DN + o];
+    }
+    n0[i] = y;
+  }
 }
 
 // One CTA (four warps) per pass of 32 observations x 8 chains; every phase is split four ways, three barriers per pass:
@@ -1788,14 +1854,12 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
     __syncthreads();
   }
   for (int grp = g0; grp < g1; ++grp) {
-    // ---- N_j(tau_g) of the octet's chains: N_0 = E2[b] M1[a] (tables of bp_ctable), N_(j+1) = L N_j; thread = entries (cc, d, l).
+    // ---- N_j(tau_g) of the octet's chains: N_0 from bp_otable, N_(j+1) = L N_j; thread = entries (cc, d, l).
     // Rows beyond a chain's own degree J are zero.  (The previous group's last forward product is behind a barrier.) ----
     if (tid < 8) sjm[tid] = (o * 8 + tid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + tid) * a.cgroups + grp] : -1;
     __syncthreads();
     {
       constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NQ = (8 * DN + BP_OTHREADS - 1) / BP_OTHREADS;
-      const int gi = a.cg_idx[grp];
-      const int ai = gi / BP_CGB, bi = gi - ai * BP_CGB;
       double Lr[NQ][BP_D];
       int Jq[NQ], eo[NQ], dq[NQ];   // degree of the entry's chain (-1: not on this path, -2: no entry), offset of (row (0, l), column (cc, 0)) in sN, d
       int Jmax = -1;
@@ -1812,10 +1876,9 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
         if (Jq[q] >= 0) {
           const size_t c = (size_t)o * 8 + cc;
           const double* lrow = a.ctab_l + c * (DD + 1) + d * BP_D;
-          const double* e2 = a.ctab_e2 + (c * BP_CGB + bi) * DD + d * BP_D;
-          const double* m1 = a.ctab_m1 + (c * (BP_CGA + 1) + ai) * DN + l;
+          n0 = a.n0tab[(c * a.cgroups + grp) * DN + rem];
 #pragma unroll
-          for (int rr = 0; rr < BP_D; ++rr) { Lr[q][rr] = lrow[rr]; n0 += e2[rr] * m1[rr * BP_N]; }
+          for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = lrow[rr];
         } else {
 #pragma unroll
           for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = 0.0;

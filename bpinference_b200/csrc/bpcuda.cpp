@@ -99,7 +99,7 @@ int model_load(bpc_model* m, int device, Loaded** out) {
         BPC_CUDA(cudaLibraryGetKernel(&L.fusedc, L.lib, "bp_fusedc"));
         BPC_CUDA(cudaLibraryGetKernel(&L.ctable, L.lib, "bp_ctable"));
         BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->spec.c_smem, device));
-        BPC_CUDA(cudaLibraryGetKernel(&L.ntable, L.lib, "bp_ntable"));
+        BPC_CUDA(cudaLibraryGetKernel(&L.otable, L.lib, "bp_otable"));
         BPC_CUDA(cudaLibraryGetKernel(&L.fusedo, L.lib, "bp_fusedo"));
         BPC_CUDA(cudaLibraryGetKernel(&L.toep, L.lib, "bp_toep"));
         // bp_fusedo: N of the octet [8 n][8 D + 4], X [2][8 n][36], Y [8 D][40], two chunks of the table [2][2 n + 1][32]  (BP_OSMEM in bp_kernels.cuh)
@@ -573,8 +573,7 @@ static int ensure_workspace(bpc_data* d, int nchains) {
         if ((rc = d->cg_jm.alloc((size_t)d->noct * 8 * d->cgroups * 4))) return rc;
         if ((rc = d->cg_flops.alloc((size_t)d->noct * 8 * d->cgroups * 8))) return rc;
         if ((rc = d->wplain.alloc((size_t)nchains * (((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n * 8))) return rc;
-        if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
-        if ((rc = d->ctab_e2.alloc((size_t)nchains * 64 * D * D * 8))) return rc;
+        if ((rc = d->n0tab.alloc((size_t)nchains * d->cgroups * D * n * 8))) return rc;
       } else if (d->cmode) {
         if ((rc = d->csg.alloc((size_t)nchains * d->cgroups * 8 * ((D * n + 7) / 8) * 8 * 8))) return rc;   // one 8-row S matrix per group
         if ((rc = d->ctab_m1.alloc((size_t)nchains * 65 * D * n * 8))) return rc;
@@ -604,6 +603,7 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   int noct; int* cg_jm; double* cg_flops; double* osg; double* wplain;
   int* fb; double* ctab_l;
   const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
+  double* n0tab;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
@@ -622,7 +622,8 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   // priors / chain rule itself (one launch)
   const bool own_io_1t = s.kind == BPC_SIMPLE_BD && d->ntiles == 1;
   const bool own_io = (d->grouped && L->grouped) || own_io_1t;
-  if (!own_io) {
+  const bool own_in = !own_io && d->wmode && d->omode;   // octet path: bp_otable does the transform
+  if (!own_io && !own_in) {
     void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
     BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
   }
@@ -634,7 +635,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               (const double*)d->cgs[d->cgsel].hmax.p, (const double*)d->cgs[d->cgsel].coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
               d->noct, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
               (int*)d->fb.p, (double*)d->ctab_l.p,
-              own_io_1t ? u_dev : nullptr, jacobian, lp_dev, grad_dev, apps};
+              (own_io_1t || own_in) ? u_dev : nullptr, jacobian, lp_dev, grad_dev, apps, (double*)d->n0tab.p};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -675,13 +676,13 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
         // bp_fused (below) only works on the chains that need sub-steps
         if (d->cmode) BPC_CUDA(cudaMemsetAsync(d->fb.p, 0, sizeof(int), st));
         if (d->omode) {
-          // octet path: per-chain tables, N_j(tau_g) of every (chain, group), the fused passes of 8 chains at a time, the Toeplitz products
+          // octet path: per chain the transform, L, series lengths and N_0(tau_g) of every group; the fused passes of 8 chains at a
+          // time; the Toeplitz products
           const int n = s.ntypes, D = n + n * (n + 1) / 2;
-          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(256), args, 0, st));
-          BPC_CUDA(cudaLaunchKernel((const void*)L->ntable, dim3((d->cgroups + 127) / 128, d->noct * 8), dim3(128), args, 0, st));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->otable, dim3(nchains), dim3(256), args, 0, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
           BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
-          g_launches += 3;
+          g_launches += 1;   // (bp_otable stands in for bp_prologue in the count below)
         } else if (d->cmode) {
           // centred W path: per-chain tables of exp(tau L), then short series around the groups' centres
           BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(256), args, 0, st));
@@ -729,8 +730,8 @@ int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned lon
     const int n = s.ntypes, D = n + n * (n + 1) / 2;
     unsigned long long b = 2ull * nchains * d->ntiles * (s.nparams + 3) * 8;   // per-CTA partial sums, written then read
     if (d->omode) {
-      // S' of every (octet, group), W of every chain and the per-chain tables, written then read
-      b += 2ull * ((unsigned long long)d->noct * d->cgroups * (8 * n) * (8 * D) + (unsigned long long)nchains * ((((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n + 65ull * D * n + 64ull * D * D)) * 8;
+      // S' of every (octet, group), W, N_0 of every group and L of every chain, written then read
+      b += 2ull * ((unsigned long long)d->noct * d->cgroups * (8 * n) * (8 * D) + (unsigned long long)nchains * ((((s.wcap + 1 + 8 + 7) / 8) * 8) * D * n + (unsigned long long)d->cgroups * D * n + D * D + 1)) * 8;
     } else {
       if (d->wmode) b += 2ull * nchains * d->ntiles * (unsigned long long)(((s.wcap + 1 + (d->cmode ? 8 : 0) + 7) / 8) * ((D * n + 7) / 8) * 64) * 8;
       if (d->cmode) b += 2ull * nchains * ((unsigned long long)d->cgroups * 8 * ((D * n + 7) / 8) * 8 + 65ull * D * n + 64ull * D * D) * 8;   // S^g per group and the per-chain tables, written then read

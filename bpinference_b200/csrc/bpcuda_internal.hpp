@@ -38,7 +38,7 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, ntable = nullptr, fusedo = nullptr, toep = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr;
   size_t obs_smem = 0, grouped_smem = 0, o_smem = 0;
 };
 
@@ -79,10 +79,10 @@ struct bpc_data {
   std::vector<double> h_t;          // sorted durations (host copy while bpc_data_create builds the groupings)
   CGrouping cgs[2];
   bpc::DevBuf ctab_m1, ctab_e2, csg;
-  // octet path (bp_ntable + bp_fusedo + bp_toep): eight chains per tensor tile; chosen per chain count (choose_tiling)
+  // octet path (bp_otable + bp_fusedo + bp_toep): eight chains per tensor tile; chosen per chain count (choose_tiling)
   bool omode = false;
   int noct = 0;
-  bpc::DevBuf cg_jm, cg_flops, osg, wplain, fb, ctab_l;
+  bpc::DevBuf cg_jm, cg_flops, osg, wplain, fb, ctab_l, n0tab;
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;

@@ -65,7 +65,7 @@ class StanData:
         _ffi.check(_ffi.lib().bpc_data_path(self.handle, int(nchains), C.byref(p), C.byref(nt), C.byref(sb)))
         names = {0: "bp_fused", 1: "bp_grouped", 2: "bp_fusedw + bp_wpost (bp_fused for chains that need sub-steps)", 3: "bp_onetype",
                  4: "bp_ctable + bp_fusedc + bp_wpost (bp_fused for chains that need sub-steps)",
-                 5: "bp_ctable + bp_ntable + bp_fusedo + bp_toep + bp_wpost (bp_fused for chains that need sub-steps)"}
+                 5: "bp_otable + bp_fusedo + bp_toep + bp_wpost (bp_fused for chains that need sub-steps)"}
         return names[p.value], nt.value, sb.value
 
     def close(self):

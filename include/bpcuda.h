@@ -147,7 +147,7 @@ int bpc_data_ngroups(const bpc_data* d);    /* distinct (env level, duration) pa
 int bpc_data_is_grouped(const bpc_data* d); /* which path log_prob takes */
 /* the kernels bpc_log_prob launches for `nchains` chains: *path = 0 bp_fused (term ring), 1 bp_grouped, 2 bp_fusedw + bp_wpost
  * (W path, bp_fused as sub-step fallback), 3 bp_onetype, 4 bp_ctable + bp_fusedc + bp_wpost (centred W path: sorted durations
- * dense enough for short series around shared centres; bp_fused as sub-step fallback), 5 bp_ctable + bp_ntable + bp_fusedo + bp_toep +
+ * dense enough for short series around shared centres; bp_fused as sub-step fallback), 5 bp_otable + bp_fusedo + bp_toep +
  * bp_wpost (octet path: the centred series with eight chains per tensor tile, from 16 chains); *ntiles = CTAs per chain (octet path:
  * per octet of chains); *scratch_bytes = per-launch partial-sum traffic */
 int bpc_data_path(bpc_data* d, int nchains, int* path, int* ntiles, unsigned long long* scratch_bytes);

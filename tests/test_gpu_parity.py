@@ -287,9 +287,9 @@ def test_centred_w_path_matches_oracle_and_w_path(nobs, chunks):
 @pytest.mark.parametrize("name,nobs,chains,grouping", [("cfg5U", 20000, 19, None), ("cfg5U", 60000, 16, None), ("cfg2", None, 24, 1),
                                                        ("cfg4", None, 17, 1)])
 def test_octet_path_matches_oracle_and_centred_path(name, nobs, chains, grouping):
-    """octet path (bp_ctable + bp_ntable + bp_fusedo + bp_toep: eight chains share the tensor tiles of a pass) against the
+    """octet path (bp_otable + bp_fusedo + bp_toep: eight chains share the tensor tiles of a pass) against the
     oracle and against bp_fusedc on the same data; a ragged last octet, chains with long and short centre series, one chain
-    that needs sub-steps (ring fallback, listed by bp_ctable) in the same call; two-type and noise models on ungrouped data."""
+    that needs sub-steps (ring fallback, listed by bp_otable) in the same call; two-type and noise models on ungrouped data."""
     import os
     cfg = syn.make_config(name, chains=chains, nobs=nobs)
     eng, om = _pair(cfg)
