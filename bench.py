@@ -334,7 +334,7 @@ def _main(args):
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        lp_h, g_h, st_h = eng.log_prob_grad(data, u_host)                # H2D of upars, 3 launches, D2H of lp/grad/status, sync
+        lp_h, g_h, st_h = eng.log_prob_grad(data, u_host)                # H2D of upars, the step's launches, D2H of lp/grad/status, sync
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
