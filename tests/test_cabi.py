@@ -68,3 +68,31 @@ def test_constrain_roundtrip_host():
     th = eng.constrain_pars(cfg["upars"])
     assert th.shape == (3, 4) and (th[:, :3] > 0).all() and (th[:, :3] < 2).all() and (th[:, 3] > 0).all()
     np.testing.assert_allclose(eng.unconstrain_pars(th), cfg["upars"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name,expect", [("cfg5U", ("bp_otable", "bp_fusedo", "bp_toep", "bp_fusedc", "bp_ctable", "bp_fusedw", "bp_wpost", "bp_fused", "bp_grouped")),
+                                         ("cfg2", ("bp_otable", "bp_fusedo", "bp_toep", "bp_grouped", "bp_fused")),
+                                         ("cfg4", ("bp_fusedo", "bp_grouped")), ("cfg1", ("bp_onetype",))])
+def test_every_module_compiles_for_sm100a_with_the_planned_resources(name, expect, tmp_path):
+    """NVRTC output of each template family (no GPU needed): the kernels of every path are in the sm_100a cubin, and the
+    headline kernel keeps what its launch geometry counts on -- 128 registers (four CTAs per SM), no spills to local memory."""
+    import shutil
+    import subprocess
+    cfg = syn.make_config(name, chains=2, nobs=64)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"], simple_bd=cfg["kind"] == "simple_bd", noise_model=cfg["kind"] == "multitype_noise")
+    cub = eng.cubin()
+    assert cub[:4] == b"\x7fELF"
+    for k in expect + ("bp_prologue", "bp_epilogue", "bp_loglik"):
+        assert k.encode() in cub, k
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    path = tmp_path / "m.cubin"
+    path.write_bytes(cub)
+    head = subprocess.run(["cuobjdump", "-sass", "-fun", "bp_prologue", str(path)], capture_output=True, text=True).stdout
+    assert "code for sm_100a" in head
+    out = subprocess.run(["cuobjdump", "-res-usage", str(path)], capture_output=True, text=True).stdout
+    res = dict(re.findall(r"Function (\w+):\s*\n\s*(REG:\d+ STACK:\d+)", out))
+    if "bp_fusedo" in expect:
+        regs, stack = (int(x.split(":")[1]) for x in res["bp_fusedo"].split())
+        assert regs <= 128 and stack == 0, res["bp_fusedo"]
