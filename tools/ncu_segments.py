@@ -1,3 +1,5 @@
+"""Stall samples of an ncu source page, in segments of N SASS lines: executions, share of the samples, opcode mix, top stall
+reasons.  usage: ncu -i rep.ncu-rep --page source --csv > src.csv; python tools/ncu_segments.py src.csv [lines per segment]"""
 import csv, sys, re, collections
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]

@@ -1,4 +1,5 @@
-"""latency of one log-density evaluation (3 kernels, device buffers, no host sync in the loop) on small problems"""
+"""latency of one log-density evaluation (device buffers, no host sync in the loop) on small problems: one launch on the grouped
+and single-tile one-type paths, prologue + kernel + epilogue otherwise"""
 import time, torch, numpy as np
 import bpinference_b200 as bp
 from bpinference_b200 import synthetic as syn, _ffi

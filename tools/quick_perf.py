@@ -1,3 +1,4 @@
+"""kernel time and evaluations per second of every synthetic config on one GPU (quick look, not the bench)."""
 import time, numpy as np, json
 import bpinference_b200 as bp
 from bpinference_b200 import synthetic as syn

@@ -1,3 +1,4 @@
+"""short sampling runs of the small configs (cfg1, cfg2, cfg4, cfg3): posterior means against the truth, R-hat, ESS, step sizes."""
 import time, numpy as np
 import bpinference_b200 as bp
 from bpinference_b200 import synthetic as syn

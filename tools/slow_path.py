@@ -1,3 +1,5 @@
+"""bp_grouped on cfg2 with 1024 chains: evaluation time when all, one or no chain needs sub-steps (the cooperative multi-step
+route against the rates near the truth): what a sampler pass costs during warm-up."""
 import time, torch, numpy as np
 import bpinference_b200 as bp
 from bpinference_b200 import synthetic as syn, _ffi
