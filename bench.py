@@ -49,7 +49,10 @@ def parse():
     ap.add_argument("--nobs", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline / reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sampling", action="store_true", help="skip the short NUTS run that reports ESS/s (rank 0, N = 1 only)")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the NUTS runs that report ESS/s (all ranks, pooled warm-up over NCCL)")
+    ap.add_argument("--sampling-iter", type=int, default=200, help="iterations (half warm-up) of the NUTS run on the main workload")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the other shapes of SURVEY.md §8(d)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the lp / gradient check of 8 chains against the CPU port")
     return ap.parse_args()
 
 
@@ -139,11 +142,29 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def bench_config(workload, chains, N):
+    """the `config` object of the JSON line: identical in both arms (the driver compares them)."""
+    return {"workload": workload + ": " + workload_description(workload, chains, N), "chains_per_gpu": chains, "observations": N,
+            "l2": "256 MiB buffer rewritten between the timed steps (L2 flush, outside each step's event pair); the 5.6 MB "
+                  "observation table is re-read by every chain of a step and is L2-resident by design",
+            "reference_arm": "jproney/bpinference is R + Stan (rstan); neither exists in this image, so --impl reference times the CPU "
+                             "restatement of the same path (oracle/, kind \"port\": closed-form moments, strictly less work than rstan's "
+                             "RK45 forward-sensitivity solve) with every host core on a bounded sample of this workload"}
+
+
 def cpu_port_rate(cfg, seconds, nthreads=0):
     """times the CPU restatement (oracle/) on a bounded sample of the workload: returns (evals/s, cores, sample text)."""
     from oracle import bp_oracle as bo
     om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
-    cores = bo.num_threads() if nthreads == 0 else nthreads
+    # every host core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    cores = host_cores() if nthreads == 0 else nthreads
     d = cfg["data"]
     N = int(d["ndatapts"])
 
@@ -177,30 +198,129 @@ def cpu_port_rate(cfg, seconds, nthreads=0):
     return chains * nobs * reps / dt, cores, "%d chains x first %d of %d observations x %d passes, %d OpenMP threads, %.1f s" % (chains, nobs, N, reps, cores, dt)
 
 
-def sampling_report(bp, syn):
-    """the second half of BASELINE.json's metric: ESS/s of the device-resident NUTS sampler on the two-type example
-    (BASELINE.json configs[1]: examples/two_type.R shape, 250 observations, 1024 parallel chains; adapt_delta 0.8 as in the example)."""
-    import subprocess as sp
-    cfg = syn.make_config("cfg2", seed=1, chains=1024)
+def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, chains, nobs, iters, warm, opt_steps, adapt_delta=0.8):
+    """the second half of BASELINE.json's metric: ESS/s of the device-resident NUTS sampler.  Chains are sharded over the ranks
+    (`chains` per GPU); the diagonal metric of every warm-up window is estimated from the draws of ALL chains of ALL ranks — the one
+    collective of the path: an all-reduce of 2 + 2 dim doubles over NCCL at every window boundary, and 4 dim doubles for split R-hat at
+    the end.  Starting values as the reference's example scripts draw them: uniform_initialize(0, 1) (examples/two_type.R:22-23)."""
+    cfg = syn.make_config(workload, seed=1, chains=chains, nobs=nobs)
     mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
-    eng = bp.stan_model(mod, cfg["priors"])
-    d = eng.data(cfg["data"])
+    eng = bp.stan_model(mod, cfg["priors"], simple_bd=cfg["kind"] == "simple_bd", noise_model=cfg["kind"] == "multitype_noise")
+    d = eng.data(cfg["data"], device=local_rank)
+    P = cfg["nparams"]
+    init = bp.uniform_initialize(np.tile([0.0, 1.0], (P, 1)), chains, rng=np.random.default_rng(100 + rank))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    # warm-up statistics pooled over the chains at the window boundaries (the cross-chain exchange of the path: an all-reduce of
-    # 1 + 2 dim doubles over NCCL when N > 1); per-chain adaptation as in rstan (pooled_adaptation=False) gives 1/3 of the ESS/s
-    # on this workload (tools/pool_test.py: 766 against 2308), because 150 warm-up draws of one chain estimate the metric poorly
-    fit = eng.sampling(d, chains=1024, iter=300, warmup=150, control=dict(adapt_delta=0.8, max_treedepth=10), seed=1, pooled_adaptation=True)
+    fit = eng.sampling(d, chains=chains, iter=iters, warmup=warm, init=init, control=dict(adapt_delta=adapt_delta, max_treedepth=10), seed=1,
+                       pooled_adaptation=True, init_opt_steps=opt_steps)
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ess = fit.ess_bulk()
+    flat = fit.draws.reshape(-1, fit.draws.shape[2])
+    dev = torch.device("cuda", local_rank)
+    # [seconds (max), ESS per parameter (sum over ranks: chains are independent), leapfrogs, divergent, sum of draws, sum of squares, count]
+    v_max = torch.tensor([dt], dtype=torch.float64, device=dev)
+    v_sum = torch.tensor(np.concatenate([ess, [fit.info["leapfrogs"], float(fit.divergent__.sum()), flat.shape[0]], flat.sum(0), (flat * flat).sum(0)]),
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(v_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(v_sum)
+    dt = float(v_max.item())
+    vs = v_sum.cpu().numpy()
+    dim = len(ess)
+    ess_all, leap, ndiv, cnt = vs[:dim], vs[dim], vs[dim + 1], vs[dim + 2]
+    mean = vs[dim + 3:2 * dim + 3] / cnt
+    sd = np.sqrt(np.maximum(vs[2 * dim + 3:3 * dim + 3] / cnt - mean * mean, 0.0))
+    truth = np.asarray(cfg["theta_true"], dtype=float)
+    z = (mean[:P] - truth) / sd[:P]
+    d.close()
     try:
-        have_rstan = sp.run(["Rscript", "-e", "library(rstan)"], capture_output=True, timeout=60).returncode == 0
+        have_rstan = subprocess.run(["Rscript", "-e", "library(rstan)"], capture_output=True, timeout=60).returncode == 0
     except Exception:
         have_rstan = False
-    return {"workload": "cfg2: two-type model, 250 observations, 1024 chains x 300 iterations (150 warm-up), NUTS, adapt_delta 0.8, "
-                        "diagonal metric and step size adapted from warm-up statistics pooled over the chains",
-            "seconds": dt, "min_ess_per_s": float(ess.min() / dt), "min_ess": float(ess.min()), "leapfrogs_per_s": fit.info["leapfrogs"] / dt,
-            "leapfrogs": fit.info["leapfrogs"], "passes": fit.info["passes"], "max_rhat": float(fit.rhat.max()),
-            "divergent": int(fit.divergent__.sum()), "rstan": "installed" if have_rstan else "rstan: not installed"}
+    return {"workload": "%s: %s; NUTS, %d iterations (%d warm-up), adapt_delta %.2f, starting values uniform(0, 1)%s; diagonal metric from warm-up "
+                        "statistics pooled over all chains of all ranks (NCCL all-reduce at the window boundaries)" % (
+                            workload, workload_description(workload, chains, int(cfg["data"]["ndatapts"])), iters, warm, adapt_delta,
+                            ", then %d steps of the device-side ascent" % opt_steps if opt_steps else ""),
+            "chains_total": int(chains * world), "seconds": dt, "min_ess_per_s": float(ess_all.min() / dt), "min_ess": float(ess_all.min()),
+            "leapfrogs_per_s": leap / dt, "leapfrogs": int(leap), "passes": fit.info["passes"], "max_rhat": float(np.nanmax(fit.rhat)),
+            "divergent": int(ndiv), "pool_exchanges": fit.info["pool_exchanges"], "collective": "torch.distributed all_reduce (NCCL)" if world > 1 else "none (one rank)",
+            "posterior_mean": [float(x) for x in mean], "posterior_sd": [float(x) for x in sd], "max_abs_z_vs_truth": float(np.abs(z).max()),
+            "ess_note": "Geyer ESS (rstan 2.19's n_eff) summed over ranks; R-hat = split R-hat over all chains",
+            "rstan": "installed" if have_rstan else "rstan: not installed (no baseline ESS/s can be measured in this image)"}
+
+
+def time_workload(bp, syn, _ffi, torch, dist, world, local_rank, rank, name, chains, steps, peaks, flush):
+    """one more shape of SURVEY.md §8(d), device-timed like the main workload (events on the launching stream, L2 flush between
+    steps): returns the entry of `other_workloads`."""
+    dev = torch.device("cuda", local_rank)
+    cfg = syn.make_config(name, seed=1, chains=chains)
+    rng = np.random.default_rng(1000 + rank)
+    upars = cfg["u_true"][None, :] + 0.1 * rng.standard_normal((chains, len(cfg["u_true"])))
+    N = int(cfg["data"]["ndatapts"])
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"], simple_bd=cfg["kind"] == "simple_bd", noise_model=cfg["kind"] == "multitype_noise")
+    data = eng.data(cfg["data"], device=local_rank)
+    L = _ffi.lib()
+    dim = eng.dim
+    u_dev = torch.from_numpy(upars).to(dev)
+    lp_dev = torch.empty(chains, dtype=torch.float64, device=dev)
+    g_dev = torch.empty(chains, dim, dtype=torch.float64, device=dev)
+    st_dev = torch.empty(chains, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(ev=None):
+        flush.zero_()
+        if ev is not None:
+            ev[0].record(stream)
+        _ffi.check(L.bpc_log_prob_dev(eng.handle, data.handle, u_dev.data_ptr(), chains, 1, lp_dev.data_ptr(), g_dev.data_ptr(),
+                                      st_dev.data_ptr(), stream.cuda_stream))
+        if ev is not None:
+            ev[1].record(stream)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    flops = float(eng.flops_per_chain(data, upars).sum())
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for ev in evs:
+        step(ev)
+    torch.cuda.synchronize()
+    ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+    bad = int((st_dev != 0).sum().item())
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    kernel_name, ntiles, _ = data.path(chains)
+    tensor = "bp_fusedo" in kernel_name or "bp_fusedc" in kernel_name or "bp_fusedw" in kernel_name
+    peak = peaks["dmma"] if tensor else peaks["dfma"]
+    per_step = ms / steps
+    out = {"workload": name + ": " + workload_description(name, chains, N), "kernel": kernel_name, "ms_per_step": per_step,
+           "value": float(world) * chains * N / (per_step * 1e-3), "unit": UNIT, "us_per_evaluation_of_all_chains": per_step * 1e3,
+           "rejected_chains": bad,
+           "roofline": {"bound": "fp64", "achieved": flops / (per_step * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flops / (per_step * 1e-3) / 1e12 / peak, "peak_kind": "DMMA loop" if tensor else "DFMA loop",
+                        "flops_per_eval": flops / (chains * N),
+                        "note": "whole step (all launches of one evaluation) against the measured FP64 peak; shapes with a few hundred "
+                                "observations per chain are launch / latency bound, which is what the small fraction says"}}
+    data.close()
+    return out
+
+
+def parity_report(eng, cfg, data, upars, nchains=8):
+    """max relative error of the device's lp / gradient against the CPU port (oracle/) for the first chains of rank 0 on ALL
+    observations of the workload, outside the timed region."""
+    from oracle import bp_oracle as bo
+    om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
+    u = np.ascontiguousarray(upars[:nchains])
+    lp, g, st = eng.log_prob_grad(data, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u, grouped=False if cfg["name"] in ("cfg5U", "cfg5K") else None, nthreads=host_cores())
+    return {"chains": int(len(u)), "observations": int(cfg["data"]["ndatapts"]), "status_equal": bool((st == st_o).all()),
+            "lp_max_rel_err": float(np.max(np.abs(lp - lp_o) / np.abs(lp_o))),
+            "grad_max_rel_err": float(np.max(np.abs(g - g_o) / np.abs(g_o).max(axis=1, keepdims=True))),
+            "checker": "oracle/ (CPU port, test infrastructure); tolerance of the tests: 1e-11 / 1e-9"}
 
 
 def run_reference(args, rank):
@@ -221,11 +341,9 @@ def run_reference(args, rank):
     _RESULT_LINE.append(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + workload_description(args.workload, chains, N),
-                   "note": "reference = jproney/bpinference's Stan templates executed by rstan (R); neither exists in this image, so this arm "
-                           "times the CPU restatement of the same path (oracle/, closed-form moments: strictly less work than rstan's RK45 "
-                           "forward-sensitivity solve) on the host cores; the rate does not depend on the GPU count"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": info[0], "kind": "port", "sample": info[1] + " per step"},
+        "config": bench_config(args.workload, chains, N),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": info[0], "kind": "port", "sample": info[1] + " per step",
+                         "note": "the CPU rate is linear in chains and does not depend on the GPU count: one host, all its cores"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -342,45 +460,76 @@ def _main(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e2e.item())
 
+    # ---- measured FP64 peaks of this device (same run): DFMA loop and DMMA loop -----------------
+    peak_tf, clock_mhz = bp.fp64_peak(local_rank, 300.0)
+    peak_dmma = bp.fp64_tensor_peak(local_rank, 300.0)
+    peaks = {"dfma": peak_tf, "dmma": peak_dmma}
+
+    # ---- the other shapes of SURVEY.md §8(d), every rank its own chains (weak scaling, no collective) ----------------------
+    others = []
+    if not args.no_other_workloads and args.workload == "cfg5U" and not args.nobs:
+        for name in ("cfg5G", "cfg5K", "cfg2", "cfg1", "cfg3", "cfg4"):
+            others.append(time_workload(bp, syn, _ffi, torch, dist, world, local_rank, rank, name, DEFAULT_CHAINS[name], 5 if name == "cfg5K" else 10,
+                                        peaks, flush))
+
+    # ---- sampling: every rank its chains, warm-up statistics pooled over all ranks ----------------------------------------
+    sampling = None
+    if not args.no_sampling:
+        sampling = {"cfg2": sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 0)}
+        if args.workload == "cfg5U" and not args.nobs:
+            sampling["cfg5U"] = sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg5U", chains, None, args.sampling_iter,
+                                                args.sampling_iter // 2, 100)
+
     if rank == 0:
         total_evals = float(world) * chains * N * args.steps
         value = total_evals / (ms_max * 1e-3)
-        peak_tf, clock_mhz = bp.fp64_peak(local_rank, 300.0)
         k_avg_ms = kms.value / max(1, kl.value)
         flops_launch = float(flops_chain.sum())
         achieved = flops_launch / (k_avg_ms * 1e-3) / 1e12
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
-            peaks = {}
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+            peaks_file = {}
+        hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
         kernel_name, ntiles, scratch_bytes = data.path(chains)
+        # algorithmic HBM bytes of one launch: the observation table once + per-chain input / output.  The
+        # kernels' own scratch (per-CTA partial sums, the octet path's S' / N_0 / W) is NOT algorithmic: it is reported as `scratch_bytes`
+        # and shows up in `traffic`.
         obs_bytes = N * 8 * ((2 * cfg["data"].get("ntypes", 1)) + 1 + (cfg["ndep"] or 0))
-        alg_bytes = obs_bytes + chains * (2 * dim + 1) * 8 + scratch_bytes
+        alg_bytes = obs_bytes + chains * (2 * dim + 1) * 8 + chains * 4
+        traffic = NCU_TRAFFIC_BYTES.get((args.workload, chains, N))
+        tensor = "bp_fusedo" in kernel_name or "bp_fusedc" in kernel_name or "bp_fusedw" in kernel_name
+        peak = peak_dmma if tensor else peak_tf
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload + ": " + workload_description(args.workload, chains, N), "chains_per_gpu": chains,
-                       "observations": N, "l2": "256 MiB buffer rewritten between the timed steps (L2 flush, outside each step's event pair); the 5.6 MB "
-                                               "observation table is re-read by every chain of a step and is L2-resident by design",
-                       "rejected_chains": bad},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, chains, N)), "traffic_unit": "bytes per launch (ncu, profiles/)",
+            "config": bench_config(args.workload, chains, N),
+            "rejected_chains": bad,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)",
                          "kernel": kernel_name, "ctas_per_chain": ntiles,
                          "kernel_ms": k_avg_ms, "flops_per_launch": flops_launch, "flops_per_eval": flops_launch / (chains * N),
-                         "peak_source": "DFMA loop measured in this run (bpc_fp64_peak): MEASURED_PEAKS.json has no FP64 figure; "
-                                        "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
-                         "hbm": {"algorithmic_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                                 "frac": alg_bytes / (k_avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+                         "peak_dmma": peak_dmma, "peak_dfma": peak_tf, "frac_of_dfma_peak": achieved / peak_tf,
+                         "peak_source": "measured in this run on this device: a register-resident DMMA (mma.sync m8n8k4 f64) loop — the kernel's flops "
+                                        "are ~85 % DMMA — and a DFMA loop (bpc_fp64_tensor_peak / bpc_fp64_peak); MEASURED_PEAKS.json has no FP64 "
+                                        "figure; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2; DMMA and DFMA share one datapath",
+                         "hbm": {"algorithmic_bytes": alg_bytes, "algorithmic_gbs": alg_bytes / (k_avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "frac": alg_bytes / (k_avg_ms * 1e-3) / 1e9 / hbm_peak, "scratch_bytes": scratch_bytes,
+                                 "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"}},
             "e2e": {"value": float(world) * chains * N * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": chains * dim * 8,
                     "d2h_bytes_per_step": chains * (dim + 1) * 8 + chains * 4,
                     "note": "bpc_log_prob with host buffers: upars H2D, lp/grad/status D2H every step; observations stay resident in the "
                             "data handle, as the data stays inside the stanfit in rstan::log_prob"},
             "gpu_launches": launches, "clocks": clk,
         }
-        if not args.no_sampling and world == 1:
-            out["sampling"] = sampling_report(bp, syn)
+        if not args.no_parity:
+            out["parity"] = parity_report(eng, cfg, data, upars)
+        if others:
+            out["other_workloads"] = others
+        if sampling:
+            out["sampling"] = sampling
         if not args.no_cpu_baseline:
             v, cores, sample = cpu_port_rate(cfg, args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,

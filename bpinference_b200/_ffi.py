@@ -44,7 +44,7 @@ class StanData(C.Structure):
 class SampleArgs(C.Structure):
     _fields_ = [("chains", C.c_int), ("iter", C.c_int), ("warmup", C.c_int), ("adapt_delta", C.c_double),
                 ("max_treedepth", C.c_int), ("seed", C.c_ulonglong), ("chain_id_offset", C.c_int),
-                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double)]
+                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double), ("init_opt_steps", C.c_int)]
 
 
 # every symbol include/bpcuda.h declares: name -> (restype, argtypes)
@@ -54,6 +54,7 @@ SYMBOLS = {
     "bpc_last_error": (C.c_char_p, []),
     "bpc_device_count": (C.c_int, []),
     "bpc_fp64_peak": (C.c_int, [C.c_int, C.c_double, _dp, _dp]),
+    "bpc_fp64_tensor_peak": (C.c_int, [C.c_int, C.c_double, _dp]),
     "bpc_check_expr": (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
     "bpc_expr_to_stan": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "bpc_expr_deparse": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
@@ -73,6 +74,8 @@ SYMBOLS = {
     "bpc_log_prob_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "bpc_log_lik": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp]),
     "bpc_moments": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp, _dp]),
+    "bpc_transformed_parameters": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp]),
+    "bpc_data_nlevels": (C.c_int, [_vp]),
     "bpc_flop_model": (C.c_int, [_vp, _dp, _dp, _dp]),
     "bpc_constrain": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "bpc_unconstrain": (C.c_int, [_vp, _dp, C.c_int, _dp]),
@@ -88,9 +91,13 @@ SYMBOLS = {
     "bpc_sampler_chain_moments": (C.c_int, [_vp, _vp, C.c_int, _dp]),
     "bpc_rhat": (C.c_int, [_dp, C.c_int, C.c_int, _dp]),
     "bpc_sampler_passes": (C.c_longlong, [_vp]),
+    "bpc_sampler_progress": (C.c_int, [_vp, _ip, _dp, _dp, _ip]),
     "bpc_sampler_draws": (C.c_int, [_vp, _dp, _dp, _ip, _ip, _ip, _dp, _dp]),
     "bpc_sampler_total_leapfrogs": (C.c_longlong, [_vp]),
     "bpc_sample": (C.c_int, [_vp, _vp, C.POINTER(SampleArgs), _dp, _dp, _ip, _ip, _ip, _dp, _dp]),
+    "bpc_sample_multi": (C.c_int, [_vp, C.POINTER(StanData), _ip, C.c_int, C.POINTER(SampleArgs), _dp, _dp, _ip, _ip, _ip, _dp, _dp, _dp,
+                                   C.POINTER(C.c_longlong)]),
+    "bpc_nccl_version": (C.c_int, []),
     "bpc_simulate": (C.c_int, [C.c_int, C.c_int, _dp, _ip, _dp, _dp, _dp, C.c_int, C.c_int, C.c_ulonglong, C.c_int, _dp]),
 }
 

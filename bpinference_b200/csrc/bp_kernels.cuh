@@ -529,7 +529,7 @@ BP_HD void bp_obs_lpgrad(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
   if (!ok) status |= BP_ST_NOT_PD;
 }
 
-// forward only: per-observation log_lik with the normalising constant (LOO block)
+// forward only: per-observation log_lik with the normalising constant (stanfiles/multitype_loo_block.stan:15-32)
 BP_HD real bp_obs_loglik(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP_S], real a1, const real (&z0)[BP_N],
                          const real (&xo)[BP_N], real t, real sigma) {
   BpPlan p;
@@ -543,10 +543,9 @@ BP_HD real bp_obs_loglik(const real (&A)[BP_N * BP_N], const real (&H)[BP_N * BP
   for (int q = 0; q < BP_S; ++q) yS[q] = real(0.0);
   real cfw;
   for (int j = 0; j < p.s; ++j) bp_series_fwd<false>(A, H, p.h, p.m, ymu, yS, true, ymu, yS, false, BpRingShared(), 0, 0, cfw);
-#if BP_NOISE
-#pragma unroll
-  for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
-#endif
+  // (no sigma_obs term, also for the noise template: generate() appends the same LOO block to both multitype templates,
+  // R/stan_utils.R:189-191, and multitype_loo_block.stan:22-31 builds sigma_t without it)
+  (void)sigma;
   real lpk;
   if (!bp_mvn_score(xo, ymu, yS, lpk, bmu, bS)) return nan_;
   return lpk - real(0.5 * BP_N * 1.8378770664093454835606594728112);   // n/2 log(2 pi)
@@ -2868,6 +2867,26 @@ extern "C" __global__ void bp_epilogue(const double* __restrict__ u, const doubl
   for (int i = 0; i < BP_NPART; ++i) acc[i] = bp_warp_sum(acc[i]);
   if (lane) return;
   bp_finish(c, acc, status[c], u, theta, jacobian, lp_out, grad_out, status, apps_out);
+}
+
+// ---- transformed parameters: the rates of every (draw, dependent-variable level) -------------------------------
+// what the `transformed parameters` block stores per draw (multitype_template.stan:105-117, one_type_template.stan:19-27):
+// r_e = f_e(Theta, function_var[v, ]) from the generated rate functions (so Stan's typing quirks are the same as on the
+// likelihood path).  theta: [ndraws][BP_DIM] CONSTRAINED values; fvar: function_var, nlev x ncols column-major; out: [ndraws][nlev][BP_E].
+extern "C" __global__ void bp_tparams(const double* __restrict__ theta, int ndraws, const double* __restrict__ fvar, int nlev, int ncols,
+                                      double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)ndraws * nlev) return;
+  const long long dr = idx / nlev;
+  const int v = (int)(idx - dr * nlev);
+  double th[BP_DIM], xk[BP_KDEP], r[BP_E];
+#pragma unroll
+  for (int k = 0; k < BP_DIM; ++k) th[k] = theta[dr * BP_DIM + k];
+#pragma unroll
+  for (int q = 0; q < BP_KDEP; ++q) xk[q] = q < ncols ? fvar[v + (size_t)nlev * q] : 0.0;
+  bp_rates(th, xk, r);
+#pragma unroll
+  for (int e = 0; e < BP_E; ++e) out[idx * BP_E + e] = r[e];
 }
 #endif  // !BP_HOSTSIM
 

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -72,6 +73,7 @@ static int compile_model(bpc_model* m) {
 }
 
 int model_load(bpc_model* m, int device, Loaded** out) {
+  std::lock_guard<std::mutex> lock(m->load_mu);
   auto it = m->loaded.find(device);
   if (it != m->loaded.end()) { *out = &it->second; return BPC_OK; }
   BPC_CUDA(cudaSetDevice(device));
@@ -80,6 +82,7 @@ int model_load(bpc_model* m, int device, Loaded** out) {
   BPC_CUDA(cudaLibraryGetKernel(&L.prologue, L.lib, "bp_prologue"));
   BPC_CUDA(cudaLibraryGetKernel(&L.epilogue, L.lib, "bp_epilogue"));
   BPC_CUDA(cudaLibraryGetKernel(&L.loglik, L.lib, "bp_loglik"));
+  BPC_CUDA(cudaLibraryGetKernel(&L.tparams, L.lib, "bp_tparams"));
   if (m->spec.kind == BPC_SIMPLE_BD) {
     BPC_CUDA(cudaLibraryGetKernel(&L.obs, L.lib, "bp_onetype"));
     L.obs_smem = 0;
@@ -358,6 +361,13 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
     if (d->var_idx[k] < 1 || d->var_idx[k] > d->ndep_levels) return fail(BPC_E_INVALID, "var_idx out of range [1, ndep_levels]");
     if (!simple && (d->times_idx[k] < 1 || d->times_idx[k] > d->ntimes_unique)) return fail(BPC_E_INVALID, "times_idx out of range [1, ntimes_unique]");
   }
+  // durations must be finite and >= 0 (they are sorted below: a NaN would break the ordering), populations and dependent variables finite
+  for (int k = 0, nt = simple ? N : d->ntimes_unique; k < nt; ++k)
+    if (!std::isfinite(d->times[k]) || d->times[k] < 0.0) return fail(BPC_E_INVALID, "times must be finite and non-negative");
+  for (size_t k = 0, nn = (size_t)N * (simple ? 1 : n); k < nn; ++k)
+    if (!std::isfinite(d->pop_vec[k]) || !std::isfinite(d->init_pop[k])) return fail(BPC_E_INVALID, "pop_vec and init_pop must be finite");
+  for (size_t k = 0, nn = (size_t)d->ndep_levels * d->ndep; k < nn; ++k)
+    if (!std::isfinite(d->function_var[k])) return fail(BPC_E_INVALID, "function_var must be finite");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(BPC_E_CUDA, "no CUDA device available: libbpcuda has no CPU fallback"); }
   if (device < 0 || device >= ndev) return fail(BPC_E_INVALID, "device index out of range");
@@ -412,6 +422,9 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
   if ((rc = up(dd->t, ht.data(), ht.size() * 8))) return rc;
   if ((rc = up(dd->xv, hv.data(), hv.size() * 8))) return rc;
   if ((rc = up(dd->perm, hp.data(), hp.size() * 4))) return rc;
+  if ((rc = up(dd->fvar, d->function_var, (size_t)d->ndep_levels * d->ndep * 8))) return rc;
+  dd->nlev = d->ndep_levels;
+  dd->ncols = d->ndep;
   // groups = runs of equal (level, duration) in the sorted order
   dd->grouped = false;
   dd->wmode = false;
@@ -490,6 +503,7 @@ void bpc_data_free(bpc_data* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   for (auto& ev : d->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (d->ws_event) cudaEventDestroy(d->ws_event);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -581,7 +595,23 @@ static int ensure_workspace(bpc_data* d, int nchains) {
       }
     }
     d->ws_chains = nchains;
+    ++d->ws_gen;
   }
+  return BPC_OK;
+}
+
+// The workspace of a data handle is shared by every entry point that takes the handle.  Every use ends by recording ws_event on
+// the stream it ran on (release_workspace) and begins by making its stream wait for that event (order_workspace): sequential use from
+// one thread on different streams is ordered, also when the earlier stream has been destroyed in the meantime (an event outlives
+// it).  Handles are single-owner and not thread-safe (include/bpcuda.h).  Neither is called while the stream is being captured.
+int order_workspace(bpc_data* d, cudaStream_t st) {
+  if (d->ws_event) BPC_CUDA(cudaStreamWaitEvent(st, d->ws_event, 0));
+  return BPC_OK;
+}
+
+int release_workspace(bpc_data* d, cudaStream_t st) {
+  if (!d->ws_event) BPC_CUDA(cudaEventCreateWithFlags(&d->ws_event, cudaEventDisableTiming));
+  BPC_CUDA(cudaEventRecord(d->ws_event, st));
   return BPC_OK;
 }
 
@@ -614,6 +644,9 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   if (rc) return rc;
   BPC_CUDA(cudaSetDevice(d->device));
   if ((rc = ensure_workspace(d, nchains))) return rc;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (cap == cudaStreamCaptureStatusNone && (rc = order_workspace(d, st))) return rc;
   const ModelSpec& s = m->spec;
   double* theta = (double*)d->theta.p;
   double* part = (double*)d->part.p;
@@ -709,6 +742,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
     BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
   g_launches += own_io ? 1 : 3;
+  if (cap == cudaStreamCaptureStatusNone && (rc = release_workspace(d, st))) return rc;
   return BPC_OK;
 }
 
@@ -788,6 +822,7 @@ int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, dou
   DevBuf ll;
   if ((rc = ll.alloc((size_t)nchains * d->N * 8))) return rc;
   cudaStream_t st = d->stream;
+  if ((rc = order_workspace(d, st))) return rc;
   BPC_CUDA(cudaMemcpyAsync(d->io_u.p, upars, (size_t)nchains * dim * 8, cudaMemcpyHostToDevice, st));
   const double* u_dev = (const double*)d->io_u.p;
   double* theta = (double*)d->theta.p;
@@ -825,6 +860,7 @@ int bpc_moments(bpc_model* m, bpc_data* d, const double* upars, int nchains, dou
   DevBuf out;
   if ((rc = out.alloc((size_t)nchains * d->N * W * 8))) return rc;
   cudaStream_t st = d->stream;
+  if ((rc = order_workspace(d, st))) return rc;
   BPC_CUDA(cudaMemcpyAsync(d->io_u.p, upars, (size_t)nchains * dim * 8, cudaMemcpyHostToDevice, st));
   const double* u_dev = (const double*)d->io_u.p;
   double* theta = (double*)d->theta.p;
@@ -849,6 +885,36 @@ int bpc_moments(bpc_model* m, bpc_data* d, const double* upars, int nchains, dou
   }
   return BPC_OK;
 }
+
+int bpc_transformed_parameters(bpc_model* m, bpc_data* d, const double* theta, int ndraws, double* rates) {
+  if (!m || !d || !theta || !rates || ndraws < 0) return fail(BPC_E_INVALID, "null argument");
+  if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
+  if (ndraws == 0) return BPC_OK;
+  Loaded* L;
+  int rc = model_load(m, d->device, &L);
+  if (rc) return rc;
+  BPC_CUDA(cudaSetDevice(d->device));
+  const ModelSpec& s = m->spec;
+  const size_t nin = (size_t)ndraws * s.dim, nout = (size_t)ndraws * d->nlev * s.nevents;
+  DevBuf in, out;
+  if ((rc = in.alloc(nin * 8))) return rc;
+  if ((rc = out.alloc(nout * 8))) return rc;
+  cudaStream_t st = d->stream;
+  BPC_CUDA(cudaMemcpyAsync(in.p, theta, nin * 8, cudaMemcpyHostToDevice, st));
+  const double* th_dev = (const double*)in.p;
+  const double* fv = (const double*)d->fvar.p;
+  double* o = (double*)out.p;
+  int nlev = d->nlev, ncols = d->ncols;
+  void* args[] = {(void*)&th_dev, (void*)&ndraws, (void*)&fv, (void*)&nlev, (void*)&ncols, (void*)&o};
+  const long long total = (long long)ndraws * nlev;
+  BPC_CUDA(cudaLaunchKernel((const void*)L->tparams, dim3((unsigned)((total + 127) / 128)), dim3(128), args, 0, st));
+  g_launches += 1;
+  BPC_CUDA(cudaMemcpyAsync(rates, out.p, nout * 8, cudaMemcpyDeviceToHost, st));
+  BPC_CUDA(cudaStreamSynchronize(st));
+  return BPC_OK;
+}
+
+int bpc_data_nlevels(const bpc_data* d) { return d ? d->nlev : -1; }
 
 int bpc_flop_model(const bpc_model* m, double* per_app_fwd, double* per_app_bwd, double* per_obs) {
   if (!m || !per_app_fwd || !per_app_bwd || !per_obs) return fail(BPC_E_INVALID, "null argument");

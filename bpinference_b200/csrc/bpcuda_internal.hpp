@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -38,7 +39,7 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr;
   size_t obs_smem = 0, grouped_smem = 0, o_smem = 0;
 };
 
@@ -53,6 +54,7 @@ struct bpc_model {
   std::string source, warnings, compile_log;
   std::vector<char> cubin;
   std::map<int, bpc::Loaded> loaded;
+  std::mutex load_mu;   // bpc_sample_multi loads the module on several devices from several threads
 };
 
 struct CGrouping {   // groups of consecutive chunks of the sorted table that share a series centre
@@ -69,6 +71,8 @@ struct bpc_data {
   int N = 0, npad = 0, ngroups = 0;
   bool grouped = false;
   bpc::DevBuf z0, xo, t, xv, perm;
+  bpc::DevBuf fvar;                 // function_var as handed over (ndep_levels x ndep, column-major): bpc_transformed_parameters
+  int nlev = 1, ncols = 1;
   bpc::DevBuf wpart;   // W path: per-CTA partial sums of the W_j matrices
   bool wmode = false;
   // centred W path (bp_ctable + bp_fusedc): groups of consecutive 32-observation chunks sharing a series centre
@@ -86,8 +90,11 @@ struct bpc_data {
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
   int group_threads = 128;
-  // workspace sized for ws_chains chains
+  // workspace sized for ws_chains chains.  ws_gen counts every re-tiling / reallocation: a sampler that replays a captured CUDA
+  // graph (raw workspace pointers and tiling baked in) compares it with the generation it captured under and re-captures.
   int ws_chains = -1, tile = 0, ntiles = 0;
+  unsigned long long ws_gen = 0;
+  cudaEvent_t ws_event = nullptr;   // recorded at the end of every use of the workspace, waited for at the start of the next
   bpc::DevBuf theta, part, apps;
   bpc::DevBuf io_u, io_lp, io_grad, io_status;
   cudaStream_t stream = nullptr;
@@ -97,6 +104,8 @@ struct bpc_data {
 
 namespace bpc {
 int model_load(bpc_model* m, int device, Loaded** out);
+int order_workspace(bpc_data* d, cudaStream_t st);
+int release_workspace(bpc_data* d, cudaStream_t st);
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
                  double* grad_dev, int* status_dev, cudaStream_t st);
 }  // namespace bpc

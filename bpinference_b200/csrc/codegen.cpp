@@ -65,10 +65,14 @@ void validate_prior(PriorSpec& p) {
   if (d.nparams != p.nparams) throw std::runtime_error("Incorrect number of parameters for prior distribution");
   for (int i = 0; i < d.nparams; ++i)
     if (p.params[i] <= 0 && d.constraints[i] == '+') throw std::runtime_error("Positive parameter required here!");
+  for (int i = 0; i < d.nparams; ++i)
+    if (!std::isfinite(p.params[i])) throw std::runtime_error("prior parameters must be finite numbers");
   if (p.name == "uniform" && p.params[1] <= p.params[0]) throw std::runtime_error("upper bound must be greater than lower in uniform distribution!");
   if (p.has_bounds) {
     if (std::isnan(p.lower) || std::isnan(p.upper)) throw std::runtime_error("bounds should be a list of 2 numbers!");
     if (p.lower >= p.upper) throw std::runtime_error("Error: lower bounder greater or equal to upper bound!");
+    // (the reference pastes the numbers into `real<lower=%s, upper=%s>`, R/stan_utils.R:399: Inf / -Inf do not survive stanc)
+    if (std::isinf(p.lower) || std::isinf(p.upper)) throw std::runtime_error("bounds must be finite numbers (use bounds = NA for an unbounded parameter)");
   }
 }
 

@@ -34,17 +34,17 @@ namespace {
 constexpr int MAXD = 12;        // max tree depth supported
 constexpr int MAXDIM = 32;      // max unconstrained dimension
 
-enum Phase { PH_INIT = 0, PH_FIND_EPS_FIRST = 1, PH_FIND_EPS = 2, PH_NUTS = 3, PH_WAIT = 4, PH_DONE = 5, PH_FAILED = 6 };
+enum Phase { PH_INIT = 0, PH_FIND_EPS_FIRST = 1, PH_FIND_EPS = 2, PH_NUTS = 3, PH_WAIT = 4, PH_DONE = 5, PH_FAILED = 6, PH_OPT = 7 };
 
 // scalar double fields
-enum { S_EPS, S_LP_CUR, S_H0, S_LSW, S_SUB_LSW, S_SUM_ACC, S_DA_MU, S_DA_SBAR, S_DA_XBAR, S_DA_CNT, S_LP_PROP, S_LP_SP, S_W_N, S_NLEAP_TOT, NSCAL };
+enum { S_EPS, S_LP_CUR, S_H0, S_LSW, S_SUB_LSW, S_SUM_ACC, S_DA_MU, S_DA_SBAR, S_DA_XBAR, S_DA_CNT, S_LP_PROP, S_LP_SP, S_W_N, S_NLEAP_TOT, S_OPT_LR, NSCAL };
 // vector double fields (dim each)
 enum { V_Q_CUR, V_G_CUR, V_QL, V_PL, V_GL, V_QR, V_PR, V_GR, V_Q_PROP, V_G_PROP, V_Q_SP, V_G_SP, V_RHO, V_RHO_SUB, V_MINV, V_W_MEAN, V_W_M2, NVEC };
 // int fields
 enum { I_PHASE, I_ITER, I_DEPTH, I_NLEAP, I_DIR, I_LEAF, I_DIVERGENT, I_FE_DIR, I_WIN_NEXT, I_WIN_SIZE, I_WIN_COUNTER, I_TRIES, I_RNG, NINT };
 
 struct Params {
-  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits;
+  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits, opt_steps;
   int init_buffer, term_buffer, base_window;
   double delta, eps0;
   unsigned long long seed;
@@ -323,6 +323,68 @@ __device__ void end_transition(const Chain& ch) {
   begin_transition(ch);
 }
 
+// ---- optional climb from the initial point (bpc_sample_args.init_opt_steps) ---------------------------------------------
+// rstan starts NUTS at the initial values.  With 10^5 observations the posterior is three or four orders of magnitude narrower
+// than the range initial values are drawn from (uniform_initialize(0, 1), R/stan_utils.R:74-87, or rstan's uniform(-2, 2)); far
+// out there the generator norm is large, every evaluation needs sub-steps (the slow path), and the first NUTS iterations are long
+// trees of tiny steps.  So, when asked to, every chain first takes init_opt_steps steps of a monotone Adam ascent on the
+// unconstrained log density (normalised steps of size lr per coordinate; a step that does not improve lp is rejected, halves lr
+// and resets the momentum; an accepted one grows lr by 1.2 up to 0.5), using the same fused log-density + gradient passes.
+// State: V_PL = first moment, V_PR = second moment, I_LEAF = steps taken, I_NLEAP = accepted steps, S_OPT_LR = lr.
+__device__ void opt_propose(const Chain& ch) {
+  const int dim = ch.P.dim;
+  const double lr = ch.s(S_OPT_LR);
+  const int t = ch.i(I_NLEAP) + 1;
+  const double b1 = 0.8, b2 = 0.99;
+  const double c1 = 1.0 - pow(b1, (double)t), c2 = 1.0 - pow(b2, (double)t);
+  for (int k = 0; k < dim; ++k) {
+    const double g = ch.v(V_G_CUR, k);
+    const double m = b1 * ch.v(V_PL, k) + (1.0 - b1) * g, v = b2 * ch.v(V_PR, k) + (1.0 - b2) * g * g;
+    ch.v(V_QL, k) = m; ch.v(V_QR, k) = v;            // tentative moments: committed when the step is accepted
+    const double den = sqrt(v / c2);
+    const double step = den > 0.0 ? lr * (m / c1) / den : 0.0;
+    ch.P.q_eval[(size_t)ch.c * dim + k] = ch.v(V_Q_CUR, k) + step;
+  }
+}
+
+__device__ void begin_opt(const Chain& ch) {
+  for (int k = 0; k < ch.P.dim; ++k) { ch.v(V_PL, k) = 0.0; ch.v(V_PR, k) = 0.0; }
+  ch.s(S_OPT_LR) = 0.25;
+  ch.i(I_LEAF) = 0;
+  ch.i(I_NLEAP) = 0;
+  ch.i(I_PHASE) = PH_OPT;
+  opt_propose(ch);
+}
+
+__device__ void opt_step(const Chain& ch) {
+  const Params& P = ch.P;
+  const int dim = P.dim, c = ch.c;
+  const double lp = P.st_eval[c] ? -INFINITY : P.lp_eval[c];
+  bool ok = isfinite(lp) && lp > ch.s(S_LP_CUR);
+  for (int k = 0; k < dim; ++k) ok = ok && isfinite(P.g_eval[(size_t)c * dim + k]);
+  if (ok) {
+    for (int k = 0; k < dim; ++k) {
+      ch.v(V_Q_CUR, k) = P.q_eval[(size_t)c * dim + k]; ch.v(V_G_CUR, k) = P.g_eval[(size_t)c * dim + k];
+      ch.v(V_PL, k) = ch.v(V_QL, k); ch.v(V_PR, k) = ch.v(V_QR, k);
+    }
+    ch.s(S_LP_CUR) = lp;
+    ch.s(S_OPT_LR) = fmin(0.5, 1.2 * ch.s(S_OPT_LR));
+    ch.i(I_NLEAP) += 1;
+  } else {
+    ch.s(S_OPT_LR) *= 0.5;
+    for (int k = 0; k < dim; ++k) ch.v(V_PL, k) = 0.0;
+  }
+  const int step = ch.i(I_LEAF) + 1;
+  ch.i(I_LEAF) = step;
+  if (step >= P.opt_steps || ch.s(S_OPT_LR) < 1e-7) {
+    ch.i(I_NLEAP) = 0;
+    ch.i(I_FE_DIR) = 0;
+    begin_eps_trial(ch, PH_FIND_EPS_FIRST);
+    return;
+  }
+  opt_propose(ch);
+}
+
 // One chain per WARP (lane 0 works): the chains of a pass are at different points of their state machines, and 32 of them in one
 // warp execute the union of all the paths taken, one after the other; alone in its warp a chain executes its own path only, and
 // the 8 x more blocks spread over the SMs.
@@ -347,10 +409,13 @@ __global__ void bp_nuts_advance(Params P) {
     }
     for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = P.q_eval[(size_t)c * dim + k]; ch.v(V_G_CUR, k) = P.g_eval[(size_t)c * dim + k]; }
     ch.s(S_LP_CUR) = lp;
+    if (P.opt_steps > 0) { begin_opt(ch); return; }
     ch.i(I_FE_DIR) = 0;
     begin_eps_trial(ch, PH_FIND_EPS_FIRST);
     return;
   }
+
+  if (phase == PH_OPT) { opt_step(ch); return; }
 
   if (phase == PH_FIND_EPS_FIRST || phase == PH_FIND_EPS) {
     double lp_new;
@@ -498,8 +563,9 @@ __global__ void bp_nuts_init(Params P, const double* __restrict__ inits_u) {
 }
 
 // pooled adaptation: this rank's (count, sum q, sum q^2) over the window of all its chains, fixed order
-__global__ void bp_pool_stats(Params P, double* __restrict__ out) {
-  const int k = threadIdx.x;   // 0 .. 2*dim
+__global__ void bp_pool_stats(Params P, double* __restrict__ out, int with_flag) {
+  const int k = threadIdx.x;   // 0 .. 2*dim (+ 1: this rank's "all chains finished" flag)
+  if (k == 2 * P.dim + 1 && with_flag) { out[k] = P.counters[0] >= P.C ? 1.0 : 0.0; return; }
   if (k > 2 * P.dim) return;
   double acc = 0.0;
   for (int c = 0; c < P.C; ++c) {
@@ -536,22 +602,29 @@ __global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
   begin_eps_trial(ch, PH_FIND_EPS_FIRST);
 }
 
-// per-dimension sums over this rank's chains of (1, chain mean, chain mean^2, chain variance) of the saved draws
+// per-dimension sums over this rank's chains of (1, mean, mean^2, variance) of the saved draws of every HALF chain: rstan's summary
+// Rhat (the number check_rhat reads, R/stan_utils.R:516-533) is split R-hat -- each chain is cut in two halves of floor(ns / 2)
+// draws (the middle draw of an odd count is dropped) and the halves are treated as chains [recalled from Stan's chains.hpp /
+// rstan 2.19 `split_potential_scale_reduction`; not checkable here].  With fewer than 4 saved draws the chain is not split.
 __global__ void bp_chain_moments(Params P, double* __restrict__ out) {
   const int k = threadIdx.x;
   if (k >= P.dim) return;
   const int ns = P.iter - P.warmup;
+  const int nh = ns >= 4 ? ns / 2 : ns, nhalves = ns >= 4 ? 2 : 1;
   double cnt = 0.0, sm = 0.0, sm2 = 0.0, sv = 0.0;
   for (int c = 0; c < P.C; ++c) {
     if (P.si[(size_t)I_PHASE * P.C + c] == PH_FAILED) continue;
-    double mean = 0.0, m2 = 0.0;
-    for (int i = 0; i < ns; ++i) {
-      const double x = P.draws[((size_t)c * ns + i) * P.dim + k];
-      const double d = x - mean;
-      mean += d / (i + 1);
-      m2 += d * (x - mean);
+    for (int hf = 0; hf < nhalves; ++hf) {
+      const int i0 = hf == 0 ? 0 : ns - nh;
+      double mean = 0.0, m2 = 0.0;
+      for (int i = 0; i < nh; ++i) {
+        const double x = P.draws[((size_t)c * ns + i0 + i) * P.dim + k];
+        const double d = x - mean;
+        mean += d / (i + 1);
+        m2 += d * (x - mean);
+      }
+      cnt += 1.0; sm += mean; sm2 += mean * mean; sv += nh > 1 ? m2 / (nh - 1) : 0.0;
     }
-    cnt += 1.0; sm += mean; sm2 += mean * mean; sv += ns > 1 ? m2 / (ns - 1) : 0.0;
   }
   out[4 * k + 0] = cnt; out[4 * k + 1] = sm; out[4 * k + 2] = sm2; out[4 * k + 3] = sv;
 }
@@ -570,6 +643,7 @@ struct bpc_sampler {
   cudaGraphExec_t graph_exec = nullptr; // small problems is launch latency, not arithmetic
   bool graph_tried = false;
   int graph_launches = 0;               // kernels of one replay
+  unsigned long long graph_ws_gen = 0;  // generation of the data handle's workspace the graph was captured under
   bool trace = std::getenv("BPC_SAMPLER_TRACE") != nullptr;
   std::chrono::steady_clock::time_point trace_t0 = std::chrono::steady_clock::now();
 };
@@ -594,6 +668,7 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   P.max_depth = a->max_treedepth; P.iter = a->iter; P.warmup = a->warmup; P.chain_offset = a->chain_id_offset;
   P.pooled = a->pooled_adaptation ? 1 : 0; P.have_inits = a->inits ? 1 : 0;
   P.delta = a->adapt_delta; P.eps0 = a->stepsize > 0 ? a->stepsize : 1.0; P.seed = a->seed;
+  P.opt_steps = a->init_opt_steps > 0 ? a->init_opt_steps : 0;
   // Stan's window schedule (windowed_adaptation): 75 / 25 / 50, rescaled to 15% / 75% / 10% for short warm-ups
   P.init_buffer = 75; P.term_buffer = 50; P.base_window = 25;
   if (P.warmup < 20) { P.init_buffer = P.warmup; P.term_buffer = 0; P.base_window = 0; }   // no metric adaptation
@@ -610,7 +685,7 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   AL(q_eval, C * dim * 8); AL(lp_eval, C * 8); AL(g_eval, C * dim * 8); AL(st_eval, C * 4);
   AL(draws, C * ns * dim * 8); AL(d_lp, C * ns * 8); AL(d_acc, C * ns * 8); AL(d_eps, C * ns * 8);
   AL(d_depth, C * ns * 4); AL(d_nleap, C * ns * 4); AL(d_div, C * ns * 4);
-  AL(counters, 16); AL(pool, (1 + 2 * dim) * 8); AL(moments, 4 * dim * 8);
+  AL(counters, 16); AL(pool, (2 + 2 * dim) * 8); AL(moments, 4 * dim * 8);
 #undef AL
   P.sd = (double*)s->sd.p; P.si = (int*)s->si.p; P.q_eval = (double*)s->q_eval.p; P.lp_eval = (double*)s->lp_eval.p;
   P.g_eval = (double*)s->g_eval.p; P.st_eval = (int*)s->st_eval.p; P.draws = (double*)s->draws.p; P.d_lp = (double*)s->d_lp.p;
@@ -618,6 +693,7 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   P.d_div = (int*)s->d_div.p; P.counters = (int*)s->counters.p;
   if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaMallocHost(&s->h_counters, 16)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+  for (int i = 0; i < 4; ++i) s->h_counters[i] = 0;
   cudaMemsetAsync(s->sd.p, 0, s->sd.cap, s->stream);
   cudaMemsetAsync(s->counters.p, 0, 16, s->stream);
   cudaMemsetAsync(s->draws.p, 0, C * ns * dim * 8, s->stream);
@@ -670,13 +746,25 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
   if ((e = cudaSetDevice(s->d->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   const Params& P = s->P;
   *state = 0;
+  if (s->h_counters[0] >= P.C) { *state = 1; return BPC_OK; }   // (last poll: every chain has finished; nothing left to run)
   long long done_passes = 0;
   // poll the finished / waiting counters every POLL passes: cheap for large problems, and for small ones the
   // polling interval bounds the tail of idle passes
   const int POLL = 16;
+  // The data handle's workspace is shared with every other entry point that takes the handle (bpc_log_prob, bpc_log_lik,
+  // bpc_moments, ...): if one of them re-tiled or reallocated it since the graph was captured, the graph's baked-in pointers and
+  // tiling are stale -- drop it, run a block eagerly (which rebuilds the workspace for this chain count) and capture again.  And if
+  // the workspace was last used on another stream, wait for that work before touching it.
+  if (s->graph_exec && s->graph_ws_gen != s->d->ws_gen) {
+    cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr;
+    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+    s->graph_tried = false;
+  }
+  { const int rc = order_workspace(s->d, s->stream); if (rc) return rc; }
+  bool eager_block_done = s->graph_exec != nullptr;   // a block must run eagerly under the current workspace before a capture
   while (done_passes < max_passes) {
     const int nb = (int)std::min<long long>(POLL, max_passes - done_passes);
-    if (nb == POLL && s->passes >= POLL && !s->graph_tried) {
+    if (nb == POLL && s->passes >= POLL && !s->graph_tried && eager_block_done && s->d->ws_chains == P.C) {
       // the first block ran eagerly (module load, workspace allocation); capture the next one and replay it from now on
       s->graph_tried = true;
       if (!getenv("BPC_NO_GRAPH") && cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -686,7 +774,7 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
         const cudaError_t ec = cudaStreamEndCapture(s->stream, &g);
         s->graph_launches = (int)(g_launches - before);
         g_launches = before;   // nothing ran during capture
-        if (rc == BPC_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&s->graph_exec, g, 0) == cudaSuccess) s->graph = g;
+        if (rc == BPC_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&s->graph_exec, g, 0) == cudaSuccess) { s->graph = g; s->graph_ws_gen = s->d->ws_gen; }
         else { if (g) cudaGraphDestroy(g); s->graph_exec = nullptr; cudaGetLastError(); }
       }
     }
@@ -696,6 +784,7 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
     } else {
       const int rc = sampler_passes(s, nb);
       if (rc) return rc;
+      eager_block_done = true;
     }
     done_passes += nb;
     s->passes += nb;
@@ -708,17 +797,17 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
     }
     if ((e = cudaMemcpyAsync(s->h_counters, P.counters, 12, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync");
     if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cuda_fail(e, "sampler pass");
-    if (s->h_counters[0] >= P.C) { *state = 1; return BPC_OK; }
-    if (P.pooled && s->h_counters[0] + s->h_counters[1] >= P.C && s->h_counters[1] > 0) { *state = 2; return BPC_OK; }
+    if (s->h_counters[0] >= P.C) { *state = 1; break; }
+    if (P.pooled && s->h_counters[0] + s->h_counters[1] >= P.C && s->h_counters[1] > 0) { *state = 2; break; }
   }
-  return BPC_OK;
+  return release_workspace(s->d, s->stream);   // (graph replays do not pass through log_prob_dev's own record)
 }
 
 int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count) {
   if (!s) return fail(BPC_E_INVALID, "null argument");
   if (stats_dev && count < 1 + 2 * s->P.dim) return fail(BPC_E_INVALID, "stats buffer too small: need 1 + 2*dim doubles");
   cudaSetDevice(s->d->device);
-  bp_pool_stats<<<1, 2 * MAXDIM + 32, 0, s->stream>>>(s->P, stats_dev ? stats_dev : (double*)s->pool.p);
+  bp_pool_stats<<<1, 2 * MAXDIM + 32, 0, s->stream>>>(s->P, stats_dev ? stats_dev : (double*)s->pool.p, (!stats_dev || count >= 2 + 2 * s->P.dim) ? 1 : 0);
   g_launches += 1;
   cudaError_t e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "bp_pool_stats");
@@ -768,8 +857,9 @@ int bpc_sampler_chain_moments(bpc_sampler* s, double* stats_dev, int count, doub
   return BPC_OK;
 }
 
-int bpc_rhat(const double* red, int dim, int n, double* rhat) {
-  if (!red || !rhat || dim < 1 || n < 2) return fail(BPC_E_INVALID, "bad argument");
+int bpc_rhat(const double* red, int dim, int draws_per_chain, double* rhat) {
+  if (!red || !rhat || dim < 1 || draws_per_chain < 2) return fail(BPC_E_INVALID, "bad argument");
+  const int n = draws_per_chain >= 4 ? draws_per_chain / 2 : draws_per_chain;   // length of the half chains the moments are of
   for (int k = 0; k < dim; ++k) {
     const double m = red[4 * k], sm = red[4 * k + 1], sm2 = red[4 * k + 2], sv = red[4 * k + 3];
     if (m < 2) { rhat[k] = std::nan(""); continue; }
@@ -793,6 +883,21 @@ long long bpc_sampler_total_leapfrogs(bpc_sampler* s) {
 }
 
 long long bpc_sampler_passes(const bpc_sampler* s) { return s ? s->passes : 0; }
+
+int bpc_sampler_progress(bpc_sampler* s, int* iter, double* stepsize, double* lp, int* phase) {
+  if (!s) return fail(BPC_E_INVALID, "null argument");
+  cudaSetDevice(s->d->device);
+  cudaStreamSynchronize(s->stream);
+  const size_t C = s->P.C;
+  cudaError_t e = cudaSuccess;
+  auto cp = [&](void* dst, const void* src, size_t bytes) { if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+  cp(iter, s->P.si + (size_t)I_ITER * C, C * 4);
+  cp(phase, s->P.si + (size_t)I_PHASE * C, C * 4);
+  cp(stepsize, s->P.sd + (size_t)S_EPS * C, C * 8);
+  cp(lp, s->P.sd + (size_t)S_LP_CUR * C, C * 8);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return BPC_OK;
+}
 
 int bpc_sample(bpc_model* m, bpc_data* d, const bpc_sample_args* a, double* draws, double* lp, int* divergent, int* treedepth,
                int* n_leapfrog, double* accept_stat, double* stepsize) {

@@ -26,26 +26,32 @@ def _f64(a, order="C"):
     return np.require(np.asarray(a, dtype=np.float64), requirements=["C" if order == "C" else "F", "A"])
 
 
+def _stan_data_struct(engine: "BpCudaModel", dat: dict):
+    """the Stan data list as the bpc_stan_data struct of include/bpcuda.h (+ the arrays it points into, to be kept alive)."""
+    simple = engine.kind == _ffi.SIMPLE_BD
+    N = int(dat["ndatapts"])
+    n = engine.ntypes
+    pop = np.asfortranarray(_f64(dat["pop_vec"]).reshape(N, n) if not simple else _f64(dat["pop_vec"]).reshape(N, 1))
+    init = np.asfortranarray(_f64(dat["init_pop"]).reshape(N, n) if not simple else _f64(dat["init_pop"]).reshape(N, 1))
+    times = _f64(np.atleast_1d(dat["times"])).ravel()
+    fv = np.asfortranarray(_f64(dat["function_var"]).reshape(int(dat["ndep_levels"]), int(dat["ndep"])))
+    vi = np.ascontiguousarray(np.asarray(dat["var_idx"], dtype=np.int32))
+    ti = None if simple else np.ascontiguousarray(np.asarray(dat["times_idx"], dtype=np.int32))
+    if simple and len(times) != N:
+        raise ValueError("times, initial populations, and final populations must all have same number of rows!")
+    sd = _ffi.StanData(N, 0 if simple else len(times), int(dat["ndep_levels"]), int(dat["ndep"]),
+                       _ffi.dptr(pop), _ffi.dptr(init), _ffi.dptr(times), None if simple else _ffi.iptr(ti), _ffi.dptr(fv), _ffi.iptr(vi))
+    return sd, (pop, init, times, fv, vi, ti)
+
+
 class StanData:
     """device copy of one Stan data list (bpc_data handle)."""
 
     def __init__(self, engine: "BpCudaModel", dat: dict, device: int = 0, grouping: int = 0):
         self.engine = engine
         L = _ffi.lib()
-        simple = engine.kind == _ffi.SIMPLE_BD
         N = int(dat["ndatapts"])
-        n = engine.ntypes
-        pop = np.asfortranarray(_f64(dat["pop_vec"]).reshape(N, n) if not simple else _f64(dat["pop_vec"]).reshape(N, 1))
-        init = np.asfortranarray(_f64(dat["init_pop"]).reshape(N, n) if not simple else _f64(dat["init_pop"]).reshape(N, 1))
-        times = _f64(np.atleast_1d(dat["times"])).ravel()
-        fv = np.asfortranarray(_f64(dat["function_var"]).reshape(int(dat["ndep_levels"]), int(dat["ndep"])))
-        vi = np.ascontiguousarray(np.asarray(dat["var_idx"], dtype=np.int32))
-        ti = None if simple else np.ascontiguousarray(np.asarray(dat["times_idx"], dtype=np.int32))
-        if simple and len(times) != N:
-            raise ValueError("times, initial populations, and final populations must all have same number of rows!")
-        sd = _ffi.StanData(N, 0 if simple else len(times), int(dat["ndep_levels"]), int(dat["ndep"]),
-                           _ffi.dptr(pop), _ffi.dptr(init), _ffi.dptr(times), None if simple else _ffi.iptr(ti), _ffi.dptr(fv), _ffi.iptr(vi))
-        self._keep = (pop, init, times, fv, vi, ti)
+        sd, self._keep = _stan_data_struct(engine, dat)
         self.handle = C.c_void_p()
         _ffi.check(L.bpc_data_create(engine.handle, C.byref(sd), int(device), int(grouping), C.byref(self.handle)))
         self.ndatapts = N
@@ -138,6 +144,9 @@ class BpCudaModel:
     def data(self, dat: dict, device: int = 0, grouping: int = 0) -> StanData:
         return StanData(self, dat, device, grouping)
 
+    def stan_data_struct(self, dat: dict):
+        return _stan_data_struct(self, dat)
+
     def _data(self, dat) -> StanData:
         return dat if isinstance(dat, StanData) else StanData(self, dat)
 
@@ -205,11 +214,18 @@ class BpCudaModel:
         return out[0] if np.ndim(theta) == 1 else out
 
     def sampling(self, dat, chains: int = 4, iter: int = 2000, warmup=None, init="random", control=None, seed: int = 1,
-                 pooled_adaptation: bool = False, device=None):
+                 pooled_adaptation: bool = False, device=None, loo: bool = False, init_opt_steps: int = 0):
         """rstan::sampling — see bpinference_b200.fit.sampling."""
         from .fit import sampling
         return sampling(self, dat, chains=chains, iter=iter, warmup=warmup, init=init, control=control, seed=seed,
-                        pooled_adaptation=pooled_adaptation, device=device)
+                        pooled_adaptation=pooled_adaptation, device=device, loo=loo, init_opt_steps=init_opt_steps)
+
+    def sampling_multi(self, dat, devices, chains: int = 4, iter: int = 2000, warmup=None, init="random", control=None, seed: int = 1,
+                       pooled_adaptation: bool = False, init_opt_steps: int = 0):
+        """the same run over several GPUs of this process (bpc_sample_multi) — see bpinference_b200.fit.sampling_multi."""
+        from .fit import sampling_multi
+        return sampling_multi(self, dat, devices, chains=chains, iter=iter, warmup=warmup, init=init, control=control, seed=seed,
+                              pooled_adaptation=pooled_adaptation, init_opt_steps=init_opt_steps)
 
     def flops_per_chain(self, dat, upars):
         d = self._data(dat)
@@ -240,3 +256,10 @@ def fp64_peak(device: int = 0, ms: float = 200.0):
     t, c = C.c_double(), C.c_double()
     _ffi.check(_ffi.lib().bpc_fp64_peak(device, ms, C.byref(t), C.byref(c)))
     return t.value, c.value
+
+
+def fp64_tensor_peak(device: int = 0, ms: float = 200.0):
+    """TFLOP/s of a register-resident DMMA (mma.sync m8n8k4 f64) loop on `device`."""
+    t = C.c_double()
+    _ffi.check(_ffi.lib().bpc_fp64_tensor_peak(device, ms, C.byref(t)))
+    return t.value

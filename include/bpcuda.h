@@ -20,6 +20,11 @@
  *   - per-chain arrays are chain-major: upars[c*dim + k].
  *   - pointers named *_dev are device pointers on the handle's device; all others
  *     are host pointers.
+ *   - handles are NOT thread-safe and a data handle has ONE owner at a time: its device workspace is
+ *     shared by every entry point that takes it (bpc_log_prob*, bpc_log_lik, bpc_moments, a sampler
+ *     created on it).  Sequential use from one thread is safe in any order, also across streams and
+ *     chain counts (a sampler notices that its workspace was re-tiled and rebuilds its CUDA graph);
+ *     concurrent use from two threads, or two samplers advancing on one data handle, is not.
  * ============================================================================= */
 #ifndef BPCUDA_H
 #define BPCUDA_H
@@ -28,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BPC_ABI_VERSION 1
+#define BPC_ABI_VERSION 2   /* 2: bpc_sample_args.init_opt_steps; pool buffers carry a trailing "rank finished" flag */
 
 /* error codes */
 enum {
@@ -111,6 +116,9 @@ int bpc_device_count(void);
 /* measured FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA); a register-resident DFMA loop
  * run for `ms` milliseconds.  This is the roofline denominator SURVEY.md §8(d) asks the builder to measure. */
 int bpc_fp64_peak(int device, double ms, double* tflops, double* sm_clock_mhz);
+/* the same for the fp64 tensor path (mma.sync m8n8k4 f64 = DMMA, which shares the FP64 datapath with DFMA on this part): the
+ * denominator for the kernels whose flops are mostly DMMA (bp_fusedo, bp_fusedc, bp_fusedw, bp_toep) */
+int bpc_fp64_tensor_peak(int device, double ms, double* tflops);
 
 /* ---- expression front end: replaces exp_to_stan / check_valid (R/stan_utils.R:205-364) ------ */
 /* validates one rate expression; on failure returns BPC_E_EXPR and bpc_last_error() is the text of the
@@ -163,12 +171,20 @@ int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nch
                      double* lp_dev, double* grad_dev, int* status_dev, void* stream);
 /* per-observation log_lik with normalising constants: the generated-quantities LOO blocks
  * (stanfiles/multitype_loo_block.stan:31, simple_birth_death_loo_block.stan:11).
- * log_lik: nchains x ndatapts, observation order = the order of the data list. */
+ * log_lik: nchains x ndatapts, observation order = the order of the data list.  As in the reference, the noise template gets
+ * the same block (R/stan_utils.R:189-191): its log_lik has no sigma_obs term.  NaN where the density does not exist. */
 int bpc_log_lik(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* log_lik);
 /* mean vector and covariance matrix of the final population of every (chain, observation): what
  * calculate_moments returns (R/calculate_moments.R:11-88: mu_mat, sigma_mat) for the rates the chain's parameters imply.
  * mu: nchains x ndatapts x ntypes; sigma: nchains x ndatapts x ntypes x ntypes (row-major), data-list order. */
 int bpc_moments(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* mu, double* sigma);
+/* the `transformed parameters` of the templates (multitype_template.stan:105-117, one_type_template.stan:19-27) for `ndraws`
+ * CONSTRAINED parameter vectors theta [ndraws x dim]: rates[(draw * ndep_levels + v) * nevents + e] = f_e(Theta, function_var[v, ]),
+ * evaluated on the device by the model's generated rate functions.  r_mat and theta[i] of the stanfit are these numbers laid
+ * out by the caller (bpinference_b200/fit.py, r-package/R/bpcuda.R): r_mat[e, p_vec[e]] of the LAST level, theta[i] =
+ * c(e_mat, r_mat of level i). */
+int bpc_transformed_parameters(bpc_model* m, bpc_data* d, const double* theta, int ndraws, double* rates);
+int bpc_data_nlevels(const bpc_data* d);   /* ndep_levels of the data list */
 /* constrained values: Theta [nchains x nparams] (+ sigma_obs) from unconstrained upars, and back */
 int bpc_constrain(const bpc_model* m, const double* upars, int nchains, double* theta);
 int bpc_unconstrain(const bpc_model* m, const double* theta, int nchains, double* upars);
@@ -204,6 +220,10 @@ typedef struct {
   int pooled_adaptation; /* 0: every chain adapts its own metric (rstan).  1: the metric of each warm-up window is estimated from
                             the draws of all chains of all ranks — the one collective on the path (see bpc_sampler_pool_*) */
   double stepsize;       /* initial step size (0 = 1.0 as rstan) */
+  int init_opt_steps;    /* 0: NUTS starts at the initial values (rstan).  > 0: every chain first climbs from its initial value with at
+                            most this many steps of a monotone Adam ascent on the unconstrained log density, using the same fused
+                            log-density + gradient passes (for data whose posterior is orders of magnitude narrower than the range the
+                            initial values are drawn from: uniform_initialize(0, 1) against a posterior sd of 1e-3 with 1e5 observations) */
 } bpc_sample_args;
 
 int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_sampler** out);
@@ -213,25 +233,46 @@ void bpc_sampler_free(bpc_sampler* s);
 int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state);
 /* pooled adaptation, state 2: bpc_sampler_pool_stats writes this rank's sums (count, sum q_k, sum q_k^2; 1 + 2*dim doubles)
  * into the caller's DEVICE buffer stats_dev; the caller adds the buffers of all ranks in place (ncclAllReduce /
- * torch.distributed.all_reduce) and hands the result to bpc_sampler_pool_apply.  On one rank both pointers may be
- * NULL: an internal buffer is used. */
+ * torch.distributed.all_reduce) and hands the result to bpc_sampler_pool_apply.  With count >= 2 + 2*dim the entry after the sums
+ * is 1.0 when every chain of this rank has finished (or failed) and 0.0 otherwise: its sum over ranks equals the number of ranks
+ * exactly when the whole run is over.  The protocol that cannot deadlock: every rank calls stats + all-reduce each time its
+ * bpc_sampler_run returns (state 1 or 2), applies the result when its state was 2, and leaves when the flag sum says everybody is
+ * done -- a finished rank keeps contributing zeros.  On one rank both pointers may be NULL: an internal buffer is used. */
 int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count);
 int bpc_sampler_pool_apply(bpc_sampler* s, const double* reduced_dev);
 /* results (host copies).  draws: chains x (iter - warmup) x dim CONSTRAINED values (Theta1..P, sigma_obs);
  * lp: lp__ ; per-draw sampler parameters as rstan::get_sampler_params reports them.  Any pointer may be NULL. */
 int bpc_sampler_draws(bpc_sampler* s, double* draws, double* lp, int* divergent, int* treedepth,
                       int* n_leapfrog, double* accept_stat, double* stepsize);
-/* sums for cross-chain convergence diagnostics: for every dimension (count of chains, sum of chain means, sum of
- * squared chain means, sum of chain variances) of the saved draws, 4*dim doubles, written to the caller's device
- * buffer (to be added over ranks) and/or to a host buffer; either may be NULL.  Then bpc_rhat. */
+/* sums for cross-chain convergence diagnostics: for every dimension (count, sum of means, sum of squared means, sum of
+ * variances) over the HALF chains of the saved draws (split R-hat, as rstan's summary reports it), 4*dim doubles, written to
+ * the caller's device buffer (to be added over ranks) and/or to a host buffer; either may be NULL.  Then bpc_rhat. */
 int bpc_sampler_chain_moments(bpc_sampler* s, double* stats_dev, int count, double* stats_host);
-/* potential scale reduction (the statistic check_rhat reads, R/stan_utils.R:516-533) from the reduced sums */
+/* split potential scale reduction (the statistic check_rhat reads, R/stan_utils.R:516-533) from the reduced sums */
 int bpc_rhat(const double* reduced_moments, int dim, int draws_per_chain, double* rhat);
 long long bpc_sampler_total_leapfrogs(bpc_sampler* s);
 long long bpc_sampler_passes(const bpc_sampler* s);
+/* where every chain is (what rstan's `refresh` prints): iterations completed, current step size, lp__ of the current point and the
+ * state-machine phase (0 initialising, 1-2 step-size search, 3 sampling, 4 waiting at a pooled window, 5 finished, 6 failed,
+ * 7 optimising its initial point).  Host arrays of `chains` entries; any pointer may be NULL. */
+int bpc_sampler_progress(bpc_sampler* s, int* iter, double* stepsize, double* lp, int* phase);
 /* convenience: whole run on one device, single rank */
 int bpc_sample(bpc_model* m, bpc_data* d, const bpc_sample_args* a, double* draws, double* lp,
                int* divergent, int* treedepth, int* n_leapfrog, double* accept_stat, double* stepsize);
+
+/* the same run on SEVERAL devices of this process (SURVEY.md §8(b) threading, §8(e)): `a->chains` chains on each of the `ndev`
+ * devices listed (global chain ids a->chain_id_offset + device_index * chains + c), the data list and the module replicated, one
+ * host thread per device, and one single-process NCCL communicator (ncclCommInitAll; NCCL is bound at run time) for the two
+ * exchanges of the path: the pooled warm-up statistics (when a->pooled_adaptation) and the half-chain moments behind split R-hat.
+ * Replaces `options(mc.cores = parallel::detectCores())` + `rstan::sampling(..., chains =)` (examples/two_type.R:20,26) for a
+ * single-process caller such as R.  a->inits, when given, holds ndev * chains rows.  Outputs hold ndev * chains chains, device-major,
+ * laid out as for bpc_sample; rhat [dim] (split R-hat over all chains) and info [4] (passes of the slowest device, leapfrogs of all
+ * chains, exchanges over NCCL, NCCL version code) may be NULL. */
+int bpc_sample_multi(bpc_model* m, const bpc_stan_data* data, const int* devices, int ndev, const bpc_sample_args* a, double* draws,
+                     double* lp, int* divergent, int* treedepth, int* n_leapfrog, double* accept_stat, double* stepsize, double* rhat,
+                     long long* info);
+/* version code of the NCCL library bpc_sample_multi binds (e.g. 22703), 0 when none can be loaded */
+int bpc_nccl_version(void);
 
 /* ---- simulate: replaces bp() / bpsims() (R/simulation.R:9-56, 69-131) -------------------------- */
 /* Gillespie simulation of `nrep` replicates on the device (Philox); pops: nrep x ntimes x ntypes. */

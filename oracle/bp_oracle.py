@@ -511,6 +511,91 @@ def mu_sigma(e_mat, p_vec, r, z0, t):
     return M.T @ z0, np.einsum("l,lij->ij", z0, V)
 
 
+
+def log_lik(model: OracleModel, data: dict, upars: np.ndarray) -> np.ndarray:
+    """per-observation log_lik [C, ndatapts] in the order of the data list, WITH the normalising constants: the
+    generated-quantities blocks stanfiles/multitype_loo_block.stan:15-32 (`multi_normal_lpdf(pop_vec[k] | mu_t, sigma_t)`) and
+    simple_birth_death_loo_block.stan:3-12 (`normal_lpdf(pop_vec[k] | mu, sigma)`), which generate(..., loo = T) appends
+    (R/stan_utils.R:173-175,189-191).  Literal restatement, one observation at a time, SciPy densities.
+
+    Reference quirk kept: generate() appends the SAME multitype LOO block to the noise template (R/stan_utils.R:189-191), and that
+    block builds sigma_t without the sigma_obs * diag(mu_t) term of multitype_noise_template.stan:153 — so log_lik of a noise model
+    is the noise-free multi_normal density."""
+    from scipy import stats
+    u = np.atleast_2d(_f(upars))
+    C = u.shape[0]
+    theta, sig, *_ = constrain(model, u)
+    r, _ = rates(model, theta, data["function_var"])
+    N = int(data["ndatapts"])
+    vi = _i(data["var_idx"]) - 1
+    out = np.full((C, N), np.nan)
+    if model.kind == "simple_bd":
+        pv, ip, tm = _f(data["pop_vec"]).ravel(), _f(data["init_pop"]).ravel(), _f(data["times"]).ravel()
+        for c in range(C):
+            b, d = r[c, vi, 0], r[c, vi, 1]
+            with np.errstate(all="ignore"):
+                e = np.exp(tm * (b - d))
+                mu = e * ip
+                sd = np.sqrt((e * (b * (2 * e - 1) - d) / (b - d) - np.exp(2 * tm * (b - d))) * ip)
+                out[c] = stats.norm.logpdf(pv, mu, sd)
+        return out
+    n = int(data["ntypes"])
+    pv, ip = _f(data["pop_vec"]).reshape(N, n), _f(data["init_pop"]).reshape(N, n)
+    tm, ti = _f(np.atleast_1d(data["times"])), _i(data["times_idx"]) - 1
+    for c in range(C):
+        cache = {}
+        for k in range(N):
+            key = (int(vi[k]), int(ti[k]))
+            if key not in cache:
+                cache[key] = moments(model.e_mat, model.p_vec, r[c, key[0]], float(tm[key[1]]))
+            M, V = cache[key]
+            mu = M.T @ ip[k]                                  # multitype_loo_block.stan:22
+            S = np.einsum("l,lij->ij", ip[k], V)              # :23-28
+            try:
+                out[c, k] = stats.multivariate_normal.logpdf(pv[k], mu, 0.5 * (S + S.T), allow_singular=False)   # :31
+            except Exception:
+                out[c, k] = np.nan
+    return out
+
+
+def transformed_parameters(model: OracleModel, data: dict, upars: np.ndarray):
+    """the transformed-parameters block as rstan stores it after the loop over dependent-variable levels
+    (multitype_template.stan:105-117, one_type_template.stan:17-28): `r_mat` keeps the values of the LAST level (it is
+    re-initialised at the top of every iteration), column-major flattening; `theta[i]` = append_array(to_array_1d(e_mat),
+    to_array_1d(r_mat)) per level (to_array_1d of a matrix is column-major), flattened by rstan as theta[1,1], theta[2,1], ...
+    (first index fastest).  Returns (names, values [C, ncols]).  One-type template: r_mat[2, ndep_levels] only."""
+    u = np.atleast_2d(_f(upars))
+    C = u.shape[0]
+    th, *_ = constrain(model, u)
+    r, _ = rates(model, th, data["function_var"])          # [C, L, E]
+    Ln, E = r.shape[1], r.shape[2]
+    if model.kind == "simple_bd":
+        names = ["r_mat[%d,%d]" % (e + 1, v + 1) for v in range(Ln) for e in range(2)]
+        vals = np.stack([r[:, v, e] for v in range(Ln) for e in range(2)], axis=1)
+        return names, vals
+    n = model.e_mat.shape[1]
+    pz = np.asarray(model.p_vec, dtype=int) - 1
+
+    def rmat(level):
+        m = np.zeros((C, E, n))
+        for e in range(E):
+            m[:, e, pz[e]] = r[:, level, e]
+        return m
+    last = rmat(Ln - 1)
+    names = ["r_mat[%d,%d]" % (e + 1, j + 1) for j in range(n) for e in range(E)]
+    cols = [last[:, e, j] for j in range(n) for e in range(E)]
+    tl = []
+    for v in range(Ln):
+        m = rmat(v)
+        ev = np.broadcast_to(model.e_mat.ravel(order="F")[None, :], (C, E * n))
+        tl.append(np.concatenate([ev, m.transpose(0, 2, 1).reshape(C, E * n)], axis=1))   # [C, 2 E n]
+    for q in range(2 * E * n):
+        for v in range(Ln):
+            names.append("theta[%d,%d]" % (v + 1, q + 1))
+            cols.append(tl[v][:, q])
+    return names, np.stack(cols, axis=1)
+
+
 def flops_per_chain(model: OracleModel, data: dict, theta: np.ndarray, sigma_obs: float = -1.0, grouped: bool = True,
                     theta_step: float = 1.0) -> int:
     """exact operation count of one chain's likelihood+adjoint for the shipped algorithm."""

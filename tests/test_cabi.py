@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert sorted(_ffi.SYMBOLS) == names          # the ctypes mirror binds exactly the declared surface
-    assert _ffi.lib().bpc_abi_version() == 1
+    assert _ffi.lib().bpc_abi_version() == 2
 
 
 def test_codegen_and_nvrtc_without_gpu():

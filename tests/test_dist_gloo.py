@@ -16,9 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _chain_moments(draws):
-    """numpy twin of bp_chain_moments (sampler.cu): per dimension (count, sum mean, sum mean^2, sum var)."""
-    m, v = draws.mean(axis=1), draws.var(axis=1, ddof=1)
-    return np.stack([np.full(draws.shape[2], draws.shape[0], dtype=float), m.sum(0), (m * m).sum(0), v.sum(0)], axis=1).ravel()
+    """numpy twin of bp_chain_moments (sampler.cu): per dimension (count, sum mean, sum mean^2, sum var) over the HALF chains."""
+    h = draws.shape[1] // 2
+    halves = np.concatenate([draws[:, :h], draws[:, draws.shape[1] - h:]], axis=0)
+    m, v = halves.mean(axis=1), halves.var(axis=1, ddof=1)
+    return np.stack([np.full(draws.shape[2], halves.shape[0], dtype=float), m.sum(0), (m * m).sum(0), v.sum(0)], axis=1).ravel()
 
 
 def _pool_stats(q):
@@ -58,12 +60,59 @@ def test_two_rank_rhat_and_pooled_variance():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # single-process statistics over all 8 chains
-    n = draws.shape[1]
-    W = draws.var(axis=1, ddof=1).mean(axis=0)
-    B_n = draws.mean(axis=1).var(axis=0, ddof=1)
+    # single-process split R-hat over all 8 chains (16 half chains)
+    h = draws.shape[1] // 2
+    draws_h = np.concatenate([draws[:, :h], draws[:, draws.shape[1] - h:]], axis=0)
+    n = h
+    W = draws_h.var(axis=1, ddof=1).mean(axis=0)
+    B_n = draws_h.mean(axis=1).var(axis=0, ddof=1)
     np.testing.assert_allclose(rhat, np.sqrt((W * (n - 1) / n + B_n) / W), rtol=1e-12)
     np.testing.assert_allclose(var, draws.reshape(-1, 3).var(axis=0, ddof=1), rtol=1e-10)
+
+
+def _pool_worker(rank, world, port, q):
+    """the pooled warm-up protocol of fit.pooled_loop with ranks that stop at different times: rank 1's chains all "fail" at once
+    (state 1 from the first call), rank 0 goes through three windows and then finishes."""
+    from bpinference_b200.fit import pooled_loop
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    script = [2, 2, 2, 1] if rank == 0 else [1]
+    calls = {"run": 0, "apply": 0}
+    buf = torch.zeros(4, dtype=torch.float64)
+
+    def run():
+        st = script[min(calls["run"], len(script) - 1)]
+        calls["run"] += 1
+        return st
+
+    def exchange():
+        st = script[min(calls["run"] - 1, len(script) - 1)]
+        buf[:] = torch.tensor([10.0 if st == 2 else 0.0, 1.0 + rank if st == 2 else 0.0, 2.0 if st == 2 else 0.0, 1.0 if st == 1 else 0.0], dtype=torch.float64)
+        dist.all_reduce(buf)
+        return float(buf[3])
+
+    def apply():
+        calls["apply"] += 1
+        assert buf[0] == 10.0        # only rank 0's window contributes: rank 1 sends zeros
+
+    n = pooled_loop(run, exchange, apply, world)
+    q.put((rank, n, calls["run"], calls["apply"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pooled_protocol_does_not_deadlock_when_a_rank_finishes_early():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_pool_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == (0, 4, 4, 3) and res[1] == (1, 4, 4, 0)     # both ranks made the same 4 exchanges; only rank 0 applied windows
 
 
 def test_reference_arm_under_two_ranks():
@@ -77,3 +126,7 @@ def test_reference_arm_under_two_ranks():
     assert len(lines) == 1
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0
+    # the thread count does not follow the OMP_NUM_THREADS=1 torchrun exports to its workers (the N > 1 ratios were void)
+    assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    import bench
+    assert j["config"] == bench.bench_config("cfg1", 4, 475)

@@ -65,7 +65,8 @@ def test_deterministic_and_chain_order_independent():
 
 
 def test_log_lik_matches_sum_and_constants():
-    for name in ("cfg2", "cfg1", "cfg4"):
+    # (cfg4, the noise template, is covered element by element in test_gpu_corners.py: the reference's LOO block has no sigma_obs term)
+    for name in ("cfg2", "cfg1"):
         cfg = syn.make_config(name, chains=3)
         eng, om = _pair(cfg)
         ll = eng.log_lik(cfg["data"], cfg["upars"])

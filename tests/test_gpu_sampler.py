@@ -149,3 +149,82 @@ def test_device_simulator_matches_analytic_moments():
     assert (bp.bp_cuda(E2, th, P2, [1000, 500], np.arange(6), 64, seed=9) == tr).all()
     dat = bp.stan_data_from_simulation(bp.bpsims(mod, th, [1000, 500], np.arange(6), 50, device=0), mod)
     assert dat["ndatapts"] == 250 and dat["ntimes_unique"] == 1 and dat["times"][0] == 1
+
+
+def test_sampler_survives_other_calls_on_its_data_handle():
+    """the sampler replays a CUDA graph with the data handle's workspace baked in.  Other entry points on the same handle
+    with another chain count re-tile / reallocate that workspace between bpc_sampler_run calls; the sampler must notice (workspace
+    generation), re-capture, and produce exactly the draws of an undisturbed run.  Also: a second sampler on a handle whose first
+    sampler (and its stream) is gone."""
+    import ctypes as C
+    from bpinference_b200 import _ffi
+    cfg = syn.make_config("cfg2", chains=32, nobs=120)
+    eng = _engine(cfg)
+    d = eng.data(cfg["data"])
+    L = _ffi.lib()
+
+    def run(disturb):
+        args = _ffi.SampleArgs(32, 120, 60, 0.8, 8, 3, 0, None, 0, 0.0, 0)
+        h = C.c_void_p()
+        _ffi.check(L.bpc_sampler_create(eng.handle, d.handle, C.byref(args), C.byref(h)))
+        st = C.c_int(0)
+        k = 0
+        while st.value != 1:
+            _ffi.check(L.bpc_sampler_run(h, 160, C.byref(st)))
+            if disturb:
+                k += 1
+                n = 5 + (k % 3) * 20                       # 5, 25, 45 chains: different tilings and workspace sizes
+                eng.log_prob_grad(d, cfg["upars"][:1].repeat(n, axis=0))
+                if k % 4 == 0:
+                    eng.log_lik(d, cfg["upars"][:2])
+        draws = np.empty((32, 60, 6))
+        nl = np.empty((32, 60), dtype=np.int32)
+        _ffi.check(L.bpc_sampler_draws(h, _ffi.dptr(draws), None, None, None, _ffi.iptr(nl), None, None))
+        L.bpc_sampler_free(h)
+        return draws, nl
+    a, na = run(False)
+    b, nb = run(True)
+    assert (a == b).all() and (na == nb).all()
+    assert np.isfinite(a).all() and a.std() > 0
+
+
+def test_stanfit_shaped_columns():
+    """N2: columns of the fit in rstan's order — Theta1..P, r_mat (column-major), theta[i, ] = (e_mat, r_mat), lp__ — so that
+    `samples[,1:6]` of vignettes/two-type-inference.Rmd:63-69 reads the six rates; the values against the oracle's restatement of the
+    transformed-parameters block (multitype_template.stan:105-117, one_type_template.stan:19-27)."""
+    for name, chains in (("cfg2", 4), ("cfg3", 4), ("cfg4", 4)):
+        cfg = syn.make_config(name, chains=chains, nobs=60 if name == "cfg2" else None)
+        eng = _engine(cfg)
+        fit = eng.sampling(cfg["data"], chains=chains, iter=60, warmup=30, seed=2, loo=(name == "cfg2"))
+        om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
+        flat = fit.draws.reshape(-1, fit.draws.shape[2])
+        names, vals = bo.transformed_parameters(om, cfg["data"], syn_unconstrain(eng, flat))
+        tn, tv = fit.transformed_parameters()
+        assert list(tn) == names
+        np.testing.assert_allclose(tv.reshape(-1, tv.shape[2]), vals, rtol=1e-13, atol=0)
+        cols = fit.colnames
+        P = cfg["nparams"]
+        assert cols[:P] == ["Theta%d" % (k + 1) for k in range(P)] and cols[-1] == "lp__"
+        M = fit.as_matrix()
+        assert M.shape == (chains * 30, len(cols))
+        np.testing.assert_array_equal(M[:, :P], flat[:, :P])
+        np.testing.assert_array_equal(M[:, -1], fit.lp__.reshape(-1))
+        ex = fit.extract()
+        if name == "cfg2":
+            assert cols[P] == "r_mat[1,1]" and cols[P + 12] == "theta[1,1]" and cols[-2] == "log_lik[60]"
+            assert ex["r_mat"].shape == (chains * 30, 6, 2) and ex["theta"].shape == (chains * 30, 1, 24) and ex["log_lik"].shape == (chains * 30, 60)
+            np.testing.assert_array_equal(ex["r_mat"][:, 0, 0], flat[:, 0])          # r_mat[1, p_vec[1]] = c[1]
+            np.testing.assert_array_equal(ex["r_mat"][:, 2, 1], flat[:, 2])          # event 3 has parent type 2
+            assert (ex["r_mat"][:, 2, 0] == 0).all()
+            ll = bo.log_lik(om, cfg["data"], syn_unconstrain(eng, flat[:3]))
+            np.testing.assert_allclose(ex["log_lik"][:3], ll, rtol=1e-10)
+            s = fit.summary()
+            assert list(s)[:6] == cols[:6] and list(s)[-1] == "lp__" and "r_mat[1,1]" in s
+        if name == "cfg3":
+            assert ex["r_mat"].shape == (chains * 30, 2, 6) and "theta" not in ex
+        if name == "cfg4":
+            assert cols[P] == "sigma_obs" and cols[P + 1] == "r_mat[1,1]"
+
+
+def syn_unconstrain(eng, theta):
+    return eng.unconstrain_pars(theta)

@@ -274,3 +274,46 @@ def test_flop_count_positive_and_grouping_cheaper():
     fg = bo.flops_per_chain(m, cfg["data"], cfg["theta_true"], grouped=True)
     fu = bo.flops_per_chain(m, cfg["data"], cfg["theta_true"], grouped=False)
     assert 0 < fg < fu
+
+
+def test_per_observation_log_lik_oracle():
+    """oracle.log_lik (literal restatement of the LOO blocks, SciPy densities) against the sum the model block accumulates:
+    sum_k log_lik[k] = lp - priors + N n/2 log(2 pi) for the templates whose LOO block matches their model block; the noise
+    template shares the noise-free block (R/stan_utils.R:189-191), so there the identity must NOT hold."""
+    for name, nobs in [("cfg2", None), ("cfg5U", 120), ("cfg1", None), ("cfg3", None), ("cfg4", None)]:
+        cfg = syn.make_config(name, chains=2, nobs=nobs)
+        om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
+        ll = bo.log_lik(om, cfg["data"], cfg["upars"])
+        lp, _, _ = bo.log_prob(om, cfg["data"], cfg["upars"], jacobian=False)
+        th, sig, *_ = bo.constrain(om, cfg["upars"])
+        prior = sum(bo.prior_logpdf(pr["name"], pr["params"], th[:, k])[0] for k, pr in enumerate(om.priors))
+        if sig is not None:
+            prior = prior - 0.5 * (sig / 0.1) ** 2
+        n = 1 if cfg["kind"] == "simple_bd" else cfg["data"]["ntypes"]
+        N = cfg["data"]["ndatapts"]
+        lhs, rhs = ll.sum(axis=1) - (-0.5 * n * N * np.log(2 * np.pi)), lp - prior
+        if name == "cfg4":
+            assert (np.abs(lhs - rhs) > 1e-3 * np.abs(rhs)).all()
+        else:
+            np.testing.assert_allclose(lhs, rhs, rtol=1e-12)
+
+
+def test_transformed_parameter_columns():
+    """r_mat / theta columns as rstan lays them out after the Theta's (multitype_template.stan:105-117; vignettes/two-type-inference.Rmd:63-69
+    reads the first columns positionally): column-major r_mat with row e non-zero in column p_vec[e] only, theta[i] = (e_mat, r_mat)."""
+    cfg = syn.make_config("cfg2", chains=2)
+    om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
+    names, vals = bo.transformed_parameters(om, cfg["data"], cfg["upars"])
+    th, *_ = bo.constrain(om, cfg["upars"])
+    E, n = 6, 2
+    assert names[:3] == ["r_mat[1,1]", "r_mat[2,1]", "r_mat[3,1]"] and names[E * n] == "theta[1,1]" and len(names) == E * n + 2 * E * n
+    r = vals[:, :E * n].reshape(2, n, E)                       # [chain, column, row]
+    for e, p in enumerate(cfg["p_vec"]):
+        np.testing.assert_allclose(r[:, p - 1, e], th[:, e])   # func_deps are c[1] .. c[6]
+        assert (r[:, 2 - p, e] == 0).all()
+    np.testing.assert_allclose(vals[:, E * n:E * n + E * n], np.tile(np.asarray(cfg["e_mat"], float).ravel(order="F"), (2, 1)))
+    np.testing.assert_allclose(vals[:, 2 * E * n:], vals[:, :E * n])
+    cfg3 = syn.make_config("cfg3", chains=2)
+    om3 = bo.OracleModel(cfg3["kind"], cfg3["e_mat"], cfg3["p_vec"], cfg3["func_deps"], cfg3["nparams"], cfg3["ndep"], cfg3["priors"])
+    names3, vals3 = bo.transformed_parameters(om3, cfg3["data"], cfg3["upars"])
+    assert names3 == ["r_mat[%d,%d]" % (e, v) for v in range(1, 7) for e in (1, 2)] and vals3.shape == (2, 12)

@@ -1,5 +1,5 @@
 """cfg2 sampling, 1024 chains x 300 iterations: per-chain against pooled warm-up adaptation (ESS/s, divergences, step sizes).
-BPC_SAMPLER_TRACE=1 prints the wall time per block of passes.  usage: python tools/pool_test.py [pooled-only]"""
+BPC_SAMPLER_TRACE=1 prints the wall time per block of passes.  usage: python tools/pooled_vs_perchain.py [pooled-only]"""
 import sys, time, numpy as np
 import bpinference_b200 as bp
 from bpinference_b200 import synthetic as syn
