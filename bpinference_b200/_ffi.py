@@ -44,7 +44,7 @@ class StanData(C.Structure):
 class SampleArgs(C.Structure):
     _fields_ = [("chains", C.c_int), ("iter", C.c_int), ("warmup", C.c_int), ("adapt_delta", C.c_double),
                 ("max_treedepth", C.c_int), ("seed", C.c_ulonglong), ("chain_id_offset", C.c_int),
-                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double), ("init_opt_steps", C.c_int)]
+                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double), ("init_opt_steps", C.c_int), ("metric", C.c_int)]
 
 
 # every symbol include/bpcuda.h declares: name -> (restype, argtypes)
@@ -77,6 +77,7 @@ SYMBOLS = {
     "bpc_transformed_parameters": (C.c_int, [_vp, _vp, _dp, C.c_int, _dp]),
     "bpc_data_nlevels": (C.c_int, [_vp]),
     "bpc_flop_model": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "bpc_flop_model_centred": (C.c_int, [_vp, _dp, _dp, _dp]),
     "bpc_constrain": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "bpc_unconstrain": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "bpc_launch_count": (C.c_longlong, [C.c_int]),
@@ -87,6 +88,7 @@ SYMBOLS = {
     "bpc_sampler_free": (None, [_vp]),
     "bpc_sampler_run": (C.c_int, [_vp, C.c_longlong, _ip]),
     "bpc_sampler_pool_stats": (C.c_int, [_vp, _vp, C.c_int]),
+    "bpc_sampler_pool_len": (C.c_int, [_vp]),
     "bpc_sampler_pool_apply": (C.c_int, [_vp, _vp]),
     "bpc_sampler_chain_moments": (C.c_int, [_vp, _vp, C.c_int, _dp]),
     "bpc_rhat": (C.c_int, [_dp, C.c_int, C.c_int, _dp]),

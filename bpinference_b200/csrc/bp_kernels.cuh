@@ -375,6 +375,78 @@ BP_HD bool bp_mvn_score(const real (&x)[BP_N], const real (&mu)[BP_N], const rea
   return true;
 }
 
+#if BP_N <= 3
+// The same score for n <= 3 through the adjugate: Sigma^-1 = adj(Sigma) / det with ONE reciprocal, positive definiteness from the
+// leading principal minors (which are cofactors), and the log-determinant NOT taken here: the caller multiplies the determinants of
+// many observations together (bp_detprod below) and takes one logarithm at the end -- the reciprocals and the logarithm are half of
+// the instructions of bp_mvn_score and its longest dependent chains.  q = r^T Sigma^-1 r; lp of the observation = -1/2 (log det + q).
+BP_HD bool bp_mvn_score_small(const real (&x)[BP_N], const real (&mu)[BP_N], const real (&S)[BP_S], real& det, real& q, real (&bmu)[BP_N],
+                              real (&bS)[BP_S]) {
+  real inv[BP_S];
+  bool ok;
+#if BP_N == 1
+  det = S[0];
+  ok = det > real(0.0);
+  inv[0] = real(1.0);
+#elif BP_N == 2
+  det = S[0] * S[2] - S[1] * S[1];
+  ok = S[0] > real(0.0) && det > real(0.0);
+  inv[0] = S[2]; inv[1] = -S[1]; inv[2] = S[0];
+#else
+  const real a = S[0], b = S[1], c = S[2], d = S[3], e = S[4], f = S[5];
+  inv[0] = d * f - e * e;
+  inv[1] = c * e - b * f;
+  inv[2] = b * e - c * d;
+  inv[3] = a * f - c * c;
+  inv[4] = b * c - a * e;
+  inv[5] = a * d - b * b;
+  det = a * inv[0] + b * inv[1] + c * inv[2];
+  ok = a > real(0.0) && inv[5] > real(0.0) && det > real(0.0);
+#endif
+  if (!ok || !bp_finite(det)) return false;
+  const real idet = real(1.0) / det;
+  real r[BP_N];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) r[i] = x[i] - mu[i];
+  q = real(0.0);
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+    real s = real(0.0);
+#pragma unroll
+    for (int j = 0; j < BP_N; ++j) s += inv[bp_sidx(i, j)] * r[j];
+    bmu[i] = s * idet;
+    q += r[i] * bmu[i];
+  }
+  if (!bp_finite(q)) return false;
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i)
+#pragma unroll
+    for (int j = i; j < BP_N; ++j) bS[bp_sidx(i, j)] = real(0.5) * (bmu[i] * bmu[j] - inv[bp_sidx(i, j)] * idet);
+  return true;
+}
+
+#ifndef BP_HOSTSIM
+// running product of determinants as (mantissa in [1, 2), exponent): prod <- prod * det, renormalised with integer operations
+struct BpDetProd {
+  double m;
+  int e;
+  double extra;   // log-determinants taken directly (determinants outside the range a product can carry)
+  __device__ __forceinline__ void init() { m = 1.0; e = 0; extra = 0.0; }
+  __device__ __forceinline__ void mul(double det) {
+    if (det > 1e-280 && det < 1e280) {
+      m *= det;
+      const int hi = __double2hiint(m), ex = ((hi >> 20) & 0x7ff) - 1023;
+      e += ex;
+      m = __hiloint2double(hi - (ex << 20), __double2loint(m));
+    } else {
+      extra += log(det);
+    }
+  }
+  __device__ __forceinline__ double logdet() const { return log(m) + (double)e * 0.69314718055994530942 + extra; }
+};
+#endif
+#endif
+
 // ||A||_1 (max column abs sum); the Lyapunov part of L is bounded by twice that
 BP_HD real bp_norm1(const real (&A)[BP_N * BP_N]) {
   real a1 = real(0.0);
@@ -508,6 +580,27 @@ BP_HD bool bp_score_obs(const real (&xo)[BP_N], real sigma, real (&ymu)[BP_N], r
 #endif
   return true;
 }
+
+#if BP_N <= 3 && !defined(BP_HOSTSIM)
+// the same through the adjugate (bp_mvn_score_small), for kernels that score many observations per thread: the quadratic forms are
+// summed in qsum and the determinants multiplied up in dp; the thread's log density is -1/2 (qsum + dp.logdet()) at the end.
+__device__ __forceinline__ bool bp_score_obs_small(const double (&xo)[BP_N], double sigma, double (&ymu)[BP_N], double (&yS)[BP_S], double& qsum,
+                                                   BpDetProd& dp, double& sb, double (&bmu)[BP_N], double (&bS)[BP_S]) {
+#if BP_NOISE
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
+#endif
+  double det, q;
+  if (!bp_mvn_score_small(xo, ymu, yS, det, q, bmu, bS)) return false;
+  qsum += q;
+  dp.mul(det);
+#if BP_NOISE
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += sigma * bS[bp_sidx(i, i)]; }
+#endif
+  return true;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // one observation of the multitype templates: forward series, score, reverse series.
@@ -1836,7 +1929,9 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   const int uXx = (xrt * 8 + g) * BP_WLD + tg;
   const int uYx = (xct * 8 + g) * BP_OYLD + tg;
   // score: row r = (2 warp + i2) BP_D + d; r & 2 = ((9 i2 + d) & 2) ^ (2 wlo) for BP_D = 9 (18 warp = 2 wlo mod 4), computed generally below
-  double lp[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
+  double qs[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};   // sums of the quadratic forms; the determinants are multiplied up (one log per thread at the end)
+  BpDetProd dp[2];
+  dp[0].init(); dp[1].init();
   int notpd = 0;                                // bit i: an observation of chain 2 warp + i had a covariance that is not positive definite
   int pass = 0;
   const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
@@ -1983,7 +2078,7 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
 #else
             const double sigma = 0.0;
 #endif
-            if (!bp_score_obs(xo, sigma, ymu, yS, lp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
+            if (!bp_score_obs_small(xo, sigma, ymu, yS, qs[i2], dp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
           }
 #pragma unroll
           for (int i = 0; i < BP_N; ++i) yrow[(i2 * BP_D + i) * BP_OYLD + (((i2 * BP_D + i) & 2) ? kB : kA)] = ok ? bmu[i] : 0.0;
@@ -2036,7 +2131,7 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial; chain 2 warp + i belongs to this warp alone ----
 #pragma unroll
   for (int i2 = 0; i2 < 2; ++i2) {
-    const double l = bp_warp_sum(lp[i2]), s2 = bp_warp_sum(sb[i2]);
+    const double l = bp_warp_sum(-0.5 * (qs[i2] + dp[i2].logdet())), s2 = bp_warp_sum(sb[i2]);
     const int c = o * 8 + 2 * warp + i2;
     if (lane == 0 && c < a.nchains) {
       double fl = 0.0;
@@ -2464,6 +2559,11 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   __syncthreads();
   // ---- phase B: observations, group by group ----
   double lp = 0.0, sb = 0.0;
+#if BP_N <= 3
+  double qsum = 0.0;      // (score through the adjugate: one reciprocal per observation, one logarithm per thread)
+  BpDetProd dprod;
+  dprod.init();
+#endif
   for (int g = 0; g < G; ++g) {
     double mom[BP_N][BP_D], acc[BP_N * BP_D];
 #pragma unroll
@@ -2489,7 +2589,11 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
         for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l][BP_N + q];
         yS[q] = sacc;
       }
+#if BP_N <= 3
+      if (!bp_score_obs_small(xo, sigma, ymu, yS, qsum, dprod, sb, bmu, bS)) { status |= BP_ST_NOT_PD; continue; }
+#else
       if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; continue; }
+#endif
 #pragma unroll
       for (int l = 0; l < BP_N; ++l) {
 #pragma unroll
@@ -2500,6 +2604,9 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
     }
     bp_block_sum(acc, red, ybar + (size_t)g * BP_N * BP_D);
   }
+#if BP_N <= 3
+  lp = -0.5 * (qsum + dprod.logdet());
+#endif
   // ---- phase A': reverse sweep of every series with the reduced cotangent ----
   double cb[BP_P];
 #pragma unroll

@@ -923,6 +923,13 @@ int bpc_flop_model(const bpc_model* m, double* per_app_fwd, double* per_app_bwd,
   return BPC_OK;
 }
 
+int bpc_flop_model_centred(const bpc_model* m, double* per_term, double* per_obs_centred, double* per_obs_octet) {
+  if (!m || !per_term || !per_obs_centred || !per_obs_octet) return fail(BPC_E_INVALID, "null argument");
+  const FlopModel f = flop_model(m->spec);
+  *per_term = f.per_term_c; *per_obs_centred = f.per_obs_c; *per_obs_octet = f.per_obs_o;
+  return BPC_OK;
+}
+
 int bpc_kernel_timing(bpc_data* d, int enable) {
   if (!d) return fail(BPC_E_INVALID, "null argument");
   d->timing = enable != 0;
@@ -962,6 +969,7 @@ int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains,
   for (int c = 0; c < nchains; ++c)
     // (a W-path chain that fell back to the ring kernel is counted with the W-path constants: a lower bound)
     flops_per_chain[c] = (s.kind == BPC_SIMPLE_BD) ? f.per_obs * d->N
+                         : (d->cmode && d->omode) ? apps[c] + f.per_obs_o * d->N   // (bp_otable counts the flops of the terms and groups)
                          : d->cmode              ? apps[c] + f.per_obs_c * d->N   // (bp_fusedc counts the flops of its terms and groups itself)
                          : d->wmode              ? apps[c] * (f.per_app_fwd + f.per_app_w) + f.per_obs_w * d->N
                                                  : apps[c] * (f.per_app_fwd + f.per_app_bwd) + (d->grouped ? f.per_obs_grouped : f.per_obs) * d->N;

@@ -44,7 +44,7 @@ struct Loaded {   // one NVRTC module loaded on one device
 };
 
 // algorithmic flop constants of the shipped kernels (SURVEY.md §8(d) convention: FMA = 2, div/sqrt/exp/log = 1)
-struct FlopModel { double per_app_fwd, per_app_bwd, per_obs, per_obs_grouped, per_app_w, per_obs_w, per_term_c, per_obs_c; };
+struct FlopModel { double per_app_fwd, per_app_bwd, per_obs, per_obs_grouped, per_app_w, per_obs_w, per_term_c, per_obs_c, per_obs_o; };
 FlopModel flop_model(const ModelSpec& s);
 
 }  // namespace bpc

@@ -101,7 +101,7 @@ int bpc_sample_multi(bpc_model* m, const bpc_stan_data* data, const int* devices
     if (r != ncclSuccess) return fail(BPC_E_CUDA, std::string("ncclCommInitAll: ") + nc.GetErrorString(r));
   }
   const int dim = bpc_model_dim(m), C = a->chains, ns = a->iter - a->warmup;
-  const int npool = 2 + 2 * dim;
+  const int npool = 2 + (a->metric == 1 ? dim + dim * (dim + 1) / 2 : 2 * dim);   // bpc_sampler_pool_len
   std::vector<Worker> W(ndev);
   // A worker that fails keeps taking part in the exchanges with zeros and a raised "finished" flag, so that nobody waits for it in
   // a collective; the first error is reported when all threads have joined.

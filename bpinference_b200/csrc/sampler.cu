@@ -34,21 +34,22 @@ namespace {
 constexpr int MAXD = 12;        // max tree depth supported
 constexpr int MAXDIM = 32;      // max unconstrained dimension
 
-enum Phase { PH_INIT = 0, PH_FIND_EPS_FIRST = 1, PH_FIND_EPS = 2, PH_NUTS = 3, PH_WAIT = 4, PH_DONE = 5, PH_FAILED = 6, PH_OPT = 7 };
+enum Phase { PH_INIT = 0, PH_FIND_EPS_FIRST = 1, PH_FIND_EPS = 2, PH_NUTS = 3, PH_WAIT = 4, PH_DONE = 5, PH_FAILED = 6, PH_OPT = 7, PH_HESS = 8 };
 
 // scalar double fields
-enum { S_EPS, S_LP_CUR, S_H0, S_LSW, S_SUB_LSW, S_SUM_ACC, S_DA_MU, S_DA_SBAR, S_DA_XBAR, S_DA_CNT, S_LP_PROP, S_LP_SP, S_W_N, S_NLEAP_TOT, S_OPT_LR, NSCAL };
+enum { S_EPS, S_LP_CUR, S_H0, S_LSW, S_SUB_LSW, S_SUM_ACC, S_DA_MU, S_DA_SBAR, S_DA_XBAR, S_DA_CNT, S_LP_PROP, S_LP_SP, S_W_N, S_NLEAP_TOT, S_OPT_LR, S_OPT_GD, S_OPT_FLAT, NSCAL };
 // vector double fields (dim each)
-enum { V_Q_CUR, V_G_CUR, V_QL, V_PL, V_GL, V_QR, V_PR, V_GR, V_Q_PROP, V_G_PROP, V_Q_SP, V_G_SP, V_RHO, V_RHO_SUB, V_MINV, V_W_MEAN, V_W_M2, NVEC };
+enum { V_Q_CUR, V_G_CUR, V_QL, V_PL, V_GL, V_QR, V_PR, V_GR, V_Q_PROP, V_G_PROP, V_Q_SP, V_G_SP, V_RHO, V_RHO_SUB, V_MINV, V_W_MEAN, V_W_M2, V_W_EVAL, NVEC };
 // int fields
-enum { I_PHASE, I_ITER, I_DEPTH, I_NLEAP, I_DIR, I_LEAF, I_DIVERGENT, I_FE_DIR, I_WIN_NEXT, I_WIN_SIZE, I_WIN_COUNTER, I_TRIES, I_RNG, NINT };
+enum { I_PHASE, I_ITER, I_DEPTH, I_NLEAP, I_DIR, I_LEAF, I_DIVERGENT, I_FE_DIR, I_WIN_NEXT, I_WIN_SIZE, I_WIN_COUNTER, I_TRIES, I_RNG, I_PSEUDO, NINT };
 
 struct Params {
-  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits, opt_steps;
+  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits, opt_steps, dense, nsum, debug, hess;
   int init_buffer, term_buffer, base_window;
   double delta, eps0;
   unsigned long long seed;
-  double* sd;          // [(NSCAL + NVEC*dim + 2*MAXD*dim)][C]
+  double* sd;          // [(NSCAL + NVEC*dim + 2*MAXD*dim + nsum)][C]
+  double* metric;      // dense metric shared by the chains of this device: mu[dim], L[dim][dim] (Sigma = L L^T, lower); then the previous (mu, L)
   int* si;             // [NINT][C]
   double* q_eval;      // [C][dim]  position at which the log density is evaluated in the next pass
   double* lp_eval;     // [C]
@@ -84,6 +85,7 @@ struct Chain {
   __device__ double& v(int f, int k) const { return P.sd[(size_t)(NSCAL + f * P.dim + k) * P.C + c]; }
   __device__ double& rck(int lvl, int k) const { return P.sd[(size_t)(NSCAL + NVEC * P.dim + lvl * P.dim + k) * P.C + c]; }
   __device__ double& rsck(int lvl, int k) const { return P.sd[(size_t)(NSCAL + NVEC * P.dim + (MAXD + lvl) * P.dim + k) * P.C + c]; }
+  __device__ double& cross(int idx) const { return P.sd[(size_t)(NSCAL + NVEC * P.dim + 2 * MAXD * P.dim + idx) * P.C + c]; }
   __device__ int& i(int f) const { return P.si[(size_t)f * P.C + c]; }
   // two uniforms in (0,1) per call
   __device__ void uniforms(double& u0, double& u1) const {
@@ -111,6 +113,47 @@ __device__ __forceinline__ double logaddexp(double a, double b) {
   return m + log1p(exp(-fabs(a - b)));
 }
 
+// ---- the metric as a change of coordinates --------------------------------------------------------------------------
+// The sampler works on w with q = mu + L w.  Diagonal metric (rstan's default diag_e): L = I, mu = 0 and the per-chain inverse
+// mass V_MINV, exactly as before.  Dense metric (rstan's dense_e; here with the covariance pooled over all chains): Sigma = L L^T is
+// shared by the chains of a device, the NUTS arithmetic runs in the whitened coordinates with a unit metric -- which IS HMC with
+// M^-1 = Sigma -- and only the two hand-offs with the log-density kernels change: q_eval = mu + L w_eval, grad_w = L^T grad_q.
+__device__ __forceinline__ void metric_to_q(const Params& P, const double* w, double* q) {
+  const int dim = P.dim;
+  if (!P.dense) { for (int k = 0; k < dim; ++k) q[k] = w[k]; return; }
+  const double* mu = P.metric;
+  const double* L = P.metric + dim;
+  for (int i = 0; i < dim; ++i) {
+    double a = mu[i];
+    for (int j = 0; j <= i; ++j) a += L[i * dim + j] * w[j];
+    q[i] = a;
+  }
+}
+
+// the point w_eval of this chain -> q_eval, where the next pass evaluates the log density
+__device__ void publish_eval(const Chain& ch) {
+  const int dim = ch.P.dim;
+  double w[MAXDIM], q[MAXDIM];
+  for (int k = 0; k < dim; ++k) w[k] = ch.v(V_W_EVAL, k);
+  metric_to_q(ch.P, w, q);
+  for (int k = 0; k < dim; ++k) ch.P.q_eval[(size_t)ch.c * dim + k] = q[k];
+}
+
+// gradient of the last pass in the sampler's coordinates: L^T grad_q
+__device__ __forceinline__ void load_grad(const Chain& ch, double* gw) {
+  const Params& P = ch.P;
+  const int dim = P.dim;
+  double g[MAXDIM];
+  for (int k = 0; k < dim; ++k) g[k] = P.g_eval[(size_t)ch.c * dim + k];
+  if (!P.dense) { for (int k = 0; k < dim; ++k) gw[k] = g[k]; return; }
+  const double* L = P.metric + dim;
+  for (int j = 0; j < dim; ++j) {
+    double a = 0.0;
+    for (int i = j; i < dim; ++i) a += L[i * dim + j] * g[i];
+    gw[j] = a;
+  }
+}
+
 // p ~ N(0, M), M = diag(1/minv); writes into vector field f
 __device__ void sample_momentum(const Chain& ch, int f) {
   const int dim = ch.P.dim;
@@ -134,8 +177,9 @@ __device__ void start_leapfrog(const Chain& ch, int fq, int fp, int fg, int dir)
   for (int k = 0; k < ch.P.dim; ++k) {
     const double ph = ch.v(fp, k) + 0.5 * e * ch.v(fg, k);
     ch.v(fp, k) = ph;
-    ch.P.q_eval[(size_t)ch.c * ch.P.dim + k] = ch.v(fq, k) + e * ch.v(V_MINV, k) * ph;
+    ch.v(V_W_EVAL, k) = ch.v(fq, k) + e * ch.v(V_MINV, k) * ph;
   }
+  publish_eval(ch);
 }
 
 // second half kick with the freshly evaluated gradient; the edge becomes the new leaf.  Returns its Hamiltonian.
@@ -143,9 +187,11 @@ __device__ double finish_leapfrog(const Chain& ch, int fq, int fp, int fg, int d
   const double e = ch.s(S_EPS) * dir;
   const int dim = ch.P.dim;
   lp_new = ch.P.st_eval[ch.c] ? -INFINITY : ch.P.lp_eval[ch.c];
+  double gw[MAXDIM];
+  load_grad(ch, gw);
   for (int k = 0; k < dim; ++k) {
-    const double g = ch.P.g_eval[(size_t)ch.c * dim + k];
-    ch.v(fq, k) = ch.P.q_eval[(size_t)ch.c * dim + k];
+    const double g = gw[k];
+    ch.v(fq, k) = ch.v(V_W_EVAL, k);
     ch.v(fg, k) = g;
     ch.v(fp, k) += 0.5 * e * g;
   }
@@ -226,8 +272,11 @@ __device__ void record_draw(const Chain& ch, int it, double accept) {
   if (sidx < 0) return;
   const int nsave = P.iter - P.warmup;
   const size_t row = (size_t)ch.c * nsave + sidx;
+  double wv[MAXDIM], qv[MAXDIM];
+  for (int k = 0; k < P.dim; ++k) wv[k] = ch.v(V_Q_CUR, k);
+  metric_to_q(P, wv, qv);
   for (int k = 0; k < P.dim; ++k) {
-    const double u = ch.v(V_Q_CUR, k);
+    const double u = qv[k];
     double th = u;
     if (k < P.P) {
       if (P.has_bounds[k]) {
@@ -275,7 +324,21 @@ __device__ void end_transition(const Chain& ch) {
     // windowed metric adaptation (Stan's var_adaptation::learn_variance)
     const int wc = ch.i(I_WIN_COUNTER);
     const bool in_window = wc >= P.init_buffer && wc < P.warmup - P.term_buffer && wc != P.warmup;
-    if (in_window) {
+    if (in_window && P.dense) {
+      // dense metric: raw sums of dq = q - mu_cur = L w and dq dq^T (the centre is shared by all chains, so the sums of all chains add)
+      ch.s(S_W_N) += 1.0;
+      double dq[MAXDIM];
+      const double* Lm = P.metric + dim;
+      for (int i = 0; i < dim; ++i) {
+        double a = 0.0;
+        for (int j = 0; j <= i; ++j) a += Lm[i * dim + j] * ch.v(V_Q_CUR, j);
+        dq[i] = a;
+        ch.v(V_W_MEAN, i) += a;
+      }
+      int idx = 0;
+      for (int i = 0; i < dim; ++i)
+        for (int j = 0; j <= i; ++j, ++idx) ch.cross(idx) += dq[i] * dq[j];
+    } else if (in_window) {
       const double n = ch.s(S_W_N) + 1.0;
       ch.s(S_W_N) = n;
       for (int k = 0; k < dim; ++k) {
@@ -326,61 +389,197 @@ __device__ void end_transition(const Chain& ch) {
 // ---- optional climb from the initial point (bpc_sample_args.init_opt_steps) ---------------------------------------------
 // rstan starts NUTS at the initial values.  With 10^5 observations the posterior is three or four orders of magnitude narrower
 // than the range initial values are drawn from (uniform_initialize(0, 1), R/stan_utils.R:74-87, or rstan's uniform(-2, 2)); far
-// out there the generator norm is large, every evaluation needs sub-steps (the slow path), and the first NUTS iterations are long
-// trees of tiny steps.  So, when asked to, every chain first takes init_opt_steps steps of a monotone Adam ascent on the
-// unconstrained log density (normalised steps of size lr per coordinate; a step that does not improve lp is rejected, halves lr
-// and resets the momentum; an accepted one grows lr by 1.2 up to 0.5), using the same fused log-density + gradient passes.
-// State: V_PL = first moment, V_PR = second moment, I_LEAF = steps taken, I_NLEAP = accepted steps, S_OPT_LR = lr.
-__device__ void opt_propose(const Chain& ch) {
+// out there the generator norm is large, every evaluation needs sub-steps (the slow path), the first NUTS iterations are long
+// trees of tiny steps, and chains that start on the wrong end of the posterior's ridge (only birth - death is sharply identified)
+// crawl along it for the whole warm-up.  So, when asked to, every chain first maximises the unconstrained log density with at
+// most init_opt_steps evaluations of L-BFGS (6 curvature pairs, backtracking Armijo line search), each evaluation being the same
+// fused log-density + gradient pass NUTS uses -- what rstan's `optimizing` would give as initial values.
+// State: x = V_Q_CUR, ascent gradient = V_G_CUR, f = S_LP_CUR; direction V_PL, step S_OPT_LR, g.d S_OPT_GD; pairs s_i / y_i in the
+// (still unused) U-turn checkpoint rows rck / rsck; I_LEAF evaluations, I_NLEAP stored pairs, I_DIR newest pair, I_DEPTH failed trials.
+constexpr int LBFGS_M = 10;
+
+__device__ void opt_direction(const Chain& ch) {
   const int dim = ch.P.dim;
-  const double lr = ch.s(S_OPT_LR);
-  const int t = ch.i(I_NLEAP) + 1;
-  const double b1 = 0.8, b2 = 0.99;
-  const double c1 = 1.0 - pow(b1, (double)t), c2 = 1.0 - pow(b2, (double)t);
-  for (int k = 0; k < dim; ++k) {
-    const double g = ch.v(V_G_CUR, k);
-    const double m = b1 * ch.v(V_PL, k) + (1.0 - b1) * g, v = b2 * ch.v(V_PR, k) + (1.0 - b2) * g * g;
-    ch.v(V_QL, k) = m; ch.v(V_QR, k) = v;            // tentative moments: committed when the step is accepted
-    const double den = sqrt(v / c2);
-    const double step = den > 0.0 ? lr * (m / c1) / den : 0.0;
-    ch.P.q_eval[(size_t)ch.c * dim + k] = ch.v(V_Q_CUR, k) + step;
+  const int np = ch.i(I_NLEAP), head = ch.i(I_DIR);
+  double q[MAXDIM], al[LBFGS_M], rho[LBFGS_M];
+  for (int k = 0; k < dim; ++k) q[k] = ch.v(V_G_CUR, k);
+  double gamma = 0.0;
+  for (int t = 0; t < np; ++t) {          // newest -> oldest
+    const int i = (head - t + LBFGS_M) % LBFGS_M;
+    double sy = 0.0, sq = 0.0, yy = 0.0;
+    for (int k = 0; k < dim; ++k) { const double sv = ch.rck(i, k), yv = ch.rsck(i, k); sy += sv * yv; sq += sv * q[k]; yy += yv * yv; }
+    rho[t] = 1.0 / sy;
+    al[t] = rho[t] * sq;
+    for (int k = 0; k < dim; ++k) q[k] -= al[t] * ch.rsck(i, k);
+    if (t == 0) gamma = sy / yy;
   }
+  double gmax = 0.0;
+  for (int k = 0; k < dim; ++k) gmax = fmax(gmax, fabs(ch.v(V_G_CUR, k)));
+  if (np == 0) gamma = gmax > 0.0 ? 0.25 / gmax : 1.0;    // first step: at most 0.25 in any coordinate
+  for (int k = 0; k < dim; ++k) q[k] *= gamma;
+  for (int t = np - 1; t >= 0; --t) {     // oldest -> newest
+    const int i = (head - t + LBFGS_M) % LBFGS_M;
+    double yr = 0.0;
+    for (int k = 0; k < dim; ++k) yr += ch.rsck(i, k) * q[k];
+    const double b = rho[t] * yr;
+    for (int k = 0; k < dim; ++k) q[k] += ch.rck(i, k) * (al[t] - b);
+  }
+  double gd = 0.0, dmax = 0.0;
+  for (int k = 0; k < dim; ++k) { gd += ch.v(V_G_CUR, k) * q[k]; dmax = fmax(dmax, fabs(q[k])); }
+  if (!(gd > 0.0) || !isfinite(gd)) {     // not an ascent direction: forget the pairs, steepest ascent
+    ch.i(I_NLEAP) = 0;
+    const double g0 = gmax > 0.0 ? 0.25 / gmax : 1.0;
+    gd = 0.0; dmax = 0.0;
+    for (int k = 0; k < dim; ++k) { q[k] = g0 * ch.v(V_G_CUR, k); gd += ch.v(V_G_CUR, k) * q[k]; dmax = fmax(dmax, fabs(q[k])); }
+  }
+  for (int k = 0; k < dim; ++k) ch.v(V_PL, k) = q[k];
+  ch.s(S_OPT_GD) = gd;
+  ch.s(S_OPT_LR) = dmax > 1.0 ? 1.0 / dmax : 1.0;          // never more than 1 in any coordinate per step
+  ch.i(I_DEPTH) = 0;
+}
+
+__device__ void opt_propose(const Chain& ch) {
+  const double a = ch.s(S_OPT_LR);
+  for (int k = 0; k < ch.P.dim; ++k) ch.v(V_W_EVAL, k) = ch.v(V_Q_CUR, k) + a * ch.v(V_PL, k);
+  publish_eval(ch);
 }
 
 __device__ void begin_opt(const Chain& ch) {
-  for (int k = 0; k < ch.P.dim; ++k) { ch.v(V_PL, k) = 0.0; ch.v(V_PR, k) = 0.0; }
-  ch.s(S_OPT_LR) = 0.25;
   ch.i(I_LEAF) = 0;
   ch.i(I_NLEAP) = 0;
+  ch.i(I_DIR) = 0;
+  ch.s(S_OPT_FLAT) = 0.0;
   ch.i(I_PHASE) = PH_OPT;
+  opt_direction(ch);
   opt_propose(ch);
+}
+
+// ---- the metric of the first warm-up iterations from the curvature at the optimum (pooled adaptation + init_opt_steps) ----------
+// NUTS with a unit metric on a posterior of scale 1e-3 spends its first window (the most expensive one: the deepest trees) learning
+// what the optimiser already knows.  After the ascent every chain takes 2 dim more evaluations -- central differences of the gradient
+// along the coordinate axes -- for the Hessian at its optimum, inverts it (Laplace approximation Sigma_c = (-H)^-1), and hands
+// (x_c, Sigma_c) to the pooled-window exchange as if it were a window of HESS_N draws with that mean and covariance: the chains wait
+// (PH_WAIT, I_PSEUDO), the statistics are added over all chains of all ranks like any other window, and the first metric (diagonal or
+// dense) is the average Laplace covariance.  A chain whose Hessian is not negative definite contributes nothing.  The window
+// schedule does not advance; the real windows refine the metric afterwards.  g(x +- delta e_k) are kept in rck / rsck.
+constexpr double HESS_N = 4.0;
+__device__ __forceinline__ double hess_delta(double x) { return 2e-6 * (1.0 + fabs(x)); }
+
+__device__ void hess_propose(const Chain& ch) {
+  const int idx = ch.i(I_LEAF), k = idx >> 1;
+  for (int j = 0; j < ch.P.dim; ++j) ch.v(V_W_EVAL, j) = ch.v(V_Q_CUR, j);
+  ch.v(V_W_EVAL, k) += ((idx & 1) ? -1.0 : 1.0) * hess_delta(ch.v(V_Q_CUR, k));
+  publish_eval(ch);
+}
+
+__device__ void begin_hess(const Chain& ch) {
+  ch.i(I_LEAF) = 0;
+  ch.i(I_DEPTH) = 0;     // 1: an evaluation failed
+  ch.i(I_PHASE) = PH_HESS;
+  hess_propose(ch);
+}
+
+__device__ void hess_step(const Chain& ch) {
+  const Params& P = ch.P;
+  const int dim = P.dim, c = ch.c;
+  const int idx = ch.i(I_LEAF), k = idx >> 1;
+  double gw[MAXDIM];
+  load_grad(ch, gw);
+  bool fin = P.st_eval[c] == 0;
+  for (int j = 0; j < dim; ++j) fin = fin && isfinite(gw[j]);
+  if (!fin) ch.i(I_DEPTH) = 1;
+  for (int j = 0; j < dim; ++j) { if (idx & 1) ch.rsck(k, j) = gw[j]; else ch.rck(k, j) = gw[j]; }
+  ch.i(I_LEAF) = idx + 1;
+  if (idx + 1 < 2 * dim) { hess_propose(ch); return; }
+  // A = -(H + H^T) / 2,  H[j][k] = (g_j(x + d e_k) - g_j(x - d e_k)) / (2 d)
+  double A[MAXD * MAXD], R[MAXD * MAXD], Sg[MAXD * MAXD];
+  bool ok = ch.i(I_DEPTH) == 0;
+  for (int a = 0; a < dim; ++a)
+    for (int b = 0; b <= a; ++b) {
+      const double hab = (ch.rck(b, a) - ch.rsck(b, a)) / (2.0 * hess_delta(ch.v(V_Q_CUR, b)));
+      const double hba = (ch.rck(a, b) - ch.rsck(a, b)) / (2.0 * hess_delta(ch.v(V_Q_CUR, a)));
+      A[a * dim + b] = A[b * dim + a] = -0.5 * (hab + hba);
+    }
+  for (int i = 0; i < dim && ok; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double a = A[i * dim + j];
+      for (int q = 0; q < j; ++q) a -= R[i * dim + q] * R[j * dim + q];
+      if (i == j) { if (!(a > 0.0) || !isfinite(a)) { ok = false; break; } R[i * dim + i] = sqrt(a); }
+      else R[i * dim + j] = a / R[j * dim + j];
+    }
+  if (ok) {   // Sigma = A^-1, column by column: R y = e_col, R^T x = y
+    for (int col = 0; col < dim; ++col) {
+      double y[MAXD];
+      for (int i = 0; i < dim; ++i) { double a = (i == col) ? 1.0 : 0.0; for (int q = 0; q < i; ++q) a -= R[i * dim + q] * y[q]; y[i] = a / R[i * dim + i]; }
+      for (int i = dim - 1; i >= 0; --i) { double a = y[i]; for (int q = i + 1; q < dim; ++q) a -= R[q * dim + i] * Sg[q * dim + col]; Sg[i * dim + col] = a / R[i * dim + i]; }
+    }
+    for (int i = 0; i < dim * dim; ++i) ok = ok && isfinite(Sg[i]);
+  }
+  if (P.debug) printf("[hess] chain %d ok %d sd0 %.3e sd1 %.3e\n", c, (int)ok, ok ? sqrt(Sg[0]) : 0.0, ok && dim > 1 ? sqrt(Sg[dim + 1]) : 0.0);
+  // the pseudo-window (coordinates: the metric is still the identity, w = q)
+  ch.s(S_W_N) = ok ? HESS_N : 0.0;
+  if (P.dense) {
+    double dq[MAXDIM];
+    const double* mu = P.metric;
+    for (int i = 0; i < dim; ++i) { dq[i] = ch.v(V_Q_CUR, i) - mu[i]; ch.v(V_W_MEAN, i) = ok ? HESS_N * dq[i] : 0.0; }
+    int t = 0;
+    for (int i = 0; i < dim; ++i)
+      for (int j = 0; j <= i; ++j, ++t) ch.cross(t) = ok ? HESS_N * (Sg[i * dim + j] + dq[i] * dq[j]) : 0.0;
+  } else {
+    for (int i = 0; i < dim; ++i) { ch.v(V_W_MEAN, i) = ok ? ch.v(V_Q_CUR, i) : 0.0; ch.v(V_W_M2, i) = ok ? HESS_N * Sg[i * dim + i] : 0.0; }
+  }
+  ch.i(I_LEAF) = 0; ch.i(I_DEPTH) = 0;
+  ch.i(I_PSEUDO) = 1;
+  ch.i(I_PHASE) = PH_WAIT;
+  atomicAdd(P.counters + 1, 1);
+}
+
+__device__ void end_opt(const Chain& ch) {
+  if (ch.P.debug) {
+    double gmax = 0.0;
+    for (int k = 0; k < ch.P.dim; ++k) gmax = fmax(gmax, fabs(ch.v(V_G_CUR, k)));
+    printf("[opt] chain %d evals %d lp %.6f gmax %.3e alpha %.3e fails %d pairs %d flat %.0f q0 %.4f q2 %.4f\n", ch.c, ch.i(I_LEAF), ch.s(S_LP_CUR), gmax,
+           ch.s(S_OPT_LR), ch.i(I_DEPTH), ch.i(I_NLEAP), ch.s(S_OPT_FLAT), ch.v(V_Q_CUR, 0), ch.P.dim > 2 ? ch.v(V_Q_CUR, 2) : 0.0);
+  }
+  ch.i(I_NLEAP) = 0; ch.i(I_DEPTH) = 0; ch.i(I_LEAF) = 0; ch.i(I_DIR) = 0;
+  if (ch.P.hess) { begin_hess(ch); return; }
+  ch.i(I_FE_DIR) = 0;
+  begin_eps_trial(ch, PH_FIND_EPS_FIRST);
 }
 
 __device__ void opt_step(const Chain& ch) {
   const Params& P = ch.P;
   const int dim = P.dim, c = ch.c;
-  const double lp = P.st_eval[c] ? -INFINITY : P.lp_eval[c];
-  bool ok = isfinite(lp) && lp > ch.s(S_LP_CUR);
-  for (int k = 0; k < dim; ++k) ok = ok && isfinite(P.g_eval[(size_t)c * dim + k]);
+  const double ft = P.st_eval[c] ? -INFINITY : P.lp_eval[c];
+  double gt[MAXDIM];
+  load_grad(ch, gt);
+  const double f = ch.s(S_LP_CUR), a = ch.s(S_OPT_LR);
+  bool ok = isfinite(ft) && ft >= f + 1e-4 * a * ch.s(S_OPT_GD);
+  for (int k = 0; k < dim; ++k) ok = ok && isfinite(gt[k]);
+  const int evals = ch.i(I_LEAF) + 1;
+  ch.i(I_LEAF) = evals;
   if (ok) {
-    for (int k = 0; k < dim; ++k) {
-      ch.v(V_Q_CUR, k) = P.q_eval[(size_t)c * dim + k]; ch.v(V_G_CUR, k) = P.g_eval[(size_t)c * dim + k];
-      ch.v(V_PL, k) = ch.v(V_QL, k); ch.v(V_PR, k) = ch.v(V_QR, k);
+    // curvature pair of the accepted step: s = x_t - x, y = g - g_t (gradient of -lp); kept when s.y > 0
+    double sy = 0.0, ss = 0.0, yy = 0.0;
+    for (int k = 0; k < dim; ++k) { const double sv = a * ch.v(V_PL, k), yv = ch.v(V_G_CUR, k) - gt[k]; sy += sv * yv; ss += sv * sv; yy += yv * yv; }
+    if (sy > 1e-10 * sqrt(ss * yy) && sy > 0.0) {
+      const int np = ch.i(I_NLEAP), head = np == 0 ? 0 : (ch.i(I_DIR) + 1) % LBFGS_M;
+      for (int k = 0; k < dim; ++k) { ch.rck(head, k) = a * ch.v(V_PL, k); ch.rsck(head, k) = ch.v(V_G_CUR, k) - gt[k]; }
+      ch.i(I_DIR) = head;
+      ch.i(I_NLEAP) = np < LBFGS_M ? np + 1 : LBFGS_M;
     }
-    ch.s(S_LP_CUR) = lp;
-    ch.s(S_OPT_LR) = fmin(0.5, 1.2 * ch.s(S_OPT_LR));
-    ch.i(I_NLEAP) += 1;
+    for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = ch.v(V_W_EVAL, k); ch.v(V_G_CUR, k) = gt[k]; }
+    ch.s(S_LP_CUR) = ft;
+    // converged: three accepted steps in a row that change lp by less than 1e-3 (a thousandth of a nat is far inside the posterior)
+    ch.s(S_OPT_FLAT) = (ft - f < 1e-3) ? ch.s(S_OPT_FLAT) + 1.0 : 0.0;
+    if (evals >= P.opt_steps || ch.s(S_OPT_FLAT) >= 3.0) { end_opt(ch); return; }
+    opt_direction(ch);
   } else {
-    ch.s(S_OPT_LR) *= 0.5;
-    for (int k = 0; k < dim; ++k) ch.v(V_PL, k) = 0.0;
-  }
-  const int step = ch.i(I_LEAF) + 1;
-  ch.i(I_LEAF) = step;
-  if (step >= P.opt_steps || ch.s(S_OPT_LR) < 1e-7) {
-    ch.i(I_NLEAP) = 0;
-    ch.i(I_FE_DIR) = 0;
-    begin_eps_trial(ch, PH_FIND_EPS_FIRST);
-    return;
+    ch.s(S_OPT_LR) = 0.5 * a;
+    const int fails = ch.i(I_DEPTH) + 1;
+    ch.i(I_DEPTH) = fails;
+    if (evals >= P.opt_steps || fails > 40) { end_opt(ch); return; }
+    if (fails == 12 && ch.i(I_NLEAP) > 0) { ch.i(I_NLEAP) = 0; opt_direction(ch); }   // a bad model of the curvature: start again from steepest ascent
   }
   opt_propose(ch);
 }
@@ -404,10 +603,15 @@ __global__ void bp_nuts_advance(Params P) {
       // rstan retries random initial values (up to 100 attempts); user-supplied inits that fail are an error there too
       if (ch.i(I_TRIES) >= 100) { ch.i(I_PHASE) = PH_FAILED; atomicAdd(P.counters + 0, 1); atomicAdd(P.counters + 2, 1); return; }
       ch.i(I_TRIES) += 1;
-      for (int k = 0; k < dim; ++k) P.q_eval[(size_t)c * dim + k] = 4.0 * ch.uniform() - 2.0;
+      for (int k = 0; k < dim; ++k) ch.v(V_W_EVAL, k) = 4.0 * ch.uniform() - 2.0;
+      publish_eval(ch);
       return;
     }
-    for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = P.q_eval[(size_t)c * dim + k]; ch.v(V_G_CUR, k) = P.g_eval[(size_t)c * dim + k]; }
+    {
+      double gw[MAXDIM];
+      load_grad(ch, gw);
+      for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = ch.v(V_W_EVAL, k); ch.v(V_G_CUR, k) = gw[k]; }
+    }
     ch.s(S_LP_CUR) = lp;
     if (P.opt_steps > 0) { begin_opt(ch); return; }
     ch.i(I_FE_DIR) = 0;
@@ -416,6 +620,7 @@ __global__ void bp_nuts_advance(Params P) {
   }
 
   if (phase == PH_OPT) { opt_step(ch); return; }
+  if (phase == PH_HESS) { hess_step(ch); return; }
 
   if (phase == PH_FIND_EPS_FIRST || phase == PH_FIND_EPS) {
     double lp_new;
@@ -449,9 +654,9 @@ __global__ void bp_nuts_advance(Params P) {
   const double eps = ch.s(S_EPS), h0 = ch.s(S_H0), sub0 = ch.s(S_SUB_LSW), sacc0 = ch.s(S_SUM_ACC), lp_e = P.lp_eval[c];
   const int fq = dir > 0 ? V_QR : V_QL, fp = dir > 0 ? V_PR : V_PL, fg = dir > 0 ? V_GR : V_GL;
   double pl[MAXDIM], ql[MAXDIM], gl[MAXDIM], ml[MAXDIM], rl[MAXDIM];
+  load_grad(ch, gl);
   for (int k = 0; k < dim; ++k) {
-    gl[k] = P.g_eval[(size_t)c * dim + k];
-    ql[k] = P.q_eval[(size_t)c * dim + k];
+    ql[k] = ch.v(V_W_EVAL, k);
     pl[k] = ch.v(fp, k);
     ml[k] = ch.v(V_MINV, k);
     rl[k] = ch.v(V_RHO_SUB, k);
@@ -519,11 +724,15 @@ __global__ void bp_nuts_advance(Params P) {
     return;
   }
   if (leaf + 1 < (1 << depth)) {   // keep extending the same sub-tree (start_leapfrog from the local copies)
+    double wn[MAXDIM], qn[MAXDIM];
     for (int k = 0; k < dim; ++k) {
       const double ph = pl[k] + 0.5 * e * gl[k];
       ch.v(fp, k) = ph;
-      P.q_eval[(size_t)c * dim + k] = ql[k] + e * ml[k] * ph;
+      wn[k] = ql[k] + e * ml[k] * ph;
+      ch.v(V_W_EVAL, k) = wn[k];
     }
+    metric_to_q(P, wn, qn);
+    for (int k = 0; k < dim; ++k) P.q_eval[(size_t)c * dim + k] = qn[k];
     return;
   }
   // sub-tree complete: biased progressive sampling at the top level, merge, tree-level U-turn check
@@ -557,26 +766,114 @@ __global__ void bp_nuts_init(Params P, const double* __restrict__ inits_u) {
     ch.v(V_MINV, k) = 1.0;
     ch.v(V_W_MEAN, k) = 0.0;
     ch.v(V_W_M2, k) = 0.0;
-    P.q_eval[(size_t)c * P.dim + k] = P.have_inits ? inits_u[(size_t)c * P.dim + k] : 4.0 * ch.uniform() - 2.0;
+    const double q0 = P.have_inits ? inits_u[(size_t)c * P.dim + k] : 4.0 * ch.uniform() - 2.0;
+    P.q_eval[(size_t)c * P.dim + k] = q0;     // (the metric starts as the identity: w = q)
+    ch.v(V_W_EVAL, k) = q0;
   }
+  for (int idx = 0; idx < P.nsum; ++idx) ch.cross(idx) = 0.0;
   if (P.have_inits) ch.i(I_TRIES) = 100;   // user-supplied initial values are not retried
 }
 
-// pooled adaptation: this rank's (count, sum q, sum q^2) over the window of all its chains, fixed order
+// ---- selection after the ascent -------------------------------------------------------------------------------------------
+// From starting values as wide as uniform(0, 1) some chains end their ascent in the wrong place: at a rate bound (a local optimum
+// where the logistic transform saturates), or still crawling along the posterior's ridge when the evaluations run out.  Their
+// log density is thousands of nats below the others'.  Left alone they would sit there for the whole run (NUTS cannot cross
+// such a gap) and, worse, poison the pooled metric.  So the Laplace pseudo-window only counts the chains of this device whose
+// log density is within PSEUDO_TOL nats of the device's best ("good" chains), and the others restart from the point of a good
+// chain (the (c mod n_good)-th one): a multi-start optimisation whose winners seed the sampler.  Chains that restart from the
+// same point separate at once -- their random-number streams differ.
+__device__ __forceinline__ double pseudo_tol(const Params& P) { return 10.0 + P.dim; }
+__device__ __forceinline__ bool pseudo_cand(const Params& P, int c) {
+  return P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT && P.si[(size_t)I_PSEUDO * P.C + c] != 0;
+}
+__device__ double pseudo_lp_max(const Params& P) {
+  double m = -INFINITY;
+  for (int c = 0; c < P.C; ++c)
+    if (pseudo_cand(P, c) && P.sd[(size_t)S_W_N * P.C + c] > 0.0) m = fmax(m, P.sd[(size_t)S_LP_CUR * P.C + c]);
+  return m;
+}
+__device__ __forceinline__ bool pseudo_good(const Params& P, int c, double lpmax) {
+  return P.sd[(size_t)S_W_N * P.C + c] > 0.0 && P.sd[(size_t)S_LP_CUR * P.C + c] >= lpmax - pseudo_tol(P);
+}
+
+__global__ void bp_pseudo_rescue(Params P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C || !pseudo_cand(P, c)) return;
+  const double lpmax = pseudo_lp_max(P);
+  if (!(lpmax > -INFINITY) || pseudo_good(P, c, lpmax)) return;
+  int ngood = 0;
+  for (int k = 0; k < P.C; ++k) ngood += pseudo_cand(P, k) && pseudo_good(P, k, lpmax);
+  if (ngood == 0) return;
+  int want = c % ngood, donor = -1;
+  for (int k = 0; k < P.C && donor < 0; ++k)
+    if (pseudo_cand(P, k) && pseudo_good(P, k, lpmax) && want-- == 0) donor = k;
+  Chain me(P, c), dn(P, donor);
+  for (int k = 0; k < P.dim; ++k) { me.v(V_Q_CUR, k) = dn.v(V_Q_CUR, k); me.v(V_G_CUR, k) = dn.v(V_G_CUR, k); }
+  // (S_LP_CUR is copied last by design of the good test: a rescued chain has S_W_N = 0 and is never a donor)
+  me.s(S_W_N) = 0.0;
+  me.s(S_LP_CUR) = dn.s(S_LP_CUR);
+  if (P.debug) printf("[rescue] chain %d <- chain %d (lp %.3f)\n", c, donor, dn.s(S_LP_CUR));
+}
+
+// pooled adaptation: this rank's window statistics over all its waiting chains, fixed order.  Layout (npool = nstat + 2 doubles):
+//   [0] count;  diagonal metric: [1 .. dim] sum q, [dim + 1 .. 2 dim] sum q^2;  dense metric: [1 .. dim] sum dq, then sum dq dq^T
+//   (lower triangle, row-major), dq = q - mu of the metric in force;  [nstat + 1] 1.0 when every chain of this rank has finished.
 __global__ void bp_pool_stats(Params P, double* __restrict__ out, int with_flag) {
-  const int k = threadIdx.x;   // 0 .. 2*dim (+ 1: this rank's "all chains finished" flag)
-  if (k == 2 * P.dim + 1 && with_flag) { out[k] = P.counters[0] >= P.C ? 1.0 : 0.0; return; }
-  if (k > 2 * P.dim) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nstat = P.dense ? P.dim + P.nsum : 2 * P.dim;
+  if (k == nstat + 1 && with_flag) { out[k] = P.counters[0] >= P.C ? 1.0 : 0.0; return; }
+  if (k > nstat) return;
   double acc = 0.0;
+  const double lpmax = pseudo_lp_max(P);     // (-inf unless this is the Laplace pseudo-window)
   for (int c = 0; c < P.C; ++c) {
     Chain ch(P, c);
     if (ch.i(I_PHASE) != PH_WAIT) continue;
+    if (ch.i(I_PSEUDO) && !pseudo_good(P, c, lpmax)) continue;   // the ascent of this chain ended in the wrong place
     const double n = ch.s(S_W_N);
     if (k == 0) acc += n;
+    else if (P.dense) acc += k <= P.dim ? ch.v(V_W_MEAN, k - 1) : ch.cross(k - 1 - P.dim);
     else if (k <= P.dim) acc += n * ch.v(V_W_MEAN, k - 1);
     else { const double m = ch.v(V_W_MEAN, k - 1 - P.dim); acc += ch.v(V_W_M2, k - 1 - P.dim) + n * m * m; }
   }
   out[k] = acc;
+}
+
+// dense metric: the new (mu, L) from the reduced sums, one thread.  The metric in force moves to the "previous" slot (bp_pool_apply
+// needs both to carry every chain's point and gradient over).  A covariance that is not positive
+// definite leaves the metric as it is.
+__global__ void bp_pool_metric(Params P, const double* __restrict__ red) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int dim = P.dim, M = dim + dim * dim;
+  // (pooled over thousands of draws the estimate needs no shrinkage towards the unit scale: Stan's 1e-3 * 5 / (n + 5) floor would
+  // swamp variances of 1e-6; n / (n + 5) stays, plus a relative jitter on the diagonal)
+  double* cur = P.metric;
+  double* prev = P.metric + M;
+  for (int i = 0; i < M; ++i) prev[i] = cur[i];
+  const double n = red[0];
+  if (!(n > dim + 1.0)) return;
+  double m[MAXDIM];
+  for (int i = 0; i < dim; ++i) m[i] = red[1 + i] / n;
+  // Cholesky of the regularised covariance into a scratch copy (the third slot)
+  double* Ln = P.metric + 2 * M + dim;
+  int idx = 0;
+  bool ok = true;
+  for (int i = 0; i < dim; ++i)
+    for (int j = 0; j <= i; ++j, ++idx) {
+      double cov = (red[1 + dim + idx] - n * m[i] * m[j]) / (n - 1.0);
+      cov = (n / (n + 5.0)) * cov * (i == j ? 1.0 + 1e-9 : 1.0);
+      double a = cov;
+      for (int k = 0; k < j; ++k) a -= Ln[i * dim + k] * Ln[j * dim + k];
+      if (i == j) {
+        if (!(a > 0.0) || !isfinite(a)) ok = false;
+        Ln[i * dim + i] = ok ? sqrt(a) : 1.0;
+      } else {
+        Ln[i * dim + j] = a / Ln[j * dim + j];
+        Ln[j * dim + i] = 0.0;
+      }
+    }
+  if (!ok) return;
+  for (int i = 0; i < dim; ++i) cur[i] += m[i];
+  for (int i = 0; i < dim * dim; ++i) cur[dim + i] = Ln[i];
 }
 
 __global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
@@ -585,17 +882,36 @@ __global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
   Chain ch(P, c);
   if (ch.i(I_PHASE) != PH_WAIT) return;
   const double n = red[0];
-  ch.i(I_WIN_COUNTER) -= 1;          // compute_next_window is defined on the counter of the window's last iteration
-  compute_next_window(ch);
-  ch.i(I_WIN_COUNTER) += 1;
-  for (int k = 0; k < P.dim; ++k) {
-    const double mean = red[1 + k] / n;
-    const double var = n > 1.0 ? (red[1 + P.dim + k] - n * mean * mean) / (n - 1.0) : 1.0;
-    // the regulariser uses the per-chain window length, as if each chain had estimated the variance itself
-    const double nw = ch.s(S_W_N);
-    ch.v(V_MINV, k) = (nw / (nw + 5.0)) * var + 1e-3 * (5.0 / (nw + 5.0));
-    ch.v(V_W_MEAN, k) = 0.0;
-    ch.v(V_W_M2, k) = 0.0;
+  const int dim = P.dim;
+  if (ch.i(I_PSEUDO)) {                // the Laplace pseudo-window of hess_step: the window schedule does not advance
+    ch.i(I_PSEUDO) = 0;
+  } else {
+    ch.i(I_WIN_COUNTER) -= 1;          // compute_next_window is defined on the counter of the window's last iteration
+    compute_next_window(ch);
+    ch.i(I_WIN_COUNTER) += 1;
+  }
+  if (P.dense) {
+    // carry the current point and gradient over to the new coordinates: q = mu0 + L0 w, g_q = L0^-T g_w; w' = L1^-1 (q - mu1), g_w' = L1^T g_q
+    const int M = dim + dim * dim;
+    const double *mu1 = P.metric, *L1 = P.metric + dim, *mu0 = P.metric + M, *L0 = P.metric + M + dim;
+    double w[MAXDIM], g[MAXDIM], q[MAXDIM], gq[MAXDIM];
+    for (int k = 0; k < dim; ++k) { w[k] = ch.v(V_Q_CUR, k); g[k] = ch.v(V_G_CUR, k); }
+    for (int i = 0; i < dim; ++i) { double a = mu0[i]; for (int j = 0; j <= i; ++j) a += L0[i * dim + j] * w[j]; q[i] = a; }
+    for (int i = dim - 1; i >= 0; --i) { double a = g[i]; for (int j = i + 1; j < dim; ++j) a -= L0[j * dim + i] * gq[j]; gq[i] = a / L0[i * dim + i]; }
+    for (int i = 0; i < dim; ++i) { double a = q[i] - mu1[i]; for (int j = 0; j < i; ++j) a -= L1[i * dim + j] * w[j]; w[i] = a / L1[i * dim + i]; }
+    for (int j = 0; j < dim; ++j) { double a = 0.0; for (int i = j; i < dim; ++i) a += L1[i * dim + j] * gq[i]; g[j] = a; }
+    for (int k = 0; k < dim; ++k) { ch.v(V_Q_CUR, k) = w[k]; ch.v(V_G_CUR, k) = g[k]; ch.v(V_W_MEAN, k) = 0.0; ch.v(V_MINV, k) = 1.0; }
+    for (int idx = 0; idx < P.nsum; ++idx) ch.cross(idx) = 0.0;
+  } else {
+    for (int k = 0; k < dim; ++k) {
+      const double mean = red[1 + k] / n;
+      const double var = n > 1.0 ? (red[1 + dim + k] - n * mean * mean) / (n - 1.0) : 1.0;
+      // (pooled over thousands of draws: Stan's shrinkage n / (n + 5) with the pooled count; its absolute 1e-3 * 5 / (n + 5) floor, meant
+      // for one chain's 25 draws of unit-scale parameters, would swamp variances of 1e-6 and is replaced by a relative one)
+      ch.v(V_MINV, k) = (n / (n + 5.0)) * var * (1.0 + 1e-9) + 1e-300;
+      ch.v(V_W_MEAN, k) = 0.0;
+      ch.v(V_W_M2, k) = 0.0;
+    }
   }
   ch.s(S_W_N) = 0.0;
   ch.i(I_FE_DIR) = 0;
@@ -635,7 +951,8 @@ struct bpc_sampler {
   bpc_model* m = nullptr;
   bpc_data* d = nullptr;
   Params P{};
-  DevBuf sd, si, q_eval, lp_eval, g_eval, st_eval, draws, d_lp, d_acc, d_eps, d_depth, d_nleap, d_div, counters, pool, moments, inits;
+  DevBuf sd, si, q_eval, lp_eval, g_eval, st_eval, draws, d_lp, d_acc, d_eps, d_depth, d_nleap, d_div, counters, pool, moments, inits, metric;
+  int npool = 0;
   long long passes = 0;
   int* h_counters = nullptr;   // pinned
   cudaStream_t stream = nullptr;
@@ -659,6 +976,9 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   if (a->chains < 1 || a->iter < 1 || a->warmup < 0 || a->warmup >= a->iter) return fail(BPC_E_INVALID, "need chains >= 1 and 0 <= warmup < iter");
   if (a->max_treedepth < 1 || a->max_treedepth > MAXD) return fail(BPC_E_INVALID, "max_treedepth must be in [1, 12]");
   if (!(a->adapt_delta > 0.0 && a->adapt_delta < 1.0)) return fail(BPC_E_INVALID, "adapt_delta must be in (0, 1)");
+  if (a->metric != 0 && a->metric != 1) return fail(BPC_E_INVALID, "metric must be 0 (diag_e) or 1 (dense_e)");
+  if (a->metric == 1 && !a->pooled_adaptation)
+    return fail(BPC_E_UNSUPPORTED, "the dense metric is estimated from the warm-up draws of all chains: it needs pooled_adaptation = 1");
   cudaError_t e;
   if ((e = cudaSetDevice(d->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   auto s = std::make_unique<bpc_sampler>();
@@ -669,6 +989,10 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   P.pooled = a->pooled_adaptation ? 1 : 0; P.have_inits = a->inits ? 1 : 0;
   P.delta = a->adapt_delta; P.eps0 = a->stepsize > 0 ? a->stepsize : 1.0; P.seed = a->seed;
   P.opt_steps = a->init_opt_steps > 0 ? a->init_opt_steps : 0;
+  P.dense = a->metric == 1 ? 1 : 0;
+  P.debug = std::getenv("BPC_SAMPLER_DEBUG") ? 1 : 0;
+  P.hess = (P.opt_steps > 0 && P.pooled && sp.dim <= MAXD && !std::getenv("BPC_NO_HESS_INIT")) ? 1 : 0;
+  P.nsum = P.dense ? sp.dim * (sp.dim + 1) / 2 : 0;
   // Stan's window schedule (windowed_adaptation): 75 / 25 / 50, rescaled to 15% / 75% / 10% for short warm-ups
   P.init_buffer = 75; P.term_buffer = 50; P.base_window = 25;
   if (P.warmup < 20) { P.init_buffer = P.warmup; P.term_buffer = 0; P.base_window = 0; }   // no metric adaptation
@@ -680,22 +1004,30 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   const size_t C = P.C, dim = P.dim, ns = P.iter - P.warmup;
   int rc;
 #define AL(buf, bytes) if ((rc = s->buf.alloc(bytes))) return rc
-  AL(sd, (NSCAL + NVEC * dim + 2 * MAXD * dim) * C * 8);
+  AL(sd, (NSCAL + NVEC * dim + 2 * MAXD * dim + (size_t)P.nsum) * C * 8);
   AL(si, (size_t)NINT * C * 4);
   AL(q_eval, C * dim * 8); AL(lp_eval, C * 8); AL(g_eval, C * dim * 8); AL(st_eval, C * 4);
   AL(draws, C * ns * dim * 8); AL(d_lp, C * ns * 8); AL(d_acc, C * ns * 8); AL(d_eps, C * ns * 8);
   AL(d_depth, C * ns * 4); AL(d_nleap, C * ns * 4); AL(d_div, C * ns * 4);
-  AL(counters, 16); AL(pool, (2 + 2 * dim) * 8); AL(moments, 4 * dim * 8);
+  s->npool = 2 + (P.dense ? (int)dim + P.nsum : 2 * (int)dim);
+  AL(counters, 16); AL(pool, (size_t)s->npool * 8); AL(moments, 4 * dim * 8); AL(metric, 3 * (dim + dim * dim) * 8);
 #undef AL
   P.sd = (double*)s->sd.p; P.si = (int*)s->si.p; P.q_eval = (double*)s->q_eval.p; P.lp_eval = (double*)s->lp_eval.p;
   P.g_eval = (double*)s->g_eval.p; P.st_eval = (int*)s->st_eval.p; P.draws = (double*)s->draws.p; P.d_lp = (double*)s->d_lp.p;
   P.d_acc = (double*)s->d_acc.p; P.d_eps = (double*)s->d_eps.p; P.d_depth = (int*)s->d_depth.p; P.d_nleap = (int*)s->d_nleap.p;
-  P.d_div = (int*)s->d_div.p; P.counters = (int*)s->counters.p;
+  P.d_div = (int*)s->d_div.p; P.counters = (int*)s->counters.p; P.metric = (double*)s->metric.p;
   if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaMallocHost(&s->h_counters, 16)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
   for (int i = 0; i < 4; ++i) s->h_counters[i] = 0;
   cudaMemsetAsync(s->sd.p, 0, s->sd.cap, s->stream);
   cudaMemsetAsync(s->counters.p, 0, 16, s->stream);
+  {   // the metric starts as the identity (mu = 0, L = I) in all three slots
+    std::vector<double> id(3 * (dim + dim * dim), 0.0);
+    for (int slot = 0; slot < 3; ++slot)
+      for (size_t k = 0; k < dim; ++k) id[slot * (dim + dim * dim) + dim + k * dim + k] = 1.0;
+    if ((e = cudaMemcpyAsync(s->metric.p, id.data(), id.size() * 8, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+    cudaStreamSynchronize(s->stream);
+  }
   cudaMemsetAsync(s->draws.p, 0, C * ns * dim * 8, s->stream);
   const double* inits_dev = nullptr;
   if (a->inits) {
@@ -805,19 +1137,27 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
 
 int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count) {
   if (!s) return fail(BPC_E_INVALID, "null argument");
-  if (stats_dev && count < 1 + 2 * s->P.dim) return fail(BPC_E_INVALID, "stats buffer too small: need 1 + 2*dim doubles");
+  if (stats_dev && count < s->npool - 1) return fail(BPC_E_INVALID, "stats buffer too small: see bpc_sampler_pool_len");
   cudaSetDevice(s->d->device);
-  bp_pool_stats<<<1, 2 * MAXDIM + 32, 0, s->stream>>>(s->P, stats_dev ? stats_dev : (double*)s->pool.p, (!stats_dev || count >= 2 + 2 * s->P.dim) ? 1 : 0);
+  bp_pool_stats<<<(s->npool + 127) / 128, 128, 0, s->stream>>>(s->P, stats_dev ? stats_dev : (double*)s->pool.p, (!stats_dev || count >= s->npool) ? 1 : 0);
   g_launches += 1;
   cudaError_t e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "bp_pool_stats");
   return BPC_OK;
 }
 
+int bpc_sampler_pool_len(const bpc_sampler* s) { return s ? s->npool : -1; }
+
 int bpc_sampler_pool_apply(bpc_sampler* s, const double* reduced_dev) {
   if (!s) return fail(BPC_E_INVALID, "null argument");
   cudaSetDevice(s->d->device);
-  bp_pool_apply<<<(s->P.C + 127) / 128, 128, 0, s->stream>>>(s->P, reduced_dev ? reduced_dev : (const double*)s->pool.p);
+  const double* red = reduced_dev ? reduced_dev : (const double*)s->pool.p;
+  if (s->P.hess) { bp_pseudo_rescue<<<(s->P.C + 127) / 128, 128, 0, s->stream>>>(s->P); g_launches += 1; }
+  if (s->P.dense) {
+    bp_pool_metric<<<1, 32, 0, s->stream>>>(s->P, red);
+    g_launches += 1;
+  }
+  bp_pool_apply<<<(s->P.C + 127) / 128, 128, 0, s->stream>>>(s->P, red);
   cudaMemsetAsync(s->P.counters + 1, 0, 4, s->stream);
   g_launches += 1;
   cudaError_t e = cudaStreamSynchronize(s->stream);

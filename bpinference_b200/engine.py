@@ -199,7 +199,10 @@ class BpCudaModel:
     def flop_model(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _ffi.check(_ffi.lib().bpc_flop_model(self.handle, C.byref(a), C.byref(b), C.byref(c)))
-        return dict(per_app_fwd=a.value, per_app_bwd=b.value, per_obs=c.value)
+        out = dict(per_app_fwd=a.value, per_app_bwd=b.value, per_obs=c.value)
+        _ffi.check(_ffi.lib().bpc_flop_model_centred(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        out.update(per_term_c=a.value, per_obs_c=b.value, per_obs_o=c.value)
+        return out
 
     def constrain_pars(self, upars):
         u = np.ascontiguousarray(np.atleast_2d(_f64(upars)))

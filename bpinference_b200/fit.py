@@ -188,6 +188,13 @@ def pooled_loop(run, exchange, apply, world: int) -> int:
             apply()
 
 
+def _metric_code(control) -> int:
+    m = control.get("metric", "diag_e")
+    if m not in ("diag_e", "dense_e"):
+        raise ValueError("control$metric must be \"diag_e\" or \"dense_e\"")
+    return 1 if m == "dense_e" else 0
+
+
 def _names(engine):
     return ["Theta%d" % (k + 1) for k in range(engine.nparams)] + (["sigma_obs"] if engine.kind == _ffi.MULTITYPE_NOISE else [])
 
@@ -239,6 +246,7 @@ def _default_device():
 
 def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[int] = None, init="random", control: Optional[dict] = None,
              seed: int = 1, pooled_adaptation: bool = False, device: Optional[int] = None, loo: bool = False, init_opt_steps: int = 0):
+    # control$metric: "diag_e" (rstan's default) or "dense_e" (needs pooled_adaptation: the covariance comes from all chains)
     """rstan::sampling(stan_mod, data = dat, chains, iter, warmup, init, control = list(adapt_delta, max_treedepth)).
 
     `chains` is the number of chains of THIS process; under torchrun every rank runs `chains` chains with global
@@ -262,13 +270,13 @@ def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[in
         inits = np.ascontiguousarray([[float(ch["Theta%d" % (k + 1)]) for k in range(engine.nparams)] for ch in init], dtype=np.float64)
     args = _ffi.SampleArgs(chains, iter, warmup, float(control.get("adapt_delta", 0.8)), int(control.get("max_treedepth", 10)), seed,
                            rank * chains, _ffi.dptr(inits) if inits is not None else None, int(bool(pooled_adaptation)),
-                           float(control.get("stepsize", 0.0)), int(init_opt_steps))
+                           float(control.get("stepsize", 0.0)), int(init_opt_steps), _metric_code(control))
     h = C.c_void_p()
     try:
         _ffi.check(L.bpc_sampler_create(engine.handle, d.handle, C.byref(args), C.byref(h)))
         state = C.c_int(0)
         dim = engine.dim
-        npool = 2 + 2 * dim
+        npool = int(L.bpc_sampler_pool_len(h))
         pool = mom = None
         if dist:
             import torch
@@ -345,7 +353,7 @@ def sampling_multi(engine, dat: dict, devices, chains: int = 4, iter: int = 2000
         inits = np.ascontiguousarray([[float(ch["Theta%d" % (k + 1)]) for k in range(engine.nparams)] for ch in init], dtype=np.float64)
     args = _ffi.SampleArgs(chains, iter, warmup, float(control.get("adapt_delta", 0.8)), int(control.get("max_treedepth", 10)), seed,
                            0, _ffi.dptr(inits) if inits is not None else None, int(bool(pooled_adaptation)),
-                           float(control.get("stepsize", 0.0)), int(init_opt_steps))
+                           float(control.get("stepsize", 0.0)), int(init_opt_steps), _metric_code(control))
     ns, dim = iter - warmup, engine.dim
     draws = np.empty((total, ns, dim))
     lp, acc, eps = np.empty((total, ns)), np.empty((total, ns)), np.empty((total, ns))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BPC_ABI_VERSION 2   /* 2: bpc_sample_args.init_opt_steps; pool buffers carry a trailing "rank finished" flag */
+#define BPC_ABI_VERSION 2   /* 2: bpc_sample_args.init_opt_steps and .metric; pool buffers carry a trailing "rank finished" flag */
 
 /* error codes */
 enum {
@@ -197,6 +197,9 @@ int bpc_kernel_time_ms(bpc_data* d, int reset, double* total_ms, long long* laun
 /* algorithmic operation counts of the shipped kernels (FMA = 2): per application of L in the forward series, per
  * application of L^T in the reverse sweep, and per observation outside the series.  No GPU needed. */
 int bpc_flop_model(const bpc_model* m, double* per_app_fwd, double* per_app_bwd, double* per_obs);
+/* the constants of the centred / octet paths: per term of the short series (coefficient, X row, forward product, one row of the S'
+ * update) and per observation outside the terms on bp_fusedc and on bp_fusedo */
+int bpc_flop_model_centred(const bpc_model* m, double* per_term, double* per_obs_centred, double* per_obs_octet);
 /* exact algorithmic flop count of one evaluation of the likelihood for chain 0 of `upars`, counted by
  * the shipped kernels themselves in a counting build (SURVEY.md §8(d) convention: FMA = 2) */
 int bpc_count_flops(bpc_model* m, bpc_data* d, const double* upars, int nchains, double* flops_per_chain);
@@ -224,6 +227,10 @@ typedef struct {
                             most this many steps of a monotone Adam ascent on the unconstrained log density, using the same fused
                             log-density + gradient passes (for data whose posterior is orders of magnitude narrower than the range the
                             initial values are drawn from: uniform_initialize(0, 1) against a posterior sd of 1e-3 with 1e5 observations) */
+  int metric;            /* 0: diag_e, rstan's default (per-chain variances, or pooled ones with pooled_adaptation).  1: dense_e -- the full
+                            covariance of the unconstrained parameters, estimated at every warm-up window from the draws of ALL chains of
+                            all ranks (needs pooled_adaptation = 1: a single chain's window is far too short for a covariance matrix).  The
+                            sampler then works in the whitened coordinates q = mu + L w, Sigma = L L^T, which is HMC with M^-1 = Sigma */
 } bpc_sample_args;
 
 int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_sampler** out);
@@ -231,14 +238,17 @@ void bpc_sampler_free(bpc_sampler* s);
 /* advances all chains by at most max_passes passes.  *state: 0 = more passes needed, 1 = all chains finished,
  * 2 = (pooled adaptation) all chains reached the end of a warm-up window and wait for the pooled metric. */
 int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state);
-/* pooled adaptation, state 2: bpc_sampler_pool_stats writes this rank's sums (count, sum q_k, sum q_k^2; 1 + 2*dim doubles)
- * into the caller's DEVICE buffer stats_dev; the caller adds the buffers of all ranks in place (ncclAllReduce /
- * torch.distributed.all_reduce) and hands the result to bpc_sampler_pool_apply.  With count >= 2 + 2*dim the entry after the sums
+/* pooled adaptation, state 2: bpc_sampler_pool_stats writes this rank's sums (diagonal metric: count, sum q_k, sum q_k^2;
+ * bpc_sampler_pool_len doubles in all) into the caller's DEVICE buffer stats_dev; the caller adds the buffers of all ranks in place (ncclAllReduce /
+ * torch.distributed.all_reduce) and hands the result to bpc_sampler_pool_apply.  With count >= bpc_sampler_pool_len the entry after the sums
  * is 1.0 when every chain of this rank has finished (or failed) and 0.0 otherwise: its sum over ranks equals the number of ranks
  * exactly when the whole run is over.  The protocol that cannot deadlock: every rank calls stats + all-reduce each time its
  * bpc_sampler_run returns (state 1 or 2), applies the result when its state was 2, and leaves when the flag sum says everybody is
  * done -- a finished rank keeps contributing zeros.  On one rank both pointers may be NULL: an internal buffer is used. */
 int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count);
+/* doubles of the pool buffer including the trailing flag: 2 + 2*dim (diagonal metric) or 2 + dim + dim*(dim+1)/2 (dense metric:
+ * count, sum dq, lower triangle of sum dq dq^T with dq = q - centre of the metric in force, flag) */
+int bpc_sampler_pool_len(const bpc_sampler* s);
 int bpc_sampler_pool_apply(bpc_sampler* s, const double* reduced_dev);
 /* results (host copies).  draws: chains x (iter - warmup) x dim CONSTRAINED values (Theta1..P, sigma_obs);
  * lp: lp__ ; per-draw sampler parameters as rstan::get_sampler_params reports them.  Any pointer may be NULL. */

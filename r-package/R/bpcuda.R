@@ -85,13 +85,14 @@ bp_sampling <- function(cm, cd, chains = 4, iter = 2000, warmup = floor(iter / 2
   inits <- if (is.list(init)) sapply(init, function(ch) unlist(ch[sprintf("Theta%d", seq_len(cm$nparams))])) else NULL
   delta <- if (is.null(control$adapt_delta)) 0.8 else control$adapt_delta
   depth <- if (is.null(control$max_treedepth)) 10L else as.integer(control$max_treedepth)
+  metric <- if (identical(control$metric, "dense_e")) 1L else 0L     # dense_e needs pooled_adaptation = TRUE
   if (length(devices) > 1) {
     if (chains %% length(devices) != 0) stop("chains must be a multiple of the number of devices")
     r <- .Call("bpc_R_sample_multi", cm$ptr, cd$dat, cm$simple_bd, as.integer(devices), as.integer(chains / length(devices)), as.integer(iter),
-               as.integer(warmup), delta, depth, as.numeric(seed), inits, pooled_adaptation, as.integer(init_opt_steps))
+               as.integer(warmup), delta, depth, as.numeric(seed), inits, pooled_adaptation, as.integer(init_opt_steps), metric)
   } else {
     r <- .Call("bpc_R_sample", cm$ptr, cd$ptr, as.integer(chains), as.integer(iter), as.integer(warmup), delta, depth, as.numeric(seed), inits,
-               pooled_adaptation, as.integer(init_opt_steps))
+               pooled_adaptation, as.integer(init_opt_steps), metric)
   }
   names(r) <- c("draws", "lp__", "divergent__", "treedepth__", "n_leapfrog__", "accept_stat__", "stepsize__", "Rhat")
   dimnames(r$draws)[[1]] <- c(sprintf("Theta%d", seq_len(cm$nparams)), if (cm$noise) "sigma_obs")

@@ -110,15 +110,15 @@ static SEXP fit_list(SEXP draws, SEXP lp, SEXP div, SEXP td, SEXP nl, SEXP acc, 
 }
 
 /* .Call("bpc_R_sample", model_ptr, data_ptr, chains, iter, warmup, adapt_delta, max_treedepth, seed, inits (nparams x chains or NULL),
- *       pooled_adaptation, init_opt_steps): one device */
-SEXP bpc_R_sample(SEXP mptr, SEXP dptr, SEXP chains, SEXP iter, SEXP warmup, SEXP delta, SEXP depth, SEXP seed, SEXP inits, SEXP pooled, SEXP optsteps) {
+ *       pooled_adaptation, init_opt_steps, metric (0 diag_e, 1 dense_e)): one device */
+SEXP bpc_R_sample(SEXP mptr, SEXP dptr, SEXP chains, SEXP iter, SEXP warmup, SEXP delta, SEXP depth, SEXP seed, SEXP inits, SEXP pooled, SEXP optsteps, SEXP metric) {
   bpc_model* m = (bpc_model*)R_ExternalPtrAddr(mptr);
   bpc_data* d = (bpc_data*)R_ExternalPtrAddr(dptr);
   if (!m || !d) Rf_error("model / data handle is NULL (an external pointer does not survive saveRDS or a new session: create it again)");
   int C = Rf_asInteger(chains), it = Rf_asInteger(iter), wu = Rf_asInteger(warmup), dim = bpc_model_dim(m), ns = it - wu;
   if (C < 1 || ns < 1) Rf_error("need chains >= 1 and warmup < iter");
   bpc_sample_args a = {C, it, wu, Rf_asReal(delta), Rf_asInteger(depth), (unsigned long long)Rf_asReal(seed), 0,
-                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps)};
+                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps), Rf_asInteger(metric)};
   SEXP draws = PROTECT(Rf_alloc3DArray(REALSXP, dim, ns, C)), lp = PROTECT(Rf_allocMatrix(REALSXP, ns, C));
   SEXP div = PROTECT(Rf_allocMatrix(INTSXP, ns, C)), td = PROTECT(Rf_allocMatrix(INTSXP, ns, C)), nl = PROTECT(Rf_allocMatrix(INTSXP, ns, C));
   SEXP acc = PROTECT(Rf_allocMatrix(REALSXP, ns, C)), eps = PROTECT(Rf_allocMatrix(REALSXP, ns, C)), rhat = PROTECT(Rf_allocVector(REALSXP, dim));
@@ -143,10 +143,10 @@ SEXP bpc_R_sample(SEXP mptr, SEXP dptr, SEXP chains, SEXP iter, SEXP warmup, SEX
 }
 
 /* .Call("bpc_R_sample_multi", model_ptr, dat, simple_bd, devices (0-based integer vector), chains PER DEVICE, iter, warmup, adapt_delta,
- *       max_treedepth, seed, inits (nparams x total chains or NULL), pooled_adaptation, init_opt_steps): bpc_sample_multi — the chains
+ *       max_treedepth, seed, inits (nparams x total chains or NULL), pooled_adaptation, init_opt_steps, metric): bpc_sample_multi — the chains
  * are sharded over the devices inside libbpcuda (one host thread per device, ncclCommInitAll); R stays single-threaded. */
 SEXP bpc_R_sample_multi(SEXP mptr, SEXP dat, SEXP simple, SEXP devices, SEXP chains, SEXP iter, SEXP warmup, SEXP delta, SEXP depth, SEXP seed,
-                        SEXP inits, SEXP pooled, SEXP optsteps) {
+                        SEXP inits, SEXP pooled, SEXP optsteps, SEXP metric) {
   bpc_model* m = (bpc_model*)R_ExternalPtrAddr(mptr);
   if (!m) Rf_error("model handle is NULL (an external pointer does not survive saveRDS or a new session: create it again)");
   SEXP dev = PROTECT(Rf_coerceVector(devices, INTSXP));
@@ -155,7 +155,7 @@ SEXP bpc_R_sample_multi(SEXP mptr, SEXP dat, SEXP simple, SEXP devices, SEXP cha
   int T = C * ndev, nprot = 0;
   bpc_stan_data sd = stan_data_of(dat, Rf_asLogical(simple), &nprot);
   bpc_sample_args a = {C, it, wu, Rf_asReal(delta), Rf_asInteger(depth), (unsigned long long)Rf_asReal(seed), 0,
-                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps)};
+                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps), Rf_asInteger(metric)};
   SEXP draws = PROTECT(Rf_alloc3DArray(REALSXP, dim, ns, T)), lp = PROTECT(Rf_allocMatrix(REALSXP, ns, T));
   SEXP div = PROTECT(Rf_allocMatrix(INTSXP, ns, T)), td = PROTECT(Rf_allocMatrix(INTSXP, ns, T)), nl = PROTECT(Rf_allocMatrix(INTSXP, ns, T));
   SEXP acc = PROTECT(Rf_allocMatrix(REALSXP, ns, T)), eps = PROTECT(Rf_allocMatrix(REALSXP, ns, T)), rhat = PROTECT(Rf_allocVector(REALSXP, dim));
@@ -229,8 +229,8 @@ SEXP bpc_R_device_count(void) { return Rf_ScalarInteger(bpc_device_count()); }
 
 static const R_CallMethodDef call_methods[] = {
     {"bpc_R_model_create", (DL_FUNC)&bpc_R_model_create, 3}, {"bpc_R_data_create", (DL_FUNC)&bpc_R_data_create, 3},
-    {"bpc_R_log_prob", (DL_FUNC)&bpc_R_log_prob, 5}, {"bpc_R_sample", (DL_FUNC)&bpc_R_sample, 11},
-    {"bpc_R_sample_multi", (DL_FUNC)&bpc_R_sample_multi, 13}, {"bpc_R_log_lik", (DL_FUNC)&bpc_R_log_lik, 4},
+    {"bpc_R_log_prob", (DL_FUNC)&bpc_R_log_prob, 5}, {"bpc_R_sample", (DL_FUNC)&bpc_R_sample, 12},
+    {"bpc_R_sample_multi", (DL_FUNC)&bpc_R_sample_multi, 14}, {"bpc_R_log_lik", (DL_FUNC)&bpc_R_log_lik, 4},
     {"bpc_R_moments", (DL_FUNC)&bpc_R_moments, 5}, {"bpc_R_transformed", (DL_FUNC)&bpc_R_transformed, 5},
     {"bpc_R_simulate", (DL_FUNC)&bpc_R_simulate, 8}, {"bpc_R_device_count", (DL_FUNC)&bpc_R_device_count, 0}, {NULL, NULL, 0}};
 

@@ -106,4 +106,78 @@ int hs_obs(const double* theta, const double* x, const double* z0, const double*
   return status;
 }
 
+#if BP_KIND != 2 && BP_N <= 3
+// The centred / octet formula for ONE (chain, observation) in scalar form, with exactly the arithmetic the octet path performs per
+// observation (bp_fusedo: stage, forward product, score through the adjugate, packed cotangent, S' update), so that its operation
+// count can be recounted with the counting scalar and its numbers compared with the direct series:
+//   X[(j, l)] = c_j(h) z0_l;  y[d] = sum_(j, l) N_j[d][l] X[(j, l)];  (det, q, b) = score(y);  S'[(j, l)][d] += X[(j, l)] b[d]
+// Nj: [J + 1][BP_D][BP_N].  out: y [BP_D], det, q, b [BP_D] (packed coordinates: off-diagonals doubled), S' [J + 1][BP_N][BP_D].
+int hs_centred_obs(int J, const double* Nj, const double* z0, const double* xo, double h, double sigma, double* y_out, double* det_out,
+                   double* q_out, double* b_out, double* sp_out, unsigned long long* ops_out) {
+  real X[8][BP_N], y[BP_D], xx[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S], b[BP_D];
+  if (J < 0 || J > 7) return -1;
+#ifdef BP_COUNTED
+  g_ops = 0;
+#endif
+  real w = real(1.0);
+  const real hh = real(h);                                     // (t_k - tau_g: one subtraction, counted below)
+  for (int d = 0; d < BP_D; ++d) y[d] = real(0.0);
+  for (int j = 0; j <= J; ++j) {
+    if (j > 0) w = w * (hh * real(bp_rk[j - 1]));
+    for (int l = 0; l < BP_N; ++l) X[j][l] = w * real(z0[l]);
+    for (int d = 0; d < BP_D; ++d)
+      for (int l = 0; l < BP_N; ++l) y[d] += real(Nj[(j * BP_D + d) * BP_N + l]) * X[j][l];
+  }
+  for (int i = 0; i < BP_N; ++i) { ymu[i] = y[i]; xx[i] = real(xo[i]); }
+  for (int q = 0; q < BP_S; ++q) yS[q] = y[BP_N + q];
+#if BP_NOISE
+  for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += real(sigma) * ymu[i];
+#endif
+  real det, q;
+  const bool ok = bp_mvn_score_small(xx, ymu, yS, det, q, bmu, bS);
+  real qsum = real(0.0), dprod = real(1.0);
+  if (ok) { qsum += q; dprod = dprod * det; }                 // the running sums of bp_fusedo (one logarithm per thread at the very end)
+#if BP_NOISE
+  real sb = real(0.0);
+  for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += real(sigma) * bS[bp_sidx(i, i)]; }
+#endif
+  for (int i = 0; i < BP_N; ++i) b[i] = bmu[i];
+  for (int qq = 0; qq < BP_S; ++qq) {
+    bool diag = false;
+    for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == qq);
+    b[BP_N + qq] = diag ? bS[qq] : bS[qq] + bS[qq];
+  }
+  for (int j = 0; j <= J; ++j)
+    for (int l = 0; l < BP_N; ++l)
+      for (int d = 0; d < BP_D; ++d) {
+        real acc = real(sp_out[(j * BP_N + l) * BP_D + d]);
+        acc += X[j][l] * b[d];
+        sp_out[(j * BP_N + l) * BP_D + d] = bp_val(acc);
+      }
+#ifdef BP_COUNTED
+  if (ops_out) ops_out[0] = g_ops + 1;                        // + the subtraction h = t - tau
+#endif
+  for (int d = 0; d < BP_D; ++d) { y_out[d] = bp_val(y[d]); b_out[d] = bp_val(b[d]); }
+  *det_out = bp_val(det);
+  *q_out = bp_val(q);
+  return ok ? 0 : 1;
+}
+
+// both scores on the same input: the LDL^T one (lp, bmu, bS) and the adjugate one (det, q, bmu, bS)
+int hs_score_both(const double* x, const double* mu, const double* S, double* lp_out, double* b1, double* det_out, double* q_out, double* b2) {
+  real xx[BP_N], m[BP_N], s[BP_S], bmu[BP_N], bS[BP_S], lp, det, q;
+  for (int i = 0; i < BP_N; ++i) { xx[i] = real(x[i]); m[i] = real(mu[i]); }
+  for (int k = 0; k < BP_S; ++k) s[k] = real(S[k]);
+  const bool ok1 = bp_mvn_score(xx, m, s, lp, bmu, bS);
+  *lp_out = bp_val(lp);
+  for (int i = 0; i < BP_N; ++i) b1[i] = bp_val(bmu[i]);
+  for (int k = 0; k < BP_S; ++k) b1[BP_N + k] = bp_val(bS[k]);
+  const bool ok2 = bp_mvn_score_small(xx, m, s, det, q, bmu, bS);
+  *det_out = bp_val(det); *q_out = bp_val(q);
+  for (int i = 0; i < BP_N; ++i) b2[i] = bp_val(bmu[i]);
+  for (int k = 0; k < BP_S; ++k) b2[BP_N + k] = bp_val(bS[k]);
+  return (ok1 ? 0 : 1) | (ok2 ? 0 : 2);
+}
+#endif
+
 }  // extern "C"

@@ -84,3 +84,46 @@ def complex_step_grad(f, r, h=1e-30):
         rc[e] += 1j * h
         g[e] = f(rc).imag / h
     return g
+
+
+def sidx(i, j, n):
+    """index of (i, j) in the packed upper triangle of a symmetric n x n matrix (bp_sidx of bp_kernels.cuh)."""
+    if i > j:
+        i, j = j, i
+    return i * n - i * (i - 1) // 2 + (j - i)
+
+
+def unpack_sym(packed, n):
+    S = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            S[i, j] = packed[sidx(i, j, n)]
+    return S
+
+
+def moment_operator(e_mat, p_vec, r):
+    """the closed linear operator L of the per-observation state y = (mu, packed Sigma):  mu' = A^T mu,
+    Sigma' = A^T Sigma + Sigma A + sum_l mu_l H_l  (DESIGN.md §2), as a dense [D, D] matrix in packed coordinates,
+    built column by column from the right-hand side applied to unit vectors."""
+    A, H, _ = generator(e_mat, p_vec, np.asarray(r, dtype=float))
+    n = A.shape[0]
+    s = n * (n + 1) // 2
+    D = n + s
+    Lm = np.zeros((D, D))
+    for c in range(D):
+        mu = np.zeros(n)
+        S = np.zeros((n, n))
+        if c < n:
+            mu[c] = 1.0
+        else:
+            for i in range(n):
+                for j in range(i, n):
+                    if sidx(i, j, n) == c - n:
+                        S[i, j] = S[j, i] = 1.0
+        dmu = A.T @ mu
+        dS = A.T @ S + S @ A + np.einsum("l,lij->ij", mu, H)
+        Lm[:n, c] = dmu
+        for i in range(n):
+            for j in range(i, n):
+                Lm[n + sidx(i, j, n), c] = dS[i, j]
+    return Lm

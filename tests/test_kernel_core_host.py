@@ -78,3 +78,60 @@ def test_flop_model_equals_counted_operations(name):
             assert abs(model - counted) <= 0.01 * counted, (model, counted)
         else:
             assert model <= 1.01 * counted and counted <= 1.25 * model, (model, counted)
+
+
+@pytest.mark.parametrize("name", ["cfg5U", "cfg2", "cfg4"])
+def test_octet_flop_constants_and_adjugate_score(name):
+    """the constants behind roofline.achieved on the octet path (per term of the short series, per observation outside the terms:
+    csrc/flops.cpp per_term_c / per_obs_o) against a recount of the octet formula with a counting scalar (tests/hostsim:
+    hs_centred_obs performs the arithmetic of one (chain, observation) of bp_fusedo in scalar form), EXACTLY; the formula's numbers
+    against the direct series; and the adjugate score of bp_fusedo against the LDL^T score of the other kernels."""
+    import ctypes as C
+    cfg, eng, om = _setup(name, 24)
+    fm = eng.flop_model()
+    n = eng.ntypes
+    S = n * (n + 1) // 2
+    D = n + S
+    dp = C.POINTER(C.c_double)
+    theta, sig, *_ = bo.constrain(om, cfg["upars"])
+    r, _ = bo.rates(om, theta, cfg["data"]["function_var"])
+    e_mat, p_vec = np.asarray(cfg["e_mat"], float), np.asarray(cfg["p_vec"])
+    # N_j = L^j exp(tau L) [e_1 .. e_n] from the oracle's moments: column l of N_0 = state from one type-l ancestor; N_j by differences of
+    # the exact states is ill-conditioned, so build L explicitly from unit-vector applications of the ODE right-hand side (refmath)
+    from tests import refmath
+    Lmat = refmath.moment_operator(e_mat, p_vec, r[0, 0])           # [D, D] packed coordinates
+    import scipy.linalg as sl
+    tau, h = 1.3, 0.011
+    E0 = sl.expm(tau * Lmat)[:, :n]
+    for J in (7, 6):
+        Nj = np.stack([np.linalg.matrix_power(Lmat, j) @ E0 for j in range(J + 1)])      # [J+1, D, n]
+        z0 = np.asarray(cfg["data"]["init_pop"], float).reshape(-1, n)[0]
+        y_exact = sl.expm((tau + h) * Lmat)[:, :n] @ z0
+        xo = y_exact[:n] + 0.7 * np.sqrt(np.diag(refmath.unpack_sym(y_exact[n:], n)))
+        sg = float(sig[0]) if sig is not None else 0.0
+        for counted in (False, True):
+            Lh = hs.build(eng, counted=counted)
+            y, b, sp = np.zeros(D), np.zeros(D), np.zeros((J + 1, n, D))
+            det, q, ops = C.c_double(), C.c_double(), (C.c_ulonglong * 2)()
+            rc = Lh.hs_centred_obs(J, np.ascontiguousarray(Nj).ctypes.data_as(dp), z0.ctypes.data_as(dp), np.ascontiguousarray(xo).ctypes.data_as(dp),
+                                   C.c_double(h), C.c_double(sg), y.ctypes.data_as(dp), C.byref(det), C.byref(q), b.ctypes.data_as(dp),
+                                   sp.ctypes.data_as(dp), ops)
+            assert rc == 0
+            if counted:
+                assert ops[0] == (J + 1) * fm["per_term_c"] + fm["per_obs_o"], (ops[0], fm)
+            else:
+                np.testing.assert_allclose(y, y_exact, rtol=1e-12)         # the short series around tau reproduces exp((tau + h) L) z0
+                # S' rows are X[(j, l)] b: the W-matrix factorisation's input
+                cj = np.cumprod(np.concatenate([[1.0], h / np.arange(1, J + 1)]))
+                np.testing.assert_allclose(sp, cj[:, None, None] * z0[None, :, None] * b[None, None, :], rtol=1e-13)
+                # both scores on the same state
+                mu, Sg = y_exact[:n].copy(), y_exact[n:].copy()
+                if sig is not None:
+                    for i in range(n):
+                        Sg[refmath.sidx(i, i, n)] += sg * mu[i]
+                lp1, b1, b2 = C.c_double(), np.zeros(D), np.zeros(D)
+                rc2 = Lh.hs_score_both(np.ascontiguousarray(xo).ctypes.data_as(dp), mu.ctypes.data_as(dp), Sg.ctypes.data_as(dp), C.byref(lp1),
+                                       b1.ctypes.data_as(dp), C.byref(det), C.byref(q), b2.ctypes.data_as(dp))
+                assert rc2 == 0
+                np.testing.assert_allclose(-0.5 * (np.log(det.value) + q.value), lp1.value, rtol=1e-13)
+                np.testing.assert_allclose(b2, b1, rtol=1e-11, atol=1e-13 * np.abs(b1).max())
