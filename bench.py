@@ -198,7 +198,7 @@ def cpu_port_rate(cfg, seconds, nthreads=0):
     return chains * nobs * reps / dt, cores, "%d chains x first %d of %d observations x %d passes, %d OpenMP threads, %.1f s" % (chains, nobs, N, reps, cores, dt)
 
 
-def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, chains, nobs, iters, warm, opt_steps, adapt_delta=0.8):
+def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, chains, nobs, iters, warm, opt_steps, dense, adapt_delta=0.8):
     """the second half of BASELINE.json's metric: ESS/s of the device-resident NUTS sampler.  Chains are sharded over the ranks
     (`chains` per GPU); the diagonal metric of every warm-up window is estimated from the draws of ALL chains of ALL ranks — the one
     collective of the path: an all-reduce of 2 + 2 dim doubles over NCCL at every window boundary, and 4 dim doubles for split R-hat at
@@ -213,8 +213,8 @@ def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, cha
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    fit = eng.sampling(d, chains=chains, iter=iters, warmup=warm, init=init, control=dict(adapt_delta=adapt_delta, max_treedepth=10), seed=1,
-                       pooled_adaptation=True, init_opt_steps=opt_steps)
+    fit = eng.sampling(d, chains=chains, iter=iters, warmup=warm, init=init, control=dict(adapt_delta=adapt_delta, max_treedepth=10, metric="dense_e" if dense else "diag_e"),
+                       seed=1, pooled_adaptation=True, init_opt_steps=opt_steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ess = fit.ess_bulk()
@@ -240,10 +240,13 @@ def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, cha
         have_rstan = subprocess.run(["Rscript", "-e", "library(rstan)"], capture_output=True, timeout=60).returncode == 0
     except Exception:
         have_rstan = False
-    return {"workload": "%s: %s; NUTS, %d iterations (%d warm-up), adapt_delta %.2f, starting values uniform(0, 1)%s; diagonal metric from warm-up "
-                        "statistics pooled over all chains of all ranks (NCCL all-reduce at the window boundaries)" % (
-                            workload, workload_description(workload, chains, int(cfg["data"]["ndatapts"])), iters, warm, adapt_delta,
-                            ", then %d steps of the device-side ascent" % opt_steps if opt_steps else ""),
+    return {"workload": "%s: %s; NUTS, %d iterations (%d warm-up), adapt_delta %.2f, starting values uniform(0, 1) followed by at most %d L-BFGS "
+                        "evaluations per chain; %s metric: Laplace covariance at the optimum first, then the %s of the warm-up draws of all "
+                        "chains of all ranks at every window (NCCL all-reduce of %d doubles), pooled step size"
+                        % (workload, workload_description(workload, chains, int(cfg["data"]["ndatapts"])), iters, warm, adapt_delta, opt_steps,
+                           "dense (dense_e)" if dense else "diagonal (diag_e)", "covariance" if dense else "variances",
+                           2 + (eng.dim + eng.dim * (eng.dim + 1) // 2 if dense else 2 * eng.dim)),
+            "treedepth_mean": float(fit.treedepth__.mean()), "n_leapfrog_mean": float(fit.n_leapfrog__.mean()), "stepsize": float(fit.stepsize__[0, -1]),
             "chains_total": int(chains * world), "seconds": dt, "min_ess_per_s": float(ess_all.min() / dt), "min_ess": float(ess_all.min()),
             "leapfrogs_per_s": leap / dt, "leapfrogs": int(leap), "passes": fit.info["passes"], "max_rhat": float(np.nanmax(fit.rhat)),
             "divergent": int(ndiv), "pool_exchanges": fit.info["pool_exchanges"], "collective": "torch.distributed all_reduce (NCCL)" if world > 1 else "none (one rank)",
@@ -475,10 +478,13 @@ def _main(args):
     # ---- sampling: every rank its chains, warm-up statistics pooled over all ranks ----------------------------------------
     sampling = None
     if not args.no_sampling:
-        sampling = {"cfg2": sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 0)}
+        # cfg2 (250 observations at ONE duration: a thin curved posterior no linear metric straightens, trees of depth 7-8 whatever the metric):
+        # pooled diagonal metric, the best of tools/cfg2_variants.py; cfg5U (100 000 observations: a near-Gaussian posterior with a strongly
+        # rotated ridge): pooled dense metric
+        sampling = {"cfg2": sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 200, False)}
         if args.workload == "cfg5U" and not args.nobs:
             sampling["cfg5U"] = sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg5U", chains, None, args.sampling_iter,
-                                                args.sampling_iter // 2, 100)
+                                                args.sampling_iter // 2, 300, True)
 
     if rank == 0:
         total_evals = float(world) * chains * N * args.steps

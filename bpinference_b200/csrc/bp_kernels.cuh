@@ -380,6 +380,9 @@ BP_HD bool bp_mvn_score(const real (&x)[BP_N], const real (&mu)[BP_N], const rea
 // leading principal minors (which are cofactors), and the log-determinant NOT taken here: the caller multiplies the determinants of
 // many observations together (bp_detprod below) and takes one logarithm at the end -- the reciprocals and the logarithm are half of
 // the instructions of bp_mvn_score and its longest dependent chains.  q = r^T Sigma^-1 r; lp of the observation = -1/2 (log det + q).
+// PACKED: bS is returned in packed coordinates (an off-diagonal entry stands for both symmetric positions: twice the value), which is
+// what the W / S' accumulations want -- the factors 1/2 and 2 are folded into the constants instead of being applied afterwards.
+template <bool PACKED = false>
 BP_HD bool bp_mvn_score_small(const real (&x)[BP_N], const real (&mu)[BP_N], const real (&S)[BP_S], real& det, real& q, real (&bmu)[BP_N],
                               real (&bS)[BP_S]) {
   real inv[BP_S];
@@ -418,10 +421,18 @@ BP_HD bool bp_mvn_score_small(const real (&x)[BP_N], const real (&mu)[BP_N], con
     q += r[i] * bmu[i];
   }
   if (!bp_finite(q)) return false;
+  // dlp/dSigma = 1/2 (bmu bmu^T - Sigma^-1): one multiply and one multiply-add per entry
+  const real mh = real(-0.5) * idet;
+  real hb[BP_N];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) hb[i] = real(0.5) * bmu[i];
 #pragma unroll
   for (int i = 0; i < BP_N; ++i)
 #pragma unroll
-    for (int j = i; j < BP_N; ++j) bS[bp_sidx(i, j)] = real(0.5) * (bmu[i] * bmu[j] - inv[bp_sidx(i, j)] * idet);
+    for (int j = i; j < BP_N; ++j) {
+      if (PACKED && i != j) bS[bp_sidx(i, j)] = bmu[i] * bmu[j] + (mh + mh) * inv[bp_sidx(i, j)];
+      else bS[bp_sidx(i, j)] = hb[i] * bmu[j] + mh * inv[bp_sidx(i, j)];
+    }
   return true;
 }
 
@@ -584,6 +595,7 @@ BP_HD bool bp_score_obs(const real (&xo)[BP_N], real sigma, real (&ymu)[BP_N], r
 #if BP_N <= 3 && !defined(BP_HOSTSIM)
 // the same through the adjugate (bp_mvn_score_small), for kernels that score many observations per thread: the quadratic forms are
 // summed in qsum and the determinants multiplied up in dp; the thread's log density is -1/2 (qsum + dp.logdet()) at the end.
+template <bool PACKED = false>
 __device__ __forceinline__ bool bp_score_obs_small(const double (&xo)[BP_N], double sigma, double (&ymu)[BP_N], double (&yS)[BP_S], double& qsum,
                                                    BpDetProd& dp, double& sb, double (&bmu)[BP_N], double (&bS)[BP_S]) {
 #if BP_NOISE
@@ -591,7 +603,7 @@ __device__ __forceinline__ bool bp_score_obs_small(const double (&xo)[BP_N], dou
   for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += sigma * ymu[i];
 #endif
   double det, q;
-  if (!bp_mvn_score_small(xo, ymu, yS, det, q, bmu, bS)) return false;
+  if (!bp_mvn_score_small<PACKED>(xo, ymu, yS, det, q, bmu, bS)) return false;
   qsum += q;
   dp.mul(det);
 #if BP_NOISE
@@ -855,6 +867,10 @@ __device__ __forceinline__ void bp_block_reduce_store(double (&vals)[BP_NPART], 
   }
 }
 
+// sampler phases 4 (waiting at a pooled window), 5 (finished), 6 (failed): nothing reads the chain's result, so it is not evaluated --
+// the passes of a run's tail, when most chains are done, cost what the chains still running cost
+__device__ __forceinline__ bool bp_skip(const int* skip, int c) { return skip != nullptr && (unsigned)(skip[c] - 4) < 3u; }
+
 struct BpObsArgs {
   double* theta;         // [C][BP_DIM]
   const double* z0;      // [BP_N][npad]   init_pop, SoA, sorted
@@ -892,6 +908,7 @@ struct BpObsArgs {
   int jacobian;
   double* lp_out; double* grad_out; double* apps_out;
   double* n0tab;         // [C][cgroups][BP_D * BP_N]  octet path: N_0(tau_g) of every (chain, group), entry d * BP_N + l (bp_otable)
+  const int* skip;       // [C] or nullptr: the sampler's phase of each chain; chains that wait or have finished (bp_skip) are not evaluated
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -959,6 +976,7 @@ __device__ __forceinline__ void bp_dmma(double& c0, double& c1, double a, double
 
 extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_WMINBLOCKS) bp_fusedw(BpObsArgs a) {
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (bp_skip(a.skip, c)) return;
   double th[BP_DIM];
 #pragma unroll
   for (int k = 0; k < BP_DIM; ++k) th[k] = a.theta[(size_t)c * BP_DIM + k];
@@ -1212,6 +1230,7 @@ __device__ __forceinline__ void bp_lbar_to_grad(const double* Zc, double (&gA)[B
 #if !BP_XDEP
 extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArgs a) {
   const int c = blockIdx.x, tid = threadIdx.x;
+  if (bp_skip(a.skip, c)) return;
   __shared__ double W[BP_CROWS * BP_WCOLS];   // W_(j+1) as [j][d * n + l]; then Y_j in place (BP_WROWS rows from bp_fusedw, BP_CROWS from bp_fusedc)
   __shared__ double Lm[BP_D * BP_D];
   __shared__ double Z[2 * BP_D * BP_D];
@@ -1290,6 +1309,7 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
 // P_j = L^j in shared memory, then every table entry is a short dot product with the coefficients c_j(time).
 extern "C" __global__ void __launch_bounds__(512) bp_ctable(BpObsArgs a) {
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  if (bp_skip(a.skip, c)) return;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
   __shared__ double Lm[DD];
   __shared__ double U[(BP_WROWS + 1) * DN];
@@ -1399,6 +1419,7 @@ __device__ __forceinline__ void bp_c_forward(const double* __restrict__ sN, cons
 
 extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fusedc(BpObsArgs a) {
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (bp_skip(a.skip, c)) return;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NW = BP_THREADS / 32;
   double a1;
 #if BP_NOISE
@@ -1827,6 +1848,11 @@ extern "C" __global__ void __launch_bounds__(256) bp_otable(BpObsArgs a) {
   const double tmax = a.nobs > 0 ? a.t[0] : 0.0;
   int* jm = a.cg_jm + (size_t)c * a.cgroups;
   double* fl = a.cg_flops + (size_t)c * a.cgroups;
+  if (bp_skip(a.skip, c)) {          // nobody takes this chain
+    if (tid == 0) a.ctab_l[(size_t)c * (DD + 1) + DD] = -1.0;
+    for (int g = tid; g < a.cgroups; g += T) { jm[g] = -1; fl[g] = 0.0; }
+    return;
+  }
   if (!bp_w_path(fin, a1, tmax)) {   // bp_fused takes this chain
     if (tid == 0) {
       a.fb[1 + atomicAdd(a.fb, 1)] = c;
@@ -1935,6 +1961,14 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   int notpd = 0;                                // bit i: an observation of chain 2 warp + i had a covariance that is not positive definite
   int pass = 0;
   const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
+  {   // an octet none of whose chains is on this path (all skipped by the sampler, or all on the sub-step fallback): nothing to do.
+      // (jm < 0 holds for every group of such a chain, so the first group decides; bp_toep masks S' by jm and reads nothing from it)
+    bool any = false;
+    if (g0 < g1)
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) any = any || (o * 8 + cc < a.nchains && a.cg_jm[(size_t)(o * 8 + cc) * a.cgroups + g0] >= 0);
+    if (!any) return;
+  }
   // the chunks of this CTA's groups are consecutive: chunk `ch` of pass p is copied into sOb[p & 1] while pass p - 1 runs
   // (thread = one 16-byte piece of one array; complete before the barrier that follows the score of pass p - 1)
   const int chend = g0 < g1 ? a.cg_chunk0[g1] : 0;
@@ -2078,18 +2112,13 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
 #else
             const double sigma = 0.0;
 #endif
-            if (!bp_score_obs_small(xo, sigma, ymu, yS, qs[i2], dp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
+            if (!bp_score_obs_small<true>(xo, sigma, ymu, yS, qs[i2], dp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
           }
 #pragma unroll
           for (int i = 0; i < BP_N; ++i) yrow[(i2 * BP_D + i) * BP_OYLD + (((i2 * BP_D + i) & 2) ? kB : kA)] = ok ? bmu[i] : 0.0;
 #pragma unroll
-          for (int q = 0; q < BP_S; ++q) {
-            bool diag = false;
-#pragma unroll
-            for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == q);
-            const double bd = diag ? bS[q] : bS[q] + bS[q];
-            yrow[(i2 * BP_D + BP_N + q) * BP_OYLD + (((i2 * BP_D + BP_N + q) & 2) ? kB : kA)] = ok ? bd : 0.0;
-          }
+          for (int q = 0; q < BP_S; ++q)     // (bS is already in packed coordinates: bp_mvn_score_small<true>)
+            yrow[(i2 * BP_D + BP_N + q) * BP_OYLD + (((i2 * BP_D + BP_N + q) & 2) ? kB : kA)] = ok ? bS[q] : 0.0;
         }
       }
       bp_cp_async_wait_all();   // the next pass's chunk has landed (this thread's piece; the barrier publishes all of them)
@@ -2163,6 +2192,12 @@ extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
   double accW[BP_CRT][2];
 #pragma unroll
   for (int rt = 0; rt < BP_CRT; ++rt) { accW[rt][0] = 0.0; accW[rt][1] = 0.0; }
+  {   // none of the octet's chains on this path: W stays unwritten (bp_wpost returns for those chains too)
+    bool any = false;
+#pragma unroll
+    for (int cc2 = 0; cc2 < 8; ++cc2) any = any || (o * 8 + cc2 < a.nchains && a.cg_jm[(size_t)(o * 8 + cc2) * a.cgroups] >= 0);
+    if (!any) return;
+  }
   for (int grp = warp; grp < a.cgroups; grp += 4) {
     const int jm = c < a.nchains ? a.cg_jm[(size_t)c * a.cgroups + grp] : -1;
     const int J = jm < 0 ? -1 : (jm & 255);
@@ -2209,6 +2244,7 @@ extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
 // BP_MSLOT * BP_D doubles per thread (a ring of series terms), laid out [slot][component][thread] (conflict-free).
 __device__ __forceinline__ void bp_fused_chain(const BpObsArgs& a, const int c) {
   const int tid = threadIdx.x;
+  if (bp_skip(a.skip, c)) return;
 
   double th[BP_DIM];
 #pragma unroll
@@ -2341,6 +2377,7 @@ struct BpGroupArgs {
   int jacobian;
   double* lp_out; double* grad_out; double* apps_out;
   int yscap;             // cooperative multi-step path: D x n blocks of shared memory for the sub-step states (0: path not available)
+  const int* skip;       // [C] or nullptr: see bp_skip
 };
 
 template <int NV>
@@ -2376,6 +2413,7 @@ __device__ __forceinline__ bool bp_group_generator(const double (&th)[BP_DIM], c
 
 extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  if (bp_skip(a.skip, c)) return;
   const int G = a.ngroups, GN = G * BP_N;
   double* ymom = bp_smem;                  // [GN][BP_D]
   double* ybar = ymom + (size_t)GN * BP_D; // [GN][BP_D]
@@ -2865,6 +2903,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_onetype(BpObsArgs a)
   __shared__ double scratch[BP_NPART * (BP_THREADS / 32)];
   const int c = blockIdx.y;
   const int tid = threadIdx.x;
+  if (bp_skip(a.skip, c)) return;
   double th[BP_DIM];
   if (a.u) {   // the transform of bp_prologue, by every thread (theta is kept for the priors)
     bp_transform(a.u + (size_t)c * BP_DIM, th);
@@ -2959,9 +2998,9 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_loglik(BpObsArgs a) 
 extern "C" __global__ void bp_epilogue(const double* __restrict__ u, const double* __restrict__ theta,
                                        const double* __restrict__ part, int ntiles, int nchains, int jacobian,
                                        double* __restrict__ lp_out, double* __restrict__ grad_out, int* __restrict__ status,
-                                       double* __restrict__ apps_out) {
+                                       double* __restrict__ apps_out, const int* __restrict__ skip) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= nchains) return;   // (warp-uniform)
+  if (c >= nchains || bp_skip(skip, c)) return;   // (warp-uniform)
   double acc[BP_NPART];
 #pragma unroll
   for (int i = 0; i < BP_NPART; ++i) acc[i] = 0.0;

@@ -621,6 +621,7 @@ struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
   int nobs, npad, ngroups, nchains, nlevels;
   const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
   int yscap;
+  const int* skip;
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
@@ -634,10 +635,11 @@ struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
   int* fb; double* ctab_l;
   const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
   double* n0tab;
+  const int* skip;
 };
 
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
-                 double* grad_dev, int* status_dev, cudaStream_t st) {
+                 double* grad_dev, int* status_dev, cudaStream_t st, const int* skip_dev) {
   if (nchains <= 0) return BPC_OK;
   Loaded* L;
   int rc = model_load(m, d->device, &L);
@@ -668,7 +670,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
               (const double*)d->cgs[d->cgsel].hmax.p, (const double*)d->cgs[d->cgsel].coef.p, d->cdelta, (double*)d->ctab_m1.p, (double*)d->ctab_e2.p, (double*)d->csg.p,
               d->noct, (int*)d->cg_jm.p, (double*)d->cg_flops.p, (double*)d->osg.p, (double*)d->wplain.p,
               (int*)d->fb.p, (double*)d->ctab_l.p,
-              (own_io_1t || own_in) ? u_dev : nullptr, jacobian, lp_dev, grad_dev, apps, (double*)d->n0tab.p};
+              (own_io_1t || own_in) ? u_dev : nullptr, jacobian, lp_dev, grad_dev, apps, (double*)d->n0tab.p, skip_dev};
     void* args[] = {(void*)&a};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->timing) {
@@ -700,7 +702,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       }
       GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
                    (const double*)d->gx.p, (const int*)d->glev.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains,
-                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps, yscap};
+                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps, yscap, skip_dev};
       void* gargs[] = {(void*)&ga};
       BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
     } else {
@@ -738,7 +740,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   if (!own_io) {
     int ntiles = d->ntiles;
     void* args[] = {(void*)&u_dev, (void*)&theta, (void*)&part, (void*)&ntiles, (void*)&nchains, (void*)&jacobian,
-                    (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps};
+                    (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps, (void*)&skip_dev};
     BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
   g_launches += own_io ? 1 : 3;
@@ -779,7 +781,7 @@ int bpc_log_prob_dev(bpc_model* m, bpc_data* d, const double* upars_dev, int nch
                      double* grad_dev, int* status_dev, void* stream) {
   if (!m || !d || !upars_dev || !lp_dev || !status_dev) return fail(BPC_E_INVALID, "null argument");
   if (d->model != m) return fail(BPC_E_INVALID, "data handle belongs to another model");
-  return log_prob_dev(m, d, upars_dev, nchains, jacobian, lp_dev, grad_dev, status_dev, (cudaStream_t)stream);
+  return log_prob_dev(m, d, upars_dev, nchains, jacobian, lp_dev, grad_dev, status_dev, (cudaStream_t)stream, nullptr);
 }
 
 int bpc_log_prob(bpc_model* m, bpc_data* d, const double* upars, int nchains, int jacobian, double* lp, double* grad,
@@ -797,7 +799,7 @@ int bpc_log_prob(bpc_model* m, bpc_data* d, const double* upars, int nchains, in
   cudaStream_t st = d->stream;
   BPC_CUDA(cudaMemcpyAsync(d->io_u.p, upars, (size_t)nchains * dim * 8, cudaMemcpyHostToDevice, st));
   rc = log_prob_dev(m, d, (const double*)d->io_u.p, nchains, jacobian, (double*)d->io_lp.p, grad ? (double*)d->io_grad.p : nullptr,
-                    (int*)d->io_status.p, st);
+                    (int*)d->io_status.p, st, nullptr);
   if (rc) return rc;
   BPC_CUDA(cudaMemcpyAsync(lp, d->io_lp.p, (size_t)nchains * 8, cudaMemcpyDeviceToHost, st));
   if (grad) BPC_CUDA(cudaMemcpyAsync(grad, d->io_grad.p, (size_t)nchains * dim * 8, cudaMemcpyDeviceToHost, st));

@@ -107,5 +107,5 @@ int model_load(bpc_model* m, int device, Loaded** out);
 int order_workspace(bpc_data* d, cudaStream_t st);
 int release_workspace(bpc_data* d, cudaStream_t st);
 int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, int jacobian, double* lp_dev,
-                 double* grad_dev, int* status_dev, cudaStream_t st);
+                 double* grad_dev, int* status_dev, cudaStream_t st, const int* skip_dev);
 }  // namespace bpc

@@ -77,9 +77,9 @@ FlopModel flop_model(const ModelSpec& sp) {
   f.per_obs = 3 + D + score;
   // grouped path: contraction y = sum_l z0_l y^(l) (D (2n - 1)) and cotangent accumulation (2 n D) instead of the plan
   f.per_obs_grouped = score + D * (2 * n - 1) + 2 * n * D;
-  // (n <= 3: bp_grouped scores through the adjugate like bp_fusedo -- 11 / 32 / 78 operations instead of the LDL^T count, plus the
+  // (n <= 3: bp_grouped scores through the adjugate like bp_fusedo -- 12 / 32 / 78 operations instead of the LDL^T count, plus the
   // two running sums; recounted in tests/test_kernel_core_host.py::test_octet_flop_constants_and_adjugate_score)
-  static const double small_score[4] = {0.0, 11.0, 32.0, 78.0};
+  static const double small_score[4] = {0.0, 12.0, 32.0, 78.0};
   if (n <= 3) f.per_obs_grouped = small_score[n] + 2 + (sp.kind == 1 ? 6.0 * n : 0.0) + D * (2 * n - 1) + 2 * n * D;
   // W path: per series term one row of the W update (2 D n); per observation the plan, the staged coefficients c_j (2 per
   // row), the packed-coordinate cotangent (S - n doublings) and the outer product b z0^T (D n)
@@ -95,7 +95,7 @@ FlopModel flop_model(const ModelSpec& sp) {
   // determinants are multiplied up, bp_mvn_score_small), the running sums of q and det (2), the packed-coordinate cotangent (S - n
   // doublings), minus the coefficient update the first term does not need (2); NO outer product b z0^T -- the S' update runs on the
   // X rows the terms already count.  Recounted with a counting scalar: tests/test_kernel_core_host.py::test_octet_flop_constants.
-  static const double small_obs[4] = {0.0, 12.0, 34.0, 82.0};
+  static const double small_obs[4] = {0.0, 13.0, 34.0, 80.0};
   f.per_obs_o = n <= 3 ? small_obs[n] + (sp.kind == 1 ? 6.0 * n : 0.0) : f.per_obs_c;
   return f;
 }

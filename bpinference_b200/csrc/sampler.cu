@@ -308,7 +308,7 @@ __device__ void end_transition(const Chain& ch) {
   const int it = ch.i(I_ITER);
   record_draw(ch, it, accept);
   ch.i(I_ITER) = it + 1;
-  bool metric_updated = false, wait = false;
+  bool metric_updated = false, wait = false, eps_wait = false;
   if (it < P.warmup) {
     // dual averaging (Stan's stepsize_adaptation::learn_stepsize: gamma 0.05, t0 10, kappa 0.75)
     const double cnt = ch.s(S_DA_CNT) + 1.0;
@@ -366,14 +366,21 @@ __device__ void end_transition(const Chain& ch) {
       }
     }
     ch.i(I_WIN_COUNTER) = wc + 1;
-    if (it + 1 == P.warmup) ch.s(S_EPS) = exp(ch.s(S_DA_XBAR));   // complete_adaptation
+    if (it + 1 == P.warmup) {
+      ch.s(S_EPS) = exp(ch.s(S_DA_XBAR));   // complete_adaptation
+      // pooled adaptation: one more exchange -- every chain samples with the geometric mean of the adapted step sizes.  With
+      // one metric for all chains there is one right step size; a chain whose own dual averaging ended a factor of two low would
+      // build trees one level deeper for the whole sampling phase and hold up the end of the run.
+      if (P.pooled) eps_wait = true;
+    }
   }
   if (ch.i(I_ITER) >= P.iter) {
     ch.i(I_PHASE) = PH_DONE;
     atomicAdd(P.counters + 0, 1);
     return;
   }
-  if (wait) {
+  if (wait || eps_wait) {
+    if (eps_wait) ch.i(I_PSEUDO) = 2;
     ch.i(I_PHASE) = PH_WAIT;
     atomicAdd(P.counters + 1, 1);
     return;
@@ -784,7 +791,7 @@ __global__ void bp_nuts_init(Params P, const double* __restrict__ inits_u) {
 // same point separate at once -- their random-number streams differ.
 __device__ __forceinline__ double pseudo_tol(const Params& P) { return 10.0 + P.dim; }
 __device__ __forceinline__ bool pseudo_cand(const Params& P, int c) {
-  return P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT && P.si[(size_t)I_PSEUDO * P.C + c] != 0;
+  return P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT && P.si[(size_t)I_PSEUDO * P.C + c] == 1;
 }
 __device__ double pseudo_lp_max(const Params& P) {
   double m = -INFINITY;
@@ -828,7 +835,11 @@ __global__ void bp_pool_stats(Params P, double* __restrict__ out, int with_flag)
   for (int c = 0; c < P.C; ++c) {
     Chain ch(P, c);
     if (ch.i(I_PHASE) != PH_WAIT) continue;
-    if (ch.i(I_PSEUDO) && !pseudo_good(P, c, lpmax)) continue;   // the ascent of this chain ended in the wrong place
+    if (ch.i(I_PSEUDO) == 2) {           // the exchange at the end of the warm-up: count and sum of log step sizes
+      if (k == 0) acc += 1.0; else if (k == 1) acc += log(ch.s(S_EPS));
+      continue;
+    }
+    if (ch.i(I_PSEUDO) == 1 && !pseudo_good(P, c, lpmax)) continue;   // the ascent of this chain ended in the wrong place
     const double n = ch.s(S_W_N);
     if (k == 0) acc += n;
     else if (P.dense) acc += k <= P.dim ? ch.v(V_W_MEAN, k - 1) : ch.cross(k - 1 - P.dim);
@@ -844,6 +855,8 @@ __global__ void bp_pool_stats(Params P, double* __restrict__ out, int with_flag)
 __global__ void bp_pool_metric(Params P, const double* __restrict__ red) {
   if (threadIdx.x || blockIdx.x) return;
   const int dim = P.dim, M = dim + dim * dim;
+  for (int c = 0; c < P.C; ++c)          // the step-size exchange at the end of the warm-up leaves the metric alone
+    if (P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT) { if (P.si[(size_t)I_PSEUDO * P.C + c] == 2) return; break; }
   // (pooled over thousands of draws the estimate needs no shrinkage towards the unit scale: Stan's 1e-3 * 5 / (n + 5) floor would
   // swamp variances of 1e-6; n / (n + 5) stays, plus a relative jitter on the diagonal)
   double* cur = P.metric;
@@ -883,6 +896,12 @@ __global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
   if (ch.i(I_PHASE) != PH_WAIT) return;
   const double n = red[0];
   const int dim = P.dim;
+  if (ch.i(I_PSEUDO) == 2) {           // end of the warm-up: the pooled step size
+    ch.i(I_PSEUDO) = 0;
+    if (n > 0.0) ch.s(S_EPS) = exp(red[1] / n);
+    begin_transition(ch);
+    return;
+  }
   if (ch.i(I_PSEUDO)) {                // the Laplace pseudo-window of hess_step: the window schedule does not advance
     ch.i(I_PSEUDO) = 0;
   } else {
@@ -908,7 +927,7 @@ __global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
       const double var = n > 1.0 ? (red[1 + dim + k] - n * mean * mean) / (n - 1.0) : 1.0;
       // (pooled over thousands of draws: Stan's shrinkage n / (n + 5) with the pooled count; its absolute 1e-3 * 5 / (n + 5) floor, meant
       // for one chain's 25 draws of unit-scale parameters, would swamp variances of 1e-6 and is replaced by a relative one)
-      ch.v(V_MINV, k) = (n / (n + 5.0)) * var * (1.0 + 1e-9) + 1e-300;
+      if (n > 1.0 && var > 0.0 && isfinite(var)) ch.v(V_MINV, k) = (n / (n + 5.0)) * var * (1.0 + 1e-9) + 1e-300;   // (else: keep the metric)
       ch.v(V_W_MEAN, k) = 0.0;
       ch.v(V_W_M2, k) = 0.0;
     }
@@ -1064,7 +1083,7 @@ void bpc_sampler_free(bpc_sampler* s) {
 static int sampler_passes(bpc_sampler* s, int nb) {
   const Params& P = s->P;
   for (int b = 0; b < nb; ++b) {
-    int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream);
+    int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream, P.si + (size_t)I_PHASE * P.C);
     if (rc) return rc;
     bp_nuts_advance<<<(P.C + 3) / 4, 128, 0, s->stream>>>(P);
     g_launches += 1;

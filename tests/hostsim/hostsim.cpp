@@ -134,7 +134,7 @@ int hs_centred_obs(int J, const double* Nj, const double* z0, const double* xo, 
   for (int i = 0; i < BP_N; ++i) yS[bp_sidx(i, i)] += real(sigma) * ymu[i];
 #endif
   real det, q;
-  const bool ok = bp_mvn_score_small(xx, ymu, yS, det, q, bmu, bS);
+  const bool ok = bp_mvn_score_small<true>(xx, ymu, yS, det, q, bmu, bS);   // bS in packed coordinates
   real qsum = real(0.0), dprod = real(1.0);
   if (ok) { qsum += q; dprod = dprod * det; }                 // the running sums of bp_fusedo (one logarithm per thread at the very end)
 #if BP_NOISE
@@ -142,11 +142,7 @@ int hs_centred_obs(int J, const double* Nj, const double* z0, const double* xo, 
   for (int i = 0; i < BP_N; ++i) { sb += bS[bp_sidx(i, i)] * ymu[i]; bmu[i] += real(sigma) * bS[bp_sidx(i, i)]; }
 #endif
   for (int i = 0; i < BP_N; ++i) b[i] = bmu[i];
-  for (int qq = 0; qq < BP_S; ++qq) {
-    bool diag = false;
-    for (int i = 0; i < BP_N; ++i) diag = diag || (bp_sidx(i, i) == qq);
-    b[BP_N + qq] = diag ? bS[qq] : bS[qq] + bS[qq];
-  }
+  for (int qq = 0; qq < BP_S; ++qq) b[BP_N + qq] = bS[qq];
   for (int j = 0; j <= J; ++j)
     for (int l = 0; l < BP_N; ++l)
       for (int d = 0; d < BP_D; ++d) {
@@ -172,7 +168,7 @@ int hs_score_both(const double* x, const double* mu, const double* S, double* lp
   *lp_out = bp_val(lp);
   for (int i = 0; i < BP_N; ++i) b1[i] = bp_val(bmu[i]);
   for (int k = 0; k < BP_S; ++k) b1[BP_N + k] = bp_val(bS[k]);
-  const bool ok2 = bp_mvn_score_small(xx, m, s, det, q, bmu, bS);
+  const bool ok2 = bp_mvn_score_small<false>(xx, m, s, det, q, bmu, bS);
   *det_out = bp_val(det); *q_out = bp_val(q);
   for (int i = 0; i < BP_N; ++i) b2[i] = bp_val(bmu[i]);
   for (int k = 0; k < BP_S; ++k) b2[BP_N + k] = bp_val(bS[k]);
