@@ -30,10 +30,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fused logp+grad (chain x observation) evaluations per second"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one `ncu --set full` capture of the default
-# workload (profiles/r01_ncu_bp_fusedo_cfg5U.txt: 27.2 MB read + 56.5 MB written — the per-(octet, group) S' matrices, 102 MB of
-# scratch per launch, are written once and streamed back by bp_toep (part of them still from L2); the per-chain tables are 28 MB, the
-# observation table 5.6 MB)
-NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 27.190e6 + 56.474e6}
+# workload (profiles/r02_ncu_bp_fusedo_cfg5U.txt: 19.6 MB read + 54.7 MB written — the per-(octet, group) S' matrices, 102 MB of
+# scratch per launch, are written once and streamed back by bp_toep, partly still from L2; the observation table is 5.6 MB).
+# Algorithmic bytes are 5.68 MB (table + per-chain input / output): the traffic is ~13 x that, all of it the kernel's own scratch,
+# at 0.5 % of the HBM bandwidth.
+NCU_TRAFFIC_BYTES = {("cfg5U", 512, 100000): 19.596e6 + 54.739e6}
 UNIT = "evals/s"
 DEFAULT_CHAINS = {"cfg5U": 512, "cfg5K": 512, "cfg5G": 512, "cfg2": 1024, "cfg1": 4, "cfg3": 4, "cfg4": 4}
 

@@ -909,6 +909,7 @@ struct BpObsArgs {
   double* lp_out; double* grad_out; double* apps_out;
   double* n0tab;         // [C][cgroups][BP_D * BP_N]  octet path: N_0(tau_g) of every (chain, group), entry d * BP_N + l (bp_otable)
   const int* skip;       // [C] or nullptr: the sampler's phase of each chain; chains that wait or have finished (bp_skip) are not evaluated
+  int operm;             // octet path: 1 = the columns of S' are in by-chain order (written by bp_fusedo9), 0 = (cc, d) order (bp_fusedo)
 };
 
 // ---- W path: the reverse sweep of a whole chain as one small matrix polynomial ---------------------
@@ -2180,6 +2181,279 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 
+// ---- bp_fusedo9: the octet passes for n = 3 (D = 9) with TWO barriers per pass ------------------------------------------
+// The same arithmetic as bp_fusedo, re-laid so that the warps of a CTA depend on each other as little as possible:
+//   * rows of Y / b (and columns of N) are ordered BY CHAIN: tile cc (cc = 0 .. 7) holds components 0 .. 7 of chain cc, tile 8 holds
+//     component 8 of the eight chains (BP_O9R).  Warp w owns chains 2w and 2w + 1: it computes their tiles of the forward product for
+//     all 32 observations, scores them, and owns the same tiles of the S' update -- so Y and b of tiles 0 .. 7 never cross a warp
+//     (__syncwarp instead of a CTA barrier).  Only tile 8 (written by observation tile, read by chain) and X (staged by term, read by
+//     all) cross warps; tile 8 is double-buffered.
+//   * the S' update of pass p - 1 and the forward product of pass p run back to back (110 tensor products per warp without a barrier
+//     in between); X of pass p + 1 is staged, and the x_obs of pass p + 1 fetched into registers, during the score of pass p.
+//   pass p:  [S'(p-1); forward(p); store Y(p)]  barrier  [score(p); stage X(p+1)]  barrier  (cp.async of chunk p + 2 issued here)
+// S' of every (octet, group) is written with its columns in the same by-chain order (a.operm tells bp_toep).
+// MEASURED (cfg5U, 512 chains x 100 000 observations): 1.991 ms per step against 1.965 for bp_fusedo -- no gain: with four CTAs per SM
+// the barriers of one CTA are covered by the other three, and what limits the passes is the shared FP64 datapath with four warps per
+// scheduler (78 % busy; registers cap the occupancy at 16 warps per SM).  Not the default; BPC_O9=1 selects it (same results, same tests).
+#if BP_D == 9
+#define BP_O9R(cc, d) ((d) < 8 ? (cc) * 8 + (d) : 64 + (cc))
+#define BP_O9SMEM ((BP_XR * BP_ONLD + 2 * BP_XR * BP_WLD + 64 * BP_OYLD + 2 * 8 * BP_OYLD + BP_OOBS) * 8)
+extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fusedo9(BpObsArgs a) {
+  const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  double* sN = bp_smem;                         // [24][BP_ONLD]        N_j[d][l] of chain cc at [(j, l)][BP_O9R(cc, d)]
+  double* sXb = sN + BP_XR * BP_ONLD;           // [2][24][BP_WLD]      X[(j, l)][obs]
+  double* sY = sXb + 2 * BP_XR * BP_WLD;        // [64][BP_OYLD]        Y, then b, of tiles 0 .. 7 (swizzled, BP_OY)
+  double* sY8 = sY + 64 * BP_OYLD;              // [2][8][BP_OYLD]      tile 8 (component 8 of chain cc in row cc), double-buffered by pass
+  double* sOb = sY8 + 2 * 8 * BP_OYLD;          // [7][32]              one chunk of the observation table (z0, xo, t)
+  __shared__ int sjm[8];
+  const int swz = (g >> 1) & 1;                 // rows with bit 1 set keep column k at k ^ 4
+  const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
+  {
+    bool any = false;
+    if (g0 < g1)
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) any = any || (o * 8 + cc < a.nchains && a.cg_jm[(size_t)(o * 8 + cc) * a.cgroups + g0] >= 0);
+    if (!any) return;
+  }
+  // per-lane bases (doubles)
+  const int fN = tg * BP_ONLD + warp * 16 + g;                    // A fragments of the forward product: + kk * 4 * BP_ONLD + t * 8   (t = 0, 1: this warp's tiles)
+  const int fN8 = tg * BP_ONLD + 64 + g;                          // ... of tile 8
+  const int fX = tg * BP_WLD + g;                                 // B fragments: + kk * 4 * BP_WLD + q * 8   (q = observation tile)
+  const int fY = (warp * 16 + g) * BP_OYLD + ((2 * tg) ^ (swz << 2));   // accumulator stores: + t * 8 * BP_OYLD + q * 8
+  const int fY8 = g * BP_OYLD + warp * 8 + ((2 * tg) ^ (swz << 2));     // tile 8, observation tile `warp`
+  const int uX = g * BP_WLD + tg;                                 // A fragments of the S' update: + rt * 8 * BP_WLD + ob * 4
+  const int uY = (warp * 16 + g) * BP_OYLD + tg;                  // B fragments: + ct * 8 * BP_OYLD + (ob ^ swz) * 4
+  const int uY8 = g * BP_OYLD + tg;                               // ... of tile 8
+  double qs[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
+  BpDetProd dp[2];
+  dp[0].init(); dp[1].init();
+  int notpd = 0;
+  const int chbeg = a.cg_chunk0[g0], chend = a.cg_chunk0[g1];
+  const double* osrc = nullptr;
+  {
+    const int ai = tid >> 4, q = tid & 15;
+    if (ai < 2 * BP_N + 1) osrc = (ai < BP_N ? a.z0 + (size_t)ai * a.npad : (ai < 2 * BP_N ? a.xo + (size_t)(ai - BP_N) * a.npad : a.t)) + 2 * q;
+    if (osrc) bp_cp_async16(sOb + tid * 2, osrc + (size_t)chbeg * 32);
+    bp_cp_async_commit();
+    bp_cp_async_wait_all();
+    __syncthreads();
+  }
+  // X rows of terms j = 2 warp, 2 warp + 1 of this lane's observation, from the chunk in sOb; also fetches this lane's x_obs
+  double xo[BP_N];
+  auto stage = [&](double* sX, double tau, bool valid) {
+    double z0[BP_N];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) { z0[i] = sOb[i * 32 + lane]; xo[i] = sOb[(BP_N + i) * 32 + lane]; }
+    const double h = valid ? sOb[2 * BP_N * 32 + lane] - tau : 0.0;
+    double we = 1.0;
+    for (int j = 1; j <= 2 * warp; ++j) we = we * (h * bp_rk[j - 1]);   // warp-uniform trip count
+    const double wo = we * (h * bp_rk[2 * warp]);
+    double* xs = sX + (2 * warp * BP_N) * BP_WLD + lane;
+#pragma unroll
+    for (int l = 0; l < BP_N; ++l) {
+      xs[l * BP_WLD] = we * z0[l];
+      xs[(BP_N + l) * BP_WLD] = wo * z0[l];
+    }
+  };
+  stage(sXb, a.cg_tau[g0], chbeg * 32 + lane < a.nobs);
+  __syncthreads();                               // every thread is done with chunk `chbeg` in sOb
+  if (osrc && chbeg + 1 < chend) bp_cp_async16(sOb + tid * 2, osrc + (size_t)(chbeg + 1) * 32);
+  bp_cp_async_commit();
+  int pass = 0;
+  for (int grp = g0; grp < g1; ++grp) {
+    // ---- N_j(tau_g) of the octet's chains (as in bp_fusedo; columns in by-chain order) ----
+    if (tid < 8) sjm[tid] = (o * 8 + tid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + tid) * a.cgroups + grp] : -1;
+    __syncthreads();                             // (also: every warp is done with the previous group's N)
+    {
+      constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NQ = (8 * DN + BP_OTHREADS - 1) / BP_OTHREADS;
+      double Lr[NQ][BP_D];
+      int Jq[NQ], eo[NQ], cq[NQ], dq[NQ];
+      int Jmax = -1;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) Jmax = max(Jmax, sjm[cc] < 0 ? -1 : (sjm[cc] & 255));
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e = tid + q * BP_OTHREADS;
+        const int cc = e / DN, rem = e - cc * DN, d = rem / BP_N, l = rem - d * BP_N;
+        Jq[q] = e < 8 * DN ? (sjm[cc & 7] < 0 ? -1 : (sjm[cc & 7] & 255)) : -2;
+        eo[q] = l * BP_ONLD;
+        cq[q] = cc & 7;
+        dq[q] = d;
+        double n0 = 0.0;
+        if (Jq[q] >= 0) {
+          const size_t c = (size_t)o * 8 + cc;
+          const double* lrow = a.ctab_l + c * (DD + 1) + d * BP_D;
+          n0 = a.n0tab[(c * a.cgroups + grp) * DN + rem];
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = lrow[rr];
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = 0.0;
+        }
+        if (Jq[q] >= -1) sN[eo[q] + BP_O9R(cq[q], d)] = n0;
+      }
+      for (int j = 1; j < BP_CJ; ++j) {
+        if (j <= Jmax) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          if (Jq[q] >= -1) {
+            double v = 0.0;
+            if (j <= Jq[q]) {
+              const double* prev = sN + (j - 1) * BP_N * BP_ONLD + eo[q];
+#pragma unroll
+              for (int rr = 0; rr < 8; ++rr) v += Lr[q][rr] * prev[cq[q] * 8 + rr];
+              v += Lr[q][8] * prev[64 + cq[q]];
+            }
+            sN[j * BP_N * BP_ONLD + eo[q] + BP_O9R(cq[q], dq[q])] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();                             // N complete (and X of the group's first pass: staged before a barrier already)
+    double accS[BP_XRT][2][2], accX[2] = {0.0, 0.0};
+#pragma unroll
+    for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
+    // S' update of the pass whose X is in sX and whose b is in sY / y8
+    auto supdate = [&](const double* sX, const double* y8) {
+      const double* px = sX + uX;
+      const double* pbE = sY + uY + (swz << 2);
+      const double* pbO = sY + uY - (swz << 2);
+      const double* p8E = y8 + uY8 + (swz << 2);
+      const double* p8O = y8 + uY8 - (swz << 2);
+      const double* px8 = px + (warp < BP_XRT ? warp : BP_XRT - 1) * 8 * BP_WLD;   // tile 8: row tile `warp`
+#pragma unroll
+      for (int ob = 0; ob < 8; ++ob) {
+        double xa[BP_XRT];
+#pragma unroll
+        for (int rt = 0; rt < BP_XRT; ++rt) xa[rt] = px[rt * 8 * BP_WLD + ob * 4];
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct) {
+          const double bf = ((ob & 1) ? pbO : pbE)[ct * 8 * BP_OYLD + ob * 4];
+#pragma unroll
+          for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][ct][0], accS[rt][ct][1], xa[rt], bf);
+        }
+        // tile 8: row tile `warp` (warps 0 .. 2; warp 3 repeats row tile 2 and drops the result)
+        bp_dmma(accX[0], accX[1], px8[ob * 4], ((ob & 1) ? p8O : p8E)[ob * 4]);
+      }
+    };
+    const double tau = a.cg_tau[grp];
+    const int ch1 = a.cg_chunk0[grp + 1];
+    bool pend = false;
+    for (int ch = a.cg_chunk0[grp]; ch < ch1; ++ch, ++pass) {
+      double* sX = sXb + (pass & 1) * (BP_XR * BP_WLD);
+      double* y8 = sY8 + (pass & 1) * (8 * BP_OYLD);
+      // ---- tensor phase: S' of the previous pass, forward product of this one ----
+      if (pend) supdate(sXb + ((pass - 1) & 1) * (BP_XR * BP_WLD), sY8 + ((pass - 1) & 1) * (8 * BP_OYLD));
+      __syncwarp();                              // this warp's reads of b (tiles 2w, 2w + 1) are done before its Y stores below
+      {
+        double accY[2][4][2], accE[2] = {0.0, 0.0};
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { accY[t][q][0] = 0.0; accY[t][q][1] = 0.0; }
+        const double* pn = sN + fN;
+        const double* px = sX + fX;
+#pragma unroll
+        for (int kk = 0; kk < BP_XKS; ++kk) {
+          double xb[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xb[q] = px[kk * 4 * BP_WLD + q * 8];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const double af = pn[kk * 4 * BP_ONLD + t * 8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bp_dmma(accY[t][q][0], accY[t][q][1], af, xb[q]);
+          }
+          bp_dmma(accE[0], accE[1], sN[fN8 + kk * 4 * BP_ONLD], px[kk * 4 * BP_WLD + warp * 8]);
+        }
+        double* py = sY + fY;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<double2*>(py + t * 8 * BP_OYLD + q * 8) = make_double2(accY[t][q][0], accY[t][q][1]);
+        *reinterpret_cast<double2*>(y8 + fY8) = make_double2(accE[0], accE[1]);
+      }
+      bp_cp_async_wait_all();                    // the chunk of pass + 1 has landed (this thread's piece; the barrier publishes all of them)
+      __syncthreads();                           // tile 8 of Y complete; every warp is done with X / y8 of pass - 1
+      // ---- score of this lane's observation under chains 2 warp and 2 warp + 1; the cotangent (packed coordinates) replaces Y ----
+      {
+        const bool valid = ch * 32 + lane < a.nobs;
+        const int k8 = lane ^ ((warp & 1) << 2);   // tile 8: rows 2 warp + i2, r & 2 = 2 (warp & 1)
+#pragma unroll
+        for (int i2 = 0; i2 < 2; ++i2) {
+          double ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+          bool ok = valid && sjm[2 * warp + i2] >= 0;
+          double* yrow = sY + (2 * warp + i2) * 8 * BP_OYLD;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            const double v = yrow[d * BP_OYLD + (lane ^ ((d & 2) << 1))];
+            if (d < BP_N) ymu[d] = v; else yS[d - BP_N] = v;
+          }
+          yS[8 - BP_N] = y8[(2 * warp + i2) * BP_OYLD + k8];
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) bmu[i] = 0.0;
+#pragma unroll
+          for (int q = 0; q < BP_S; ++q) bS[q] = 0.0;
+          if (ok) {
+#if BP_NOISE
+            const double sigma = a.theta[(size_t)(o * 8 + 2 * warp + i2) * BP_DIM + BP_P];
+#else
+            const double sigma = 0.0;
+#endif
+            if (!bp_score_obs_small<true>(xo, sigma, ymu, yS, qs[i2], dp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
+          }
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            const double v = d < BP_N ? bmu[d < BP_N ? d : 0] : bS[d < BP_N ? 0 : d - BP_N];
+            yrow[d * BP_OYLD + (lane ^ ((d & 2) << 1))] = ok ? v : 0.0;
+          }
+          y8[(2 * warp + i2) * BP_OYLD + k8] = ok ? bS[8 - BP_N] : 0.0;
+        }
+      }
+      // ---- X of the next pass (and its x_obs), from the chunk that landed during the tensor phase ----
+      if (ch + 1 < chend) stage(sXb + ((pass + 1) & 1) * (BP_XR * BP_WLD), ch + 1 < ch1 ? tau : a.cg_tau[grp + 1], (ch + 1) * 32 + lane < a.nobs);
+      __syncthreads();                           // b (tile 8) and X of pass + 1 complete; every thread is done with the chunk in sOb
+      if (osrc && ch + 2 < chend) bp_cp_async16(sOb + tid * 2, osrc + (size_t)(ch + 2) * 32);
+      bp_cp_async_commit();
+      pend = true;
+    }
+    // ---- the group's last S' update, then S' to global memory: rows (j, l), columns in by-chain order ----
+    if (pend) supdate(sXb + ((pass - 1) & 1) * (BP_XR * BP_WLD), sY8 + ((pass - 1) & 1) * (8 * BP_OYLD));
+    double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
+#pragma unroll
+    for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+        __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (warp * 2 + ct) * 8 + 2 * tg), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
+    if (warp < BP_XRT) __stcg(reinterpret_cast<double2*>(sg + (size_t)(warp * 8 + g) * BP_OU + 64 + 2 * tg), make_double2(accX[0], accX[1]));
+  }
+  // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial; chain 2 warp + i belongs to this warp alone ----
+#pragma unroll
+  for (int i2 = 0; i2 < 2; ++i2) {
+    const double l = bp_warp_sum(-0.5 * (qs[i2] + dp[i2].logdet())), s2 = bp_warp_sum(sb[i2]);
+    const int c = o * 8 + 2 * warp + i2;
+    if (lane == 0 && c < a.nchains) {
+      double fl = 0.0;
+      bool mine = false;
+      for (int grp = g0; grp < g1; ++grp) { fl += a.cg_flops[(size_t)c * a.cgroups + grp]; mine = mine || a.cg_jm[(size_t)c * a.cgroups + grp] >= 0; }
+      if (mine || g0 >= g1 || a.cg_jm[(size_t)c * a.cgroups] >= 0) {
+        double* p = a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART;
+        p[0] = l;
+#pragma unroll
+        for (int k = 0; k < BP_P; ++k) p[1 + k] = 0.0;
+        p[BP_P + 1] = s2;
+        p[BP_P + 2] = fl;
+      }
+    }
+  }
+  notpd = __reduce_or_sync(0xffffffffu, notpd);
+  if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
+}
+#endif  // BP_D == 9
+
 // W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
 // (Variants measured on cfg5U and not kept: eight warps with four groups in flight, software-pipelined loads, a group-major
 // layout of S' that this kernel could stream -- all within a few microseconds of this one, 82 .. 93 us; ncu: tensor path 39 % busy.)
@@ -2187,7 +2461,12 @@ extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
   const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
   __shared__ double red[4][BP_CRT * 64];
-  const int u = ct * 8 + g, cc = u / BP_D;        // this lane's column of the B fragments: chain cc of the octet
+  const int u = ct * 8 + g;                       // this lane's column of the B fragments: chain cc of the octet
+#if BP_D == 9
+  const int cc = a.operm ? (u < 64 ? u >> 3 : u - 64) : u / BP_D;
+#else
+  const int cc = u / BP_D;
+#endif
   const int c = o * 8 + cc;
   double accW[BP_CRT][2];
 #pragma unroll
@@ -2229,7 +2508,12 @@ extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
     const double sacc = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
     const int rt = i >> 6, ln = (i & 63) >> 1, e = i & 1;
     const int row = rt * 8 + (ln >> 2), uu = ct * 8 + (ln & 3) * 2 + e;
+#if BP_D == 9
+    const int cc2 = a.operm ? (uu < 64 ? uu >> 3 : uu - 64) : uu / BP_D, d = a.operm ? (uu < 64 ? uu & 7 : 8) : uu % BP_D;
+    const int c2 = o * 8 + cc2;
+#else
     const int c2 = o * 8 + uu / BP_D, d = uu % BP_D;
+#endif
     if (row < BP_CROWS && c2 < a.nchains) a.wplain[((size_t)c2 * BP_CROWS + row) * BP_WCOLS + d * BP_N + l] = sacc;
   }
 }
