@@ -2662,6 +2662,14 @@ struct BpGroupArgs {
   double* lp_out; double* grad_out; double* apps_out;
   int yscap;             // cooperative multi-step path: D x n blocks of shared memory for the sub-step states (0: path not available)
   const int* skip;       // [C] or nullptr: see bp_skip
+  // phase B on its own grid (data with many observations per group; bp_groupb): mode 0 = bp_grouped does everything (one launch),
+  // 1 = phase A only (moments -> gmom, status reset), 2 = phases A and A' around bp_groupb's partial sums
+  int mode, ntb;         // ntb: tiles of phase B
+  const int* tgroup;     // [ntb] group of the tile
+  const int* tstart;     // [ntb + 1] first observation of the tile (tiles of a group are consecutive; tstart[ntb] = nobs)
+  const int* gtile0;     // [G + 1] first tile of each group
+  double* gmom;          // [C][G * BP_N][BP_D] single-ancestor moments (phase A -> phase B)
+  double* ypart;         // [C][ntb][BP_N * BP_D + 2] per-tile sums of the cotangents, lp and d/dsigma_obs (phase B -> phase A')
 };
 
 template <int NV>
@@ -2693,6 +2701,95 @@ __device__ __forceinline__ bool bp_group_generator(const double (&th)[BP_DIM], c
   bp_assemble(r, A, H);
   a1 = bp_norm1(A);
   return fin;
+}
+
+// phase B for one observation: y_k = sum_l z0_kl y^(g,l), score, cotangents ybar^(g,l) += z0_kl ybar_k
+struct BpGroupBAcc {
+  double lp, sb;
+#if BP_N <= 3
+  double qsum;
+  BpDetProd dprod;
+#endif
+  __device__ __forceinline__ void init() {
+    lp = 0.0; sb = 0.0;
+#if BP_N <= 3
+    qsum = 0.0; dprod.init();
+#endif
+  }
+  __device__ __forceinline__ double total() const {
+#if BP_N <= 3
+    return -0.5 * (qsum + dprod.logdet());
+#else
+    return lp;
+#endif
+  }
+};
+
+// (mom: [BP_N][BP_D] flattened -- registers in bp_grouped, shared memory (broadcast reads) in bp_groupb)
+__device__ __forceinline__ bool bp_groupb_obs(const BpGroupArgs& a, int k, double sigma, const double* __restrict__ mom, double (&acc)[BP_N * BP_D],
+                                              BpGroupBAcc& s) {
+  double z0[BP_N], xo[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) {
+    double sacc = z0[0] * mom[i];
+#pragma unroll
+    for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l * BP_D + i];
+    ymu[i] = sacc;
+  }
+#pragma unroll
+  for (int q = 0; q < BP_S; ++q) {
+    double sacc = z0[0] * mom[BP_N + q];
+#pragma unroll
+    for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l * BP_D + BP_N + q];
+    yS[q] = sacc;
+  }
+#if BP_N <= 3
+  if (!bp_score_obs_small(xo, sigma, ymu, yS, s.qsum, s.dprod, s.sb, bmu, bS)) return false;
+#else
+  if (!bp_score_obs(xo, sigma, ymu, yS, s.lp, s.sb, bmu, bS)) return false;
+#endif
+#pragma unroll
+  for (int l = 0; l < BP_N; ++l) {
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) acc[l * BP_D + i] += z0[l] * bmu[i];
+#pragma unroll
+    for (int q = 0; q < BP_S; ++q) acc[l * BP_D + BP_N + q] += z0[l] * bS[q];
+  }
+  return true;
+}
+
+// phase B of bp_grouped on its own grid (tiles, chains): data with many observations per (level, duration) group.  One CTA per chain
+// cannot hide the latency of 10^5 observations (profiles/r02_ncu_bp_grouped_cfg5G.txt: 12 % of the warps, long_scoreboard 6 cycles
+// per issue); here every tile of <= 4096 observations of one group is a CTA.  Per-tile sums go to ypart in fixed order (no atomics).
+extern "C" __global__ void __launch_bounds__(128, 4) bp_groupb(BpGroupArgs a) {
+  const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  if (bp_skip(a.skip, c)) return;
+  __shared__ double red[(BP_N * BP_D + 2) * 4];
+  const int g = a.tgroup[tile], k0 = a.tstart[tile], k1 = a.tstart[tile + 1];
+#if BP_NOISE
+  const double sigma = a.theta[(size_t)c * BP_DIM + BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  __shared__ double mom[BP_N * BP_D];
+  double vals[BP_N * BP_D + 2];      // the cotangent sums, then lp and d/dsigma_obs
+  double (&acc)[BP_N * BP_D] = *reinterpret_cast<double (*)[BP_N * BP_D]>(vals);
+  const double* gm = a.gmom + ((size_t)c * a.ngroups * BP_N + (size_t)g * BP_N) * BP_D;
+  if (tid < BP_N * BP_D) mom[tid] = gm[tid];
+#pragma unroll
+  for (int i = 0; i < BP_N * BP_D; ++i) acc[i] = 0.0;
+  __syncthreads();
+  BpGroupBAcc s;
+  s.init();
+  int status = 0;
+  for (int k = k0 + tid; k < k1; k += 128)
+    if (!bp_groupb_obs(a, k, sigma, mom, acc, s)) status |= BP_ST_NOT_PD;
+  vals[BP_N * BP_D] = s.total();
+  vals[BP_N * BP_D + 1] = s.sb;
+  bp_block_sum(vals, red, a.ypart + ((size_t)c * a.ntb + tile) * (BP_N * BP_D + 2));
+  if (status) atomicOr(a.status + c, status);
 }
 
 extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
@@ -2879,56 +2976,45 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   }
   }
   __syncthreads();
+  if (a.mode == 1) {   // phase A only: the moments go to global memory for bp_groupb; the status is reset before its CTAs OR into it
+    double* gm = a.gmom + (size_t)c * GN * BP_D;
+    for (int i = tid; i < GN * BP_D; i += T) gm[i] = ymom[i];
+    if (tid == 0) a.status[c] = 0;
+    __syncthreads();
+    if (status) atomicOr(a.status + c, status);
+    return;
+  }
   // ---- phase B: observations, group by group ----
   double lp = 0.0, sb = 0.0;
-#if BP_N <= 3
-  double qsum = 0.0;      // (score through the adjugate: one reciprocal per observation, one logarithm per thread)
-  BpDetProd dprod;
-  dprod.init();
-#endif
-  for (int g = 0; g < G; ++g) {
-    double mom[BP_N][BP_D], acc[BP_N * BP_D];
-#pragma unroll
-    for (int l = 0; l < BP_N; ++l)
-#pragma unroll
-      for (int q = 0; q < BP_D; ++q) { mom[l][q] = ymom[(size_t)(g * BP_N + l) * BP_D + q]; acc[l * BP_D + q] = 0.0; }
-    const int k1 = a.gstart[g + 1];
-    for (int k = a.gstart[g] + tid; k < k1; k += T) {
-      double z0[BP_N], xo[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
-#pragma unroll
-      for (int i = 0; i < BP_N; ++i) {
-        double sacc = z0[0] * mom[0][i];
-#pragma unroll
-        for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l][i];
-        ymu[i] = sacc;
-      }
-#pragma unroll
-      for (int q = 0; q < BP_S; ++q) {
-        double sacc = z0[0] * mom[0][BP_N + q];
-#pragma unroll
-        for (int l = 1; l < BP_N; ++l) sacc += z0[l] * mom[l][BP_N + q];
-        yS[q] = sacc;
-      }
-#if BP_N <= 3
-      if (!bp_score_obs_small(xo, sigma, ymu, yS, qsum, dprod, sb, bmu, bS)) { status |= BP_ST_NOT_PD; continue; }
-#else
-      if (!bp_score_obs(xo, sigma, ymu, yS, lp, sb, bmu, bS)) { status |= BP_ST_NOT_PD; continue; }
-#endif
-#pragma unroll
-      for (int l = 0; l < BP_N; ++l) {
-#pragma unroll
-        for (int i = 0; i < BP_N; ++i) acc[l * BP_D + i] += z0[l] * bmu[i];
-#pragma unroll
-        for (int q = 0; q < BP_S; ++q) acc[l * BP_D + BP_N + q] += z0[l] * bS[q];
-      }
+  if (a.mode == 2) {
+    // bp_groupb did phase B: sum its per-tile cotangents group by group in tile order; lp and sb by thread 0
+    constexpr int NV = BP_N * BP_D + 2;
+    const double* yp = a.ypart + (size_t)c * a.ntb * NV;
+    for (int i = tid; i < GN * BP_D; i += T) {
+      const int g = i / (BP_N * BP_D), e = i - g * (BP_N * BP_D);
+      double sacc = 0.0;
+      for (int tI = a.gtile0[g]; tI < a.gtile0[g + 1]; ++tI) sacc += yp[(size_t)tI * NV + e];
+      ybar[i] = sacc;
     }
-    bp_block_sum(acc, red, ybar + (size_t)g * BP_N * BP_D);
+    if (tid == 0) {
+      for (int tI = 0; tI < a.ntb; ++tI) { lp += yp[(size_t)tI * NV + BP_N * BP_D]; sb += yp[(size_t)tI * NV + BP_N * BP_D + 1]; }
+    }
+    __syncthreads();
+  } else {
+    BpGroupBAcc sB;
+    sB.init();
+    for (int g = 0; g < G; ++g) {
+      double mom[BP_N * BP_D], acc[BP_N * BP_D];
+#pragma unroll
+      for (int i = 0; i < BP_N * BP_D; ++i) { mom[i] = ymom[(size_t)g * BP_N * BP_D + i]; acc[i] = 0.0; }
+      const int k1 = a.gstart[g + 1];
+      for (int k = a.gstart[g] + tid; k < k1; k += T)
+        if (!bp_groupb_obs(a, k, sigma, mom, acc, sB)) status |= BP_ST_NOT_PD;
+      bp_block_sum(acc, red, ybar + (size_t)g * BP_N * BP_D);
+    }
+    lp = sB.total();
+    sb = sB.sb;
   }
-#if BP_N <= 3
-  lp = -0.5 * (qsum + dprod.logdet());
-#endif
   // ---- phase A': reverse sweep of every series with the reduced cotangent ----
   double cb[BP_P];
 #pragma unroll
@@ -3101,7 +3187,7 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   if (a.u) {
     // the chain's status: OR over the CTA; then the work of bp_epilogue by one thread
     __shared__ int sst;
-    if (tid == 0) sst = 0;
+    if (tid == 0) sst = a.mode == 2 ? a.status[c] : 0;   // (mode 2: the bits phase A and bp_groupb left)
     __syncthreads();
     if (status) atomicOr(&sst, status);
     bp_block_sum(vals, red, a.part + (size_t)c * BP_NPART);   // (ends with a barrier; the sums are also in global memory)

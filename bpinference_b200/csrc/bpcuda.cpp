@@ -93,6 +93,7 @@ int model_load(bpc_model* m, int device, Loaded** out) {
     L.obs_smem = (size_t)m->spec.mslot * D * m->spec.threads * sizeof(double);
     BPC_CUDA(cudaKernelSetAttributeForDevice(L.obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.obs_smem, device));
     if (cudaLibraryGetKernel(&L.grouped, L.lib, "bp_grouped") != cudaSuccess) { L.grouped = nullptr; cudaGetLastError(); }
+    if (cudaLibraryGetKernel(&L.groupb, L.lib, "bp_groupb") != cudaSuccess) { L.groupb = nullptr; cudaGetLastError(); }
     BPC_CUDA(cudaLibraryGetKernel(&L.moments, L.lib, "bp_moments"));
     if (!m->spec.xdep) {
       BPC_CUDA(cudaLibraryGetKernel(&L.fusedw, L.lib, "bp_fusedw"));
@@ -469,6 +470,24 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
       dd->grouped = true;
       dd->ngroups = G;
       dd->group_threads = N <= 2048 ? 32 : (N <= 8192 ? 64 : 128);
+      // many observations per chain: phase B on its own grid (bp_groupb), tiles of <= 4096 observations that do not straddle a group
+      // (BPC_GROUPB=0 keeps the single launch; small data, which is what a sampler pass on the reference's examples is made of, too)
+      const char* gb = std::getenv("BPC_GROUPB");
+      if (N >= 16384 && !(gb && std::atoi(gb) == 0)) {
+        std::vector<int> tg, ts, gt0;
+        int tsz = 4096;   // (cfg5G, 512 chains x 100 000 observations: 512 -> 1.29 ms, 1024 -> 1.03, 2048 -> 0.90, 4096 -> 0.85)
+        if (const char* ev = std::getenv("BPC_GROUPB_TILE")) { const int v = std::atoi(ev); if (v >= 128 && v <= (1 << 20)) tsz = v; }
+        for (int g = 0; g < G; ++g) {
+          gt0.push_back((int)tg.size());
+          for (int k = gs[g]; k < gs[g + 1]; k += tsz) { tg.push_back(g); ts.push_back(k); }
+        }
+        gt0.push_back((int)tg.size());
+        ts.push_back(N);
+        dd->ntb = (int)tg.size();
+        if ((rc = up(dd->tgroup, tg.data(), tg.size() * 4))) return rc;
+        if ((rc = up(dd->tstart, ts.data(), ts.size() * 4))) return rc;
+        if ((rc = up(dd->gtile0, gt0.data(), gt0.size() * 4))) return rc;
+      }
     }
   }
   // W path (bp_fusedw + bp_wpost): rates independent of per-observation variables, ungrouped data, n <= 3
@@ -582,6 +601,10 @@ static int ensure_workspace(bpc_data* d, int nchains) {
     if (d->grouped) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
       if ((rc = d->ring.alloc((size_t)nchains * s.mslot * D * d->ngroups * n * 8))) return rc;
+      if (d->ntb > 0) {
+        if ((rc = d->gmom.alloc((size_t)nchains * d->ngroups * n * D * 8))) return rc;
+        if ((rc = d->ypart.alloc((size_t)nchains * d->ntb * (n * D + 2) * 8))) return rc;
+      }
     }
     if (d->wmode) {
       const int n = s.ntypes, D = n + n * (n + 1) / 2;
@@ -630,6 +653,7 @@ struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
   const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
   int yscap;
   const int* skip;
+  int mode, ntb; const int* tgroup; const int* tstart; const int* gtile0; double* gmom; double* ypart;
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
@@ -711,9 +735,20 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       }
       GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
                    (const double*)d->gx.p, (const int*)d->glev.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains,
-                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps, yscap, skip_dev};
+                   d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps, yscap, skip_dev,
+                   0, d->ntb, (const int*)d->tgroup.p, (const int*)d->tstart.p, (const int*)d->gtile0.p, (double*)d->gmom.p, (double*)d->ypart.p};
       void* gargs[] = {(void*)&ga};
-      BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+      if (d->ntb > 0 && L->groupb && u_dev) {
+        // phases A | B | A' as three launches: phase B gets (tiles x chains) CTAs instead of one per chain
+        ga.mode = 1;
+        BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+        BPC_CUDA(cudaLaunchKernel((const void*)L->groupb, dim3(d->ntb, nchains), dim3(128), gargs, 0, st));
+        ga.mode = 2;
+        BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+        g_launches += 2;
+      } else {
+        BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+      }
     } else {
       if (d->wmode) {
         // chains whose series need one sub-step: W accumulation on the fp64 tensor path + one per-chain matrix polynomial;

@@ -39,7 +39,7 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr, groupb = nullptr;
   size_t obs_smem = 0, grouped_smem = 0, o_smem = 0, o9_smem = 0;
 };
 
@@ -89,6 +89,9 @@ struct bpc_data {
   bpc::DevBuf cg_jm, cg_flops, osg, wplain, fb, ctab_l, n0tab;
   bpc::DevBuf gstart, gt, gx, glev, ring;
   int nlevels = 1;   // grouped path: first observation, duration and dependent variables of each group; term ring
+  // phase B of the grouped path on its own grid (many observations per group): tiles of <= 4096 observations of one group
+  int ntb = 0;
+  bpc::DevBuf tgroup, tstart, gtile0, gmom, ypart;
   int group_threads = 128;
   // workspace sized for ws_chains chains.  ws_gen counts every re-tiling / reallocation: a sampler that replays a captured CUDA
   // graph (raw workspace pointers and tiling baked in) compares it with the generation it captured under and re-captures.

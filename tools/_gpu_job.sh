@@ -1,7 +1,5 @@
-set -x
 export PYTHONPATH=$PWD
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_corners.py -q -x -k "octet or full_size or bench_shape or unbounded or deterministic" > gpurun_out/r2_gputest7.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2_gputest7.log
-B="python bench.py --steps 20 --warmup 5 --no-sampling --no-other-workloads --no-cpu-baseline"
-BPC_O9=0 $B > gpurun_out/r2_bench_o9_off.json 2> gpurun_out/r2_bench_o9_off.err
-$B > gpurun_out/r2_bench_o9_on.json 2> gpurun_out/r2_bench_o9_on.err
-tail -5 gpurun_out/r2_gputest7.log; cut -c1-330 gpurun_out/r2_bench_o9_off.json; cut -c1-330 gpurun_out/r2_bench_o9_on.json; tail -3 gpurun_out/r2_bench_o9_on.err
+B="python bench.py --workload cfg5G --steps 20 --warmup 5 --no-sampling --no-other-workloads --no-cpu-baseline --no-parity"
+for t in 512 1024 2048 4096; do BPC_GROUPB_TILE=$t $B 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read()); print('tile $t', j['ms_per_step'])"; done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_cfg5G.csv python bench.py --workload cfg5G --steps 2 --warmup 3 --no-sampling --no-other-workloads --no-cpu-baseline --no-parity > /dev/null 2>&1
+python tools/launch_times.py gpurun_out/r2_launches_cfg5G.csv | grep bp_
