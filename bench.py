@@ -199,7 +199,7 @@ def cpu_port_rate(cfg, seconds, nthreads=0):
     return chains * nobs * reps / dt, cores, "%d chains x first %d of %d observations x %d passes, %d OpenMP threads, %.1f s" % (chains, nobs, N, reps, cores, dt)
 
 
-def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, chains, nobs, iters, warm, opt_steps, dense, adapt_delta=0.8):
+def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, chains, nobs, iters, warm, opt_steps, dense, subsample=0, adapt_delta=0.8):
     """the second half of BASELINE.json's metric: ESS/s of the device-resident NUTS sampler.  Chains are sharded over the ranks
     (`chains` per GPU); the diagonal metric of every warm-up window is estimated from the draws of ALL chains of ALL ranks — the one
     collective of the path: an all-reduce of 2 + 2 dim doubles over NCCL at every window boundary, and 4 dim doubles for split R-hat at
@@ -215,7 +215,7 @@ def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, cha
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     fit = eng.sampling(d, chains=chains, iter=iters, warmup=warm, init=init, control=dict(adapt_delta=adapt_delta, max_treedepth=10, metric="dense_e" if dense else "diag_e"),
-                       seed=1, pooled_adaptation=True, init_opt_steps=opt_steps)
+                       seed=1, pooled_adaptation=True, init_opt_steps=opt_steps, init_opt_subsample=subsample)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ess = fit.ess_bulk()
@@ -242,7 +242,7 @@ def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, cha
     except Exception:
         have_rstan = False
     return {"workload": "%s: %s; NUTS, %d iterations (%d warm-up), adapt_delta %.2f, starting values uniform(0, 1) followed by at most %d L-BFGS "
-                        "evaluations per chain; %s metric: Laplace covariance at the optimum first, then the %s of the warm-up draws of all "
+                        "evaluations per chain" + (" on a subsample of %d observations and as many on all of them" % subsample if subsample else "") + "; %s metric: Laplace covariance at the optimum first, then the %s of the warm-up draws of all "
                         "chains of all ranks at every window (NCCL all-reduce of %d doubles), pooled step size"
                         % (workload, workload_description(workload, chains, int(cfg["data"]["ndatapts"])), iters, warm, adapt_delta, opt_steps,
                            "dense (dense_e)" if dense else "diagonal (diag_e)", "covariance" if dense else "variances",
@@ -485,7 +485,7 @@ def _main(args):
         sampling = {"cfg2": sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 200, False)}
         if args.workload == "cfg5U" and not args.nobs:
             sampling["cfg5U"] = sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg5U", chains, None, args.sampling_iter,
-                                                args.sampling_iter // 2, 300, True)
+                                                args.sampling_iter // 2, 300, True, subsample=5000)
 
     if rank == 0:
         total_evals = float(world) * chains * N * args.steps

@@ -44,7 +44,7 @@ class StanData(C.Structure):
 class SampleArgs(C.Structure):
     _fields_ = [("chains", C.c_int), ("iter", C.c_int), ("warmup", C.c_int), ("adapt_delta", C.c_double),
                 ("max_treedepth", C.c_int), ("seed", C.c_ulonglong), ("chain_id_offset", C.c_int),
-                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double), ("init_opt_steps", C.c_int), ("metric", C.c_int)]
+                ("inits", C.POINTER(C.c_double)), ("pooled_adaptation", C.c_int), ("stepsize", C.c_double), ("init_opt_steps", C.c_int), ("metric", C.c_int), ("init_opt_data", C.c_void_p)]
 
 
 # every symbol include/bpcuda.h declares: name -> (restype, argtypes)

@@ -778,8 +778,11 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
         BPC_CUDA(cudaLaunchKernel((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
         g_launches += 2;
       }
-      // (centred / octet W paths: bp_ctable listed the chains that need sub-steps; a few rows of CTAs walk that list)
-      BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, d->cmode ? std::min(nchains, 8) : nchains), dim3(s.threads), args, L->obs_smem, st));
+      // (centred / octet W paths: bp_ctable / bp_otable listed the chains that need sub-steps; a few rows of CTAs walk that list -- at
+      // least 8, and enough to fill the device when the data has few tiles: far from the mode, e.g. during the ascent from wide starting
+      // values on a subsample, EVERY chain is on the list; rows that find nothing to do return at once)
+      const int fb_rows = std::min(nchains, std::max(8, (148 * 4 + d->ntiles - 1) / std::max(1, d->ntiles)));
+      BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, d->cmode ? fb_rows : nchains), dim3(s.threads), args, L->obs_smem, st));
     }
     if (d->timing) {
       BPC_CUDA(cudaEventRecord(e1, st));

@@ -117,6 +117,7 @@ int bpc_sample_multi(bpc_model* m, const bpc_stan_data* data, const int* devices
     if (!w.rc && (rc = bpc_data_create(m, data, w.device, 0, &w.data))) failw(rc);
     bpc_sample_args la = *a;
     la.chain_id_offset = a->chain_id_offset + w.index * C;
+    la.init_opt_data = nullptr;   // (a subsample handle belongs to one device; the multi-device run does the one-stage ascent)
     if (a->inits) la.inits = a->inits + (size_t)w.index * C * m->spec.nparams;
     if (!w.rc && (rc = bpc_sampler_create(m, w.data, &la, &w.sampler))) failw(rc);
     int state = 0;

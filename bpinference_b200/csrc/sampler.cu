@@ -41,10 +41,10 @@ enum { S_EPS, S_LP_CUR, S_H0, S_LSW, S_SUB_LSW, S_SUM_ACC, S_DA_MU, S_DA_SBAR, S
 // vector double fields (dim each)
 enum { V_Q_CUR, V_G_CUR, V_QL, V_PL, V_GL, V_QR, V_PR, V_GR, V_Q_PROP, V_G_PROP, V_Q_SP, V_G_SP, V_RHO, V_RHO_SUB, V_MINV, V_W_MEAN, V_W_M2, V_W_EVAL, NVEC };
 // int fields
-enum { I_PHASE, I_ITER, I_DEPTH, I_NLEAP, I_DIR, I_LEAF, I_DIVERGENT, I_FE_DIR, I_WIN_NEXT, I_WIN_SIZE, I_WIN_COUNTER, I_TRIES, I_RNG, I_PSEUDO, NINT };
+enum { I_PHASE, I_ITER, I_DEPTH, I_NLEAP, I_DIR, I_LEAF, I_DIVERGENT, I_FE_DIR, I_WIN_NEXT, I_WIN_SIZE, I_WIN_COUNTER, I_TRIES, I_RNG, I_PSEUDO, I_STAGE, NINT };
 
 struct Params {
-  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits, opt_steps, dense, nsum, debug, hess;
+  int C, dim, P, noise, max_depth, iter, warmup, chain_offset, pooled, have_inits, opt_steps, dense, nsum, debug, hess, two_stage;
   int init_buffer, term_buffer, base_window;
   double delta, eps0;
   unsigned long long seed;
@@ -549,6 +549,16 @@ __device__ void end_opt(const Chain& ch) {
            ch.s(S_OPT_LR), ch.i(I_DEPTH), ch.i(I_NLEAP), ch.s(S_OPT_FLAT), ch.v(V_Q_CUR, 0), ch.P.dim > 2 ? ch.v(V_Q_CUR, 2) : 0.0);
   }
   ch.i(I_NLEAP) = 0; ch.i(I_DEPTH) = 0; ch.i(I_LEAF) = 0; ch.i(I_DIR) = 0;
+  if (ch.P.two_stage && ch.i(I_STAGE) == 0) {
+    // end of the first stage (ascent on the subsample, bpc_sample_args.init_opt_data): wait until every chain of every rank is here;
+    // the exchange that follows restarts the chains that ended in a wrong basin and switches the evaluation to the full data
+    ch.i(I_STAGE) = 1;
+    ch.i(I_PSEUDO) = 3;
+    ch.s(S_W_N) = 1.0;
+    ch.i(I_PHASE) = PH_WAIT;
+    atomicAdd(ch.P.counters + 1, 1);
+    return;
+  }
   if (ch.P.hess) { begin_hess(ch); return; }
   ch.i(I_FE_DIR) = 0;
   begin_eps_trial(ch, PH_FIND_EPS_FIRST);
@@ -791,7 +801,8 @@ __global__ void bp_nuts_init(Params P, const double* __restrict__ inits_u) {
 // same point separate at once -- their random-number streams differ.
 __device__ __forceinline__ double pseudo_tol(const Params& P) { return 10.0 + P.dim; }
 __device__ __forceinline__ bool pseudo_cand(const Params& P, int c) {
-  return P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT && P.si[(size_t)I_PSEUDO * P.C + c] == 1;
+  const int ps = P.si[(size_t)I_PSEUDO * P.C + c];
+  return P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT && (ps == 1 || ps == 3);
 }
 __device__ double pseudo_lp_max(const Params& P) {
   double m = -INFINITY;
@@ -839,6 +850,7 @@ __global__ void bp_pool_stats(Params P, double* __restrict__ out, int with_flag)
       if (k == 0) acc += 1.0; else if (k == 1) acc += log(ch.s(S_EPS));
       continue;
     }
+    if (ch.i(I_PSEUDO) == 3) continue;    // the stage switch of the two-stage ascent: a barrier, no statistics
     if (ch.i(I_PSEUDO) == 1 && !pseudo_good(P, c, lpmax)) continue;   // the ascent of this chain ended in the wrong place
     const double n = ch.s(S_W_N);
     if (k == 0) acc += n;
@@ -856,7 +868,7 @@ __global__ void bp_pool_metric(Params P, const double* __restrict__ red) {
   if (threadIdx.x || blockIdx.x) return;
   const int dim = P.dim, M = dim + dim * dim;
   for (int c = 0; c < P.C; ++c)          // the step-size exchange at the end of the warm-up leaves the metric alone
-    if (P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT) { if (P.si[(size_t)I_PSEUDO * P.C + c] == 2) return; break; }
+    if (P.si[(size_t)I_PHASE * P.C + c] == PH_WAIT) { if (P.si[(size_t)I_PSEUDO * P.C + c] >= 2) return; break; }
   // (pooled over thousands of draws the estimate needs no shrinkage towards the unit scale: Stan's 1e-3 * 5 / (n + 5) floor would
   // swamp variances of 1e-6; n / (n + 5) stays, plus a relative jitter on the diagonal)
   double* cur = P.metric;
@@ -896,6 +908,15 @@ __global__ void bp_pool_apply(Params P, const double* __restrict__ red) {
   if (ch.i(I_PHASE) != PH_WAIT) return;
   const double n = red[0];
   const int dim = P.dim;
+  if (ch.i(I_PSEUDO) == 3) {           // stage switch: evaluate the point the first stage reached on the full data, then the second ascent
+    ch.i(I_PSEUDO) = 0;
+    ch.s(S_W_N) = 0.0;
+    ch.i(I_TRIES) = 100;               // (no random restarts from here)
+    for (int k = 0; k < dim; ++k) ch.v(V_W_EVAL, k) = ch.v(V_Q_CUR, k);
+    publish_eval(ch);
+    ch.i(I_PHASE) = PH_INIT;
+    return;
+  }
   if (ch.i(I_PSEUDO) == 2) {           // end of the warm-up: the pooled step size
     ch.i(I_PSEUDO) = 0;
     if (n > 0.0) ch.s(S_EPS) = exp(red[1] / n);
@@ -969,6 +990,8 @@ __global__ void bp_chain_moments(Params P, double* __restrict__ out) {
 struct bpc_sampler {
   bpc_model* m = nullptr;
   bpc_data* d = nullptr;
+  bpc_data* d_opt = nullptr;            // two-stage ascent: the subsample the first stage is evaluated on, while stage1 is set
+  bool stage1 = false;
   Params P{};
   DevBuf sd, si, q_eval, lp_eval, g_eval, st_eval, draws, d_lp, d_acc, d_eps, d_depth, d_nleap, d_div, counters, pool, moments, inits, metric;
   int npool = 0;
@@ -1010,6 +1033,11 @@ int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_
   P.opt_steps = a->init_opt_steps > 0 ? a->init_opt_steps : 0;
   P.dense = a->metric == 1 ? 1 : 0;
   P.debug = std::getenv("BPC_SAMPLER_DEBUG") ? 1 : 0;
+  P.two_stage = (a->init_opt_data != nullptr && P.opt_steps > 0 && a->pooled_adaptation) ? 1 : 0;
+  if (a->init_opt_data && (a->init_opt_data->model != m || a->init_opt_data->device != d->device))
+    return fail(BPC_E_INVALID, "init_opt_data must be a data handle of the same model on the same device");
+  s->d_opt = P.two_stage ? a->init_opt_data : nullptr;
+  s->stage1 = P.two_stage != 0;
   P.hess = (P.opt_steps > 0 && P.pooled && sp.dim <= MAXD && !std::getenv("BPC_NO_HESS_INIT")) ? 1 : 0;
   P.nsum = P.dense ? sp.dim * (sp.dim + 1) / 2 : 0;
   // Stan's window schedule (windowed_adaptation): 75 / 25 / 50, rescaled to 15% / 75% / 10% for short warm-ups
@@ -1083,7 +1111,7 @@ void bpc_sampler_free(bpc_sampler* s) {
 static int sampler_passes(bpc_sampler* s, int nb) {
   const Params& P = s->P;
   for (int b = 0; b < nb; ++b) {
-    int rc = log_prob_dev(s->m, s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream, P.si + (size_t)I_PHASE * P.C);
+    int rc = log_prob_dev(s->m, s->stage1 ? s->d_opt : s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream, P.si + (size_t)I_PHASE * P.C);
     if (rc) return rc;
     bp_nuts_advance<<<(P.C + 3) / 4, 128, 0, s->stream>>>(P);
     g_launches += 1;
@@ -1096,6 +1124,7 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
   cudaError_t e;
   if ((e = cudaSetDevice(s->d->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   const Params& P = s->P;
+  bpc_data* cur = s->stage1 ? s->d_opt : s->d;   // the data handle the passes evaluate (two-stage ascent: the subsample first)
   *state = 0;
   if (s->h_counters[0] >= P.C) { *state = 1; return BPC_OK; }   // (last poll: every chain has finished; nothing left to run)
   long long done_passes = 0;
@@ -1106,16 +1135,16 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
   // bpc_moments, ...): if one of them re-tiled or reallocated it since the graph was captured, the graph's baked-in pointers and
   // tiling are stale -- drop it, run a block eagerly (which rebuilds the workspace for this chain count) and capture again.  And if
   // the workspace was last used on another stream, wait for that work before touching it.
-  if (s->graph_exec && s->graph_ws_gen != s->d->ws_gen) {
+  if (s->graph_exec && s->graph_ws_gen != cur->ws_gen) {
     cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr;
     if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
     s->graph_tried = false;
   }
-  { const int rc = order_workspace(s->d, s->stream); if (rc) return rc; }
+  { const int rc = order_workspace(cur, s->stream); if (rc) return rc; }
   bool eager_block_done = s->graph_exec != nullptr;   // a block must run eagerly under the current workspace before a capture
   while (done_passes < max_passes) {
     const int nb = (int)std::min<long long>(POLL, max_passes - done_passes);
-    if (nb == POLL && s->passes >= POLL && !s->graph_tried && eager_block_done && s->d->ws_chains == P.C) {
+    if (nb == POLL && s->passes >= POLL && !s->graph_tried && eager_block_done && cur->ws_chains == P.C) {
       // the first block ran eagerly (module load, workspace allocation); capture the next one and replay it from now on
       s->graph_tried = true;
       if (!getenv("BPC_NO_GRAPH") && cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -1125,7 +1154,7 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
         const cudaError_t ec = cudaStreamEndCapture(s->stream, &g);
         s->graph_launches = (int)(g_launches - before);
         g_launches = before;   // nothing ran during capture
-        if (rc == BPC_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&s->graph_exec, g, 0) == cudaSuccess) { s->graph = g; s->graph_ws_gen = s->d->ws_gen; }
+        if (rc == BPC_OK && ec == cudaSuccess && g && cudaGraphInstantiate(&s->graph_exec, g, 0) == cudaSuccess) { s->graph = g; s->graph_ws_gen = cur->ws_gen; }
         else { if (g) cudaGraphDestroy(g); s->graph_exec = nullptr; cudaGetLastError(); }
       }
     }
@@ -1151,7 +1180,7 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
     if (s->h_counters[0] >= P.C) { *state = 1; break; }
     if (P.pooled && s->h_counters[0] + s->h_counters[1] >= P.C && s->h_counters[1] > 0) { *state = 2; break; }
   }
-  return release_workspace(s->d, s->stream);   // (graph replays do not pass through log_prob_dev's own record)
+  return release_workspace(cur, s->stream);   // (graph replays do not pass through log_prob_dev's own record)
 }
 
 int bpc_sampler_pool_stats(bpc_sampler* s, double* stats_dev, int count) {
@@ -1171,7 +1200,15 @@ int bpc_sampler_pool_apply(bpc_sampler* s, const double* reduced_dev) {
   if (!s) return fail(BPC_E_INVALID, "null argument");
   cudaSetDevice(s->d->device);
   const double* red = reduced_dev ? reduced_dev : (const double*)s->pool.p;
-  if (s->P.hess) { bp_pseudo_rescue<<<(s->P.C + 127) / 128, 128, 0, s->stream>>>(s->P); g_launches += 1; }
+  if (s->stage1) {
+    // the first exchange of a two-stage run is the stage switch: from here on the passes evaluate the full data (the graph captured
+    // on the subsample's kernels and workspace is dropped)
+    s->stage1 = false;
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+    s->graph_tried = false;
+  }
+  if (s->P.hess || s->P.two_stage) { bp_pseudo_rescue<<<(s->P.C + 127) / 128, 128, 0, s->stream>>>(s->P); g_launches += 1; }
   if (s->P.dense) {
     bp_pool_metric<<<1, 32, 0, s->stream>>>(s->P, red);
     g_launches += 1;

@@ -56,6 +56,7 @@ class StanData:
         _ffi.check(L.bpc_data_create(engine.handle, C.byref(sd), int(device), int(grouping), C.byref(self.handle)))
         self.ndatapts = N
         self.device = device
+        self.source = dat          # the Stan data list (fit.sampling draws the subsample of a two-stage ascent from it)
 
     @property
     def ngroups(self) -> int:
@@ -217,11 +218,12 @@ class BpCudaModel:
         return out[0] if np.ndim(theta) == 1 else out
 
     def sampling(self, dat, chains: int = 4, iter: int = 2000, warmup=None, init="random", control=None, seed: int = 1,
-                 pooled_adaptation: bool = False, device=None, loo: bool = False, init_opt_steps: int = 0):
+                 pooled_adaptation: bool = False, device=None, loo: bool = False, init_opt_steps: int = 0, init_opt_subsample: int = 0):
         """rstan::sampling — see bpinference_b200.fit.sampling."""
         from .fit import sampling
         return sampling(self, dat, chains=chains, iter=iter, warmup=warmup, init=init, control=control, seed=seed,
-                        pooled_adaptation=pooled_adaptation, device=device, loo=loo, init_opt_steps=init_opt_steps)
+                        pooled_adaptation=pooled_adaptation, device=device, loo=loo, init_opt_steps=init_opt_steps,
+                        init_opt_subsample=init_opt_subsample)
 
     def sampling_multi(self, dat, devices, chains: int = 4, iter: int = 2000, warmup=None, init="random", control=None, seed: int = 1,
                        pooled_adaptation: bool = False, init_opt_steps: int = 0):

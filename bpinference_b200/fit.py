@@ -195,6 +195,23 @@ def _metric_code(control) -> int:
     return 1 if m == "dense_e" else 0
 
 
+def subsample_data(dat: dict, n: int, seed: int, simple_bd: bool) -> dict:
+    """a Stan data list with n of the observations of `dat`, drawn without replacement (the same draw on every rank: the seed is the run's)."""
+    N = int(dat["ndatapts"])
+    idx = np.sort(np.random.default_rng(10_000 + int(seed)).choice(N, size=n, replace=False))
+    s = dict(dat)
+    s["ndatapts"] = n
+    for k in ("pop_vec", "init_pop"):
+        a = np.asarray(dat[k])
+        s[k] = a[idx] if a.ndim == 1 else a.reshape(N, -1)[idx]
+    s["var_idx"] = np.asarray(dat["var_idx"])[idx]
+    if simple_bd:
+        s["times"] = np.asarray(dat["times"])[idx]
+    else:
+        s["times_idx"] = np.asarray(dat["times_idx"])[idx]
+    return s
+
+
 def _names(engine):
     return ["Theta%d" % (k + 1) for k in range(engine.nparams)] + (["sigma_obs"] if engine.kind == _ffi.MULTITYPE_NOISE else [])
 
@@ -245,7 +262,8 @@ def _default_device():
 
 
 def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[int] = None, init="random", control: Optional[dict] = None,
-             seed: int = 1, pooled_adaptation: bool = False, device: Optional[int] = None, loo: bool = False, init_opt_steps: int = 0):
+             seed: int = 1, pooled_adaptation: bool = False, device: Optional[int] = None, loo: bool = False, init_opt_steps: int = 0,
+             init_opt_subsample: int = 0):
     # control$metric: "diag_e" (rstan's default) or "dense_e" (needs pooled_adaptation: the covariance comes from all chains)
     """rstan::sampling(stan_mod, data = dat, chains, iter, warmup, init, control = list(adapt_delta, max_treedepth)).
 
@@ -254,7 +272,9 @@ def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[in
     loo: also return log_lik [chains, draws, ndatapts] (generate(..., loo = T), R/stan_utils.R:173-175,189-191).
     init_opt_steps > 0: every chain first climbs from its initial point with that many steps of a device-side optimiser (see
     bpc_sample_args.init_opt_steps) — an extension for data sets whose posterior is orders of magnitude narrower than the range the
-    initial values are drawn from; 0 is rstan's behaviour."""
+    initial values are drawn from; 0 is rstan's behaviour.
+    init_opt_subsample = n > 0 (with init_opt_steps and pooled_adaptation, `dat` a data list): the ascent first runs on n observations
+    drawn at random from the list (far from the mode every evaluation costs many times one near it), then on all of them."""
     L = _ffi.lib()
     control = control or {}
     warmup = iter // 2 if warmup is None else warmup
@@ -268,9 +288,15 @@ def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[in
         if len(init) != chains:
             raise ValueError("init must have one entry per chain")
         inits = np.ascontiguousarray([[float(ch["Theta%d" % (k + 1)]) for k in range(engine.nparams)] for ch in init], dtype=np.float64)
+    d_sub = None
+    if init_opt_subsample and init_opt_steps > 0 and pooled_adaptation and 0 < init_opt_subsample < d.ndatapts:
+        if not isinstance(d.source, dict):
+            raise ValueError("init_opt_subsample needs the Stan data list the handle was made from")
+        d_sub = engine.data(subsample_data(d.source, int(init_opt_subsample), seed, engine.kind == _ffi.SIMPLE_BD), device=d.device)
     args = _ffi.SampleArgs(chains, iter, warmup, float(control.get("adapt_delta", 0.8)), int(control.get("max_treedepth", 10)), seed,
                            rank * chains, _ffi.dptr(inits) if inits is not None else None, int(bool(pooled_adaptation)),
-                           float(control.get("stepsize", 0.0)), int(init_opt_steps), _metric_code(control))
+                           float(control.get("stepsize", 0.0)), int(init_opt_steps), _metric_code(control),
+                           d_sub.handle if d_sub is not None else None)
     h = C.c_void_p()
     try:
         _ffi.check(L.bpc_sampler_create(engine.handle, d.handle, C.byref(args), C.byref(h)))
@@ -330,6 +356,8 @@ def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[in
     finally:
         if h:
             L.bpc_sampler_free(h)
+        if d_sub is not None:
+            d_sub.close()
         if own_data:
             d.close()
     return BpFit(_names(engine), draws, lp, div, td, nl, acc, eps, rhat, info, tpars=tpars, log_lik=log_lik)
@@ -353,7 +381,7 @@ def sampling_multi(engine, dat: dict, devices, chains: int = 4, iter: int = 2000
         inits = np.ascontiguousarray([[float(ch["Theta%d" % (k + 1)]) for k in range(engine.nparams)] for ch in init], dtype=np.float64)
     args = _ffi.SampleArgs(chains, iter, warmup, float(control.get("adapt_delta", 0.8)), int(control.get("max_treedepth", 10)), seed,
                            0, _ffi.dptr(inits) if inits is not None else None, int(bool(pooled_adaptation)),
-                           float(control.get("stepsize", 0.0)), int(init_opt_steps), _metric_code(control))
+                           float(control.get("stepsize", 0.0)), int(init_opt_steps), _metric_code(control), None)
     ns, dim = iter - warmup, engine.dim
     draws = np.empty((total, ns, dim))
     lp, acc, eps = np.empty((total, ns)), np.empty((total, ns)), np.empty((total, ns))

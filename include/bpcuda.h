@@ -231,6 +231,10 @@ typedef struct {
                             covariance of the unconstrained parameters, estimated at every warm-up window from the draws of ALL chains of
                             all ranks (needs pooled_adaptation = 1: a single chain's window is far too short for a covariance matrix).  The
                             sampler then works in the whitened coordinates q = mu + L w, Sigma = L L^T, which is HMC with M^-1 = Sigma */
+  bpc_data* init_opt_data; /* NULL, or (with init_opt_steps > 0 and pooled_adaptation) a data handle holding a SUBSAMPLE of the observations, on the
+                            same device: the ascent then has two stages -- on the subsample until it converges (far from the mode every evaluation
+                            needs sub-steps and costs many times one near it, so the long way is travelled at a fraction of the cost), then, after
+                            an exchange in which all chains wait for each other, on the full data from there.  The handle stays the caller's */
 } bpc_sample_args;
 
 int bpc_sampler_create(bpc_model* m, bpc_data* d, const bpc_sample_args* a, bpc_sampler** out);

@@ -164,7 +164,7 @@ def test_sampler_survives_other_calls_on_its_data_handle():
     L = _ffi.lib()
 
     def run(disturb):
-        args = _ffi.SampleArgs(32, 120, 60, 0.8, 8, 3, 0, None, 0, 0.0, 0, 0)
+        args = _ffi.SampleArgs(32, 120, 60, 0.8, 8, 3, 0, None, 0, 0.0, 0, 0, None)
         h = C.c_void_p()
         _ffi.check(L.bpc_sampler_create(eng.handle, d.handle, C.byref(args), C.byref(h)))
         st = C.c_int(0)

@@ -1,5 +1,6 @@
+set -x
 export PYTHONPATH=$PWD
-B="python bench.py --workload cfg5G --steps 20 --warmup 5 --no-sampling --no-other-workloads --no-cpu-baseline --no-parity"
-for t in 512 1024 2048 4096; do BPC_GROUPB_TILE=$t $B 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read()); print('tile $t', j['ms_per_step'])"; done
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_cfg5G.csv python bench.py --workload cfg5G --steps 2 --warmup 3 --no-sampling --no-other-workloads --no-cpu-baseline --no-parity > /dev/null 2>&1
-python tools/launch_times.py gpurun_out/r2_launches_cfg5G.csv | grep bp_
+timeout 120 python tools/sample_cfg5.py cfg5U 100000 512 200 100 1 300 1 5000 > gpurun_out/r2_samp_u_full_2stage.log 2>&1
+timeout 120 python tools/sample_cfg5.py cfg5U 100000 512 200 100 1 300 1 0 > gpurun_out/r2_samp_u_full_1stage.log 2>&1
+python -m pytest tests/test_gpu_sampler_stats.py tests/test_gpu_sampler.py -q -x > gpurun_out/r2_gputest9.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2_gputest9.log
+tail -12 gpurun_out/r2_samp_u_full_2stage.log; tail -4 gpurun_out/r2_samp_u_full_1stage.log; tail -5 gpurun_out/r2_gputest9.log

@@ -14,6 +14,7 @@ budget = float(sys.argv[5]) if len(sys.argv) > 5 else 120.0
 pooled = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 opt_steps = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 dense = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+nsub = int(sys.argv[9]) if len(sys.argv) > 9 else 0
 cfg = syn.make_config(wl, seed=1, chains=chains, nobs=nobs)
 mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
 eng = bp.stan_model(mod, cfg["priors"])
@@ -22,7 +23,11 @@ P = cfg["nparams"]
 init = bp.uniform_initialize(np.tile([0.0, 1.0], (P, 1)), chains, rng=np.random.default_rng(3))
 inits = np.ascontiguousarray([[ch["Theta%d" % (k + 1)] for k in range(P)] for ch in init])
 L = _ffi.lib()
-args = _ffi.SampleArgs(chains, iters, iters // 2, 0.8, 10, 1, 0, _ffi.dptr(inits), pooled, 0.0, opt_steps, dense)
+d_sub = None
+if nsub:
+    from bpinference_b200.fit import subsample_data
+    d_sub = eng.data(subsample_data(cfg["data"], nsub, 1, False))
+args = _ffi.SampleArgs(chains, iters, iters // 2, 0.8, 10, 1, 0, _ffi.dptr(inits), pooled, 0.0, opt_steps, dense, d_sub.handle if d_sub is not None else None)
 h = C.c_void_p()
 _ffi.check(L.bpc_sampler_create(eng.handle, d.handle, C.byref(args), C.byref(h)))
 state = C.c_int(0)
