@@ -241,12 +241,14 @@ def sampling_report(bp, syn, torch, dist, rank, world, local_rank, workload, cha
         have_rstan = subprocess.run(["Rscript", "-e", "library(rstan)"], capture_output=True, timeout=60).returncode == 0
     except Exception:
         have_rstan = False
-    return {"workload": "%s: %s; NUTS, %d iterations (%d warm-up), adapt_delta %.2f, starting values uniform(0, 1) followed by at most %d L-BFGS "
-                        "evaluations per chain" + (" on a subsample of %d observations and as many on all of them" % subsample if subsample else "") + "; %s metric: Laplace covariance at the optimum first, then the %s of the warm-up draws of all "
-                        "chains of all ranks at every window (NCCL all-reduce of %d doubles), pooled step size"
-                        % (workload, workload_description(workload, chains, int(cfg["data"]["ndatapts"])), iters, warm, adapt_delta, opt_steps,
-                           "dense (dense_e)" if dense else "diagonal (diag_e)", "covariance" if dense else "variances",
-                           2 + (eng.dim + eng.dim * (eng.dim + 1) // 2 if dense else 2 * eng.dim)),
+    desc = "%s: %s; NUTS, %d iterations (%d warm-up), adapt_delta %.2f, starting values uniform(0, 1) followed by at most %d L-BFGS evaluations per chain" % (
+        workload, workload_description(workload, chains, int(cfg["data"]["ndatapts"])), iters, warm, adapt_delta, opt_steps)
+    if subsample:
+        desc += " on a subsample of %d observations and as many on all of them" % subsample
+    desc += "; %s metric: Laplace covariance at the optimum first, then the %s of the warm-up draws of all chains of all ranks at every window " \
+            "(NCCL all-reduce of %d doubles), pooled step size" % ("dense (dense_e)" if dense else "diagonal (diag_e)", "covariance" if dense else "variances",
+                                                                    2 + (eng.dim + eng.dim * (eng.dim + 1) // 2 if dense else 2 * eng.dim))
+    return {"workload": desc,
             "treedepth_mean": float(fit.treedepth__.mean()), "n_leapfrog_mean": float(fit.n_leapfrog__.mean()), "stepsize": float(fit.stepsize__[0, -1]),
             "chains_total": int(chains * world), "seconds": dt, "min_ess_per_s": float(ess_all.min() / dt), "min_ess": float(ess_all.min()),
             "leapfrogs_per_s": leap / dt, "leapfrogs": int(leap), "passes": fit.info["passes"], "max_rhat": float(np.nanmax(fit.rhat)),
@@ -485,7 +487,7 @@ def _main(args):
         sampling = {"cfg2": sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 200, False)}
         if args.workload == "cfg5U" and not args.nobs:
             sampling["cfg5U"] = sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg5U", chains, None, args.sampling_iter,
-                                                args.sampling_iter // 2, 300, True, subsample=5000)
+                                                args.sampling_iter // 2, 300, True, subsample=500)
 
     if rank == 0:
         total_evals = float(world) * chains * N * args.steps

@@ -1247,8 +1247,9 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
   for (int e = 0; e < BP_E; ++e) fin = fin && isfinite(r[e]);
   bp_assemble(r, A, H);
   const double a1 = bp_norm1(A);
-  if (!bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0)) return;
-  // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
+  const bool wpath = bp_w_path(fin, a1, a.nobs > 0 ? a.t[0] : 0.0);   // (uniform over the CTA)
+  if (!wpath && !(a.wmode == 3 && a.u)) return;                         // bp_fused handled this chain; bp_epilogue finishes it
+  if (wpath) {
   // sum the tile partials in tile order; fragment element (rt, ct, lane, e) is W[8 rt + lane/4][8 ct + 2 (lane%4) + e]
   const int frag = a.wmode == 1 ? BP_WFRAG : BP_CFRAG, rows = a.wmode == 1 ? BP_WROWS : BP_CROWS;
 #if BP_N <= 3
@@ -1289,6 +1290,26 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
     double* p0 = a.part + (size_t)c * a.ntiles * BP_NPART;
 #pragma unroll
     for (int k = 0; k < BP_P; ++k) p0[1 + k] += cb[k];
+  }
+  }
+  // octet path: the work of bp_epilogue for this chain by the CTA's first warp (one launch less per evaluation): tile sums in the same
+  // fixed order (lane i takes tiles i, i + 32, ..., then the shuffle tree), priors, Jacobian, chain rule, rejection.  Chains on the
+  // sub-step fallback arrive here with the partials bp_fused wrote (it is launched before this kernel).
+  if (a.wmode == 3 && a.u) {
+    __syncthreads();     // thread 0's update of the first tile partial is visible to the first warp
+    if (tid < 32) {
+      double acc[BP_NPART];
+#pragma unroll
+      for (int i = 0; i < BP_NPART; ++i) acc[i] = 0.0;
+      for (int tI = tid; tI < a.ntiles; tI += 32) {
+        const double* p = a.part + ((size_t)c * a.ntiles + tI) * BP_NPART;
+#pragma unroll
+        for (int i = 0; i < BP_NPART; ++i) acc[i] += __ldcg(p + i);
+      }
+#pragma unroll
+      for (int i = 0; i < BP_NPART; ++i) acc[i] = bp_warp_sum(acc[i]);
+      if (tid == 0) bp_finish(c, acc, a.status[c], a.u, a.theta, a.jacobian, a.lp_out, a.grad_out, a.status, a.apps_out);
+    }
   }
 }
 

@@ -775,6 +775,11 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
         } else {
           BPC_CUDA(cudaLaunchKernel((const void*)L->fusedw, dim3(d->ntiles, nchains), dim3(s.threads), args, s.w_smem, st));
         }
+        // octet path: the sub-step fallback goes first, so that bp_wpost can also do the epilogue's work (one launch less)
+        if (d->omode) {
+          const int fbr = std::min(nchains, std::max(8, (148 * 4 + d->ntiles - 1) / std::max(1, d->ntiles)));
+          BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, fbr), dim3(s.threads), args, L->obs_smem, st));
+        }
         BPC_CUDA(cudaLaunchKernel((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
         g_launches += 2;
       }
@@ -782,20 +787,22 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       // least 8, and enough to fill the device when the data has few tiles: far from the mode, e.g. during the ascent from wide starting
       // values on a subsample, EVERY chain is on the list; rows that find nothing to do return at once)
       const int fb_rows = std::min(nchains, std::max(8, (148 * 4 + d->ntiles - 1) / std::max(1, d->ntiles)));
-      BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, d->cmode ? fb_rows : nchains), dim3(s.threads), args, L->obs_smem, st));
+      if (!(d->wmode && d->omode))
+        BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, d->cmode ? fb_rows : nchains), dim3(s.threads), args, L->obs_smem, st));
     }
     if (d->timing) {
       BPC_CUDA(cudaEventRecord(e1, st));
       d->timing_events.emplace_back(e0, e1);
     }
   }
-  if (!own_io) {
+  const bool folded = !own_io && d->wmode && d->omode;   // octet path: bp_wpost did the epilogue
+  if (!own_io && !folded) {
     int ntiles = d->ntiles;
     void* args[] = {(void*)&u_dev, (void*)&theta, (void*)&part, (void*)&ntiles, (void*)&nchains, (void*)&jacobian,
                     (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps, (void*)&skip_dev};
     BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
-  g_launches += own_io ? 1 : 3;
+  g_launches += own_io ? 1 : (folded ? 2 : 3);
   if (cap == cudaStreamCaptureStatusNone && (rc = release_workspace(d, st))) return rc;
   return BPC_OK;
 }

@@ -1004,7 +1004,8 @@ struct bpc_sampler {
   int graph_launches = 0;               // kernels of one replay
   unsigned long long graph_ws_gen = 0;  // generation of the data handle's workspace the graph was captured under
   bool trace = std::getenv("BPC_SAMPLER_TRACE") != nullptr;
-  std::chrono::steady_clock::time_point trace_t0 = std::chrono::steady_clock::now();
+  bool trace_fine = std::getenv("BPC_SAMPLER_TRACE") != nullptr && std::atoi(std::getenv("BPC_SAMPLER_TRACE")) >= 2;
+  std::chrono::steady_clock::time_point trace_t0 = std::chrono::steady_clock::now(), trace_t1 = std::chrono::steady_clock::now();
 };
 
 extern "C" {
@@ -1168,6 +1169,13 @@ int bpc_sampler_run(bpc_sampler* s, long long max_passes, int* state) {
     }
     done_passes += nb;
     s->passes += nb;
+    if (s->trace_fine && s->passes <= 4096) {   // BPC_SAMPLER_TRACE=2: every block of 16 passes of the start of the run
+      cudaStreamSynchronize(s->stream);
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[sampler] passes %lld  %.1f us per pass (block of %d)%s\n", s->passes,
+                   std::chrono::duration<double, std::micro>(now - s->trace_t1).count() / nb, nb, s->stage1 ? "  stage 1 (subsample)" : "");
+      s->trace_t1 = std::chrono::steady_clock::now();
+    }
     if (s->trace && s->passes / 2048 != (s->passes - nb) / 2048) {   // BPC_SAMPLER_TRACE: wall time per block of passes and where the chains are
       cudaStreamSynchronize(s->stream);
       const auto now = std::chrono::steady_clock::now();

@@ -96,3 +96,31 @@ def test_every_module_compiles_for_sm100a_with_the_planned_resources(name, expec
     if "bp_fusedo" in expect:
         regs, stack = (int(x.split(":")[1]) for x in res["bp_fusedo"].split())
         assert regs <= 128 and stack == 0, res["bp_fusedo"]
+
+
+def test_non_finite_bounds_parameters_and_data_are_rejected():
+    """(0, Inf) bounds used to produce Theta = Inf / NaN and silently rejected chains; NaN durations broke the sort in
+    bpc_data_create.  Both are refused at the boundary now, before any device work."""
+    L = _ffi.lib()
+    for lo, hi in ((0.0, np.inf), (-np.inf, 1.0)):
+        pr = _ffi.Prior(b"normal", 2, (ctypes.c_double * 3)(0.0, 1.0, 0.0), 1, lo, hi)
+        assert L.bpc_check_prior(ctypes.byref(pr)) == _ffi.E_PRIOR and b"finite" in L.bpc_last_error()
+    pr = _ffi.Prior(b"normal", 2, (ctypes.c_double * 3)(np.nan, 1.0, 0.0), 0, 0.0, 0.0)
+    assert L.bpc_check_prior(ctypes.byref(pr)) == _ffi.E_PRIOR
+    mod = bp.bp_model([[2.0], [0.0]], [1, 1], ["c[1]", "c[2]"], 2, 0)
+    with pytest.raises(ValueError, match="finite"):
+        bp.stan_model(mod, [dict(name="normal", params=[0.0, 1.0], bounds=[0.0, float("inf")])] * 2)
+    cfg = syn.make_config("cfg2", chains=2, nobs=20)
+    mod2 = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod2, cfg["priors"])
+    for key, bad, msg in (("times", np.array([np.nan]), "times"), ("times", np.array([-1.0]), "times"), ("init_pop", None, "finite")):
+        d = dict(cfg["data"])
+        if bad is None:
+            a = np.array(d[key], dtype=float)
+            a[3, 1] = np.inf
+            d[key] = a
+        else:
+            d[key] = bad
+        with pytest.raises(_ffi.BpcError) as e:
+            eng.data(d)
+        assert e.value.code == _ffi.E_INVALID and msg in str(e.value)
