@@ -2690,7 +2690,9 @@ struct BpGroupArgs {
   const int* tstart;     // [ntb + 1] first observation of the tile (tiles of a group are consecutive; tstart[ntb] = nobs)
   const int* gtile0;     // [G + 1] first tile of each group
   double* gmom;          // [C][G * BP_N][BP_D] single-ancestor moments (phase A -> phase B)
-  double* ypart;         // [C][ntb][BP_N * BP_D + 2] per-tile sums of the cotangents, lp and d/dsigma_obs (phase B -> phase A')
+  double* ypart;         // [C][ntb][BP_N * BP_D + 2] per-tile sums of the cotangents, lp and d/dsigma_obs (phase B -> phase A');
+                         // ypt != 0 (bp_groupc): [ntb][BP_N * BP_D + 2][C]
+  int ypt;
 };
 
 template <int NV>
@@ -2746,12 +2748,10 @@ struct BpGroupBAcc {
   }
 };
 
-// (mom: [BP_N][BP_D] flattened -- registers in bp_grouped, shared memory (broadcast reads) in bp_groupb)
-__device__ __forceinline__ bool bp_groupb_obs(const BpGroupArgs& a, int k, double sigma, const double* __restrict__ mom, double (&acc)[BP_N * BP_D],
-                                              BpGroupBAcc& s) {
-  double z0[BP_N], xo[BP_N], ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
-#pragma unroll
-  for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+// (mom: [BP_N][BP_D] flattened -- registers in bp_grouped and bp_groupc, shared memory (broadcast reads) in bp_groupb)
+__device__ __forceinline__ bool bp_groupb_core(const double (&z0)[BP_N], const double (&xo)[BP_N], double sigma, const double* __restrict__ mom,
+                                               double (&acc)[BP_N * BP_D], BpGroupBAcc& s) {
+  double ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
 #pragma unroll
   for (int i = 0; i < BP_N; ++i) {
     double sacc = z0[0] * mom[i];
@@ -2779,6 +2779,14 @@ __device__ __forceinline__ bool bp_groupb_obs(const BpGroupArgs& a, int k, doubl
     for (int q = 0; q < BP_S; ++q) acc[l * BP_D + BP_N + q] += z0[l] * bS[q];
   }
   return true;
+}
+
+__device__ __forceinline__ bool bp_groupb_obs(const BpGroupArgs& a, int k, double sigma, const double* __restrict__ mom, double (&acc)[BP_N * BP_D],
+                                              BpGroupBAcc& s) {
+  double z0[BP_N], xo[BP_N];
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) { z0[i] = a.z0[(size_t)i * a.npad + k]; xo[i] = a.xo[(size_t)i * a.npad + k]; }
+  return bp_groupb_core(z0, xo, sigma, mom, acc, s);
 }
 
 // phase B of bp_grouped on its own grid (tiles, chains): data with many observations per (level, duration) group.  One CTA per chain
@@ -2810,6 +2818,52 @@ extern "C" __global__ void __launch_bounds__(128, 4) bp_groupb(BpGroupArgs a) {
   vals[BP_N * BP_D] = s.total();
   vals[BP_N * BP_D + 1] = s.sb;
   bp_block_sum(vals, red, a.ypart + ((size_t)c * a.ntb + tile) * (BP_N * BP_D + 2));
+  if (status) atomicOr(a.status + c, status);
+}
+
+// Phase B with ONE THREAD PER CHAIN (>= 128 chains): a CTA stages a tile of <= BP_GC_TILE observations of one group in shared memory
+// and each of its 128 threads sweeps the whole tile for its own chain -- every observation is read from L2 once per 128 chains
+// instead of once per chain, all threads read the same shared-memory word (broadcast), they run in lockstep (same observations,
+// different parameters), and the cotangent sums of a (tile, chain) are the thread's own: no reduction at all.  The per-tile sums go
+// to ypart in the transposed layout [tile][value][chain] (coalesced); bp_grouped mode 2 adds the tiles of every group in tile order.
+#define BP_GC_TILE 512
+#ifndef BP_GC_MINBLOCKS
+#define BP_GC_MINBLOCKS 3
+#endif
+extern "C" __global__ void __launch_bounds__(128, BP_GC_MINBLOCKS) bp_groupc(BpGroupArgs a) {
+  const int tile = blockIdx.x, tid = threadIdx.x, c = blockIdx.y * 128 + tid;
+  __shared__ double sz[2 * BP_N][BP_GC_TILE];
+  const int g = a.tgroup[tile], k0 = a.tstart[tile], nk = a.tstart[tile + 1] - k0;
+  for (int i = tid; i < nk; i += 128) {
+#pragma unroll
+    for (int q = 0; q < BP_N; ++q) { sz[q][i] = a.z0[(size_t)q * a.npad + k0 + i]; sz[BP_N + q][i] = a.xo[(size_t)q * a.npad + k0 + i]; }
+  }
+  __syncthreads();
+  if (c >= a.nchains || bp_skip(a.skip, c)) return;
+#if BP_NOISE
+  const double sigma = a.theta[(size_t)c * BP_DIM + BP_P];
+#else
+  const double sigma = 0.0;
+#endif
+  double mom[BP_N * BP_D], acc[BP_N * BP_D];
+  const double* gm = a.gmom + ((size_t)c * a.ngroups * BP_N + (size_t)g * BP_N) * BP_D;
+#pragma unroll
+  for (int i = 0; i < BP_N * BP_D; ++i) { mom[i] = gm[i]; acc[i] = 0.0; }
+  BpGroupBAcc s;
+  s.init();
+  int status = 0;
+  for (int i = 0; i < nk; ++i) {
+    double z0[BP_N], xo[BP_N];
+#pragma unroll
+    for (int q = 0; q < BP_N; ++q) { z0[q] = sz[q][i]; xo[q] = sz[BP_N + q][i]; }
+    if (!bp_groupb_core(z0, xo, sigma, mom, acc, s)) status |= BP_ST_NOT_PD;
+  }
+  constexpr int NV = BP_N * BP_D + 2;
+  double* yp = a.ypart + (size_t)tile * NV * a.nchains + c;
+#pragma unroll
+  for (int i = 0; i < BP_N * BP_D; ++i) yp[(size_t)i * a.nchains] = acc[i];
+  yp[(size_t)(BP_N * BP_D) * a.nchains] = s.total();
+  yp[(size_t)(BP_N * BP_D + 1) * a.nchains] = s.sb;
   if (status) atomicOr(a.status + c, status);
 }
 
@@ -3010,15 +3064,19 @@ extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
   if (a.mode == 2) {
     // bp_groupb did phase B: sum its per-tile cotangents group by group in tile order; lp and sb by thread 0
     constexpr int NV = BP_N * BP_D + 2;
-    const double* yp = a.ypart + (size_t)c * a.ntb * NV;
+    // element e of tile tI of this chain: [C][ntb][NV] (bp_groupb) or [ntb][NV][C] (bp_groupc)
+    const size_t st_t = a.ypt ? (size_t)NV * a.nchains : (size_t)NV, st_e = a.ypt ? (size_t)a.nchains : (size_t)1;
+    const double* yp = a.ypart + (a.ypt ? (size_t)c : (size_t)c * a.ntb * NV);
     for (int i = tid; i < GN * BP_D; i += T) {
       const int g = i / (BP_N * BP_D), e = i - g * (BP_N * BP_D);
       double sacc = 0.0;
-      for (int tI = a.gtile0[g]; tI < a.gtile0[g + 1]; ++tI) sacc += yp[(size_t)tI * NV + e];
+      for (int tI = a.gtile0[g]; tI < a.gtile0[g + 1]; ++tI) sacc += yp[(size_t)tI * st_t + e * st_e];
       ybar[i] = sacc;
     }
-    if (tid == 0) {
-      for (int tI = 0; tI < a.ntb; ++tI) { lp += yp[(size_t)tI * NV + BP_N * BP_D]; sb += yp[(size_t)tI * NV + BP_N * BP_D + 1]; }
+    if (tid < 2) {          // thread 0: lp, thread 1: d/dsigma_obs (both enter the block sums below from one thread each)
+      double sacc = 0.0;
+      for (int tI = 0; tI < a.ntb; ++tI) sacc += yp[(size_t)tI * st_t + (BP_N * BP_D + tid) * st_e];
+      if (tid == 0) lp = sacc; else sb = sacc;
     }
     __syncthreads();
   } else {

@@ -94,6 +94,7 @@ int model_load(bpc_model* m, int device, Loaded** out) {
     BPC_CUDA(cudaKernelSetAttributeForDevice(L.obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.obs_smem, device));
     if (cudaLibraryGetKernel(&L.grouped, L.lib, "bp_grouped") != cudaSuccess) { L.grouped = nullptr; cudaGetLastError(); }
     if (cudaLibraryGetKernel(&L.groupb, L.lib, "bp_groupb") != cudaSuccess) { L.groupb = nullptr; cudaGetLastError(); }
+    if (cudaLibraryGetKernel(&L.groupc, L.lib, "bp_groupc") != cudaSuccess) { L.groupc = nullptr; cudaGetLastError(); }
     BPC_CUDA(cudaLibraryGetKernel(&L.moments, L.lib, "bp_moments"));
     if (!m->spec.xdep) {
       BPC_CUDA(cudaLibraryGetKernel(&L.fusedw, L.lib, "bp_fusedw"));
@@ -487,6 +488,20 @@ int bpc_data_create(const bpc_model* m, const bpc_stan_data* d, int device, int 
         if ((rc = up(dd->tgroup, tg.data(), tg.size() * 4))) return rc;
         if ((rc = up(dd->tstart, ts.data(), ts.size() * 4))) return rc;
         if ((rc = up(dd->gtile0, gt0.data(), gt0.size() * 4))) return rc;
+        // the same for bp_groupc (one thread per chain, from 128 chains): tiles of <= 256 observations (BP_GC_TILE)
+        tg.clear(); ts.clear(); gt0.clear();
+        int tsc = 256;
+        if (const char* ev = std::getenv("BPC_GROUPC_TILE")) { const int v = std::atoi(ev); if (v >= 32 && v <= 512) tsc = v; }
+        for (int g = 0; g < G; ++g) {
+          gt0.push_back((int)tg.size());
+          for (int k = gs[g]; k < gs[g + 1]; k += tsc) { tg.push_back(g); ts.push_back(k); }
+        }
+        gt0.push_back((int)tg.size());
+        ts.push_back(N);
+        dd->ntc = (int)tg.size();
+        if ((rc = up(dd->tgroup_c, tg.data(), tg.size() * 4))) return rc;
+        if ((rc = up(dd->tstart_c, ts.data(), ts.size() * 4))) return rc;
+        if ((rc = up(dd->gtile0_c, gt0.data(), gt0.size() * 4))) return rc;
       }
     }
   }
@@ -603,7 +618,7 @@ static int ensure_workspace(bpc_data* d, int nchains) {
       if ((rc = d->ring.alloc((size_t)nchains * s.mslot * D * d->ngroups * n * 8))) return rc;
       if (d->ntb > 0) {
         if ((rc = d->gmom.alloc((size_t)nchains * d->ngroups * n * D * 8))) return rc;
-        if ((rc = d->ypart.alloc((size_t)nchains * d->ntb * (n * D + 2) * 8))) return rc;
+        if ((rc = d->ypart.alloc((size_t)nchains * std::max(d->ntb, d->ntc) * (n * D + 2) * 8))) return rc;
       }
     }
     if (d->wmode) {
@@ -653,7 +668,7 @@ struct GroupArgs {   // must match BpGroupArgs in bp_kernels.cuh
   const double* u; int jacobian; double* lp_out; double* grad_out; double* apps_out;
   int yscap;
   const int* skip;
-  int mode, ntb; const int* tgroup; const int* tstart; const int* gtile0; double* gmom; double* ypart;
+  int mode, ntb; const int* tgroup; const int* tstart; const int* gtile0; double* gmom; double* ypart; int ypt;
 };
 
 struct ObsArgs {   // must match BpObsArgs in bp_kernels.cuh
@@ -736,13 +751,18 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       GroupArgs ga{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const int*)d->gstart.p, (const double*)d->gt.p,
                    (const double*)d->gx.p, (const int*)d->glev.p, (double*)d->ring.p, part, status_dev, d->N, d->npad, d->ngroups, nchains,
                    d->nlevels, u_dev, jacobian, lp_dev, grad_dev, apps, yscap, skip_dev,
-                   0, d->ntb, (const int*)d->tgroup.p, (const int*)d->tstart.p, (const int*)d->gtile0.p, (double*)d->gmom.p, (double*)d->ypart.p};
+                   0, d->ntb, (const int*)d->tgroup.p, (const int*)d->tstart.p, (const int*)d->gtile0.p, (double*)d->gmom.p, (double*)d->ypart.p, 0};
       void* gargs[] = {(void*)&ga};
       if (d->ntb > 0 && L->groupb && u_dev) {
-        // phases A | B | A' as three launches: phase B gets (tiles x chains) CTAs instead of one per chain
+        // phases A | B | A' as three launches: phase B gets (tiles x chains) CTAs instead of one per chain -- or, from 128 chains,
+        // (small tiles x blocks of 128 chains) CTAs with one thread per chain (BPC_GROUPC=0 keeps bp_groupb)
+        const char* gc = std::getenv("BPC_GROUPC");
+        const bool per_chain = nchains >= 128 && L->groupc && d->ntc > 0 && !(gc && std::atoi(gc) == 0);
+        if (per_chain) { ga.ntb = d->ntc; ga.tgroup = (const int*)d->tgroup_c.p; ga.tstart = (const int*)d->tstart_c.p; ga.gtile0 = (const int*)d->gtile0_c.p; ga.ypt = 1; }
         ga.mode = 1;
         BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
-        BPC_CUDA(cudaLaunchKernel((const void*)L->groupb, dim3(d->ntb, nchains), dim3(128), gargs, 0, st));
+        if (per_chain) BPC_CUDA(cudaLaunchKernel((const void*)L->groupc, dim3(d->ntc, (nchains + 127) / 128), dim3(128), gargs, 0, st));
+        else BPC_CUDA(cudaLaunchKernel((const void*)L->groupb, dim3(d->ntb, nchains), dim3(128), gargs, 0, st));
         ga.mode = 2;
         BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
         g_launches += 2;

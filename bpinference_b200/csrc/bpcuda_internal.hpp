@@ -39,7 +39,7 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr, groupb = nullptr;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr, groupb = nullptr, groupc = nullptr;
   size_t obs_smem = 0, grouped_smem = 0, o_smem = 0, o9_smem = 0;
 };
 
@@ -92,6 +92,9 @@ struct bpc_data {
   // phase B of the grouped path on its own grid (many observations per group): tiles of <= 4096 observations of one group
   int ntb = 0;
   bpc::DevBuf tgroup, tstart, gtile0, gmom, ypart;
+  // ... and with one thread per chain from 128 chains (bp_groupc): tiles of <= 256 observations
+  int ntc = 0;
+  bpc::DevBuf tgroup_c, tstart_c, gtile0_c;
   int group_threads = 128;
   // workspace sized for ws_chains chains.  ws_gen counts every re-tiling / reallocation: a sampler that replays a captured CUDA
   // graph (raw workspace pointers and tiling baked in) compares it with the generation it captured under and re-captures.

@@ -209,6 +209,10 @@ std::string generate_cuda(ModelSpec& m) {
     if (const char* ev = std::getenv("BPC_OMINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 4) omin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_OMINBLOCKS %d\n", omin);
     s += buf;
+    int gcmin = 3;   // bp_groupc: CTAs per SM the register budget is cut for (3: 158 registers, no spills; 4: 128 registers, 128 bytes spilled)
+    if (const char* ev = std::getenv("BPC_GC_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 4) gcmin = v; }
+    std::snprintf(buf, sizeof buf, "#define BP_GC_MINBLOCKS %d\n", gcmin);
+    s += buf;
   }
   s += "#ifdef BP_HOSTSIM\n#define BP_HD inline\n#define BP_GLOBAL_CONST static const\n#else\n"
        "#define BP_HD __device__ __forceinline__\n#define BP_GLOBAL_CONST __constant__ const\ntypedef double real;\n#endif\n";

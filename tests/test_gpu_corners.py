@@ -164,3 +164,44 @@ def test_octet_path_matches_oracle_at_bench_shape():
     assert (st == 0).all() and (st_o == 0).all()
     np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
     np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+
+
+@pytest.mark.parametrize("chains,kernel", [(16, "bp_groupb"), (130, "bp_groupc")])
+def test_grouped_path_with_phase_b_on_its_own_grid(chains, kernel):
+    """grouped data with >= 16 384 observations: bp_grouped (phase A) -> bp_groupb ((tiles, chains) CTAs) or, from 128 chains, bp_groupc
+    (one thread per chain, tiles staged in shared memory; 130 chains: a ragged last block) -> bp_grouped (phase A', epilogue) against
+    the oracle and against the single-launch path (BPC_GROUPB=0); a not-positive-definite observation rejects exactly its chains;
+    deterministic."""
+    import os
+    cfg = syn.make_config("cfg5G", chains=chains, nobs=20000)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    eng = bp.stan_model(mod, cfg["priors"])
+    om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
+    u = cfg["upars"].copy()
+    u[1] += 0.75
+    u[2] -= 1.5
+    u[3] += 2.2                                    # sub-steps in phases A / A'
+    d = eng.data(cfg["data"])
+    assert d.grouped
+    lp, g, st = eng.log_prob_grad(d, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
+    assert st.tolist() == st_o.tolist() and (st == 0).all()
+    np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
+    for c in range(chains):
+        np.testing.assert_allclose(g[c], g_o[c], rtol=1e-9, atol=1e-10 * np.abs(g_o[c]).max())
+    b = eng.log_prob_grad(d, u)
+    assert (b[0] == lp).all() and (b[1] == g).all()
+    os.environ["BPC_GROUPB"] = "0"
+    try:
+        d1 = eng.data(cfg["data"])
+        lp1, g1, st1 = eng.log_prob_grad(d1, u)
+    finally:
+        del os.environ["BPC_GROUPB"]
+    np.testing.assert_allclose(lp, lp1, rtol=1e-12)
+    np.testing.assert_allclose(g, g1, rtol=1e-9, atol=1e-11 * np.abs(g1).max())
+    bad = dict(cfg["data"])
+    ip = np.array(bad["init_pop"], dtype=float)
+    ip[777] = 0.0                                  # Sigma = 0 for one observation: multi_normal rejects every chain
+    bad["init_pop"] = ip
+    lpb, gb, stb = eng.log_prob_grad(bad, u)
+    assert (stb & 1).all() and np.isneginf(lpb).all() and (gb == 0).all()
