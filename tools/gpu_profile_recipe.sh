@@ -1,3 +1,5 @@
+# the profiling recipe of round 2 (run under gpurun): plain run first, ncu launch list, ncu --set full of the dominant kernels,
+# compute-sanitizer attempts (closed on this pool: see profiles/r02_compute_sanitizer_closed_on_this_pool.txt)
 set -x
 export PYTHONPATH=$PWD
 B="python bench.py --steps 2 --warmup 3 --no-sampling --no-other-workloads --no-cpu-baseline --no-parity"
