@@ -345,8 +345,10 @@ def sampling(engine, dat, chains: int = 4, iter: int = 2000, warmup: Optional[in
                     total_chains=int(round(red[0] / half)), pool_exchanges=exchanges, world=world)
         log_lik = None
         if loo:
+            # (C x draws x N doubles, as rstan stores them; evaluated in batches of at most 2^26 values on the device)
             u = engine.unconstrain_pars(draws.reshape(-1, dim))
-            log_lik = engine.log_lik(d, u).reshape(chains, ns, -1)
+            step = max(1, (1 << 26) // max(1, d.ndatapts))
+            log_lik = np.concatenate([engine.log_lik(d, u[i:i + step]) for i in range(0, len(u), step)], axis=0).reshape(chains, ns, -1)
         if own_data:
             # the transformed parameters need the data handle: evaluate them now, before it is closed
             tp = _tpars_fn(engine, d, draws)()
