@@ -2202,6 +2202,309 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 
+// ---- bp_fusedo2: the octet passes with WARP-SPECIALISED roles -------------------------------------------------------------
+// ncu on bp_fusedo (profiles/r02_ncu_bp_fusedo_cfg5U.txt): the shared FP64 datapath is 78 % busy; the warps spend 36 % of their time in the
+// score phase, which holds 20 % of the datapath work -- its dependent chains queue behind the 16-cycle tensor products of the other
+// CTAs' warps, and the three barriers of a pass tie the four schedulers of the SM together.  Here a CTA has EIGHT warps with two roles:
+//   tensor warps 0 .. 3   stage X of pass p, forward product of pass p (into Y buffer p mod 3), then the S' update of pass p - 2
+//   score warps 4 .. 7    score of pass p (Y -> cotangent b in place)
+// Y is triple-buffered and the S' update lags TWO passes behind the forward product, so a score may take up to two tensor pass-times
+// before a tensor warp waits for it; X has four buffers (X of pass p is read again by the S' update of pass p during pass p + 2, and
+// written for pass p + 4 ... p + 1 before the tensor warps' barrier of that pass).  The hand-offs are named barriers (bar.arrive by the
+// producer, bar.sync by the consumer; ids below).  Observation data come straight from global memory into registers, one pass ahead.
+// Same arithmetic, same tile split and shared-memory layouts as bp_fusedo, same results bit for bit.
+// MEASURED (cfg5U, 512 chains x 100 000 observations; tools/exp/dmma_issue_probe.cu shows that ONE warp per scheduler with two
+// accumulator chains already saturates DMMA issue, so four tensor warps per CTA are enough): see DESIGN.md §4.
+#define BP_O2THREADS 256
+#define BP_O2SMEM ((BP_XR * BP_ONLD + 4 * BP_XR * BP_WLD + 3 * BP_OU * BP_OYLD) * 8)
+#define BP_B_FULLY 1      // + Y buffer (3): Y of a pass is complete         tensor -> score
+#define BP_B_FULLB 4      // + Y buffer (3): the cotangent replaced Y        score -> tensor
+#define BP_B_TENSOR 7     // the four tensor warps among themselves
+// (barrier ids as immediates: with a run-time id ptxas reserves all 16 barriers for the CTA)
+template <int ID, int N> __device__ __forceinline__ void bp_bar_sync_i() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> __device__ __forceinline__ void bp_bar_arrive_i() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+#define bp_bar_sync(id, n) bp_bar_sync_i<id, n>()
+#define bp_bar_sync3(id, k) do { if ((k) == 0) bp_bar_sync_i<(id), 256>(); else if ((k) == 1) bp_bar_sync_i<(id) + 1, 256>(); else bp_bar_sync_i<(id) + 2, 256>(); } while (0)
+#define bp_bar_arrive3(id, k) do { if ((k) == 0) bp_bar_arrive_i<(id), 256>(); else if ((k) == 1) bp_bar_arrive_i<(id) + 1, 256>(); else bp_bar_arrive_i<(id) + 2, 256>(); } while (0)
+
+extern "C" __global__ void __launch_bounds__(BP_O2THREADS, 2) bp_fusedo2(BpObsArgs a) {
+  const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp8 = tid >> 5;
+  const int warp = warp8 & 3, rtid = tid & 127;       // index within the role
+  const bool scorer = warp8 >= 4;
+  const int g = lane >> 2, tg = lane & 3;
+  double* sN = bp_smem;                               // [BP_XR][BP_ONLD]
+  double* sXb = sN + BP_XR * BP_ONLD;                 // [4][BP_XR][BP_WLD]    X of pass p in buffer p mod 4
+  double* sYb = sXb + 4 * BP_XR * BP_WLD;             // [3][BP_OU][BP_OYLD]   Y, then b, of pass p in buffer p mod 3
+  __shared__ int sjm[8];
+  const int g0 = blockIdx.x * a.cgpc, g1 = min(a.cgroups, g0 + a.cgpc);
+  {
+    bool any = false;
+    if (g0 < g1)
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) any = any || (o * 8 + cc < a.nchains && a.cg_jm[(size_t)(o * 8 + cc) * a.cgroups + g0] >= 0);
+    if (!any) return;
+  }
+  const int chbeg = a.cg_chunk0[g0], chend = a.cg_chunk0[g1], npass = chend - chbeg;
+  const int swz = (g >> 1) & 1;
+
+  if (!scorer) {
+    // =========================================== tensor warps ===========================================
+    const int wlo = warp & 1, whi = warp >> 1;
+    const int fN = tg * BP_ONLD + whi * (BP_OHT * 8) + g;
+    const int fNx = tg * BP_ONLD + 2 * BP_OHT * 8 + g;
+    const int fX = tg * BP_WLD + wlo * 16 + g;
+    const int fXx = tg * BP_WLD + (2 * wlo + whi) * 8 + g;
+    const int fY = (whi * (BP_OHT * 8) + g) * BP_OYLD + wlo * 16 + ((2 * tg) ^ (swz << 2));
+    const int fYx = (2 * BP_OHT * 8 + g) * BP_OYLD + (2 * wlo + whi) * 8 + ((2 * tg) ^ (swz << 2));
+    const int uX = g * BP_WLD + tg;
+    const int uY = (warp * (BP_OTW * 8) + g) * BP_OYLD + tg;
+    const int wx = min(warp, BP_OREM * BP_XRT - 1);
+    const int xct = 4 * BP_OTW + wx / BP_XRT, xrt = wx % BP_XRT;
+    const int uXx = (xrt * 8 + g) * BP_WLD + tg;
+    const int uYx = (xct * 8 + g) * BP_OYLD + tg;
+    // this lane's observation of the next pass (z0, t), loaded one pass ahead
+    double nz0[BP_N], nt;
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) nz0[i] = a.z0[(size_t)i * a.npad + (size_t)chbeg * 32 + lane];
+    nt = a.t[(size_t)chbeg * 32 + lane];
+    int pass = 0, y3 = 0, x4 = 0;                     // pass mod 3, pass mod 4
+    for (int grp = g0; grp < g1; ++grp) {
+      // ---- N_j(tau_g) of the octet's chains, by the 128 tensor threads (as in bp_fusedo) ----
+      if (rtid < 8) sjm[rtid] = (o * 8 + rtid < a.nchains) ? a.cg_jm[(size_t)(o * 8 + rtid) * a.cgroups + grp] : -1;
+      bp_bar_sync(BP_B_TENSOR, 128);                  // (every tensor warp has finished the previous group's products)
+      {
+        constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NQ = (8 * DN + 127) / 128;
+        double Lr[NQ][BP_D];
+        int Jq[NQ], eo[NQ], dq[NQ];
+        int Jmax = -1;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) Jmax = max(Jmax, sjm[cc] < 0 ? -1 : (sjm[cc] & 255));
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int e = rtid + q * 128;
+          const int cc = e / DN, rem = e - cc * DN, d = rem / BP_N, l = rem - d * BP_N;
+          Jq[q] = e < 8 * DN ? (sjm[cc & 7] < 0 ? -1 : (sjm[cc & 7] & 255)) : -2;
+          eo[q] = l * BP_ONLD + cc * BP_D;
+          dq[q] = d;
+          double n0 = 0.0;
+          if (Jq[q] >= 0) {
+            const size_t c = (size_t)o * 8 + cc;
+            const double* lrow = a.ctab_l + c * (DD + 1) + d * BP_D;
+            n0 = a.n0tab[(c * a.cgroups + grp) * DN + rem];
+#pragma unroll
+            for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = lrow[rr];
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < BP_D; ++rr) Lr[q][rr] = 0.0;
+          }
+          if (Jq[q] >= -1) sN[eo[q] + d] = n0;
+        }
+        for (int j = 1; j < BP_CJ; ++j) {
+          if (j <= Jmax) bp_bar_sync(BP_B_TENSOR, 128);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            if (Jq[q] >= -1) {
+              double v = 0.0;
+              if (j <= Jq[q]) {
+                const double* prev = sN + (j - 1) * BP_N * BP_ONLD + eo[q];
+#pragma unroll
+                for (int rr = 0; rr < BP_D; ++rr) v += Lr[q][rr] * prev[rr];
+              }
+              sN[j * BP_N * BP_ONLD + eo[q] + dq[q]] = v;
+            }
+          }
+        }
+      }
+      const double tau = a.cg_tau[grp];
+      double accS[BP_XRT][BP_OTW ? BP_OTW : 1][2], accX[2] = {0.0, 0.0};
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < (BP_OTW ? BP_OTW : 1); ++ct) { accS[rt][ct][0] = 0.0; accS[rt][ct][1] = 0.0; }
+      auto supdate = [&](int xbuf, int ybuf) {
+        const double* sX = sXb + xbuf * (BP_XR * BP_WLD);
+        const double* px = sX + uX;
+        const double* sY = sYb + ybuf * (BP_OU * BP_OYLD);
+        const double* pbE = sY + uY + (swz << 2);
+        const double* pbO = sY + uY - (swz << 2);
+#pragma unroll
+        for (int ob = 0; ob < 8; ++ob) {
+#if BP_OTW
+          double xa[BP_XRT];
+#pragma unroll
+          for (int rt = 0; rt < BP_XRT; ++rt) xa[rt] = px[rt * 8 * BP_WLD + ob * 4];
+#pragma unroll
+          for (int ct = 0; ct < BP_OTW; ++ct) {
+            const double bf = ((ob & 1) ? pbO : pbE)[ct * 8 * BP_OYLD + ob * 4];
+#pragma unroll
+            for (int rt = 0; rt < BP_XRT; ++rt) bp_dmma(accS[rt][ct][0], accS[rt][ct][1], xa[rt], bf);
+          }
+#endif
+          bp_dmma(accX[0], accX[1], sX[uXx + ob * 4], sY[uYx + ((ob & 1) ? -(swz << 2) : (swz << 2)) + ob * 4]);
+        }
+      };
+      const int ch0 = a.cg_chunk0[grp], ch1 = a.cg_chunk0[grp + 1];
+      for (int ch = ch0; ch < ch1; ++ch, ++pass, y3 = (y3 == 2 ? 0 : y3 + 1), x4 = (x4 + 1) & 3) {
+        {   // stage: terms j = 2 warp, 2 warp + 1 of this lane's observation
+          const bool valid = ch * 32 + lane < a.nobs;
+          double z0[BP_N];
+#pragma unroll
+          for (int i = 0; i < BP_N; ++i) z0[i] = nz0[i];
+          const double h = valid ? nt - tau : 0.0;
+          if (ch + 1 < chend) {
+#pragma unroll
+            for (int i = 0; i < BP_N; ++i) nz0[i] = a.z0[(size_t)i * a.npad + (size_t)(ch + 1) * 32 + lane];
+            nt = a.t[(size_t)(ch + 1) * 32 + lane];
+          }
+          double we = 1.0;
+          for (int j = 1; j <= 2 * warp; ++j) we = we * (h * bp_rk[j - 1]);
+          const double wo = we * (h * bp_rk[2 * warp]);
+          double* xs = sXb + x4 * (BP_XR * BP_WLD) + (2 * warp * BP_N) * BP_WLD + lane;
+#pragma unroll
+          for (int l = 0; l < BP_N; ++l) {
+            xs[l * BP_WLD] = we * z0[l];
+            xs[(BP_N + l) * BP_WLD] = wo * z0[l];
+          }
+        }
+        bp_bar_sync(BP_B_TENSOR, 128);                // X (and, for the group's first pass, N) staged; every tensor warp is past the S' update of pass - 3
+        {
+          double accY[BP_OHT][2][2], accE[2] = {0.0, 0.0};
+#pragma unroll
+          for (int t = 0; t < BP_OHT; ++t)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { accY[t][q][0] = 0.0; accY[t][q][1] = 0.0; }
+          const double* sX = sXb + x4 * (BP_XR * BP_WLD);
+          double* sY = sYb + y3 * (BP_OU * BP_OYLD);
+          const double* pn = sN + fN;
+          const double* px = sX + fX;
+#pragma unroll
+          for (int kk = 0; kk < BP_XKS; ++kk) {
+            const double xb0 = px[kk * 4 * BP_WLD], xb1 = px[kk * 4 * BP_WLD + 8];
+#pragma unroll
+            for (int t = 0; t < BP_OHT; ++t) {
+              const double af = pn[kk * 4 * BP_ONLD + t * 8];
+              bp_dmma(accY[t][0][0], accY[t][0][1], af, xb0);
+              bp_dmma(accY[t][1][0], accY[t][1][1], af, xb1);
+            }
+#if BP_OEX
+            bp_dmma(accE[0], accE[1], sN[fNx + kk * 4 * BP_ONLD], sX[fXx + kk * 4 * BP_WLD]);
+#endif
+          }
+          double* py = sY + fY;
+#pragma unroll
+          for (int t = 0; t < BP_OHT; ++t)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) *reinterpret_cast<double2*>(py + t * 8 * BP_OYLD + q * 8) = make_double2(accY[t][q][0], accY[t][q][1]);
+#if BP_OEX
+          *reinterpret_cast<double2*>(sY + fYx) = make_double2(accE[0], accE[1]);
+#endif
+        }
+        bp_bar_arrive3(BP_B_FULLY, y3);               // Y of this pass is complete
+        if (ch - ch0 >= 2) {                          // the S' update of pass - 2
+          const int yb = (y3 == 2 ? 0 : y3 + 1);      // (pass - 2) mod 3
+          bp_bar_sync3(BP_B_FULLB, yb);               // its cotangent is in its Y buffer
+          supdate((x4 + 2) & 3, yb);
+        }
+      }
+      // ---- the group's last two S' updates, then S' to global memory ----
+      for (int back = min(2, ch1 - ch0); back >= 1; --back) {
+        const int yb = (y3 + 3 - back) % 3;           // (pass - back) mod 3
+        bp_bar_sync3(BP_B_FULLB, yb);
+        supdate((x4 + 4 - back) & 3, yb);
+      }
+      double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
+#if BP_OTW
+#pragma unroll
+      for (int rt = 0; rt < BP_XRT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < BP_OTW; ++ct)
+          __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (warp * BP_OTW + ct) * 8 + 2 * tg), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
+#endif
+      if (warp < BP_OREM * BP_XRT) __stcg(reinterpret_cast<double2*>(sg + (size_t)(xrt * 8 + g) * BP_OU + xct * 8 + 2 * tg), make_double2(accX[0], accX[1]));
+    }
+    return;
+  }
+
+  // ============================================= score warps =============================================
+  double qs[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
+  BpDetProd dp[2];
+  dp[0].init(); dp[1].init();
+  int notpd = 0;
+  int pgrp = g0 - 1;                                  // group of the pass being scored
+  bool onp[2] = {false, false};                       // chains 2 warp, 2 warp + 1 are on this path in group pgrp
+  double nxo[BP_N];                                   // this lane's observed counts of the next pass
+#pragma unroll
+  for (int i = 0; i < BP_N; ++i) nxo[i] = a.xo[(size_t)i * a.npad + (size_t)chbeg * 32 + lane];
+  int y3 = 0;
+  for (int p = 0; p < npass; ++p, y3 = (y3 == 2 ? 0 : y3 + 1)) {
+    const int ch = chbeg + p;
+    const bool valid = ch * 32 + lane < a.nobs;
+    double* sY = sYb + y3 * (BP_OU * BP_OYLD);
+    while (pgrp < g0 || ch >= a.cg_chunk0[pgrp + 1]) {
+      ++pgrp;
+#pragma unroll
+      for (int i2 = 0; i2 < 2; ++i2) onp[i2] = o * 8 + 2 * warp + i2 < a.nchains && a.cg_jm[(size_t)(o * 8 + 2 * warp + i2) * a.cgroups + pgrp] >= 0;
+    }
+    double xo[BP_N];
+#pragma unroll
+    for (int i = 0; i < BP_N; ++i) xo[i] = nxo[i];
+    if (p + 1 < npass) {
+#pragma unroll
+      for (int i = 0; i < BP_N; ++i) nxo[i] = a.xo[(size_t)i * a.npad + (size_t)(ch + 1) * 32 + lane];
+    }
+    bp_bar_sync3(BP_B_FULLY, y3);                     // Y of this pass is complete
+    {
+      const int rbase = 2 * warp * BP_D;
+      const int kA = lane ^ ((rbase & 2) << 1), kB = kA ^ 4;
+      double* yrow = sY + rbase * BP_OYLD;
+#pragma unroll
+      for (int i2 = 0; i2 < 2; ++i2) {
+        double ymu[BP_N], yS[BP_S], bmu[BP_N], bS[BP_S];
+        bool ok = valid && onp[i2];
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) { ymu[i] = yrow[(i2 * BP_D + i) * BP_OYLD + (((i2 * BP_D + i) & 2) ? kB : kA)]; bmu[i] = 0.0; }
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q) { yS[q] = yrow[(i2 * BP_D + BP_N + q) * BP_OYLD + (((i2 * BP_D + BP_N + q) & 2) ? kB : kA)]; bS[q] = 0.0; }
+        if (ok) {
+#if BP_NOISE
+          const double sigma = a.theta[(size_t)(o * 8 + 2 * warp + i2) * BP_DIM + BP_P];
+#else
+          const double sigma = 0.0;
+#endif
+          if (!bp_score_obs_small<true>(xo, sigma, ymu, yS, qs[i2], dp[i2], sb[i2], bmu, bS)) { notpd |= 1 << i2; ok = false; }
+        }
+#pragma unroll
+        for (int i = 0; i < BP_N; ++i) yrow[(i2 * BP_D + i) * BP_OYLD + (((i2 * BP_D + i) & 2) ? kB : kA)] = ok ? bmu[i] : 0.0;
+#pragma unroll
+        for (int q = 0; q < BP_S; ++q)
+          yrow[(i2 * BP_D + BP_N + q) * BP_OYLD + (((i2 * BP_D + BP_N + q) & 2) ? kB : kA)] = ok ? bS[q] : 0.0;
+      }
+    }
+    bp_bar_arrive3(BP_B_FULLB, y3);                   // the cotangent replaced Y
+  }
+  // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial ----
+#pragma unroll
+  for (int i2 = 0; i2 < 2; ++i2) {
+    const double l = bp_warp_sum(-0.5 * (qs[i2] + dp[i2].logdet())), s2 = bp_warp_sum(sb[i2]);
+    const int c = o * 8 + 2 * warp + i2;
+    if (lane == 0 && c < a.nchains) {
+      double fl = 0.0;
+      bool mine = false;
+      for (int grp = g0; grp < g1; ++grp) { fl += a.cg_flops[(size_t)c * a.cgroups + grp]; mine = mine || a.cg_jm[(size_t)c * a.cgroups + grp] >= 0; }
+      if (mine || g0 >= g1 || a.cg_jm[(size_t)c * a.cgroups] >= 0) {
+        double* p = a.part + ((size_t)c * a.ntiles + blockIdx.x) * BP_NPART;
+        p[0] = l;
+#pragma unroll
+        for (int k = 0; k < BP_P; ++k) p[1 + k] = 0.0;
+        p[BP_P + 1] = s2;
+        p[BP_P + 2] = fl;
+      }
+    }
+  }
+  notpd = __reduce_or_sync(0xffffffffu, notpd);
+  if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
+}
+
 // ---- bp_fusedo9: the octet passes for n = 3 (D = 9) with TWO barriers per pass ------------------------------------------
 // The same arithmetic as bp_fusedo, re-laid so that the warps of a CTA depend on each other as little as possible:
 //   * rows of Y / b (and columns of N) are ordered BY CHAIN: tile cc (cc = 0 .. 7) holds components 0 .. 7 of chain cc, tile 8 holds

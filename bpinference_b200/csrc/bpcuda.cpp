@@ -118,6 +118,12 @@ int model_load(bpc_model* m, int device, Loaded** out) {
           L.o9_smem = ((size_t)24 * 76 + 2 * 24 * 36 + 64 * 40 + 2 * 8 * 40 + 7 * 32) * sizeof(double);
           BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedo9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.o9_smem, device));
         } else { L.fusedo9 = nullptr; cudaGetLastError(); }
+        // bp_fusedo2 (warp-specialised: four tensor warps + four score warps, X and Y double-buffered): BPC_O2=1 selects it
+        const char* o2 = std::getenv("BPC_O2");
+        if (o2 && std::atoi(o2) == 1 && cudaLibraryGetKernel(&L.fusedo2, L.lib, "bp_fusedo2") == cudaSuccess) {
+          L.o2_smem = ((size_t)8 * n * (8 * D + 4) + 4 * (size_t)8 * n * 36 + 3 * (size_t)8 * D * 40) * sizeof(double);   // BP_O2SMEM
+          BPC_CUDA(cudaKernelSetAttributeForDevice(L.fusedo2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.o2_smem, device));
+        } else { L.fusedo2 = nullptr; cudaGetLastError(); }
       }
     }
   }
@@ -779,7 +785,9 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
           // time; the Toeplitz products
           const int n = s.ntypes, D = n + n * (n + 1) / 2;
           BPC_CUDA(cudaLaunchKernel((const void*)L->otable, dim3(nchains), dim3(256), args, 0, st));
-          if (L->fusedo9) {   // n = 3, BPC_O9=1: the two-barrier layout
+          if (L->fusedo2) {   // BPC_O2=1: the warp-specialised kernel
+            BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo2, dim3(d->ntiles, d->noct), dim3(256), args, L->o2_smem, st));
+          } else if (L->fusedo9) {   // n = 3, BPC_O9=1: the two-barrier layout
             a.operm = 1;
             BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo9, dim3(d->ntiles, d->noct), dim3(128), args, L->o9_smem, st));
           } else {

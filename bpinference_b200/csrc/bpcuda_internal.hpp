@@ -39,8 +39,8 @@ struct DevBuf {
 
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr, groupb = nullptr, groupc = nullptr;
-  size_t obs_smem = 0, grouped_smem = 0, o_smem = 0, o9_smem = 0;
+  cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr, fusedo2 = nullptr, groupb = nullptr, groupc = nullptr;
+  size_t obs_smem = 0, grouped_smem = 0, o_smem = 0, o9_smem = 0, o2_smem = 0;
 };
 
 // algorithmic flop constants of the shipped kernels (SURVEY.md §8(d) convention: FMA = 2, div/sqrt/exp/log = 1)

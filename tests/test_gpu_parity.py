@@ -356,6 +356,39 @@ def test_octet_path_one_type_multitype_template():
     np.testing.assert_allclose(g, g2, rtol=1e-9, atol=1e-11 * np.abs(g2).max())
 
 
+@pytest.mark.parametrize("env", ["BPC_O2", "BPC_O9"])
+@pytest.mark.parametrize("name,nobs,chains,grouping", [("cfg5U", 40000, 19, None), ("cfg2", None, 24, 1)])
+def test_octet_kernel_variants_agree_bitwise(env, name, nobs, chains, grouping):
+    """the measured alternatives of the octet passes (bp_fusedo2: tensor warps + score warps with named barriers; bp_fusedo9: n = 3,
+    two barriers per pass) do the arithmetic of bp_fusedo: identical lp and gradient for bp_fusedo2 (same order of operations), round-off
+    agreement for bp_fusedo9; a ragged last octet and a chain on the sub-step fallback included.  (The variant is chosen when a model's kernels are loaded.)"""
+    import os
+    cfg = syn.make_config(name, chains=chains, nobs=nobs)
+    u = cfg["upars"].copy()
+    if name == "cfg5U":
+        u[1] += 0.75
+        u[2] -= 1.5
+        u[11] += 2.2
+    kw = {} if grouping is None else {"grouping": grouping}
+    eng, _ = _pair(cfg)
+    d = eng.data(cfg["data"], **kw)
+    assert "bp_fusedo" in d.path(chains)[0]
+    lp, g, st = eng.log_prob_grad(d, u)
+    os.environ[env] = "1"
+    try:
+        eng2, _ = _pair(cfg)
+        d2 = eng2.data(cfg["data"], **kw)
+        lp2, g2, st2 = eng2.log_prob_grad(d2, u)
+    finally:
+        del os.environ[env]
+    assert st.tolist() == st2.tolist()
+    if env == "BPC_O2":                  # same operations in the same order
+        assert (lp == lp2).all() and (g == g2).all()
+    else:                                # bp_fusedo9 sums the observations of a pass in another order
+        np.testing.assert_allclose(lp2, lp, rtol=1e-13)
+        np.testing.assert_allclose(g2, g, rtol=1e-10, atol=1e-12 * np.abs(g).max())
+
+
 @pytest.mark.parametrize("name,nobs,chains", [("cfg2", None, 12), ("cfg5G", 1200, 12), ("cfg4", None, 8)])
 def test_grouped_multi_step_cooperative_path(name, nobs, chains):
     """bp_grouped picks its path per chain: single-step cooperative (rates near the truth), cooperative with sub-steps
