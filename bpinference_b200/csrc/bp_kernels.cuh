@@ -783,8 +783,19 @@ __device__ __forceinline__ void bp_transform(const double* __restrict__ u, doubl
 #endif
 }
 
+// Programmatic dependent launch (griddepcontrol): every kernel of an evaluation starts with bp_pdl_enter().  Launched with the
+// programmatic-stream-serialization attribute (bpc::pdl_launch) its CTAs may become resident while the previous kernel of the stream is
+// still running; `wait` returns once that kernel has completed and its writes are visible, `launch_dependents` then lets the NEXT kernel
+// of the stream do the same.  Both are no-ops in a kernel launched the ordinary way.  Every CTA executes the wait before anything else
+// (also the ones that return early): a grid that completes has therefore waited for its predecessor, and completion stays transitive.
+__device__ __forceinline__ void bp_pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 extern "C" __global__ void bp_prologue(const double* __restrict__ u, int nchains, double* __restrict__ theta,
                                        int* __restrict__ status) {
+  bp_pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchains) return;
   double th[BP_DIM];
@@ -976,6 +987,7 @@ __device__ __forceinline__ void bp_dmma(double& c0, double& c1, double a, double
 }
 
 extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_WMINBLOCKS) bp_fusedw(BpObsArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (bp_skip(a.skip, c)) return;
   double th[BP_DIM];
@@ -1230,6 +1242,7 @@ __device__ __forceinline__ void bp_lbar_to_grad(const double* Zc, double (&gA)[B
 // per chain: W_j summed over tiles -> Lbar -> (gA, gH) -> Theta-bar, added to the chain's first tile partial
 #if !BP_XDEP
 extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.x, tid = threadIdx.x;
   if (bp_skip(a.skip, c)) return;
   __shared__ double W[BP_CROWS * BP_WCOLS];   // W_(j+1) as [j][d * n + l]; then Y_j in place (BP_WROWS rows from bp_fusedw, BP_CROWS from bp_fusedc)
@@ -1330,6 +1343,7 @@ extern "C" __global__ void __launch_bounds__(BP_WPOST_THREADS) bp_wpost(BpObsArg
 // per chain: the two tables M(tau) is assembled from.  One CTA per chain; Krylov blocks U_j = L^j [e_1 .. e_n] and powers
 // P_j = L^j in shared memory, then every table entry is a short dot product with the coefficients c_j(time).
 extern "C" __global__ void __launch_bounds__(512) bp_ctable(BpObsArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   if (bp_skip(a.skip, c)) return;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
@@ -1440,6 +1454,7 @@ __device__ __forceinline__ void bp_c_forward(const double* __restrict__ sN, cons
 }
 
 extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fusedc(BpObsArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (bp_skip(a.skip, c)) return;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D, NW = BP_THREADS / 32;
@@ -1841,6 +1856,7 @@ __device__ __forceinline__ void bp_cp_async_wait_all() { asm volatile("cp.async.
 // (chain, group), and N_0(tau_g) = exp(tau_g L) [e_1 .. e_n] = sum_(j <= m_g) c_j(tau_g) U_j from the Krylov blocks U_j = L^j [e_1 .. e_n]
 // (c_j(tau_g): the coefficient table bp_toep uses).  One CTA per chain.
 extern "C" __global__ void __launch_bounds__(256) bp_otable(BpObsArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
   __shared__ double Lm[DD];
@@ -1954,6 +1970,7 @@ extern "C" __global__ void __launch_bounds__(256) bp_otable(BpObsArgs a) {
 #define BP_OTW (BP_D / 4)                         // S update: (cc, d) tiles owned by each warp with all their row tiles
 #define BP_OREM (BP_D - 4 * BP_OTW)               // remaining (cc, d) tiles: their BP_OREM * BP_XRT (<= 4) tiles go to warps 0, 1, ..
 extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fusedo(BpObsArgs a) {
+  bp_pdl_enter();
   const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
   double* sN = bp_smem;                         // [BP_XR][BP_ONLD]     N_j[d][l] of chain cc at [(j, l)][cc * BP_D + d]
@@ -2228,6 +2245,7 @@ template <int ID, int N> __device__ __forceinline__ void bp_bar_arrive_i() { asm
 #define bp_bar_arrive3(id, k) do { if ((k) == 0) bp_bar_arrive_i<(id), 256>(); else if ((k) == 1) bp_bar_arrive_i<(id) + 1, 256>(); else bp_bar_arrive_i<(id) + 2, 256>(); } while (0)
 
 extern "C" __global__ void __launch_bounds__(BP_O2THREADS, 2) bp_fusedo2(BpObsArgs a) {
+  bp_pdl_enter();
   const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp8 = tid >> 5;
   const int warp = warp8 & 3, rtid = tid & 127;       // index within the role
   const bool scorer = warp8 >= 4;
@@ -2523,6 +2541,7 @@ extern "C" __global__ void __launch_bounds__(BP_O2THREADS, 2) bp_fusedo2(BpObsAr
 #define BP_O9R(cc, d) ((d) < 8 ? (cc) * 8 + (d) : 64 + (cc))
 #define BP_O9SMEM ((BP_XR * BP_ONLD + 2 * BP_XR * BP_WLD + 64 * BP_OYLD + 2 * 8 * BP_OYLD + BP_OOBS) * 8)
 extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fusedo9(BpObsArgs a) {
+  bp_pdl_enter();
   const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
   double* sN = bp_smem;                         // [24][BP_ONLD]        N_j[d][l] of chain cc at [(j, l)][BP_O9R(cc, d)]
@@ -2782,6 +2801,7 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
 // (Variants measured on cfg5U and not kept: eight warps with four groups in flight, software-pipelined loads, a group-major
 // layout of S' that this kernel could stream -- all within a few microseconds of this one, 82 .. 93 us; ncu: tensor path 39 % busy.)
 extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
+  bp_pdl_enter();
   const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
   __shared__ double red[4][BP_CRT * 64];
@@ -2941,6 +2961,7 @@ __device__ __forceinline__ void bp_fused_chain(const BpObsArgs& a, const int c) 
 // grid (tiles, chains).  On the centred / octet W paths (wmode >= 2) the chains that need sub-steps are rare: bp_ctable lists them
 // (fb[0] = count, fb[1 ..] = chain ids) and a few rows of CTAs walk the list instead of one row per chain exiting at once.
 extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_MINBLOCKS) bp_fused(BpObsArgs a) {
+  bp_pdl_enter();
   if (a.wmode >= 2) {
     const int nfb = a.fb[0];
     for (int i = blockIdx.y; i < nfb; i += gridDim.y) {
@@ -3096,6 +3117,7 @@ __device__ __forceinline__ bool bp_groupb_obs(const BpGroupArgs& a, int k, doubl
 // cannot hide the latency of 10^5 observations (profiles/r02_ncu_bp_grouped_cfg5G.txt: 12 % of the warps, long_scoreboard 6 cycles
 // per issue); here every tile of <= 4096 observations of one group is a CTA.  Per-tile sums go to ypart in fixed order (no atomics).
 extern "C" __global__ void __launch_bounds__(128, 4) bp_groupb(BpGroupArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   if (bp_skip(a.skip, c)) return;
   __shared__ double red[(BP_N * BP_D + 2) * 4];
@@ -3134,6 +3156,7 @@ extern "C" __global__ void __launch_bounds__(128, 4) bp_groupb(BpGroupArgs a) {
 #define BP_GC_MINBLOCKS 3
 #endif
 extern "C" __global__ void __launch_bounds__(128, BP_GC_MINBLOCKS) bp_groupc(BpGroupArgs a) {
+  bp_pdl_enter();
   const int tile = blockIdx.x, tid = threadIdx.x, c = blockIdx.y * 128 + tid;
   __shared__ double sz[2 * BP_N][BP_GC_TILE];
   const int g = a.tgroup[tile], k0 = a.tstart[tile], nk = a.tstart[tile + 1] - k0;
@@ -3171,6 +3194,7 @@ extern "C" __global__ void __launch_bounds__(128, BP_GC_MINBLOCKS) bp_groupc(BpG
 }
 
 extern "C" __global__ void __launch_bounds__(128) bp_grouped(BpGroupArgs a) {
+  bp_pdl_enter();
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   if (bp_skip(a.skip, c)) return;
   const int G = a.ngroups, GN = G * BP_N;
@@ -3652,6 +3676,7 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_moments(BpObsArgs a)
 #else   // BP_KIND == 2
 // ---- one-type template: thread per (chain, observation) -----------------------------------------
 extern "C" __global__ void __launch_bounds__(BP_THREADS) bp_onetype(BpObsArgs a) {
+  bp_pdl_enter();
   __shared__ double scratch[BP_NPART * (BP_THREADS / 32)];
   const int c = blockIdx.y;
   const int tid = threadIdx.x;
@@ -3751,6 +3776,7 @@ extern "C" __global__ void bp_epilogue(const double* __restrict__ u, const doubl
                                        const double* __restrict__ part, int ntiles, int nchains, int jacobian,
                                        double* __restrict__ lp_out, double* __restrict__ grad_out, int* __restrict__ status,
                                        double* __restrict__ apps_out, const int* __restrict__ skip) {
+  bp_pdl_enter();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= nchains || bp_skip(skip, c)) return;   // (warp-uniform)
   double acc[BP_NPART];

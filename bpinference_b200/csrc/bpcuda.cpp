@@ -712,9 +712,16 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   const bool own_io_1t = s.kind == BPC_SIMPLE_BD && d->ntiles == 1;
   const bool own_io = (d->grouped && L->grouped) || own_io_1t;
   const bool own_in = !own_io && d->wmode && d->omode;   // octet path: bp_otable does the transform
+  // programmatic dependent launch between the kernels of one evaluation (MEASURED: cfg5U 1.967 -> 1.962 ms per step, cfg5G 0.637 ->
+  // 0.633; a single-launch evaluation has nothing to gain, and replayed from the sampler's CUDA graph the programmatic edges made the
+  // cfg2 passes 14 % SLOWER, so captured launches stay ordinary)
+  const bool pdl = cap == cudaStreamCaptureStatusNone && pdl_enabled() && (!own_io || (d->grouped && d->ntb > 0));
+  auto launch = [pdl](const void* f, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+    return pdl ? pdl_launch(f, grid, block, args, smem, stream) : cudaLaunchKernel(f, grid, block, args, smem, stream);
+  };
   if (!own_io && !own_in) {
     void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
-    BPC_CUDA(cudaLaunchKernel((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
+    BPC_CUDA(launch((const void*)L->prologue, dim3((nchains + 127) / 128), dim3(128), args, 0, st));
   }
   {
     ObsArgs a{theta, (const double*)d->z0.p, (const double*)d->xo.p, (const double*)d->t.p, (const double*)d->xv.p,
@@ -766,14 +773,14 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
         const bool per_chain = nchains >= 128 && L->groupc && d->ntc > 0 && !(gc && std::atoi(gc) == 0);
         if (per_chain) { ga.ntb = d->ntc; ga.tgroup = (const int*)d->tgroup_c.p; ga.tstart = (const int*)d->tstart_c.p; ga.gtile0 = (const int*)d->gtile0_c.p; ga.ypt = 1; }
         ga.mode = 1;
-        BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
-        if (per_chain) BPC_CUDA(cudaLaunchKernel((const void*)L->groupc, dim3(d->ntc, (nchains + 127) / 128), dim3(128), gargs, 0, st));
-        else BPC_CUDA(cudaLaunchKernel((const void*)L->groupb, dim3(d->ntb, nchains), dim3(128), gargs, 0, st));
+        BPC_CUDA(launch((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+        if (per_chain) BPC_CUDA(launch((const void*)L->groupc, dim3(d->ntc, (nchains + 127) / 128), dim3(128), gargs, 0, st));
+        else BPC_CUDA(launch((const void*)L->groupb, dim3(d->ntb, nchains), dim3(128), gargs, 0, st));
         ga.mode = 2;
-        BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+        BPC_CUDA(launch((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
         g_launches += 2;
       } else {
-        BPC_CUDA(cudaLaunchKernel((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
+        BPC_CUDA(launch((const void*)L->grouped, dim3(nchains), dim3(T), gargs, smem, st));
       }
     } else {
       if (d->wmode) {
@@ -784,31 +791,31 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
           // octet path: per chain the transform, L, series lengths and N_0(tau_g) of every group; the fused passes of 8 chains at a
           // time; the Toeplitz products
           const int n = s.ntypes, D = n + n * (n + 1) / 2;
-          BPC_CUDA(cudaLaunchKernel((const void*)L->otable, dim3(nchains), dim3(256), args, 0, st));
+          BPC_CUDA(launch((const void*)L->otable, dim3(nchains), dim3(256), args, 0, st));
           if (L->fusedo2) {   // BPC_O2=1: the warp-specialised kernel
-            BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo2, dim3(d->ntiles, d->noct), dim3(256), args, L->o2_smem, st));
+            BPC_CUDA(launch((const void*)L->fusedo2, dim3(d->ntiles, d->noct), dim3(256), args, L->o2_smem, st));
           } else if (L->fusedo9) {   // n = 3, BPC_O9=1: the two-barrier layout
             a.operm = 1;
-            BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo9, dim3(d->ntiles, d->noct), dim3(128), args, L->o9_smem, st));
+            BPC_CUDA(launch((const void*)L->fusedo9, dim3(d->ntiles, d->noct), dim3(128), args, L->o9_smem, st));
           } else {
-            BPC_CUDA(cudaLaunchKernel((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
+            BPC_CUDA(launch((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
           }
-          BPC_CUDA(cudaLaunchKernel((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
+          BPC_CUDA(launch((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
           g_launches += 1;   // (bp_otable stands in for bp_prologue in the count below)
         } else if (d->cmode) {
           // centred W path: per-chain tables of exp(tau L), then short series around the groups' centres
-          BPC_CUDA(cudaLaunchKernel((const void*)L->ctable, dim3(nchains), dim3(256), args, 0, st));
-          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedc, dim3(d->ntiles, nchains), dim3(s.threads), args, s.c_smem, st));
+          BPC_CUDA(launch((const void*)L->ctable, dim3(nchains), dim3(256), args, 0, st));
+          BPC_CUDA(launch((const void*)L->fusedc, dim3(d->ntiles, nchains), dim3(s.threads), args, s.c_smem, st));
           g_launches += 1;
         } else {
-          BPC_CUDA(cudaLaunchKernel((const void*)L->fusedw, dim3(d->ntiles, nchains), dim3(s.threads), args, s.w_smem, st));
+          BPC_CUDA(launch((const void*)L->fusedw, dim3(d->ntiles, nchains), dim3(s.threads), args, s.w_smem, st));
         }
         // octet path: the sub-step fallback goes first, so that bp_wpost can also do the epilogue's work (one launch less)
         if (d->omode) {
           const int fbr = std::min(nchains, std::max(8, (148 * 4 + d->ntiles - 1) / std::max(1, d->ntiles)));
-          BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, fbr), dim3(s.threads), args, L->obs_smem, st));
+          BPC_CUDA(launch((const void*)L->obs, dim3(d->ntiles, fbr), dim3(s.threads), args, L->obs_smem, st));
         }
-        BPC_CUDA(cudaLaunchKernel((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
+        BPC_CUDA(launch((const void*)L->wpost, dim3(nchains), dim3(s.w_post_threads), args, 0, st));
         g_launches += 2;
       }
       // (centred / octet W paths: bp_ctable / bp_otable listed the chains that need sub-steps; a few rows of CTAs walk that list -- at
@@ -816,7 +823,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
       // values on a subsample, EVERY chain is on the list; rows that find nothing to do return at once)
       const int fb_rows = std::min(nchains, std::max(8, (148 * 4 + d->ntiles - 1) / std::max(1, d->ntiles)));
       if (!(d->wmode && d->omode))
-        BPC_CUDA(cudaLaunchKernel((const void*)L->obs, dim3(d->ntiles, d->cmode ? fb_rows : nchains), dim3(s.threads), args, L->obs_smem, st));
+        BPC_CUDA(launch((const void*)L->obs, dim3(d->ntiles, d->cmode ? fb_rows : nchains), dim3(s.threads), args, L->obs_smem, st));
     }
     if (d->timing) {
       BPC_CUDA(cudaEventRecord(e1, st));
@@ -828,7 +835,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
     int ntiles = d->ntiles;
     void* args[] = {(void*)&u_dev, (void*)&theta, (void*)&part, (void*)&ntiles, (void*)&nchains, (void*)&jacobian,
                     (void*)&lp_dev, (void*)&grad_dev, (void*)&status_dev, (void*)&apps, (void*)&skip_dev};
-    BPC_CUDA(cudaLaunchKernel((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
+    BPC_CUDA(launch((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
   g_launches += own_io ? 1 : (folded ? 2 : 3);
   if (cap == cudaStreamCaptureStatusNone && (rc = release_workspace(d, st))) return rc;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -14,6 +15,29 @@ namespace bpc {
 
 extern thread_local std::string g_last_error;
 extern thread_local long long g_launches;
+
+// Launch of a kernel of the evaluation / sampler chains with programmatic dependent launch: the kernel's CTAs may become resident while
+// the previous kernel of the stream still runs; every such kernel starts with bp_pdl_enter() (griddepcontrol.wait: the previous kernel
+// has completed and flushed), so the order of the stream is kept.  Used for eager launches only (log_prob_dev has the measurement).
+// BPC_PDL=0: ordinary launches.
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("BPC_PDL"); return !(e && std::atoi(e) == 0); }();
+  return on;
+}
+inline cudaError_t pdl_launch(const void* f, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t st) {
+  if (!pdl_enabled()) return cudaLaunchKernel(f, grid, block, args, smem, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, f, args);
+}
 int fail(int code, const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 

@@ -1114,7 +1114,7 @@ static int sampler_passes(bpc_sampler* s, int nb) {
   for (int b = 0; b < nb; ++b) {
     int rc = log_prob_dev(s->m, s->stage1 ? s->d_opt : s->d, P.q_eval, P.C, 1, P.lp_eval, P.g_eval, P.st_eval, s->stream, P.si + (size_t)I_PHASE * P.C);
     if (rc) return rc;
-    bp_nuts_advance<<<(P.C + 3) / 4, 128, 0, s->stream>>>(P);
+    bp_nuts_advance<<<(P.C + 3) / 4, 128, 0, s->stream>>>(P);   // (ordinary launch: see the measurement at bpc::pdl_launch's use in log_prob_dev)
     g_launches += 1;
   }
   return BPC_OK;
