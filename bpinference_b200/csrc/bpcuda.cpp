@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -716,8 +717,17 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
   // 0.633; a single-launch evaluation has nothing to gain, and replayed from the sampler's CUDA graph the programmatic edges made the
   // cfg2 passes 14 % SLOWER, so captured launches stay ordinary)
   const bool pdl = cap == cudaStreamCaptureStatusNone && pdl_enabled() && (!own_io || (d->grouped && d->ntb > 0));
-  auto launch = [pdl](const void* f, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
-    return pdl ? pdl_launch(f, grid, block, args, smem, stream) : cudaLaunchKernel(f, grid, block, args, smem, stream);
+  // BPC_KTIME=1 (diagnostic): an event pair around every launch of this evaluation, the times of the kernels in launch order on stderr
+  // after a synchronize (warm numbers of the step's kernels in their real sequence, next to the cold per-kernel times ncu reports)
+  static const bool ktime = [] { const char* e = std::getenv("BPC_KTIME"); return e && std::atoi(e) == 1; }();
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
+  const bool kt = ktime && cap == cudaStreamCaptureStatusNone;
+  auto launch = [pdl, kt, &kev](const void* f, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (kt) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, stream); }
+    const cudaError_t e = pdl ? pdl_launch(f, grid, block, args, smem, stream) : cudaLaunchKernel(f, grid, block, args, smem, stream);
+    if (kt) { cudaEventRecord(b, stream); kev.emplace_back(a, b); }
+    return e;
   };
   if (!own_io && !own_in) {
     void* args[] = {(void*)&u_dev, (void*)&nchains, (void*)&theta, (void*)&status_dev};
@@ -838,6 +848,12 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
     BPC_CUDA(launch((const void*)L->epilogue, dim3((nchains + 3) / 4), dim3(128), args, 0, st));
   }
   g_launches += own_io ? 1 : (folded ? 2 : 3);
+  if (kt) {
+    cudaStreamSynchronize(st);
+    std::fprintf(stderr, "[ktime]");
+    for (auto& ev : kev) { float ms = 0.f; cudaEventElapsedTime(&ms, ev.first, ev.second); std::fprintf(stderr, " %.1f", ms * 1e3); cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    std::fprintf(stderr, " us\n");
+  }
   if (cap == cudaStreamCaptureStatusNone && (rc = release_workspace(d, st))) return rc;
   return BPC_OK;
 }
