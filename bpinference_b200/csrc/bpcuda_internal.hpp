@@ -61,6 +61,25 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
+struct HostBuf {   // pinned host memory (staging of the host-buffer entry points: one asynchronous copy each way)
+  void* p = nullptr;
+  size_t cap = 0;
+  int alloc(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    cap = bytes;
+    return 0;
+  }
+  ~HostBuf() { if (p) cudaFreeHost(p); }
+  HostBuf() = default;
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+};
+
 struct Loaded {   // one NVRTC module loaded on one device
   cudaLibrary_t lib = nullptr;
   cudaKernel_t prologue = nullptr, obs = nullptr, epilogue = nullptr, loglik = nullptr, grouped = nullptr, moments = nullptr, fusedw = nullptr, wpost = nullptr, fusedc = nullptr, ctable = nullptr, otable = nullptr, fusedo = nullptr, toep = nullptr, tparams = nullptr, fusedo9 = nullptr, fusedo2 = nullptr, groupb = nullptr, groupc = nullptr;
@@ -126,7 +145,8 @@ struct bpc_data {
   unsigned long long ws_gen = 0;
   cudaEvent_t ws_event = nullptr;   // recorded at the end of every use of the workspace, waited for at the start of the next
   bpc::DevBuf theta, part, apps;
-  bpc::DevBuf io_u, io_lp, io_grad, io_status;
+  bpc::DevBuf io_u, io_status, io_out;
+  bpc::HostBuf h_in, h_out;
   cudaStream_t stream = nullptr;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
