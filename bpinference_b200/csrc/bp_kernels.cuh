@@ -1855,12 +1855,14 @@ __device__ __forceinline__ void bp_cp_async_wait_all() { asm volatile("cp.async.
 // the path decision (chains that need sub-steps go to bp_fused's list), L, the series lengths (J, m) and algorithmic flops of every
 // (chain, group), and N_0(tau_g) = exp(tau_g L) [e_1 .. e_n] = sum_(j <= m_g) c_j(tau_g) U_j from the Krylov blocks U_j = L^j [e_1 .. e_n]
 // (c_j(tau_g): the coefficient table bp_toep uses).  One CTA per chain.
+#define BP_OT_GROUPS 128                         // groups per batch of the N_0 loop (one thread each)
 extern "C" __global__ void __launch_bounds__(256) bp_otable(BpObsArgs a) {
   bp_pdl_enter();
   const int c = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   constexpr int DN = BP_D * BP_N, DD = BP_D * BP_D;
   __shared__ double Lm[DD];
   __shared__ double U[(BP_WROWS + 1) * DN];
+  __shared__ double n0s[BP_OT_GROUPS * DN];    // N_0 rows of a batch of groups on their way to global memory
   double th[BP_DIM];
   if (a.u) {
     bp_transform(a.u + (size_t)c * BP_DIM, th);
@@ -1939,18 +1941,35 @@ extern "C" __global__ void __launch_bounds__(256) bp_otable(BpObsArgs a) {
     }
     __syncthreads();
   }
+  // N_0 of the groups: thread = one group with its D n sums in registers, so that a term costs ONE coefficient load and D n broadcast
+  // reads of U (one (group, entry) per thread made this loop LSU-bound: two memory instructions per FMA, 22 of the kernel's 38 us);
+  // the rows go through shared memory to be stored coalesced.  Same operations in the same order for every entry.
   double* n0 = a.n0tab + (size_t)c * a.cgroups * DN;
-  for (int i = tid; i < a.cgroups * DN; i += T) {
-    const int g = i / DN, o = i - g * DN;
-    const int q = jm[g];
-    double y = 0.0;
-    if (q >= 0) {
-      const int mg = q >> 8;
-      const double* cf = a.cg_coef + (size_t)g * BP_CCTAB + 8;
-      y = U[o];
-      for (int j = 1; j <= mg; ++j) y += cf[j] * U[j * DN + o];
+  for (int gb = 0; gb < a.cgroups; gb += BP_OT_GROUPS) {
+    const int g = gb + tid;
+    if (tid < BP_OT_GROUPS && g < a.cgroups) {
+      const int q = jm[g];
+      double y[DN];
+#pragma unroll
+      for (int o = 0; o < DN; ++o) y[o] = 0.0;
+      if (q >= 0) {
+        const int mg = q >> 8;
+        const double* cf = a.cg_coef + (size_t)g * BP_CCTAB + 8;
+#pragma unroll
+        for (int o = 0; o < DN; ++o) y[o] = U[o];
+        for (int j = 1; j <= mg; ++j) {
+          const double cj = cf[j];
+#pragma unroll
+          for (int o = 0; o < DN; ++o) y[o] += cj * U[j * DN + o];
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < DN; ++o) n0s[tid * DN + o] = y[o];
     }
-    n0[i] = y;
+    __syncthreads();
+    const int cnt = min(BP_OT_GROUPS, a.cgroups - gb) * DN;
+    for (int i = tid; i < cnt; i += T) n0[(size_t)gb * DN + i] = n0s[i];
+    __syncthreads();
   }
 }
 
