@@ -2819,7 +2819,10 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
 // W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
 // (Variants measured on cfg5U and not kept: eight warps with four groups in flight, software-pipelined loads, a group-major
 // layout of S' that this kernel could stream -- all within a few microseconds of this one, 82 .. 93 us; ncu: tensor path 39 % busy.)
-extern "C" __global__ void __launch_bounds__(128) bp_toep(BpObsArgs a) {
+#ifndef BP_TOEP_MINBLOCKS
+#define BP_TOEP_MINBLOCKS 8                       // (measured: more CTAs per SM spill and are slower, codegen.cpp)
+#endif
+extern "C" __global__ void __launch_bounds__(128, BP_TOEP_MINBLOCKS) bp_toep(BpObsArgs a) {
   bp_pdl_enter();
   const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;

@@ -213,6 +213,11 @@ std::string generate_cuda(ModelSpec& m) {
     if (const char* ev = std::getenv("BPC_GC_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 4) gcmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_GC_MINBLOCKS %d\n", gcmin);
     s += buf;
+    int tmin = 8;    // bp_toep: CTAs per SM.  MEASURED on cfg5U (1.46 waves at 8): 8 -> 62 us (62 registers, no spills), 10 -> 74, 12 -> 82 (one wave,
+                     // 40 registers, 84 bytes spilled), 16 -> 123: the spills cost more than the second wave
+    if (const char* ev = std::getenv("BPC_TOEP_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) tmin = v; }
+    std::snprintf(buf, sizeof buf, "#define BP_TOEP_MINBLOCKS %d\n", tmin);
+    s += buf;
   }
   s += "#ifdef BP_HOSTSIM\n#define BP_HD inline\n#define BP_GLOBAL_CONST static const\n#else\n"
        "#define BP_HD __device__ __forceinline__\n#define BP_GLOBAL_CONST __constant__ const\ntypedef double real;\n#endif\n";
