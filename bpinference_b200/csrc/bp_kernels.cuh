@@ -2238,6 +2238,7 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 
+#if BP_ALT_KERNELS   // the measured alternatives of bp_fusedo (BPC_O2 / BPC_O9): compiled only when asked for (codegen.cpp)
 // ---- bp_fusedo2: the octet passes with WARP-SPECIALISED roles -------------------------------------------------------------
 // ncu on bp_fusedo (profiles/r02_ncu_bp_fusedo_cfg5U.txt): the shared FP64 datapath is 78 % busy; the warps spend 36 % of their time in the
 // score phase, which holds 20 % of the datapath work -- its dependent chains queue behind the 16-cycle tensor products of the other
@@ -2815,6 +2816,7 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
   if (lane < 2 && ((notpd >> lane) & 1) && o * 8 + 2 * warp + lane < a.nchains) atomicOr(a.status + o * 8 + 2 * warp + lane, BP_ST_NOT_PD);
 }
 #endif  // BP_D == 9
+#endif  // BP_ALT_KERNELS
 
 // W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
 // (Variants measured on cfg5U and not kept: eight warps with four groups in flight, software-pipelined loads, a group-major

@@ -213,6 +213,13 @@ std::string generate_cuda(ModelSpec& m) {
     if (const char* ev = std::getenv("BPC_GC_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 4) gcmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_GC_MINBLOCKS %d\n", gcmin);
     s += buf;
+    {   // bp_fusedo2 / bp_fusedo9 are compiled only for a process that selects one of them (they add about a second to every model build)
+      const char* o2 = std::getenv("BPC_O2");
+      const char* o9 = std::getenv("BPC_O9");
+      const char* alt = std::getenv("BPC_ALT_KERNELS");
+      const bool on = (o2 && std::atoi(o2) == 1) || (o9 && std::atoi(o9) == 1) || (alt && std::atoi(alt) == 1);
+      s += on ? "#define BP_ALT_KERNELS 1\n" : "#define BP_ALT_KERNELS 0\n";
+    }
     int tmin = 8;    // bp_toep: CTAs per SM.  MEASURED on cfg5U (1.46 waves at 8): 8 -> 62 us (62 registers, no spills), 10 -> 74, 12 -> 82 (one wave,
                      // 40 registers, 84 bytes spilled), 16 -> 123: the spills cost more than the second wave
     if (const char* ev = std::getenv("BPC_TOEP_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) tmin = v; }
