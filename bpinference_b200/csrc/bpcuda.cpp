@@ -45,7 +45,17 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Modules already compiled by this process, by generated source (it holds every macro of the build): creating the same model again
+// (a second stan_model() of the same description, the engine a sampler test rebuilds) costs a map lookup instead of ~8 s of NVRTC.
+static std::mutex g_cubin_mu;
+static std::map<std::string, std::pair<std::vector<char>, std::string>> g_cubin_cache;
+
 static int compile_model(bpc_model* m) {
+  {
+    std::lock_guard<std::mutex> lock(g_cubin_mu);
+    auto it = g_cubin_cache.find(m->source);
+    if (it != g_cubin_cache.end()) { m->cubin = it->second.first; m->compile_log = it->second.second; return BPC_OK; }
+  }
   nvrtcProgram prog;
   const char* hdr_src[] = {bp_kernels_cuh_text};
   const char* hdr_name[] = {"bp_kernels.cuh"};
@@ -70,6 +80,11 @@ static int compile_model(bpc_model* m) {
   nvrtcGetCUBIN(prog, m->cubin.data());
   nvrtcDestroyProgram(&prog);
   m->compile_log = log;
+  {
+    std::lock_guard<std::mutex> lock(g_cubin_mu);
+    if (g_cubin_cache.size() >= 64) g_cubin_cache.clear();   // (bounded: a process that builds hundreds of different models keeps the last ones)
+    g_cubin_cache.emplace(m->source, std::make_pair(m->cubin, m->compile_log));
+  }
   return BPC_OK;
 }
 
