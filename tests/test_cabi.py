@@ -98,6 +98,26 @@ def test_every_module_compiles_for_sm100a_with_the_planned_resources(name, expec
         assert regs <= 128 and stack == 0, res["bp_fusedo"]
 
 
+def test_module_cache_and_alternative_kernels_on_request(monkeypatch):
+    """the same model description built twice in one process is compiled once (the cache key is the generated source, macros
+    included); the measured alternatives of the octet passes (bp_fusedo2 / bp_fusedo9) are in a module only when BPC_O2 / BPC_O9 asks."""
+    import time
+    cfg = syn.make_config("cfg5U", chains=2, nobs=64)
+    mod = bp.bp_model(cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"])
+    monkeypatch.delenv("BPC_O2", raising=False)
+    monkeypatch.delenv("BPC_O9", raising=False)
+    monkeypatch.delenv("BPC_ALT_KERNELS", raising=False)
+    a = bp.stan_model(mod, cfg["priors"])
+    t0 = time.perf_counter()
+    b = bp.stan_model(mod, cfg["priors"])
+    assert time.perf_counter() - t0 < 1.0
+    assert a.cubin() == b.cubin() and a.cuda_source == b.cuda_source
+    assert b"bp_fusedo2" not in a.cubin() and b"bp_fusedo9" not in a.cubin() and b"bp_fusedo" in a.cubin()
+    monkeypatch.setenv("BPC_O2", "1")
+    c = bp.stan_model(mod, cfg["priors"])
+    assert c.cuda_source != a.cuda_source and b"bp_fusedo2" in c.cubin() and b"bp_fusedo9" in c.cubin()
+
+
 def test_non_finite_bounds_parameters_and_data_are_rejected():
     """(0, Inf) bounds used to produce Theta = Inf / NaN and silently rejected chains; NaN durations broke the sort in
     bpc_data_create.  Both are refused at the boundary now, before any device work."""
