@@ -1834,6 +1834,14 @@ extern "C" __global__ void __launch_bounds__(BP_THREADS, BP_CMINBLOCKS) bp_fused
 // builds N_j = L N_(j-1) of its octet in the group prologue, bp_toep is the Toeplitz product W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for all groups at once, bp_wpost finishes.
 #define BP_OU (8 * BP_D)                         // columns of an octet: (cc, d)
 #define BP_ONLD (BP_OU + 4)                      // row stride of the staged N (conflict-free A fragments: stride = 12 mod 16)
+// S' of one (octet, group) in global memory: element (row (j, l), column 8 ct + c8) at ((ct n + l) 8 + j) 8 + c8, i.e. the 8 x 8 block
+// (all j, the 8 columns of tile ct) that one CTA of bp_toep reads is 512 contiguous bytes (row-major [(j, l)][column] made it eight
+// 64-byte pieces: bp_toep ran at 1.7 TB/s on 103 MB, bound by that access pattern).  The stores of the passes' kernels are 64-byte
+// pieces inside the group's 8 n x 8 D block either way.
+__device__ __forceinline__ int bp_osg_off(int row, int col) {
+  const int j = row / BP_N, l = row - j * BP_N;
+  return ((((col >> 3) * BP_N + l) * BP_CJ + j) << 3) + (col & 7);
+}
 #define BP_OTHREADS 128                          // one CTA = four warps on the same pass
 #ifndef BP_OMINBLOCKS
 #define BP_OMINBLOCKS 4
@@ -2202,17 +2210,18 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
         }
       }
     }
-    // ---- the group's S', row-major [(j, l)][(cc, d)]: every tile from the warp that owns it ----
-    // (a layout that bp_toep could stream, [tile][l][group][j][8], scatters these stores and costs more here than it saves there)
+    // ---- the group's S' in the block layout of bp_osg_off: every tile from the warp that owns it ----
+    // (a layout with the GROUP inside, [tile][l][group][j][8], scatters these stores over the octet's whole region and costs more here
+    // than it saves in bp_toep; re-ordering inside the group's own block is free here)
     double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
 #if BP_OTW
 #pragma unroll
     for (int rt = 0; rt < BP_XRT; ++rt)
 #pragma unroll
       for (int ct = 0; ct < BP_OTW; ++ct)
-        __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (warp * BP_OTW + ct) * 8 + 2 * tg), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
+        __stcg(reinterpret_cast<double2*>(sg + bp_osg_off(rt * 8 + g, (warp * BP_OTW + ct) * 8 + 2 * tg)), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
 #endif
-    if (warp < BP_OREM * BP_XRT) __stcg(reinterpret_cast<double2*>(sg + (size_t)(xrt * 8 + g) * BP_OU + xct * 8 + 2 * tg), make_double2(accX[0], accX[1]));
+    if (warp < BP_OREM * BP_XRT) __stcg(reinterpret_cast<double2*>(sg + bp_osg_off(xrt * 8 + g, xct * 8 + 2 * tg)), make_double2(accX[0], accX[1]));
     // (the next group's prologue barrier separates this group's last S update from the next writes of N and Y)
   }
   // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial; chain 2 warp + i belongs to this warp alone ----
@@ -2456,9 +2465,9 @@ extern "C" __global__ void __launch_bounds__(BP_O2THREADS, 2) bp_fusedo2(BpObsAr
       for (int rt = 0; rt < BP_XRT; ++rt)
 #pragma unroll
         for (int ct = 0; ct < BP_OTW; ++ct)
-          __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (warp * BP_OTW + ct) * 8 + 2 * tg), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
+          __stcg(reinterpret_cast<double2*>(sg + bp_osg_off(rt * 8 + g, (warp * BP_OTW + ct) * 8 + 2 * tg)), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
 #endif
-      if (warp < BP_OREM * BP_XRT) __stcg(reinterpret_cast<double2*>(sg + (size_t)(xrt * 8 + g) * BP_OU + xct * 8 + 2 * tg), make_double2(accX[0], accX[1]));
+      if (warp < BP_OREM * BP_XRT) __stcg(reinterpret_cast<double2*>(sg + bp_osg_off(xrt * 8 + g, xct * 8 + 2 * tg)), make_double2(accX[0], accX[1]));
     }
     return;
   }
@@ -2790,8 +2799,8 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
     for (int rt = 0; rt < BP_XRT; ++rt)
 #pragma unroll
       for (int ct = 0; ct < 2; ++ct)
-        __stcg(reinterpret_cast<double2*>(sg + (size_t)(rt * 8 + g) * BP_OU + (warp * 2 + ct) * 8 + 2 * tg), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
-    if (warp < BP_XRT) __stcg(reinterpret_cast<double2*>(sg + (size_t)(warp * 8 + g) * BP_OU + 64 + 2 * tg), make_double2(accX[0], accX[1]));
+        __stcg(reinterpret_cast<double2*>(sg + bp_osg_off(rt * 8 + g, (warp * 2 + ct) * 8 + 2 * tg)), make_double2(accS[rt][ct][0], accS[rt][ct][1]));
+    if (warp < BP_XRT) __stcg(reinterpret_cast<double2*>(sg + bp_osg_off(warp * 8 + g, 64 + 2 * tg)), make_double2(accX[0], accX[1]));
   }
   // ---- per chain: lp (+ d/dsigma_obs, flops of this CTA's groups) into the tile partial; chain 2 warp + i belongs to this warp alone ----
 #pragma unroll
@@ -2856,7 +2865,7 @@ extern "C" __global__ void __launch_bounds__(128, BP_TOEP_MINBLOCKS) bp_toep(BpO
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const int j = ks * 4 + tg;
-      const double v = __ldcs(sg + (size_t)(j * BP_N + l) * BP_OU + u);
+      const double v = __ldcs(sg + bp_osg_off(j * BP_N + l, u));   // (a warp reads 256 contiguous bytes)
       bf[ks] = j <= J ? v : 0.0;   // rows beyond the chain's own degree hold X b products of terms the chain does not have
     }
 #pragma unroll
