@@ -2827,17 +2827,23 @@ extern "C" __global__ void __launch_bounds__(BP_OTHREADS, BP_OMINBLOCKS) bp_fuse
 #endif  // BP_D == 9
 #endif  // BP_ALT_KERNELS
 
-// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per (column tile, l); its warps split the groups.
-// (Variants measured on cfg5U and not kept: eight warps with four groups in flight, software-pipelined loads, a group-major
-// layout of S' that this kernel could stream -- all within a few microseconds of this one, 82 .. 93 us; ncu: tensor path 39 % busy.)
+// W_n = sum_g sum_j c_(n-j)(tau_g) S^g_j for every chain of an octet: one CTA per column tile (8 of the octet's 8 D columns) with all
+// n ancestors l; its warps split the groups.  The A fragments (the coefficients c_(n-j)(tau_g)) are shared by the n products of a group,
+// the B fragments of the n ancestors are n x 512 contiguous bytes (bp_osg_off), and the (D, octets) grid is ONE wave of 4 CTAs per SM.
+// MEASURED on cfg5U (live, BPC_KTIME=1): one CTA per (column tile, l), 8 CTAs per SM, S' row-major: 62 us (29 us of them DMMA; ncu:
+// tensor path 48 % busy, long_scoreboard 12 cycles per issue); block layout of S': 57.7; this kernel with 5 CTAs per SM (96 registers,
+// 104 bytes spilled): 56, the same with the next group's loads issued ahead: 51.6; with 4 CTAs per SM (no spills): 45.4, with or
+// without issuing the loads ahead; 3 CTAs per SM (two waves): 56 .. 64.
+// (Not kept earlier: eight warps with four groups in flight, a group-major layout of S', more CTAs per SM through a register cap
+// (74 .. 123 us), octets in reverse order (no change: it is not DRAM against L2).)
 #ifndef BP_TOEP_MINBLOCKS
-#define BP_TOEP_MINBLOCKS 8                       // (measured: more CTAs per SM spill and are slower, codegen.cpp)
+#define BP_TOEP_MINBLOCKS 4
 #endif
 extern "C" __global__ void __launch_bounds__(128, BP_TOEP_MINBLOCKS) bp_toep(BpObsArgs a) {
   bp_pdl_enter();
-  const int o = blockIdx.y, ct = blockIdx.x / BP_N, l = blockIdx.x - ct * BP_N;
+  const int o = blockIdx.y, ct = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
-  __shared__ double red[4][BP_CRT * 64];
+  __shared__ double red[4][BP_N * BP_CRT * 64];
   const int u = ct * 8 + g;                       // this lane's column of the B fragments: chain cc of the octet
 #if BP_D == 9
   const int cc = a.operm ? (u < 64 ? u >> 3 : u - 64) : u / BP_D;
@@ -2845,9 +2851,11 @@ extern "C" __global__ void __launch_bounds__(128, BP_TOEP_MINBLOCKS) bp_toep(BpO
   const int cc = u / BP_D;
 #endif
   const int c = o * 8 + cc;
-  double accW[BP_CRT][2];
+  double accW[BP_N][BP_CRT][2];
 #pragma unroll
-  for (int rt = 0; rt < BP_CRT; ++rt) { accW[rt][0] = 0.0; accW[rt][1] = 0.0; }
+  for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+    for (int rt = 0; rt < BP_CRT; ++rt) { accW[l][rt][0] = 0.0; accW[l][rt][1] = 0.0; }
   {   // none of the octet's chains on this path: W stays unwritten (bp_wpost returns for those chains too)
     bool any = false;
 #pragma unroll
@@ -2861,29 +2869,39 @@ extern "C" __global__ void __launch_bounds__(128, BP_TOEP_MINBLOCKS) bp_toep(BpO
     const int rows = __reduce_max_sync(0xffffffffu, jm < 0 ? 0 : (jm >> 8) + J);
     const double* sg = a.osg + ((size_t)o * a.cgroups + grp) * BP_XR * BP_OU;
     const double* cf = a.cg_coef + (size_t)grp * BP_CCTAB + 8;
-    double bf[2];
+    double bf[BP_N][2];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int j = ks * 4 + tg;
-      const double v = __ldcs(sg + bp_osg_off(j * BP_N + l, u));   // (a warp reads 256 contiguous bytes)
-      bf[ks] = j <= J ? v : 0.0;   // rows beyond the chain's own degree hold X b products of terms the chain does not have
-    }
+    for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int j = ks * 4 + tg;
+        const double v = __ldcs(sg + bp_osg_off(j * BP_N + l, u));   // (a warp reads 256 contiguous bytes)
+        bf[l][ks] = j <= J ? v : 0.0;   // rows beyond the chain's own degree hold X b products of terms the chain does not have
+      }
 #pragma unroll
     for (int rt = 0; rt < BP_CRT; ++rt)
       if (rt * 8 < rows) {
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const int ix = (rt * 8 + g + 1) - (ks * 4 + tg);   // c_(n-j)(tau_g), n = 8 rt + g + 1, j = 4 ks + tg (the table is zero outside 0 .. BP_WCAP + 1)
-          bp_dmma(accW[rt][0], accW[rt][1], cf[ix], bf[ks]);
+          const double af = cf[ix];
+#pragma unroll
+          for (int l = 0; l < BP_N; ++l) bp_dmma(accW[l][rt][0], accW[l][rt][1], af, bf[l][ks]);
         }
       }
   }
 #pragma unroll
-  for (int rt = 0; rt < BP_CRT; ++rt) { red[warp][rt * 64 + lane * 2] = accW[rt][0]; red[warp][rt * 64 + lane * 2 + 1] = accW[rt][1]; }
+  for (int l = 0; l < BP_N; ++l)
+#pragma unroll
+    for (int rt = 0; rt < BP_CRT; ++rt) {
+      red[warp][(l * BP_CRT + rt) * 64 + lane * 2] = accW[l][rt][0];
+      red[warp][(l * BP_CRT + rt) * 64 + lane * 2 + 1] = accW[l][rt][1];
+    }
   __syncthreads();
-  for (int i = tid; i < BP_CRT * 64; i += 128) {
+  for (int i = tid; i < BP_N * BP_CRT * 64; i += 128) {
     const double sacc = (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]);
-    const int rt = i >> 6, ln = (i & 63) >> 1, e = i & 1;
+    const int l = i / (BP_CRT * 64), i1 = i - l * (BP_CRT * 64);
+    const int rt = i1 >> 6, ln = (i1 & 63) >> 1, e = i1 & 1;
     const int row = rt * 8 + (ln >> 2), uu = ct * 8 + (ln & 3) * 2 + e;
 #if BP_D == 9
     const int cc2 = a.operm ? (uu < 64 ? uu >> 3 : uu - 64) : uu / BP_D, d = a.operm ? (uu < 64 ? uu & 7 : 8) : uu % BP_D;

@@ -825,7 +825,7 @@ int log_prob_dev(bpc_model* m, bpc_data* d, const double* u_dev, int nchains, in
           } else {
             BPC_CUDA(launch((const void*)L->fusedo, dim3(d->ntiles, d->noct), dim3(128), args, L->o_smem, st));
           }
-          BPC_CUDA(launch((const void*)L->toep, dim3(D * n, d->noct), dim3(128), args, 0, st));
+          BPC_CUDA(launch((const void*)L->toep, dim3(D, d->noct), dim3(128), args, 0, st));
           g_launches += 1;   // (bp_otable stands in for bp_prologue in the count below)
         } else if (d->cmode) {
           // centred W path: per-chain tables of exp(tau L), then short series around the groups' centres

@@ -220,8 +220,8 @@ std::string generate_cuda(ModelSpec& m) {
       const bool on = (o2 && std::atoi(o2) == 1) || (o9 && std::atoi(o9) == 1) || (alt && std::atoi(alt) == 1);
       s += on ? "#define BP_ALT_KERNELS 1\n" : "#define BP_ALT_KERNELS 0\n";
     }
-    int tmin = 8;    // bp_toep: CTAs per SM.  MEASURED on cfg5U (1.46 waves at 8): 8 -> 62 us (62 registers, no spills), 10 -> 74, 12 -> 82 (one wave,
-                     // 40 registers, 84 bytes spilled), 16 -> 123: the spills cost more than the second wave
+    int tmin = 4;    // bp_toep: CTAs per SM the register budget is cut for (n = 3: 30 accumulator doubles per thread; the (D, octets) grid of 512
+                     // chains is one wave at 4; measurements at the kernel)
     if (const char* ev = std::getenv("BPC_TOEP_MINBLOCKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) tmin = v; }
     std::snprintf(buf, sizeof buf, "#define BP_TOEP_MINBLOCKS %d\n", tmin);
     s += buf;
