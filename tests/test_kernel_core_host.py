@@ -135,3 +135,34 @@ def test_octet_flop_constants_and_adjugate_score(name):
                 assert rc2 == 0
                 np.testing.assert_allclose(-0.5 * (np.log(det.value) + q.value), lp1.value, rtol=1e-13)
                 np.testing.assert_allclose(b2, b1, rtol=1e-11, atol=1e-13 * np.abs(b1).max())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_s_prime_block_layout_is_a_bijection_and_contiguous_for_bp_toep(n, tmp_path):
+    """bp_osg_off (the position of S'[(j, l)][column] inside a group's block, written by bp_fusedo and read by bp_toep): the function's own
+    text from csrc/bp_kernels.cuh compiled for the host.  Every element of the 8 n x 8 D block has its own slot, the 8 x 8 elements
+    (all j, the 8 columns of one tile) of one ancestor l are 64 consecutive doubles and the n ancestors of a tile follow each other --
+    what makes a CTA of bp_toep read n x 512 contiguous bytes per group."""
+    import ctypes
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "bpinference_b200", "csrc", "bp_kernels.cuh")).read()
+    m = re.search(r"__device__ __forceinline__ int bp_osg_off\(int row, int col\) \{.*?\n\}\n", text, re.S)
+    assert m, "bp_osg_off not found"
+    src = tmp_path / "osg.cpp"
+    src.write_text("#define __device__\n#define __forceinline__ inline\n#define BP_N %d\n#define BP_CJ 8\n%s\nextern \"C\" int osg(int r, int c) { return bp_osg_off(r, c); }\n"
+                   % (n, m.group(0)))
+    lib = tmp_path / "osg.so"
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", str(src), "-o", str(lib)], check=True)
+    f = ctypes.CDLL(str(lib)).osg
+    D = n + n * (n + 1) // 2
+    rows, cols = 8 * n, 8 * D
+    off = np.array([[f(r, c) for c in range(cols)] for r in range(rows)])
+    assert sorted(off.ravel().tolist()) == list(range(rows * cols))
+    for ct in range(D):
+        for l in range(n):
+            blk = np.array([[off[j * n + l, ct * 8 + c8] for c8 in range(8)] for j in range(8)])
+            base = (ct * n + l) * 64
+            assert (blk == base + np.arange(64).reshape(8, 8)).all()
