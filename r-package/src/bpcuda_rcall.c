@@ -118,7 +118,7 @@ SEXP bpc_R_sample(SEXP mptr, SEXP dptr, SEXP chains, SEXP iter, SEXP warmup, SEX
   int C = Rf_asInteger(chains), it = Rf_asInteger(iter), wu = Rf_asInteger(warmup), dim = bpc_model_dim(m), ns = it - wu;
   if (C < 1 || ns < 1) Rf_error("need chains >= 1 and warmup < iter");
   bpc_sample_args a = {C, it, wu, Rf_asReal(delta), Rf_asInteger(depth), (unsigned long long)Rf_asReal(seed), 0,
-                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps), Rf_asInteger(metric)};
+                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps), Rf_asInteger(metric), NULL};
   SEXP draws = PROTECT(Rf_alloc3DArray(REALSXP, dim, ns, C)), lp = PROTECT(Rf_allocMatrix(REALSXP, ns, C));
   SEXP div = PROTECT(Rf_allocMatrix(INTSXP, ns, C)), td = PROTECT(Rf_allocMatrix(INTSXP, ns, C)), nl = PROTECT(Rf_allocMatrix(INTSXP, ns, C));
   SEXP acc = PROTECT(Rf_allocMatrix(REALSXP, ns, C)), eps = PROTECT(Rf_allocMatrix(REALSXP, ns, C)), rhat = PROTECT(Rf_allocVector(REALSXP, dim));
@@ -155,7 +155,7 @@ SEXP bpc_R_sample_multi(SEXP mptr, SEXP dat, SEXP simple, SEXP devices, SEXP cha
   int T = C * ndev, nprot = 0;
   bpc_stan_data sd = stan_data_of(dat, Rf_asLogical(simple), &nprot);
   bpc_sample_args a = {C, it, wu, Rf_asReal(delta), Rf_asInteger(depth), (unsigned long long)Rf_asReal(seed), 0,
-                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps), Rf_asInteger(metric)};
+                       Rf_isNull(inits) ? NULL : REAL(inits), Rf_asLogical(pooled), 0.0, Rf_asInteger(optsteps), Rf_asInteger(metric), NULL};
   SEXP draws = PROTECT(Rf_alloc3DArray(REALSXP, dim, ns, T)), lp = PROTECT(Rf_allocMatrix(REALSXP, ns, T));
   SEXP div = PROTECT(Rf_allocMatrix(INTSXP, ns, T)), td = PROTECT(Rf_allocMatrix(INTSXP, ns, T)), nl = PROTECT(Rf_allocMatrix(INTSXP, ns, T));
   SEXP acc = PROTECT(Rf_allocMatrix(REALSXP, ns, T)), eps = PROTECT(Rf_allocMatrix(REALSXP, ns, T)), rhat = PROTECT(Rf_allocVector(REALSXP, dim));

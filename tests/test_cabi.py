@@ -118,6 +118,51 @@ def test_module_cache_and_alternative_kernels_on_request(monkeypatch):
     assert c.cuda_source != a.cuda_source and b"bp_fusedo2" in c.cubin() and b"bp_fusedo9" in c.cubin()
 
 
+def test_r_shim_compiles_against_the_header():
+    """r-package/src/bpcuda_rcall.c (the .Call binding INTEGRATION.md describes) cannot be built here -- R is not in the image -- but it
+    can be type-checked: against include/bpcuda.h (every bpc_* call with the header's argument list) and against declarations of the
+    part of R's C API it uses (tests/r_stub, written for this test).  Also: every registered routine exists with the registered
+    number of SEXP arguments, and the R wrappers call only registered routines."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "r-package", "src", "bpcuda_rcall.c")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-Werror=int-conversion", "-Werror=missing-field-initializers", "-I" + os.path.join(root, "tests", "r_stub"),
+                        "-I" + os.path.join(root, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    reg = dict((m.group(1), int(m.group(2))) for m in re.finditer(r'\{"(bpc_R_\w+)", \(DL_FUNC\)&\1, (\d+)\}', text))
+    assert len(reg) >= 10
+    for name, nargs in reg.items():
+        m = re.search(r"SEXP %s\(([^)]*)\)\s*\{" % name, text)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == nargs and all(p.strip().startswith("SEXP ") for p in params), (name, nargs, m.group(1))
+    rtext = "\n".join(ln.split("#")[0] for ln in open(os.path.join(root, "r-package", "R", "bpcuda.R")).read().splitlines())
+    calls = []
+    for m in re.finditer(r"\.Call\(", rtext):          # every .Call(...) with its top-level arguments
+        depth, args, cur, i = 1, [], "", m.end()
+        while depth:
+            ch = rtext[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if depth == 1 and ch == ",":
+                args.append(cur)
+                cur = ""
+            elif depth:
+                cur += ch
+            i += 1
+        args.append(cur)
+        calls.append((args[0].strip().strip('"'), len(args) - 1))
+    assert len(calls) >= 10
+    for name, nargs in calls:
+        assert reg.get(name) == nargs, (name, nargs, reg.get(name))
+
+
 def test_non_finite_bounds_parameters_and_data_are_rejected():
     """(0, Inf) bounds used to produce Theta = Inf / NaN and silently rejected chains; NaN durations broke the sort in
     bpc_data_create.  Both are refused at the boundary now, before any device work."""
