@@ -205,3 +205,44 @@ def test_grouped_path_with_phase_b_on_its_own_grid(chains, kernel):
     bad["init_pop"] = ip
     lpb, gb, stb = eng.log_prob_grad(bad, u)
     assert (stb & 1).all() and np.isneginf(lpb).all() and (gb == 0).all()
+
+
+def _unbox(v):
+    """what jsonlite::write_json(auto_unbox = TRUE) makes of an R value: matrices row by row, length-one vectors as scalars"""
+    a = np.asarray(v)
+    if a.ndim == 0 or (a.ndim == 1 and a.size == 1):
+        return a.reshape(-1)[0].item()
+    return a.tolist()
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4"])
+def test_rstan_dump_comparer_reads_a_dump_shaped_like_parity_dump_R(name):
+    """tools/compare_rstan_dump.py (the Python half of SURVEY.md §8(f) N4) on a dump with the layout r-package/parity_dump.R writes
+    through jsonlite -- matrices row by row, `upars` / `grad` one COLUMN per fixture point, length-one vectors unboxed, log densities up
+    to the additive constant Stan drops -- with the CPU oracle standing in for rstan.  Checks the comparer's plumbing (model and priors
+    rebuilt from the JSON, data list, orientation, differences of lp); the numbers rstan would put there need a machine with R."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("compare_rstan_dump", os.path.join(root, "tools", "compare_rstan_dump.py"))
+    cmp_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cmp_mod)
+    cfg = syn.make_config(name, chains=5)
+    om = bo.OracleModel(cfg["kind"], cfg["e_mat"], cfg["p_vec"], cfg["func_deps"], cfg["nparams"], cfg["ndep"], cfg["priors"])
+    u = cfg["upars"]
+    lp, g, st = bo.log_prob(om, cfg["data"], u)
+    lp_nj, _, _ = bo.log_prob(om, cfg["data"], u, jacobian=False)
+    assert (st == 0).all()
+    entry = dict(name=name, simple_bd=cfg["kind"] == "simple_bd", noise_model=cfg["kind"] == "multitype_noise",
+                 model=dict(e_mat=_unbox(cfg["e_mat"]), p_vec=_unbox(cfg["p_vec"]), func_deps=list(cfg["func_deps"]), nparams=cfg["nparams"], ndep=cfg["ndep"]),
+                 priors=[dict(name=p["name"], params=_unbox(p["params"]), bounds=_unbox(p["bounds"]) if p.get("bounds") is not None else "NA") for p in cfg["priors"]],
+                 dat={k: _unbox(v) for k, v in cfg["data"].items()}, upars=u.T.tolist(),
+                 lp=(lp + 1234.5).tolist(), lp_nojac=(lp_nj - 77.0).tolist(), grad=g.T.tolist())
+    if name == "cfg2":
+        entry["log_lik"] = bo.log_lik(om, cfg["data"], u[:1])[0].tolist()
+    out = cmp_mod.compare(json.loads(json.dumps(entry)))
+    assert out["status"] == [0] * 5
+    assert out["lp_diff_rel"] < 1e-10 and out["lp_nojac_diff_rel"] < 1e-10 and out["grad_rel"] < 1e-8
+    if name == "cfg2":
+        assert out["log_lik_rel"] < 1e-10

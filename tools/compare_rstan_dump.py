@@ -21,15 +21,23 @@ def _mat(x, nrow=None):
 def compare(entry):
     m, dat = entry["model"], dict(entry["dat"])
     e_mat = _mat(m["e_mat"])
-    mod = bp.bp_model(e_mat, m["p_vec"], list(m["func_deps"]), int(m["nparams"]), int(m["ndep"]))
+    func_deps = [m["func_deps"]] if isinstance(m["func_deps"], str) else list(m["func_deps"])
+    mod = bp.bp_model(e_mat, np.atleast_1d(m["p_vec"]).tolist(), func_deps, int(m["nparams"]), int(m["ndep"]))
     priors = []
     for pr in entry["priors"]:
         b = pr.get("bounds")
         has = isinstance(b, list) and len(b) == 2 and all(v is not None for v in b)
         priors.append(dict(name=pr["name"], params=np.atleast_1d(pr["params"]).tolist(), bounds=b if has else None))
     eng = bp.stan_model(mod, priors, simple_bd=bool(entry["simple_bd"]), noise_model=bool(entry["noise_model"]))
-    for k in ("pop_vec", "init_pop", "function_var"):
-        dat[k] = np.asarray(dat[k], dtype=float)
+    # jsonlite's auto_unbox turns every length-one vector into a scalar (`times` of a one-duration design, ...): back to arrays
+    for k in ("pop_vec", "init_pop", "function_var", "e_mat", "times"):
+        if k in dat:
+            dat[k] = np.atleast_1d(np.asarray(dat[k], dtype=float))
+    for k in ("p_vec", "times_idx", "var_idx"):
+        if k in dat:
+            dat[k] = np.atleast_1d(np.asarray(dat[k], dtype=int))
+    if "function_var" in dat and dat["function_var"].ndim == 1:
+        dat["function_var"] = dat["function_var"].reshape(-1, max(1, int(dat.get("ndep", 1)) or 1))
     upars = np.asarray(entry["upars"], dtype=float).T                 # R writes dim x points column-major
     lp, grad, st = eng.log_prob_grad(dat, upars)
     lp_nj, _, _ = eng.log_prob_grad(dat, upars, adjust_transform=False)
