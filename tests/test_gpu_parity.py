@@ -324,6 +324,29 @@ def test_octet_path_matches_oracle_and_centred_path(name, nobs, chains, grouping
     np.testing.assert_allclose(g3, g[:5], rtol=1e-9, atol=1e-11 * np.abs(g).max())
 
 
+def test_octet_path_with_more_groups_than_one_batch_of_the_group_table():
+    """narrow groups (8 chunks instead of 32): more than 128 groups, so bp_otable's N_0 loop (one thread per group, batches of 128)
+    takes a second batch, bp_fusedo runs short groups and bp_toep sums over many of them; against the oracle."""
+    import os
+    cfg = syn.make_config("cfg5U", chains=16, nobs=40000)
+    eng, om = _pair(cfg)
+    u = cfg["upars"].copy()
+    u[1] += 0.75
+    u[2] -= 1.5
+    os.environ["BPC_CGROUP_CHUNKS"] = "8"
+    try:
+        d = eng.data(cfg["data"])
+    finally:
+        del os.environ["BPC_CGROUP_CHUNKS"]
+    name, ctas, _ = d.path(16)
+    assert "bp_fusedo" in name and ctas > 128, (name, ctas)
+    lp, g, st = eng.log_prob_grad(d, u)
+    lp_o, g_o, st_o = bo.log_prob(om, cfg["data"], u)
+    assert st.tolist() == st_o.tolist() and (st == 0).all()
+    np.testing.assert_allclose(lp, lp_o, rtol=1e-11)
+    np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-10 * np.abs(g_o).max())
+
+
 def test_octet_path_one_type_multitype_template():
     """ntypes = 1 under the multitype template with per-observation durations: the octet path's smallest shape
     (D = 2: two (cc, d) tiles, one row tile) against the oracle and against bp_fusedc."""
