@@ -472,11 +472,21 @@ def _main(args):
     peaks = {"dfma": peak_tf, "dmma": peak_dmma}
 
     # ---- the other shapes of SURVEY.md §8(d), every rank its own chains (weak scaling, no collective) ----------------------
+    def side(fn, *a, **k):
+        """the side blocks of the line (other shapes, sampling) must not cost the headline: on ONE rank a failure becomes an `error` entry.
+        With several ranks the call stays unguarded -- a rank that swallowed an exception would leave the others waiting in a collective."""
+        if world > 1:
+            return fn(*a, **k)
+        try:
+            return fn(*a, **k)
+        except Exception as e:      # noqa: BLE001 (reported in the JSON line)
+            return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
     others = []
     if not args.no_other_workloads and args.workload == "cfg5U" and not args.nobs:
         for name in ("cfg5G", "cfg5K", "cfg2", "cfg1", "cfg3", "cfg4"):
-            others.append(time_workload(bp, syn, _ffi, torch, dist, world, local_rank, rank, name, DEFAULT_CHAINS[name], 5 if name == "cfg5K" else 10,
-                                        peaks, flush))
+            others.append(side(time_workload, bp, syn, _ffi, torch, dist, world, local_rank, rank, name, DEFAULT_CHAINS[name], 5 if name == "cfg5K" else 10,
+                               peaks, flush))
 
     # ---- sampling: every rank its chains, warm-up statistics pooled over all ranks ----------------------------------------
     sampling = None
@@ -484,10 +494,10 @@ def _main(args):
         # cfg2 (250 observations at ONE duration: a thin curved posterior no linear metric straightens, trees of depth 7-8 whatever the metric):
         # pooled diagonal metric, the best of tools/cfg2_variants.py; cfg5U (100 000 observations: a near-Gaussian posterior with a strongly
         # rotated ridge): pooled dense metric
-        sampling = {"cfg2": sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 200, False)}
+        sampling = {"cfg2": side(sampling_report, bp, syn, torch, dist, rank, world, local_rank, "cfg2", 1024, None, 300, 150, 200, False)}
         if args.workload == "cfg5U" and not args.nobs:
-            sampling["cfg5U"] = sampling_report(bp, syn, torch, dist, rank, world, local_rank, "cfg5U", chains, None, args.sampling_iter,
-                                                args.sampling_iter // 2, 300, True, subsample=500)
+            sampling["cfg5U"] = side(sampling_report, bp, syn, torch, dist, rank, world, local_rank, "cfg5U", chains, None, args.sampling_iter,
+                                     args.sampling_iter // 2, 300, True, subsample=500)
 
     if rank == 0:
         total_evals = float(world) * chains * N * args.steps
